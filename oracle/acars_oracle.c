@@ -1,0 +1,435 @@
+/*
+ * TEST INFRASTRUCTURE — NOT PRODUCT CODE.  See acars_oracle.h for scope and parity status.
+ *
+ * Restatement of the reference's algorithm for the hot path; every function cites the
+ * reference file:line it follows.  Build: -O2 -ffp-contract=off (strict IEEE, no FMA
+ * contraction), the same flags as the in-place reference build it is pinned against.
+ * Third-party arithmetic on the path is glibc libm only (sincos, hypotf, cosf, sincosf,
+ * log10); this file calls the same entry points the reference reaches.
+ */
+#define _GNU_SOURCE
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include "acars_oracle.h"
+
+/* ------------------------------------------------------------------ tables */
+
+/* msk.c:44-48 — half-cosine matched filter, oversampled x12, negative lobes clamped */
+void orc_build_h(float *h)
+{
+	for (int i = 0; i < ORC_FLENO; i++) {
+		h[i] = cosf(2.0 * M_PI * 600.0 / ORC_INTRATE / ORC_MFLTOVER * (i - (ORC_FLENO - 1) / 2));
+		if (h[i] < 0) h[i] = 0;
+	}
+}
+
+/* syndrom.h:15-49 — the table there is the reflected CCITT CRC (poly 0x8408, "Kermit"),
+ * stepped one byte at a time; this computes the same step bitwise. */
+uint16_t orc_crc_step(uint16_t crc, uint8_t c)
+{
+	crc ^= c;
+	for (int k = 0; k < 8; k++)
+		crc = (crc & 1) ? (uint16_t)((crc >> 1) ^ 0x8408) : (uint16_t)(crc >> 1);
+	return crc;
+}
+
+/* syndrom.h:52-295 — syndrom[bit + 8*p] is the CRC left by a single wrong bit `bit` in the
+ * byte that sits p bytes before the end of (text + 2 CRC bytes); CRC is linear, init 0. */
+uint16_t orc_syndrome(int bit, int p)
+{
+	uint16_t crc = orc_crc_step(0, (uint8_t)(1u << bit));
+	while (p-- > 0) crc = orc_crc_step(crc, 0);
+	return crc;
+}
+
+/* syndrom.h:4-13 used as numbits[c]&1: 1 when the byte has an odd number of set bits */
+int orc_odd_parity(uint8_t c)
+{
+	c ^= c >> 4; c ^= c >> 2; c ^= c >> 1;
+	return c & 1;
+}
+
+/* ------------------------------------------------------------------ channelizer front-end */
+
+/* rtl.c:245-247 — MHz string value to Hz, rounded to the 12.5 kHz raster */
+int orc_round_freq(double mhz)
+{
+	return ((int)(1000000 * mhz + ORC_INTRATE / 2) / ORC_INTRATE) * ORC_INTRATE;
+}
+
+/* rtl.c:255 — channel[].Fr is an int assigned from a float cast of the frequency */
+int orc_stored_fr(unsigned fd) { return (int)(float)fd; }
+
+/* rtl.c:131-168 — pick the tuner centre: highest Fc (1 Hz steps, downward) such that every
+ * channel is >= 2*INTRATE from DC, <= rate/2 - 2*INTRATE away, and no two are mirror images */
+unsigned orc_choose_fc(const unsigned *freqs, int n, int K)
+{
+	unsigned f[64];
+	int rate = ORC_INTRATE * K;
+	if (n > 64) return 0;
+	memcpy(f, freqs, n * sizeof(unsigned));
+	for (int i = 1; i < n; i++)            /* ascending sort (the reference bubble-sorts) */
+		for (int j = i; j > 0 && f[j - 1] > f[j]; j--) { unsigned t = f[j]; f[j] = f[j - 1]; f[j - 1] = t; }
+	if ((long long)f[n - 1] - f[0] > rate - 4 * ORC_INTRATE) return 0;
+	long long fc;
+	for (fc = (long long)f[n - 1] + 2 * ORC_INTRATE; fc > (long long)f[0] - 2 * ORC_INTRATE; fc--) {
+		int k;
+		for (k = 0; k < n; k++) {
+			long long d = llabs(fc - f[k]);
+			if (d > rate / 2 - 2 * ORC_INTRATE) break;
+			if (d < 2 * ORC_INTRATE) break;
+			if (k > 0 && fc - f[k - 1] == (long long)f[k] - fc) break;
+		}
+		if (k == n) break;
+	}
+	return (unsigned)fc;
+}
+
+/* rtl.c:283-286 — per-channel table: NCO x boxcar(K) x 1/127.5 scaling, one float complex per tap */
+void orc_build_wf(int fr_stored, unsigned fc, int K, float *wf)
+{
+	float rate = (float)(ORC_INTRATE * K);
+	float am = (float)(((float)fr_stored - (float)fc) / rate * 2.0 * M_PI);
+	for (int ind = 0; ind < K; ind++) {
+		float ph = am * ind, sn, cs;
+		sincosf(-ph, &sn, &cs);                 /* cexpf(-j ph), rtl.c:285 */
+		float re = cs / (float)K, im = sn / (float)K;   /* complex / int */
+		wf[2 * ind] = (float)((double)re / 127.5);      /* complex / double, stored float */
+		wf[2 * ind + 1] = (float)((double)im / 127.5);
+	}
+}
+
+/* rtl.c:334-354 — u8 IQ -> per channel |sum_k (x_k - 127.37) * wf_k| over K samples, no overlap.
+ * float complex arithmetic spelled out: product (ac-bd, ad+bc), then accumulate, in tap order. */
+void orc_channelize(const uint8_t *iq, int nout, int K, int nch, const float *wf, float *dm)
+{
+	for (int m = 0; m < nout; m++) {
+		const uint8_t *p = iq + (size_t)m * K * 2;
+		for (int ch = 0; ch < nch; ch++) {
+			const float *w = wf + (size_t)ch * 2 * K;
+			float dr = 0, di = 0;
+			for (int ind = 0; ind < K; ind++) {
+				float a = (float)p[2 * ind] - 127.37f, b = (float)p[2 * ind + 1] - 127.37f;
+				float c = w[2 * ind], d = w[2 * ind + 1];
+				float pr = a * c - b * d, pi = a * d + b * c;
+				dr = dr + pr;
+				di = di + pi;
+			}
+			dm[(size_t)ch * nout + m] = hypotf(dr, di);     /* cabsf, rtl.c:353 */
+		}
+	}
+}
+
+/* ------------------------------------------------------------------ frame sync (acars.c) */
+
+#define SYN 0x16
+#define SOH 0x01
+#define STX 0x02
+#define ETX 0x83
+#define ETB 0x97
+#define DLE 0x7f
+#define MAXPERR 3
+
+static void sink_msg(orc_sink_t *s, const orc_msg_t *m)
+{
+	if (!s) return;
+	if (s->nmsg == s->capmsg) {
+		s->capmsg = s->capmsg ? 2 * s->capmsg : 64;
+		s->msgs = realloc(s->msgs, s->capmsg * sizeof(orc_msg_t));
+	}
+	s->msgs[s->nmsg++] = *m;
+}
+
+/* acars.c:239-244 */
+static void frame_reset(orc_chan_t *c)
+{
+	c->state = ORC_WSYN;
+	c->MskDf = 0;
+	c->nbits = 1;
+}
+
+/* acars.c:350-369 — level estimate and hand-off to the block queue */
+static void frame_put(orc_chan_t *c, orc_sink_t *sink)
+{
+	c->blk.lvl = (float)(10 * log10(c->MskLvlSum / c->MskBitCount));
+	sink_msg(sink, &c->blk);
+	c->have_blk = 0;
+	c->state = ORC_END;
+	c->nbits = 8;
+}
+
+/* acars.c:246-375 — one assembled byte (or one bit while hunting for SYN) */
+void orc_decode_byte(orc_chan_t *c, orc_sink_t *sink)
+{
+	unsigned char r = c->outbits;
+	switch (c->state) {
+	case ORC_WSYN:
+		if (r == SYN || r == (unsigned char)~SYN) {
+			if (r != SYN) c->MskS ^= 2;             /* inverted polarity, acars.c:258-259 */
+			c->state = ORC_SYN2; c->nbits = 8;
+		} else
+			c->nbits = 1;
+		return;
+	case ORC_SYN2:
+		if (r == SYN) { c->state = ORC_SOH1; c->nbits = 8; return; }
+		if (r == (unsigned char)~SYN) { c->MskS ^= 2; c->nbits = 8; return; }
+		frame_reset(c);
+		return;
+	case ORC_SOH1:
+		if (r != SOH) { frame_reset(c); return; }
+		c->have_blk = 1;
+		c->blk.chn = c->chn; c->blk.len = 0; c->blk.err = 0;
+		c->state = ORC_TXT; c->nbits = 8;
+		c->MskLvlSum = 0; c->MskBitCount = 0;
+		return;
+	case ORC_TXT:
+		c->blk.txt[c->blk.len++] = r;
+		if (!orc_odd_parity(r) && ++c->blk.err > MAXPERR + 1) { frame_reset(c); return; }
+		if (r == ETX || r == ETB) { c->state = ORC_CRC1; c->nbits = 8; return; }
+		if (c->blk.len > 20 && r == DLE) {            /* missed the end of text, acars.c:324-333 */
+			c->blk.len -= 3;
+			c->blk.crc[0] = c->blk.txt[c->blk.len];
+			c->blk.crc[1] = c->blk.txt[c->blk.len + 1];
+			frame_put(c, sink);
+			return;
+		}
+		if (c->blk.len > 240) { frame_reset(c); return; }
+		c->nbits = 8;
+		return;
+	case ORC_CRC1:
+		c->blk.crc[0] = r; c->state = ORC_CRC2; c->nbits = 8;
+		return;
+	case ORC_CRC2:
+		c->blk.crc[1] = r;
+		frame_put(c, sink);
+		return;
+	case ORC_END:
+		frame_reset(c);
+		c->nbits = 8;
+		return;
+	}
+}
+
+/* ------------------------------------------------------------------ block FEC (acars.c:39-215) */
+
+/* acars.c:39-64 */
+static int fix_parity_errs(orc_msg_t *m, uint16_t crc, const int *pr, int pn)
+{
+	if (pn > 0) {
+		for (int i = 0; i < 8; i++)
+			if (fix_parity_errs(m, crc ^ orc_syndrome(i, m->len - *pr + 1), pr + 1, pn - 1)) {
+				m->txt[*pr] ^= (1 << i);
+				return 1;
+			}
+		return 0;
+	}
+	if (crc == 0) return 1;
+	for (int i = 0; i < 16; i++)
+		if (orc_syndrome(i & 7, i >> 3) == crc) return 1;
+	return 0;
+}
+
+/* acars.c:66-90 */
+static int fix_double_err(orc_msg_t *m, uint16_t crc)
+{
+	for (int i = 0; i < 16; i++)
+		if (orc_syndrome(i & 7, i >> 3) == crc) return 1;
+	for (int k = 0; k < m->len; k++) {
+		int p = m->len - k + 1;
+		for (int i = 0; i < 8; i++)
+			for (int j = 0; j < 8; j++) {
+				if (i == j) continue;
+				if ((crc ^ orc_syndrome(i, p) ^ orc_syndrome(j, p)) == 0) {
+					m->txt[k] ^= (1 << i);
+					m->txt[k] ^= (1 << j);
+					return 1;
+				}
+			}
+	}
+	return 0;
+}
+
+/* acars.c:123-209 — returns 1 when the reference would call outputmsg(), 0 when it drops */
+int orc_block_fec(orc_msg_t *m)
+{
+	int pr[MAXPERR], pn = 0;
+	uint16_t crc = 0;
+	if (m->len < 13) return 0;
+	m->txt[12] &= (ETX | STX);
+	m->txt[12] |= (ETX & STX);
+	for (int i = 0; i < m->len; i++)
+		if (!orc_odd_parity(m->txt[i])) { if (pn < MAXPERR) pr[pn] = i; pn++; }
+	if (pn > MAXPERR) return 0;
+	m->err = pn;
+	for (int i = 0; i < m->len; i++) crc = orc_crc_step(crc, m->txt[i]);
+	crc = orc_crc_step(crc, m->crc[0]);
+	crc = orc_crc_step(crc, m->crc[1]);
+	if (pn) { if (!fix_parity_errs(m, crc, pr, pn)) return 0; }
+	else if (crc && !fix_double_err(m, crc)) return 0;
+	pn = 0;
+	for (int i = 0; i < m->len; i++) {
+		if (!orc_odd_parity(m->txt[i])) pn++;
+		m->txt[i] &= 0x7f;
+	}
+	return pn == 0;
+}
+
+/* ------------------------------------------------------------------ MSK demodulator (msk.c) */
+
+void orc_chan_init(orc_chan_t *c, int chn)
+{
+	memset(c, 0, sizeof(*c));      /* msk.c:34-40 */
+	c->chn = chn;
+	c->nbits = 8;                  /* acars.c:230-234 */
+	c->state = ORC_WSYN;
+}
+
+/* msk.c:53-63 */
+static inline void put_bit(orc_chan_t *c, float v, orc_sink_t *sink)
+{
+	c->outbits >>= 1;
+	if (v > 0) c->outbits |= 0x80;
+	if (sink && sink->bits && sink->nbits < sink->capbits) sink->bits[sink->nbits++] = v > 0;
+	c->nbit_total++;
+	if (--c->nbits <= 0) orc_decode_byte(c, sink);
+}
+
+/* msk.c:67-137 — numerics contract of SURVEY.md §8(a): double VCO, float ring, float MF */
+void orc_demod(orc_chan_t *c, const float *h, const float *dm, int len, orc_sink_t *sink)
+{
+	const double pllc = (double)0.52f, pllg = (double)38e-4f;     /* msk.c:65-66, float constants */
+	unsigned idx = c->idx;
+	double p = c->MskPhi;
+	for (int n = 0; n < len; n++) {
+		double s = 1800.0 / ORC_INTRATE * 2.0 * M_PI + c->MskDf;    /* msk.c:81 */
+		double sn, cs;
+		p += s;
+		if (p >= 2.0 * M_PI) p -= 2.0 * M_PI;
+		sincos(-p, &sn, &cs);                                      /* cexp(-p*I), msk.c:90 */
+		c->inb_re[idx] = (float)((double)dm[n] * cs);
+		c->inb_im[idx] = (float)((double)dm[n] * sn);
+		idx = (idx + 1) % ORC_FLEN;
+
+		c->MskClk = (float)((double)c->MskClk + s);                /* msk.c:95, float state */
+		if ((double)c->MskClk >= 3 * M_PI / 2.0 - s / 2) {
+			float vr = 0, vi = 0, lvl, vo;
+			double dphi, d;
+			int o;
+			c->MskClk = (float)((double)c->MskClk - 3 * M_PI / 2.0);
+			o = (int)(ORC_MFLTOVER * ((double)c->MskClk / s + 0.5));   /* msk.c:103 */
+			if (o > ORC_MFLTOVER) o = ORC_MFLTOVER;
+			for (int j = 0; j < ORC_FLEN; j++, o += ORC_MFLTOVER) {
+				unsigned k = (j + idx) % ORC_FLEN;
+				vr = vr + h[o] * c->inb_re[k];
+				vi = vi + h[o] * c->inb_im[k];
+			}
+			lvl = hypotf(vr, vi);                                  /* cabsf, msk.c:110 */
+			d = (double)lvl + 1e-8;
+			vr = (float)((double)vr / d);
+			vi = (float)((double)vi / d);
+			c->MskLvlSum += lvl * lvl / 4;
+			c->MskBitCount++;
+			if (c->MskS & 1) { vo = vi; dphi = (vo >= 0) ? -vr : vr; }
+			else             { vo = vr; dphi = (vo >= 0) ? vi : -vi; }
+			put_bit(c, (c->MskS & 2) ? -vo : vo, sink);
+			c->MskS++;
+			c->MskDf = pllc * c->MskDf + (1.0 - pllc) * pllg * dphi;   /* msk.c:130 */
+		}
+	}
+	c->idx = idx;
+	c->MskPhi = p;
+}
+
+/* ------------------------------------------------------------------ whole path, one stream */
+
+struct orc_stream {
+	int K, nch;
+	float *wf, *dm;
+	float h[ORC_FLENO];
+	orc_chan_t *ch;
+	orc_sink_t raw;
+	orc_msg_t *out; int nout, capout;
+};
+
+orc_stream_t *orc_stream_new(int K, int nch, const float *wf)
+{
+	orc_stream_t *s = calloc(1, sizeof(*s));
+	s->K = K; s->nch = nch;
+	s->wf = malloc(sizeof(float) * 2 * K * nch);
+	memcpy(s->wf, wf, sizeof(float) * 2 * K * nch);
+	s->dm = malloc(sizeof(float) * ORC_OUTBLK * nch);
+	s->ch = malloc(sizeof(orc_chan_t) * nch);
+	for (int i = 0; i < nch; i++) orc_chan_init(&s->ch[i], i);
+	orc_build_h(s->h);
+	return s;
+}
+
+void orc_stream_free(orc_stream_t *s)
+{
+	if (!s) return;
+	free(s->wf); free(s->dm); free(s->ch); free(s->raw.msgs); free(s->out); free(s);
+}
+
+/* rtl.c:314-361: channelize one block for all channels, then demod channel by channel;
+ * decoded blocks go through the FEC in emission order (block-major, channel, time). */
+int orc_stream_blocks(orc_stream_t *s, const uint8_t *iq, int nblk)
+{
+	for (int b = 0; b < nblk; b++) {
+		orc_channelize(iq + (size_t)b * ORC_OUTBLK * s->K * 2, ORC_OUTBLK, s->K, s->nch, s->wf, s->dm);
+		for (int c = 0; c < s->nch; c++)
+			orc_demod(&s->ch[c], s->h, s->dm + (size_t)c * ORC_OUTBLK, ORC_OUTBLK, &s->raw);
+		for (int i = 0; i < s->raw.nmsg; i++) {
+			orc_msg_t m = s->raw.msgs[i];
+			if (!orc_block_fec(&m)) continue;
+			if (s->nout == s->capout) {
+				s->capout = s->capout ? 2 * s->capout : 64;
+				s->out = realloc(s->out, s->capout * sizeof(orc_msg_t));
+			}
+			s->out[s->nout++] = m;
+		}
+		s->raw.nmsg = 0;
+	}
+	return s->nout;
+}
+
+int orc_stream_msgs(orc_stream_t *s, orc_msg_t *out, int max)
+{
+	int n = s->nout < max ? s->nout : max;
+	memcpy(out, s->out, n * sizeof(orc_msg_t));
+	memmove(s->out, s->out + n, (s->nout - n) * sizeof(orc_msg_t));
+	s->nout -= n;
+	return n;
+}
+
+orc_chan_t *orc_stream_chan(orc_stream_t *s, int ch) { return &s->ch[ch]; }
+const float *orc_stream_dm(orc_stream_t *s, int ch) { return s->dm + (size_t)ch * ORC_OUTBLK; }
+
+/* ------------------------------------------------------------------ CPU baseline ("port") */
+
+typedef struct { int K, nch, nbuf, nblk; const float *wf; const uint8_t *iq; } bench_arg_t;
+
+static void *bench_thread(void *a)
+{
+	bench_arg_t *b = a;
+	orc_stream_t *s = orc_stream_new(b->K, b->nch, b->wf);
+	size_t blk = (size_t)ORC_OUTBLK * b->K * 2;
+	for (int i = 0; i < b->nblk; i++) orc_stream_blocks(s, b->iq + (size_t)(i % b->nbuf) * blk, 1);
+	orc_stream_free(s);
+	return NULL;
+}
+
+double orc_bench_streams(int nthreads, int K, int nch, const float *wf, const uint8_t *iq, int nbuf, int nblk)
+{
+	pthread_t th[256];
+	bench_arg_t a = { K, nch, nbuf, nblk, wf, iq };
+	struct timespec t0, t1;
+	if (nthreads > 256) nthreads = 256;
+	clock_gettime(CLOCK_MONOTONIC, &t0);
+	for (int i = 0; i < nthreads; i++) pthread_create(&th[i], NULL, bench_thread, &a);
+	for (int i = 0; i < nthreads; i++) pthread_join(th[i], NULL);
+	clock_gettime(CLOCK_MONOTONIC, &t1);
+	return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}

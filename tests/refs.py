@@ -1,0 +1,313 @@
+"""ctypes front-ends for the two CPU checkers under oracle/ (TEST INFRASTRUCTURE).
+
+RefLib    — oracle/_ref/libacarsref_*.so: the unmodified reference compiled in place.
+            It is process-global (the reference keeps its state in globals), so one
+            instance at a time per process.
+OracleLib — oracle/libacars_oracle.so: the re-entrant C restatement.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+ORACLE_DIR = ROOT / "oracle"
+
+
+def ensure_built() -> None:
+    """Build oracle/ (and oracle/_ref when /root/reference exists); no-op when up to date."""
+    subprocess.run(["make", "-s", "-C", str(ORACLE_DIR), "all"], check=True,
+                   stdout=subprocess.DEVNULL)
+
+
+class Msg(C.Structure):
+    _fields_ = [("chn", C.c_int), ("len", C.c_int), ("err", C.c_int), ("lvl", C.c_float),
+                ("txt", C.c_ubyte * 250), ("crc", C.c_ubyte * 2)]
+
+    def as_tuple(self):
+        return (self.chn, self.len, self.err, bytes(self.txt[:self.len]), bytes(self.crc))
+
+    def key(self):
+        return self.as_tuple() + (np.float32(self.lvl).tobytes(),)
+
+
+class RefState(C.Structure):
+    _fields_ = [("MskPhi", C.c_double), ("MskDf", C.c_double), ("MskLvlSum", C.c_double),
+                ("MskClk", C.c_float), ("MskBitCount", C.c_int), ("MskS", C.c_uint), ("idx", C.c_uint),
+                ("nbits", C.c_int), ("state", C.c_int), ("outbits", C.c_ubyte), ("inb", C.c_float * 22)]
+
+    def vec(self):
+        return (self.MskPhi, self.MskDf, self.MskLvlSum, self.MskClk, self.MskBitCount, self.MskS,
+                self.idx, self.nbits, self.state, self.outbits, tuple(self.inb))
+
+
+class OrcChan(C.Structure):
+    _fields_ = [("chn", C.c_int), ("MskPhi", C.c_double), ("MskDf", C.c_double), ("MskLvlSum", C.c_double),
+                ("MskClk", C.c_float), ("MskBitCount", C.c_int), ("MskS", C.c_uint), ("idx", C.c_uint),
+                ("inb_re", C.c_float * 11), ("inb_im", C.c_float * 11), ("outbits", C.c_ubyte),
+                ("nbits", C.c_int), ("state", C.c_int), ("have_blk", C.c_int), ("blk", Msg),
+                ("nbit_total", C.c_uint64)]
+
+    def vec(self):
+        inb = []
+        for i in range(11):
+            inb += [self.inb_re[i], self.inb_im[i]]
+        return (self.MskPhi, self.MskDf, self.MskLvlSum, self.MskClk, self.MskBitCount, self.MskS,
+                self.idx, self.nbits, self.state, self.outbits, tuple(inb))
+
+
+class OrcSink(C.Structure):
+    _fields_ = [("msgs", C.POINTER(Msg)), ("nmsg", C.c_int), ("capmsg", C.c_int),
+                ("bits", C.POINTER(C.c_uint8)), ("nbits", C.c_int64), ("capbits", C.c_int64)]
+
+
+def ref_available(variant: str = "O2") -> bool:
+    return (ORACLE_DIR / "_ref" / f"libacarsref_{variant}.so").exists()
+
+
+def best_fast_variant() -> str:
+    """-Ofast build matching the host: AVX-512 when the CPU has it, else AVX2+FMA."""
+    try:
+        flags = open("/proc/cpuinfo").read()
+    except OSError:
+        flags = ""
+    return "v4" if " avx512f" in flags and " avx512vl" in flags and " avx512bw" in flags else "v3"
+
+
+class RefLib:
+    def __init__(self, variant: str = "O2"):
+        self.lib = C.CDLL(str(ORACLE_DIR / "_ref" / f"libacarsref_{variant}.so"))
+        L = self.lib
+        L.ref_open_rtl.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_char_p)]
+        L.ref_rtl_block.argtypes = [C.c_void_p, C.c_uint]
+        L.ref_rtl_run.argtypes = [C.c_void_p, C.c_uint, C.c_int, C.c_int]
+        L.ref_get_wf.argtypes = [C.c_int, C.c_void_p]
+        L.ref_get_dm.argtypes = [C.c_int, C.c_void_p, C.c_int]
+        L.ref_audio_chunk.argtypes = [C.c_int, C.c_void_p, C.c_int]
+        L.ref_state.argtypes = [C.c_int, C.POINTER(RefState)]
+        L.ref_msgs.argtypes = [C.POINTER(Msg), C.c_int]
+        L.ref_center_freq.restype = C.c_uint
+        L.ref_tab_syndrom.argtypes = [C.c_void_p, C.c_int]
+        L.ref_tab_crc.argtypes = [C.c_void_p]
+        L.ref_tab_numbits.argtypes = [C.c_void_p]
+        self.K = None
+
+    def open_rtl(self, K: int, freqs_mhz) -> None:
+        strs = [("%.4f" % f).encode() for f in freqs_mhz]
+        arr = (C.c_char_p * len(strs))(*strs)
+        r = self.lib.ref_open_rtl(K, len(strs), arr)
+        if r:
+            raise RuntimeError(f"ref_open_rtl -> {r}")
+        self.K = K
+
+    def open_audio(self, nch: int) -> None:
+        if self.lib.ref_open_audio(nch):
+            raise RuntimeError("ref_open_audio failed")
+
+    @property
+    def nbch(self) -> int:
+        return self.lib.ref_nbch()
+
+    @property
+    def fc(self) -> int:
+        return self.lib.ref_center_freq()
+
+    def chan_freq(self, ch: int) -> int:
+        return self.lib.ref_chan_freq(ch)
+
+    def wf(self, ch: int) -> np.ndarray:
+        out = np.empty(2 * self.K, dtype=np.float32)
+        self.lib.ref_get_wf(ch, out.ctypes.data)
+        return out
+
+    def block(self, buf: np.ndarray) -> None:
+        assert buf.dtype == np.uint8 and buf.flags.c_contiguous
+        self.lib.ref_rtl_block(buf.ctypes.data, buf.size)
+
+    def run(self, bufs: np.ndarray, nblk: int) -> None:
+        assert bufs.dtype == np.uint8 and bufs.flags.c_contiguous and bufs.ndim == 2
+        self.lib.ref_rtl_run(bufs.ctypes.data, bufs.shape[1], bufs.shape[0], nblk)
+
+    def dm(self, ch: int, n: int = 1024) -> np.ndarray:
+        out = np.empty(n, dtype=np.float32)
+        self.lib.ref_get_dm(ch, out.ctypes.data, n)
+        return out
+
+    def audio(self, ch: int, x: np.ndarray) -> None:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        self.lib.ref_audio_chunk(ch, x.ctypes.data, len(x))
+
+    def state(self, ch: int) -> RefState:
+        s = RefState()
+        self.lib.ref_state(ch, C.byref(s))
+        return s
+
+    def msgs(self, flush: bool = True):
+        if flush:
+            self.lib.ref_flush()
+        out = []
+        buf = (Msg * 256)()
+        while True:
+            n = self.lib.ref_msgs(buf, 256)
+            for i in range(n):
+                m = Msg()
+                C.memmove(C.byref(m), C.byref(buf[i]), C.sizeof(Msg))
+                out.append(m)
+            if n < 256:
+                return out
+
+    def tables(self):
+        n = self.lib.ref_tab_syndrom(None, 0)
+        syn = np.empty(n, dtype=np.uint16)
+        self.lib.ref_tab_syndrom(syn.ctypes.data, n)
+        crc = np.empty(256, dtype=np.uint16)
+        self.lib.ref_tab_crc(crc.ctypes.data)
+        nb = np.empty(256, dtype=np.uint8)
+        self.lib.ref_tab_numbits(nb.ctypes.data)
+        return syn, crc, nb
+
+    def close(self) -> None:
+        self.lib.ref_close()
+
+
+class OracleLib:
+    def __init__(self):
+        self.lib = C.CDLL(str(ORACLE_DIR / "libacars_oracle.so"))
+        L = self.lib
+        L.orc_build_h.argtypes = [C.c_void_p]
+        L.orc_crc_step.argtypes = [C.c_uint16, C.c_uint8]
+        L.orc_crc_step.restype = C.c_uint16
+        L.orc_syndrome.argtypes = [C.c_int, C.c_int]
+        L.orc_syndrome.restype = C.c_uint16
+        L.orc_odd_parity.argtypes = [C.c_uint8]
+        L.orc_choose_fc.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_choose_fc.restype = C.c_uint
+        L.orc_round_freq.argtypes = [C.c_double]
+        L.orc_stored_fr.argtypes = [C.c_uint]
+        L.orc_build_wf.argtypes = [C.c_int, C.c_uint, C.c_int, C.c_void_p]
+        L.orc_channelize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_chan_init.argtypes = [C.POINTER(OrcChan), C.c_int]
+        L.orc_demod.argtypes = [C.POINTER(OrcChan), C.c_void_p, C.c_void_p, C.c_int, C.POINTER(OrcSink)]
+        L.orc_block_fec.argtypes = [C.POINTER(Msg)]
+        L.orc_stream_new.argtypes = [C.c_int, C.c_int, C.c_void_p]
+        L.orc_stream_new.restype = C.c_void_p
+        L.orc_stream_free.argtypes = [C.c_void_p]
+        L.orc_stream_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_stream_msgs.argtypes = [C.c_void_p, C.POINTER(Msg), C.c_int]
+        L.orc_stream_chan.argtypes = [C.c_void_p, C.c_int]
+        L.orc_stream_chan.restype = C.POINTER(OrcChan)
+        L.orc_stream_dm.argtypes = [C.c_void_p, C.c_int]
+        L.orc_stream_dm.restype = C.POINTER(C.c_float)
+        L.orc_bench_streams.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.orc_bench_streams.restype = C.c_double
+        self._h = np.empty(133, dtype=np.float32)
+        L.orc_build_h(self._h.ctypes.data)
+
+    @property
+    def h(self) -> np.ndarray:
+        return self._h
+
+    def plan(self, K: int, freqs_mhz):
+        """(freqs_hz, stored Fr per channel, Fc) the way initRtl derives them (rtl.c:243-268)."""
+        fd = np.array([self.lib.orc_round_freq(float(f)) for f in freqs_mhz], dtype=np.uint32)
+        fc = self.lib.orc_choose_fc(fd.ctypes.data, len(fd), K)
+        fr = [self.lib.orc_stored_fr(int(f)) for f in fd]
+        return [int(f) for f in fd], fr, int(fc)
+
+    def wf(self, K: int, freqs_mhz) -> np.ndarray:
+        _, fr, fc = self.plan(K, freqs_mhz)
+        out = np.empty((len(fr), 2 * K), dtype=np.float32)
+        for i, f in enumerate(fr):
+            self.lib.orc_build_wf(f, fc, K, out[i].ctypes.data)
+        return out
+
+    def channelize(self, iq: np.ndarray, K: int, wf: np.ndarray) -> np.ndarray:
+        iq = np.ascontiguousarray(iq, dtype=np.uint8).reshape(-1)
+        nout = iq.size // (2 * K)
+        nch = wf.shape[0]
+        dm = np.empty((nch, nout), dtype=np.float32)
+        wf = np.ascontiguousarray(wf, dtype=np.float32)
+        self.lib.orc_channelize(iq.ctypes.data, nout, K, nch, wf.ctypes.data, dm.ctypes.data)
+        return dm
+
+    def new_chan(self, chn: int) -> OrcChan:
+        c = OrcChan()
+        self.lib.orc_chan_init(C.byref(c), chn)
+        return c
+
+    def demod(self, chan: OrcChan, dm: np.ndarray, sink: "Sink | None" = None) -> None:
+        dm = np.ascontiguousarray(dm, dtype=np.float32)
+        self.lib.orc_demod(C.byref(chan), self._h.ctypes.data, dm.ctypes.data, len(dm),
+                           C.byref(sink.c) if sink else None)
+
+    def fec(self, m: Msg):
+        """Returns a fixed copy, or None when the reference would drop the block."""
+        out = Msg()
+        C.memmove(C.byref(out), C.byref(m), C.sizeof(Msg))
+        return out if self.lib.orc_block_fec(C.byref(out)) else None
+
+
+class Sink:
+    """Collects pre-FEC blocks and (optionally) the raw bit stream of orc_demod."""
+
+    def __init__(self, capbits: int = 0):
+        self.c = OrcSink()
+        self._bits = np.zeros(max(capbits, 1), dtype=np.uint8)
+        if capbits:
+            self.c.bits = self._bits.ctypes.data_as(C.POINTER(C.c_uint8))
+            self.c.capbits = capbits
+
+    def msgs(self):
+        out = []
+        for i in range(self.c.nmsg):
+            m = Msg()
+            C.memmove(C.byref(m), C.byref(self.c.msgs[i]), C.sizeof(Msg))
+            out.append(m)
+        return out
+
+    def bits(self) -> np.ndarray:
+        return self._bits[: self.c.nbits].copy()
+
+
+class OracleStream:
+    """Whole path for one stream through the restatement (rtl.c:314-361 order)."""
+
+    def __init__(self, lib: OracleLib, K: int, wf: np.ndarray):
+        self.lib, self.K, self.nch = lib, K, wf.shape[0]
+        wf = np.ascontiguousarray(wf, dtype=np.float32)
+        self.p = lib.lib.orc_stream_new(K, self.nch, wf.ctypes.data)
+
+    def blocks(self, iq: np.ndarray) -> int:
+        iq = np.ascontiguousarray(iq, dtype=np.uint8)
+        nblk = iq.size // (2048 * self.K)
+        return self.lib.lib.orc_stream_blocks(self.p, iq.ctypes.data, nblk)
+
+    def msgs(self):
+        out = []
+        buf = (Msg * 256)()
+        while True:
+            n = self.lib.lib.orc_stream_msgs(self.p, buf, 256)
+            for i in range(n):
+                m = Msg()
+                C.memmove(C.byref(m), C.byref(buf[i]), C.sizeof(Msg))
+                out.append(m)
+            if n < 256:
+                return out
+
+    def chan(self, ch: int) -> OrcChan:
+        return self.lib.lib.orc_stream_chan(self.p, ch).contents
+
+    def dm(self, ch: int) -> np.ndarray:
+        return np.ctypeslib.as_array(self.lib.lib.orc_stream_dm(self.p, ch), shape=(1024,)).copy()
+
+    def close(self):
+        if self.p:
+            self.lib.lib.orc_stream_free(self.p)
+            self.p = None
+
+    def __del__(self):
+        self.close()
