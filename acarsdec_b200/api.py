@@ -1,0 +1,283 @@
+"""ctypes binding of the C ABI in include/acars_b200.h.
+
+This is host-side convenience for the tests and bench.py; the product is the shared library.
+There is no CPU fallback: importing works anywhere (so the symbol tests can run on a CPU-only
+box), but creating a Context without a B200 raises, and a missing libacars_b200.so raises at
+import of this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libacars_b200.so"
+
+OUTBLK = 1024
+TXTMAX = 250
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int), ("K", C.c_int), ("nstreams", C.c_int), ("nch", C.c_int),
+                ("max_blocks", C.c_int), ("flags", C.c_int)]
+
+
+class Msg(C.Structure):
+    _fields_ = [("stream", C.c_int), ("chn", C.c_int), ("len", C.c_int), ("err", C.c_int), ("lvl", C.c_float),
+                ("block", C.c_uint64), ("pos", C.c_uint64), ("soh_pos", C.c_uint64),
+                ("txt", C.c_ubyte * TXTMAX), ("crc", C.c_ubyte * 2)]
+
+    def as_tuple(self):
+        """(chn, len, err, txt, crc) — the fields the reference's msgblk_t carries."""
+        return (self.chn, self.len, self.err, bytes(self.txt[:self.len]), bytes(self.crc))
+
+    def key(self):
+        return self.as_tuple() + (np.float32(self.lvl).tobytes(),)
+
+
+class ChanState(C.Structure):
+    _fields_ = [("MskPhi", C.c_double), ("MskDf", C.c_double), ("MskLvlSum", C.c_double), ("MskClk", C.c_float),
+                ("MskBitCount", C.c_int), ("MskS", C.c_uint), ("idx", C.c_uint), ("nbits", C.c_int),
+                ("Acarsstate", C.c_int), ("outbits", C.c_uint), ("blk_len", C.c_int), ("blk_err", C.c_int),
+                ("pos", C.c_uint64), ("soh_pos", C.c_uint64), ("inb_re", C.c_float * 11), ("inb_im", C.c_float * 11),
+                ("blk_crc", C.c_ubyte * 2), ("blk_txt", C.c_ubyte * TXTMAX)]
+
+    def vec(self):
+        """Same tuple shape as tests/refs.py RefState.vec() / OrcChan.vec()."""
+        inb = []
+        for i in range(11):
+            inb += [self.inb_re[i], self.inb_im[i]]
+        return (self.MskPhi, self.MskDf, self.MskLvlSum, self.MskClk, self.MskBitCount, self.MskS, self.idx,
+                self.nbits, self.Acarsstate, self.outbits & 0xFF, tuple(inb))
+
+
+class Stats(C.Structure):
+    _fields_ = [("submits", C.c_uint64), ("kernel_launches", C.c_uint64), ("blocks", C.c_uint64),
+                ("raw_frames", C.c_uint64), ("fec_dropped", C.c_uint64), ("chan_ms", C.c_double),
+                ("demod_ms", C.c_double), ("chan_launches", C.c_uint64), ("demod_launches", C.c_uint64)]
+
+
+# every symbol include/acars_b200.h declares: (name, restype, argtypes)
+ABI = [
+    ("acb_round_freq", C.c_int, [C.c_double]),
+    ("acb_stored_fr", C.c_int, [C.c_uint]),
+    ("acb_choose_fc", C.c_uint, [C.c_void_p, C.c_int, C.c_int]),
+    ("acb_build_wf", None, [C.c_int, C.c_uint, C.c_int, C.c_void_p]),
+    ("acb_build_h", None, [C.c_void_p]),
+    ("acb_create", C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
+    ("acb_destroy", None, [C.c_void_p]),
+    ("acb_last_error", C.c_char_p, []),
+    ("acb_version", C.c_char_p, []),
+    ("acb_set_plan", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_uint)]),
+    ("acb_set_wf", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    ("acb_reset", C.c_int, [C.c_void_p]),
+    ("acb_submit_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
+    ("acb_submit_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
+    ("acb_submit_dm_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    ("acb_sync", C.c_int, [C.c_void_p]),
+    ("acb_drain", C.c_int, [C.c_void_p, C.POINTER(Msg), C.c_int]),
+    ("acb_host_alloc", C.c_void_p, [C.c_size_t]),
+    ("acb_host_free", None, [C.c_void_p]),
+    ("acb_device_alloc", C.c_void_p, [C.c_void_p, C.c_size_t]),
+    ("acb_device_free", None, [C.c_void_p, C.c_void_p]),
+    ("acb_copy_to_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    ("acb_read_dm", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    ("acb_get_state", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(ChanState)]),
+    ("acb_set_state", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(ChanState)]),
+    ("acb_get_stats", C.c_int, [C.c_void_p, C.POINTER(Stats), C.c_int]),
+    ("acb_block_fec", C.c_int, [C.POINTER(Msg)]),
+    ("acb_crc_update", C.c_uint16, [C.c_uint16, C.c_uint8]),
+    ("acb_syndrome", C.c_uint16, [C.c_int]),
+]
+
+_lib = None
+
+
+def load():
+    """Load libacars_b200.so (built in-tree by acarsdec_b200.build); raises if it is missing."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise ImportError(f"{LIB_PATH} is missing: run `python -m acarsdec_b200.build` (needs nvcc). "
+                              "There is no CPU fallback.")
+        lib = C.CDLL(str(LIB_PATH))
+        for name, res, args in ABI:
+            fn = getattr(lib, name)     # AttributeError if the library does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+class AcbError(RuntimeError):
+    pass
+
+
+def _check(lib, rc: int) -> int:
+    if rc < 0:
+        raise AcbError(f"acars_b200 error {rc}: {lib.acb_last_error().decode()}")
+    return rc
+
+
+# ---- front-end planning (host; same results as initRtl) ----
+
+def plan(K: int, freqs_mhz):
+    """(freqs_hz, stored Fr, Fc) as initRtl derives them (rtl.c:243-268)."""
+    lib = load()
+    fd = np.array([lib.acb_round_freq(float(f)) for f in freqs_mhz], dtype=np.uint32)
+    fc = lib.acb_choose_fc(fd.ctypes.data, len(fd), K)
+    return [int(f) for f in fd], [lib.acb_stored_fr(int(f)) for f in fd], int(fc)
+
+
+def build_wf(K: int, freqs_mhz) -> np.ndarray:
+    lib = load()
+    _, fr, fc = plan(K, freqs_mhz)
+    out = np.empty((len(fr), 2 * K), dtype=np.float32)
+    for i, f in enumerate(fr):
+        lib.acb_build_wf(f, fc, K, out[i].ctypes.data)
+    return out
+
+
+def build_h() -> np.ndarray:
+    h = np.empty(133, dtype=np.float32)
+    load().acb_build_h(h.ctypes.data)
+    return h
+
+
+def block_fec(msg: Msg):
+    out = Msg()
+    C.memmove(C.byref(out), C.byref(msg), C.sizeof(Msg))
+    return out if load().acb_block_fec(C.byref(out)) else None
+
+
+class PinnedBuffer:
+    """uint8 numpy view over cudaHostAlloc memory (acb_host_alloc)."""
+
+    def __init__(self, nbytes: int):
+        self.lib = load()
+        self.ptr = self.lib.acb_host_alloc(nbytes)
+        if not self.ptr:
+            raise AcbError(self.lib.acb_last_error().decode())
+        self.nbytes = nbytes
+        self.array = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(self.ptr))
+
+    def close(self):
+        if self.ptr:
+            self.lib.acb_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        self.close()
+
+
+class Context:
+    """N streams x C channels on one GPU (acb_ctx_t)."""
+
+    def __init__(self, K: int, nstreams: int, nch: int, max_blocks: int, device: int = 0, flags: int = 0):
+        self.lib = load()
+        self.K, self.nstreams, self.nch, self.max_blocks = K, nstreams, nch, max_blocks
+        self.block_bytes = OUTBLK * K * 2
+        cfg = Config(device, K, nstreams, nch, max_blocks, flags)
+        h = C.c_void_p()
+        rc = self.lib.acb_create(C.byref(cfg), C.byref(h))
+        if rc < 0:
+            msg = self.lib.acb_last_error().decode()
+            if h:
+                self.lib.acb_destroy(h)
+            raise AcbError(f"acb_create failed ({rc}): {msg}")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.acb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_plan(self, stream: int, freqs_hz) -> int:
+        f = np.asarray(freqs_hz, dtype=np.uint32)
+        fc = C.c_uint()
+        _check(self.lib, self.lib.acb_set_plan(self.h, stream, f.ctypes.data, len(f), C.byref(fc)))
+        return fc.value
+
+    def set_wf(self, stream: int, wf: np.ndarray) -> None:
+        wf = np.ascontiguousarray(wf, dtype=np.float32)
+        _check(self.lib, self.lib.acb_set_wf(self.h, stream, wf.ctypes.data, wf.shape[0]))
+
+    def reset(self) -> None:
+        _check(self.lib, self.lib.acb_reset(self.h))
+
+    def submit_host(self, iq, nblk: int, stream_stride: int | None = None) -> None:
+        """iq: uint8 array (nstreams, nblk*block_bytes) or a raw pointer + stride."""
+        if isinstance(iq, np.ndarray):
+            assert iq.dtype == np.uint8 and iq.flags.c_contiguous
+            ptr = iq.ctypes.data
+            if stream_stride is None:
+                stream_stride = iq.strides[0] if iq.ndim == 2 else nblk * self.block_bytes
+        else:
+            ptr = iq
+        _check(self.lib, self.lib.acb_submit_host(self.h, ptr, stream_stride, nblk))
+
+    def submit_device(self, dev_ptr: int, nblk: int, stream_stride: int) -> None:
+        _check(self.lib, self.lib.acb_submit_device(self.h, dev_ptr, stream_stride, nblk))
+
+    def submit_dm(self, dm: np.ndarray) -> None:
+        """dm: float32 (nstreams, nsamp, nch)."""
+        dm = np.ascontiguousarray(dm, dtype=np.float32)
+        assert dm.shape[0] == self.nstreams and dm.shape[2] == self.nch
+        _check(self.lib, self.lib.acb_submit_dm_host(self.h, dm.ctypes.data, dm.shape[1]))
+
+    def sync(self) -> int:
+        return _check(self.lib, self.lib.acb_sync(self.h))
+
+    def drain(self):
+        out = []
+        buf = (Msg * 256)()
+        while True:
+            n = self.lib.acb_drain(self.h, buf, 256)
+            for i in range(n):
+                m = Msg()
+                C.memmove(C.byref(m), C.byref(buf[i]), C.sizeof(Msg))
+                out.append(m)
+            if n < 256:
+                return out
+
+    def read_dm(self, nsamp: int) -> np.ndarray:
+        out = np.empty((self.nstreams, nsamp, self.nch), dtype=np.float32)
+        _check(self.lib, self.lib.acb_read_dm(self.h, out.ctypes.data, out.size))
+        return out
+
+    def get_state(self, stream: int, chn: int) -> ChanState:
+        s = ChanState()
+        _check(self.lib, self.lib.acb_get_state(self.h, stream, chn, C.byref(s)))
+        return s
+
+    def set_state(self, stream: int, chn: int, s: ChanState) -> None:
+        _check(self.lib, self.lib.acb_set_state(self.h, stream, chn, C.byref(s)))
+
+    def stats(self, reset: bool = False) -> Stats:
+        s = Stats()
+        _check(self.lib, self.lib.acb_get_stats(self.h, C.byref(s), int(reset)))
+        return s
+
+    def device_alloc(self, nbytes: int) -> int:
+        p = self.lib.acb_device_alloc(self.h, nbytes)
+        if not p:
+            raise AcbError(self.lib.acb_last_error().decode())
+        return p
+
+    def device_free(self, p: int) -> None:
+        self.lib.acb_device_free(self.h, p)
+
+    def copy_to_device(self, dst: int, src: np.ndarray) -> None:
+        src = np.ascontiguousarray(src)
+        _check(self.lib, self.lib.acb_copy_to_device(self.h, dst, src.ctypes.data, src.nbytes))

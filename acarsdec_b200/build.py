@@ -1,0 +1,72 @@
+"""Build the native libraries in-tree with nvcc for sm_100a (no JIT cache: the .so files travel
+to the GPU box with the repo snapshot).
+
+  acarsdec_b200/libacars_b200.so         context API (include/acars_b200.h): CUDA kernels + host runtime
+  acarsdec_b200/libacarsdec_compat.so    the reference's own symbols (include/acarsdec_compat.h)
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+ROOT = PKG.parent
+CSRC = PKG / "csrc"
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+# -fmad=false: the numerics contract forbids contracting separate mul/add;
+# the kernels also spell rounding-sensitive steps with __f*_rn intrinsics.
+NVCC_FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall",
+              "-Xptxas", "-v"]
+
+LIB = PKG / "libacars_b200.so"
+COMPAT = PKG / "libacarsdec_compat.so"
+LIB_SRC = [CSRC / "kernels.cu", CSRC / "context.cu", CSRC / "hostmath.cpp"]
+COMPAT_SRC = [CSRC / "compat.cpp"]
+HEADERS = [CSRC / "acb_internal.h", CSRC / "frame_sm.h", ROOT / "include" / "acars_b200.h",
+           ROOT / "include" / "acarsdec_compat.h"]
+
+
+def nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found: the CUDA extension cannot be built (there is no CPU fallback)")
+
+
+def _stale(target: Path, deps) -> bool:
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(Path(d).exists() and Path(d).stat().st_mtime > t for d in deps)
+
+
+def _run(cmd, log: Path) -> None:
+    r = subprocess.run([str(c) for c in cmd], capture_output=True, text=True)
+    log.write_text(r.stdout + r.stderr)
+    if r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("build failed: " + " ".join(str(c) for c in cmd))
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    (PKG / "build").mkdir(exist_ok=True)
+    if force or _stale(LIB, LIB_SRC + HEADERS + [Path(__file__)]):
+        cmd = [nvcc(), *ARCH, *NVCC_FLAGS, "-shared", "-o", LIB, *LIB_SRC, "-I", ROOT / "include"]
+        _run(cmd, PKG / "build" / "libacars_b200.log")
+        if verbose:
+            print((PKG / "build" / "libacars_b200.log").read_text())
+    if all(p.exists() for p in COMPAT_SRC) and (force or _stale(COMPAT, COMPAT_SRC + HEADERS + [LIB])):
+        cmd = [nvcc(), *ARCH, "-O2", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-shared",
+               "-o", COMPAT, *COMPAT_SRC, "-I", ROOT / "include", "-L", PKG, "-lacars_b200",
+               "-Xlinker", "-rpath,$ORIGIN", "-lpthread"]
+        _run(cmd, PKG / "build" / "libacarsdec_compat.log")
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)
+    print("built", LIB)

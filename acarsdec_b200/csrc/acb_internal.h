@@ -1,0 +1,72 @@
+/* Internal device/host shared layouts of libacars_b200 (not part of the C ABI). */
+#ifndef ACB_INTERNAL_H
+#define ACB_INTERNAL_H
+
+#include <stdint.h>
+
+namespace acb {
+
+constexpr int FLEN = 11;        /* msk.c:25  INTRATE/1200 + 1 */
+constexpr int MFLTOVER = 12;    /* msk.c:26 */
+constexpr int FLENO = 133;      /* msk.c:27 */
+constexpr int OUTBLK = 1024;    /* rtl.c:49 */
+constexpr int TXTCAP = 256;     /* >= acarsdec.h:55's 250, padded */
+
+/* Persistent per-(stream,channel) demodulator + framing state in HBM: what channel_t carries
+ * between demodMSK calls (acarsdec.h:76-89; msk.c:71-72,134-135), plus the frame being
+ * assembled (msgblk_t, acarsdec.h:48-57).  8-byte aligned, 448 bytes. */
+struct ChainState {
+	double phi, df, lvlsum;           /* MskPhi, MskDf, MskLvlSum */
+	float clk;                        /* MskClk (float state!) */
+	int bitcount;                     /* MskBitCount */
+	unsigned S, idx;                  /* MskS, idx */
+	int nbits, state;                 /* nbits, Acarsstate */
+	unsigned outbits;
+	int blk_len;
+	int blk_err;
+	int pad0;
+	unsigned long long pos;           /* envelope samples consumed so far */
+	unsigned long long soh_pos;       /* pos at the SOH of the frame in progress */
+	float inb_re[FLEN], inb_im[FLEN]; /* msk.c:40 ring */
+	unsigned char crc[2];
+	unsigned char pad1[6];
+	unsigned char txt[TXTCAP];
+};
+
+/* A completed (pre-FEC) frame, device -> host. */
+struct RawFrame {
+	int stream, chn, len, err;
+	double lvlsum;
+	int bitcount;
+	int pad0;
+	unsigned long long pos, soh_pos;
+	unsigned char crc[2];
+	unsigned char pad1[6];
+	unsigned char txt[TXTCAP];
+};
+
+struct RingCtl {
+	unsigned count;                   /* frames appended (may exceed capacity: overflow) */
+	unsigned pad[3];
+};
+
+/* channelizer tile geometry */
+constexpr int CH_TILE = 128;          /* outputs per tile = threads per CTA */
+constexpr int CH_GROUP = 8;           /* channels accumulated per pass */
+
+} // namespace acb
+
+/* kernels.cu entry points (host-callable launchers) */
+struct CUstream_st;
+namespace acb {
+int launch_channelize(const uint8_t *iq, size_t stream_stride, const float *wf4, float *dm,
+                      int K, int nch, int nstreams, int nblk, CUstream_st *stream);
+int launch_channelize_generic(const uint8_t *iq, size_t stream_stride, const float *wf4, float *dm,
+                              int K, int nch, int nstreams, int nblk, CUstream_st *stream);
+int launch_demod(ChainState *st, const float *dm, int nsamp, int nch, int nstreams,
+                 RawFrame *ring, RingCtl *ctl, unsigned cap, CUstream_st *stream);
+int upload_matched_filter(const float *h);
+size_t channelize_smem_bytes(int K);
+} // namespace acb
+
+#endif

@@ -1,0 +1,490 @@
+/*
+ * libacars_b200 context: device memory, streams, submit/sync/drain (C ABI in include/acars_b200.h).
+ *
+ * Replaces, for N streams x C channels at once, what the reference does per RTL block on its
+ * input thread (in_callback rtl.c:314-361 -> demodMSK msk.c:67 -> decodeAcars acars.c:246) and
+ * on its blk_thread (acars.c:93-215).  Data flow per submit:
+ *
+ *   host u8 IQ --copy stream--> d_iq[buf] --compute stream--> K1 k_channelize -> d_dm (HBM)
+ *                                                        --> K2 k_demod      -> frame ring (HBM)
+ *   acb_sync: D2H of the frames appended since the last sync -> block FEC on the host -> queue
+ *
+ * Input staging is double-buffered so the H2D copy of submit i+1 overlaps the kernels of i.
+ */
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <deque>
+#include <vector>
+
+#include "../../include/acars_b200.h"
+#include "acb_internal.h"
+
+using namespace acb;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+	return code;
+}
+
+#define CU(call)                                                                                   \
+	do {                                                                                           \
+		cudaError_t e_ = (call);                                                                   \
+		if (e_ != cudaSuccess)                                                                     \
+			return fail(ACB_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+	} while (0)
+
+extern "C" const char *acb_last_error(void) { return g_err; }
+extern "C" const char *acb_version(void) { return "acars_b200 0.1 (sm_100a)"; }
+
+struct EvTriple { cudaEvent_t a, b, c; bool chan; };
+
+struct acb_ctx {
+	acb_config_t cfg;
+	int ngrp;
+	size_t blk_bytes;            /* 1024*K*2 */
+	cudaStream_t s_copy, s_comp;
+	uint8_t *d_iq[2];
+	cudaEvent_t ev_copied[2], ev_consumed[2];
+	bool buf_used[2];
+	int next_buf;
+	float *d_wf4;                /* [stream][grp][K][8] float4 (c, d, -d, c) */
+	float *d_dm;                 /* [stream][nsamp][nch] */
+	size_t dm_floats;
+	ChainState *d_state;
+	RawFrame *d_ring;
+	RingCtl *d_ctl;
+	unsigned ring_cap;
+	RawFrame *h_ring;            /* pinned */
+	RingCtl *h_ctl;              /* pinned */
+	float *h_dm_stage;           /* pinned, for submit_dm_host */
+	int last_nsamp;
+	std::vector<unsigned long long> group_starts;   /* emission-order groups since last sync */
+	unsigned long long pos;      /* envelope samples submitted so far (all chains move together) */
+	std::deque<acb_msg_t> outq;
+	std::vector<EvTriple> ev_inflight, ev_free;
+	acb_stats_t stats;
+	bool use_generic;
+};
+
+static int ctx_use(acb_ctx *c)
+{
+	CU(cudaSetDevice(c->cfg.device));
+	return ACB_OK;
+}
+
+extern "C" void *acb_host_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+		fail(ACB_ERR_CUDA, "cudaHostAlloc(%zu) failed", bytes);
+		return nullptr;
+	}
+	return p;
+}
+extern "C" void acb_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" void *acb_device_alloc(acb_ctx_t *c, size_t bytes)
+{
+	void *p = nullptr;
+	if (!c || ctx_use(c)) return nullptr;
+	if (cudaMalloc(&p, bytes) != cudaSuccess) {
+		fail(ACB_ERR_NOMEM, "cudaMalloc(%zu) failed", bytes);
+		return nullptr;
+	}
+	return p;
+}
+extern "C" void acb_device_free(acb_ctx_t *c, void *p) { if (c && p && !ctx_use(c)) cudaFree(p); }
+
+extern "C" int acb_copy_to_device(acb_ctx_t *c, void *dst, const void *src, size_t bytes)
+{
+	if (!c) return fail(ACB_ERR_ARG, "null context");
+	if (int r = ctx_use(c)) return r;
+	CU(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+	return ACB_OK;
+}
+
+static int reset_states(acb_ctx *c)
+{
+	const size_t n = (size_t)c->cfg.nstreams * c->cfg.nch;
+	std::vector<ChainState> init(n);
+	memset(init.data(), 0, n * sizeof(ChainState));
+	for (auto &s : init) {       /* initMsk msk.c:34-40 zeroes; initAcars acars.c:230-234 */
+		s.nbits = 8;
+		s.state = 0;             /* WSYN */
+	}
+	CU(cudaMemcpy(c->d_state, init.data(), n * sizeof(ChainState), cudaMemcpyHostToDevice));
+	CU(cudaMemset(c->d_ctl, 0, sizeof(RingCtl)));
+	c->pos = 0;
+	c->group_starts.clear();
+	c->outq.clear();
+	return ACB_OK;
+}
+
+extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
+{
+	if (!cfg || !out) return fail(ACB_ERR_ARG, "null argument");
+	if (cfg->K < 1 || cfg->K > ACB_MAXK) return fail(ACB_ERR_ARG, "K=%d out of range 1..%d", cfg->K, ACB_MAXK);
+	if (cfg->nstreams < 1 || cfg->nch < 1 || cfg->max_blocks < 1) return fail(ACB_ERR_ARG, "nstreams/nch/max_blocks must be >= 1");
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+		return fail(ACB_ERR_CUDA, "no CUDA device: libacars_b200 has no CPU fallback");
+	if (cfg->device < 0 || cfg->device >= ndev) return fail(ACB_ERR_ARG, "device %d of %d", cfg->device, ndev);
+	CU(cudaSetDevice(cfg->device));
+	cudaDeviceProp prop;
+	CU(cudaGetDeviceProperties(&prop, cfg->device));
+	if (prop.major != 10)
+		return fail(ACB_ERR_CUDA, "device %d is sm_%d%d; this library carries sm_100a code only", cfg->device, prop.major, prop.minor);
+
+	acb_ctx *c = new acb_ctx();
+	c->cfg = *cfg;
+	c->ngrp = (cfg->nch + CH_GROUP - 1) / CH_GROUP;
+	c->blk_bytes = (size_t)OUTBLK * cfg->K * 2;
+	c->use_generic = (cfg->K % 8) != 0 || channelize_smem_bytes(cfg->K) > 200 * 1024;
+	c->next_buf = 0;
+	c->last_nsamp = 0;
+	memset(&c->stats, 0, sizeof(c->stats));
+	*out = c;
+
+	CU(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+	CU(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+	const size_t in_bytes = (size_t)cfg->nstreams * cfg->max_blocks * c->blk_bytes;
+	for (int i = 0; i < 2; i++) {
+		c->d_iq[i] = nullptr;
+		c->buf_used[i] = false;
+		if (!(cfg->flags & ACB_FLAG_NO_INPUT_STAGING)) CU(cudaMalloc(&c->d_iq[i], in_bytes));
+		CU(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+		CU(cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
+	}
+	const size_t wf_floats = (size_t)cfg->nstreams * c->ngrp * cfg->K * CH_GROUP * 4;
+	CU(cudaMalloc(&c->d_wf4, wf_floats * sizeof(float)));
+	CU(cudaMemset(c->d_wf4, 0, wf_floats * sizeof(float)));
+	c->dm_floats = (size_t)cfg->nstreams * cfg->max_blocks * OUTBLK * cfg->nch;
+	CU(cudaMalloc(&c->d_dm, c->dm_floats * sizeof(float)));
+	const size_t nchain = (size_t)cfg->nstreams * cfg->nch;
+	CU(cudaMalloc(&c->d_state, nchain * sizeof(ChainState)));
+	/* a frame needs >= 20 bytes on air = 833 envelope samples, so < 2 per chain per block */
+	size_t cap = nchain * (2 * (size_t)cfg->max_blocks + 4) * 2;
+	if (cap > (1u << 22)) cap = 1u << 22;
+	c->ring_cap = (unsigned)cap;
+	CU(cudaMalloc(&c->d_ring, cap * sizeof(RawFrame)));
+	CU(cudaMalloc(&c->d_ctl, sizeof(RingCtl)));
+	CU(cudaHostAlloc(&c->h_ring, cap * sizeof(RawFrame), cudaHostAllocDefault));
+	CU(cudaHostAlloc(&c->h_ctl, sizeof(RingCtl), cudaHostAllocDefault));
+	c->h_dm_stage = nullptr;
+
+	float h[FLENO];
+	acb_build_h(h);
+	CU((cudaError_t)upload_matched_filter(h));
+	if (int r = reset_states(c)) return r;
+	return ACB_OK;
+}
+
+extern "C" void acb_destroy(acb_ctx_t *c)
+{
+	if (!c) return;
+	if (ctx_use(c) == ACB_OK) {
+		cudaDeviceSynchronize();
+		for (int i = 0; i < 2; i++) {
+			if (c->d_iq[i]) cudaFree(c->d_iq[i]);
+			cudaEventDestroy(c->ev_copied[i]);
+			cudaEventDestroy(c->ev_consumed[i]);
+		}
+		for (auto &e : c->ev_inflight) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); cudaEventDestroy(e.c); }
+		for (auto &e : c->ev_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); cudaEventDestroy(e.c); }
+		cudaFree(c->d_wf4); cudaFree(c->d_dm); cudaFree(c->d_state); cudaFree(c->d_ring); cudaFree(c->d_ctl);
+		cudaFreeHost(c->h_ring); cudaFreeHost(c->h_ctl);
+		if (c->h_dm_stage) cudaFreeHost(c->h_dm_stage);
+		cudaStreamDestroy(c->s_copy); cudaStreamDestroy(c->s_comp);
+	}
+	delete c;
+}
+
+extern "C" int acb_reset(acb_ctx_t *c)
+{
+	if (!c) return fail(ACB_ERR_ARG, "null context");
+	if (int r = ctx_use(c)) return r;
+	CU(cudaDeviceSynchronize());
+	return reset_states(c);
+}
+
+extern "C" int acb_set_wf(acb_ctx_t *c, int stream, const float *wf, int nch)
+{
+	if (!c || !wf) return fail(ACB_ERR_ARG, "null argument");
+	if (stream < 0 || stream >= c->cfg.nstreams || nch != c->cfg.nch) return fail(ACB_ERR_ARG, "stream/nch mismatch");
+	if (int r = ctx_use(c)) return r;
+	const int K = c->cfg.K;
+	std::vector<float> t((size_t)c->ngrp * K * CH_GROUP * 4, 0.0f);
+	for (int ch = 0; ch < nch; ch++) {
+		const int g = ch / CH_GROUP, cc = ch % CH_GROUP;
+		for (int ind = 0; ind < K; ind++) {
+			const float re = wf[((size_t)ch * K + ind) * 2], im = wf[((size_t)ch * K + ind) * 2 + 1];
+			float *o = &t[(((size_t)g * K + ind) * CH_GROUP + cc) * 4];
+			o[0] = re; o[1] = im; o[2] = -im; o[3] = re;      /* (c, d, -d, c): see cmac() */
+		}
+	}
+	CU(cudaStreamSynchronize(c->s_comp));
+	CU(cudaMemcpy(c->d_wf4 + (size_t)stream * t.size(), t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+	return ACB_OK;
+}
+
+extern "C" int acb_set_plan(acb_ctx_t *c, int stream, const unsigned *freqs_hz, int nch, unsigned *fc_out)
+{
+	if (!c || !freqs_hz) return fail(ACB_ERR_ARG, "null argument");
+	if (nch != c->cfg.nch) return fail(ACB_ERR_ARG, "nch mismatch");
+	const unsigned fc = acb_choose_fc(freqs_hz, nch, c->cfg.K);
+	if (fc == 0) return fail(ACB_ERR_PLAN, "Frequencies too far apart");    /* rtl.c:149-152 */
+	std::vector<float> wf((size_t)nch * c->cfg.K * 2);
+	for (int ch = 0; ch < nch; ch++)
+		acb_build_wf(acb_stored_fr(freqs_hz[ch]), fc, c->cfg.K, &wf[(size_t)ch * c->cfg.K * 2]);
+	if (fc_out) *fc_out = fc;
+	return acb_set_wf(c, stream, wf.data(), nch);
+}
+
+static EvTriple get_events(acb_ctx *c)
+{
+	EvTriple e;
+	if (!c->ev_free.empty()) {
+		e = c->ev_free.back();
+		c->ev_free.pop_back();
+	} else {
+		cudaEventCreate(&e.a); cudaEventCreate(&e.b); cudaEventCreate(&e.c);
+	}
+	return e;
+}
+
+/* queue K1+K2 (or K2 only) on the compute stream for `nblk` blocks / `nsamp` envelope samples */
+static int run_kernels(acb_ctx *c, const uint8_t *d_iq, size_t stride, int nblk, int nsamp)
+{
+	EvTriple ev = get_events(c);
+	ev.chan = d_iq != nullptr;
+	CU(cudaEventRecord(ev.a, c->s_comp));
+	if (d_iq) {
+		int r = c->use_generic
+		            ? launch_channelize_generic(d_iq, stride, c->d_wf4, c->d_dm, c->cfg.K, c->cfg.nch, c->cfg.nstreams, nblk, c->s_comp)
+		            : launch_channelize(d_iq, stride, c->d_wf4, c->d_dm, c->cfg.K, c->cfg.nch, c->cfg.nstreams, nblk, c->s_comp);
+		if (r) return fail(ACB_ERR_CUDA, "channelizer launch: %s", cudaGetErrorString((cudaError_t)r));
+		c->stats.kernel_launches++;
+		c->stats.chan_launches++;
+	}
+	CU(cudaEventRecord(ev.b, c->s_comp));
+	int r = launch_demod(c->d_state, c->d_dm, nsamp, c->cfg.nch, c->cfg.nstreams, c->d_ring, c->d_ctl, c->ring_cap, c->s_comp);
+	if (r) return fail(ACB_ERR_CUDA, "demod launch: %s", cudaGetErrorString((cudaError_t)r));
+	c->stats.kernel_launches++;
+	c->stats.demod_launches++;
+	CU(cudaEventRecord(ev.c, c->s_comp));
+	c->ev_inflight.push_back(ev);
+	c->stats.submits++;
+	c->last_nsamp = nsamp;
+	return ACB_OK;
+}
+
+static int check_blocks(acb_ctx *c, const void *p, size_t stride, int nblk)
+{
+	if (!c || !p) return fail(ACB_ERR_ARG, "null argument");
+	if (nblk < 1 || nblk > c->cfg.max_blocks) return fail(ACB_ERR_ARG, "nblk=%d outside 1..%d", nblk, c->cfg.max_blocks);
+	if (c->cfg.nstreams > 1 && stride < (size_t)nblk * c->blk_bytes) return fail(ACB_ERR_ARG, "stream_stride smaller than one stream's input");
+	if (stride % 16) return fail(ACB_ERR_ARG, "stream_stride must be a multiple of 16 bytes");
+	return ACB_OK;
+}
+
+extern "C" int acb_submit_device(acb_ctx_t *c, const uint8_t *iq_dev, size_t stride, int nblk)
+{
+	if (int r = check_blocks(c, iq_dev, stride, nblk)) return r;
+	if (int r = ctx_use(c)) return r;
+	if (((uintptr_t)iq_dev) % 16) return fail(ACB_ERR_ARG, "device input must be 16-byte aligned");
+	for (int b = 0; b < nblk; b++) c->group_starts.push_back(c->pos + (unsigned long long)b * OUTBLK);
+	if (int r = run_kernels(c, iq_dev, stride, nblk, nblk * OUTBLK)) return r;
+	c->pos += (unsigned long long)nblk * OUTBLK;
+	c->stats.blocks += (uint64_t)nblk * c->cfg.nstreams;
+	return ACB_OK;
+}
+
+extern "C" int acb_submit_host(acb_ctx_t *c, const uint8_t *iq, size_t stride, int nblk)
+{
+	if (int r = check_blocks(c, iq, stride, nblk)) return r;
+	if (int r = ctx_use(c)) return r;
+	if (!c->d_iq[0]) return fail(ACB_ERR_ARG, "context created with ACB_FLAG_NO_INPUT_STAGING");
+	const int b = c->next_buf;
+	c->next_buf ^= 1;
+	const size_t per_stream = (size_t)nblk * c->blk_bytes;
+	/* the kernels that last read this staging buffer must be done before it is overwritten */
+	if (c->buf_used[b]) CU(cudaStreamWaitEvent(c->s_copy, c->ev_consumed[b], 0));
+	if (stride == per_stream || c->cfg.nstreams == 1) {
+		CU(cudaMemcpyAsync(c->d_iq[b], iq, per_stream * c->cfg.nstreams, cudaMemcpyHostToDevice, c->s_copy));
+	} else {
+		CU(cudaMemcpy2DAsync(c->d_iq[b], per_stream, iq, stride, per_stream, c->cfg.nstreams, cudaMemcpyHostToDevice, c->s_copy));
+	}
+	CU(cudaEventRecord(c->ev_copied[b], c->s_copy));
+	CU(cudaStreamWaitEvent(c->s_comp, c->ev_copied[b], 0));
+	for (int k = 0; k < nblk; k++) c->group_starts.push_back(c->pos + (unsigned long long)k * OUTBLK);
+	if (int r = run_kernels(c, c->d_iq[b], per_stream, nblk, nblk * OUTBLK)) return r;
+	CU(cudaEventRecord(c->ev_consumed[b], c->s_comp));
+	c->buf_used[b] = true;
+	c->pos += (unsigned long long)nblk * OUTBLK;
+	c->stats.blocks += (uint64_t)nblk * c->cfg.nstreams;
+	return ACB_OK;
+}
+
+extern "C" int acb_submit_dm_host(acb_ctx_t *c, const float *dm, int nsamp)
+{
+	if (!c || !dm) return fail(ACB_ERR_ARG, "null argument");
+	if (int r = ctx_use(c)) return r;
+	const size_t n = (size_t)c->cfg.nstreams * nsamp * c->cfg.nch;
+	if (nsamp < 1 || n > c->dm_floats) return fail(ACB_ERR_ARG, "nsamp=%d exceeds max_blocks*1024", nsamp);
+	/* d_dm may still be read by a previous demod: same stream, so the copy is ordered after it */
+	CU(cudaMemcpyAsync(c->d_dm, dm, n * sizeof(float), cudaMemcpyHostToDevice, c->s_comp));
+	c->group_starts.push_back(c->pos);
+	if (int r = run_kernels(c, nullptr, 0, 0, nsamp)) return r;
+	/* pageable source: the async copy has been staged by the time it returns; pinned sources
+	 * must stay untouched until acb_sync */
+	c->pos += (unsigned long long)nsamp;
+	return ACB_OK;
+}
+
+extern "C" int acb_sync(acb_ctx_t *c)
+{
+	if (!c) return fail(ACB_ERR_ARG, "null context");
+	if (int r = ctx_use(c)) return r;
+	CU(cudaMemcpyAsync(c->h_ctl, c->d_ctl, sizeof(RingCtl), cudaMemcpyDeviceToHost, c->s_comp));
+	CU(cudaStreamSynchronize(c->s_comp));
+	unsigned count = c->h_ctl->count;
+	const bool overflow = count > c->ring_cap;
+	if (overflow) count = c->ring_cap;
+	if (count) {
+		CU(cudaMemcpyAsync(c->h_ring, c->d_ring, (size_t)count * sizeof(RawFrame), cudaMemcpyDeviceToHost, c->s_comp));
+		CU(cudaMemsetAsync(c->d_ctl, 0, sizeof(RingCtl), c->s_comp));
+		CU(cudaStreamSynchronize(c->s_comp));
+	}
+	for (auto &e : c->ev_inflight) {
+		float ms = 0;
+		if (e.chan && cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) c->stats.chan_ms += ms;
+		if (cudaEventElapsedTime(&ms, e.b, e.c) == cudaSuccess) c->stats.demod_ms += ms;
+		c->ev_free.push_back(e);
+	}
+	c->ev_inflight.clear();
+
+	/* emission order of the reference: per input block, channel by channel, then time
+	 * (rtl.c:357-360; soundfile.c:71-77); streams are interleaved as if served in turn */
+	struct Key { unsigned long long group; int stream, chn; unsigned long long pos; unsigned idx; };
+	std::vector<Key> keys(count);
+	const auto &gs = c->group_starts;
+	for (unsigned i = 0; i < count; i++) {
+		const RawFrame &f = c->h_ring[i];
+		size_t g = std::upper_bound(gs.begin(), gs.end(), f.pos) - gs.begin();
+		keys[i] = Key{ g, f.stream, f.chn, f.pos, i };
+	}
+	std::sort(keys.begin(), keys.end(), [](const Key &a, const Key &b) {
+		if (a.group != b.group) return a.group < b.group;
+		if (a.stream != b.stream) return a.stream < b.stream;
+		if (a.chn != b.chn) return a.chn < b.chn;
+		return a.pos < b.pos;
+	});
+	for (const Key &k : keys) {
+		const RawFrame &f = c->h_ring[k.idx];
+		acb_msg_t m;
+		memset(&m, 0, sizeof(m));
+		m.stream = f.stream; m.chn = f.chn; m.len = f.len; m.err = f.err;
+		m.lvl = (float)(10 * log10(f.lvlsum / f.bitcount));          /* acars.c:351 */
+		m.block = f.pos / OUTBLK; m.pos = f.pos; m.soh_pos = f.soh_pos;
+		memcpy(m.txt, f.txt, ACB_TXTMAX);
+		m.crc[0] = f.crc[0]; m.crc[1] = f.crc[1];
+		c->stats.raw_frames++;
+		if (acb_block_fec(&m)) c->outq.push_back(m);
+		else c->stats.fec_dropped++;
+	}
+	c->group_starts.clear();
+	if (overflow) return fail(ACB_ERR_OVERFLOW, "device frame ring overflowed (%u slots): sync more often", c->ring_cap);
+	return (int)c->outq.size();
+}
+
+extern "C" int acb_drain(acb_ctx_t *c, acb_msg_t *out, int max)
+{
+	if (!c || (!out && max > 0)) return fail(ACB_ERR_ARG, "null argument");
+	int n = 0;
+	while (n < max && !c->outq.empty()) {
+		out[n++] = c->outq.front();
+		c->outq.pop_front();
+	}
+	return n;
+}
+
+extern "C" int acb_read_dm(acb_ctx_t *c, float *out, size_t nfloats)
+{
+	if (!c || !out) return fail(ACB_ERR_ARG, "null argument");
+	if (int r = ctx_use(c)) return r;
+	const size_t have = (size_t)c->cfg.nstreams * c->last_nsamp * c->cfg.nch;
+	if (nfloats > have) return fail(ACB_ERR_ARG, "asked for %zu floats, last submit produced %zu", nfloats, have);
+	CU(cudaStreamSynchronize(c->s_comp));
+	CU(cudaMemcpy(out, c->d_dm, nfloats * sizeof(float), cudaMemcpyDeviceToHost));
+	return ACB_OK;
+}
+
+static void to_api(const ChainState &s, acb_chan_state_t *o)
+{
+	memset(o, 0, sizeof(*o));
+	o->MskPhi = s.phi; o->MskDf = s.df; o->MskLvlSum = s.lvlsum; o->MskClk = s.clk;
+	o->MskBitCount = s.bitcount; o->MskS = s.S; o->idx = s.idx; o->nbits = s.nbits;
+	o->Acarsstate = s.state; o->outbits = s.outbits; o->blk_len = s.blk_len; o->blk_err = s.blk_err;
+	o->pos = s.pos; o->soh_pos = s.soh_pos;
+	memcpy(o->inb_re, s.inb_re, sizeof(o->inb_re));
+	memcpy(o->inb_im, s.inb_im, sizeof(o->inb_im));
+	o->blk_crc[0] = s.crc[0]; o->blk_crc[1] = s.crc[1];
+	memcpy(o->blk_txt, s.txt, ACB_TXTMAX);
+}
+
+static void from_api(const acb_chan_state_t *i, ChainState &s)
+{
+	memset(&s, 0, sizeof(s));
+	s.phi = i->MskPhi; s.df = i->MskDf; s.lvlsum = i->MskLvlSum; s.clk = i->MskClk;
+	s.bitcount = i->MskBitCount; s.S = i->MskS; s.idx = i->idx % FLEN; s.nbits = i->nbits;
+	s.state = i->Acarsstate; s.outbits = i->outbits & 0xffu; s.blk_len = i->blk_len; s.blk_err = i->blk_err;
+	s.pos = i->pos; s.soh_pos = i->soh_pos;
+	memcpy(s.inb_re, i->inb_re, sizeof(s.inb_re));
+	memcpy(s.inb_im, i->inb_im, sizeof(s.inb_im));
+	s.crc[0] = i->blk_crc[0]; s.crc[1] = i->blk_crc[1];
+	memcpy(s.txt, i->blk_txt, ACB_TXTMAX);
+}
+
+extern "C" int acb_get_state(acb_ctx_t *c, int stream, int chn, acb_chan_state_t *out)
+{
+	if (!c || !out) return fail(ACB_ERR_ARG, "null argument");
+	if (stream < 0 || stream >= c->cfg.nstreams || chn < 0 || chn >= c->cfg.nch) return fail(ACB_ERR_ARG, "stream/chn out of range");
+	if (int r = ctx_use(c)) return r;
+	ChainState s;
+	CU(cudaStreamSynchronize(c->s_comp));
+	CU(cudaMemcpy(&s, c->d_state + (size_t)stream * c->cfg.nch + chn, sizeof(s), cudaMemcpyDeviceToHost));
+	to_api(s, out);
+	return ACB_OK;
+}
+
+extern "C" int acb_set_state(acb_ctx_t *c, int stream, int chn, const acb_chan_state_t *in)
+{
+	if (!c || !in) return fail(ACB_ERR_ARG, "null argument");
+	if (stream < 0 || stream >= c->cfg.nstreams || chn < 0 || chn >= c->cfg.nch) return fail(ACB_ERR_ARG, "stream/chn out of range");
+	if (in->blk_len < 0 || in->blk_len > 248) return fail(ACB_ERR_ARG, "blk_len out of range");
+	if (int r = ctx_use(c)) return r;
+	ChainState s;
+	from_api(in, s);
+	CU(cudaStreamSynchronize(c->s_comp));
+	CU(cudaMemcpy(c->d_state + (size_t)stream * c->cfg.nch + chn, &s, sizeof(s), cudaMemcpyHostToDevice));
+	return ACB_OK;
+}
+
+extern "C" int acb_get_stats(acb_ctx_t *c, acb_stats_t *out, int reset)
+{
+	if (!c || !out) return fail(ACB_ERR_ARG, "null argument");
+	*out = c->stats;
+	if (reset) memset(&c->stats, 0, sizeof(c->stats));
+	return ACB_OK;
+}

@@ -1,0 +1,217 @@
+/*
+ * Host-side pieces of the hot path that the reference also runs on the host, written so that
+ * their results are bit-identical to the reference's when built against the same glibc:
+ *
+ *   front-end planning  — frequency rounding, chooseFc, the per-channel mixer/boxcar table
+ *                         (initRtl, rtl.c:243-287) and the matched filter (initMsk, msk.c:44-48);
+ *                         these run once and use libm (sincosf, cosf), so they stay on the CPU
+ *                         and the tables are uploaded;
+ *   block FEC           — blk_thread's parity/CRC/syndrome repair (acars.c:39-215), integer
+ *                         only, one call per decoded frame; CRC and syndrome tables are
+ *                         generated at start-up instead of stored (syndrom.h).
+ *
+ * Must be compiled without FMA contraction / fast-math (build uses -ffp-contract=off).
+ */
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "../../include/acars_b200.h"
+
+/* ------------------------------------------------------------------ front-end planning */
+
+extern "C" int acb_round_freq(double mhz)
+{
+	/* rtl.c:245-247: nearest multiple of INTRATE, computed in int */
+	return ((int)(1000000 * mhz + ACB_INTRATE / 2) / ACB_INTRATE) * ACB_INTRATE;
+}
+
+extern "C" int acb_stored_fr(unsigned freq_hz)
+{
+	/* rtl.c:255: channel[].Fr (an int) receives (float)Fd — frequencies off the 8 Hz float
+	 * grid above 2^27 move by up to 4 Hz, and the table below is built from the moved value */
+	return (int)(float)freq_hz;
+}
+
+extern "C" unsigned acb_choose_fc(const unsigned *freqs_hz, int n, int K)
+{
+	/* rtl.c:131-168.  Candidates run downward in 1 Hz steps from (highest + 2*INTRATE); the
+	 * first that keeps every channel inside [2*INTRATE, rate/2 - 2*INTRATE] of the centre
+	 * with no channel the mirror image of its lower neighbour wins. */
+	if (n <= 0 || !freqs_hz) return 0;
+	std::vector<long long> f(freqs_hz, freqs_hz + n);
+	std::sort(f.begin(), f.end());
+	const long long rate = (long long)ACB_INTRATE * K, guard = 2 * ACB_INTRATE;
+	if (f.back() - f.front() > rate - 2 * guard) return 0;
+	long long fc = f.back() + guard;
+	for (; fc > f.front() - guard; fc--) {
+		bool ok = true;
+		for (int i = 0; i < n && ok; i++) {
+			const long long d = llabs(fc - f[i]);
+			ok = d <= rate / 2 - guard && d >= guard && !(i > 0 && fc - f[i - 1] == f[i] - fc);
+		}
+		if (ok) break;
+	}
+	return (unsigned)fc;      /* like the reference, an exhausted scan returns its last candidate */
+}
+
+extern "C" void acb_build_wf(int fr_stored, unsigned fc_hz, int K, float *wf)
+{
+	/* rtl.c:283-286.  Types matter: the offset is a float difference divided by a float rate,
+	 * scaled by 2*pi in double and stored back to float; the phase of tap `ind` is the float
+	 * product AMFreq*ind; the unit vector comes from cexpf (= sincosf of the imaginary part);
+	 * "/rtlMult" is a float division, "/127.5" a double division rounded to float. */
+	const float rate = (float)(ACB_INTRATE * K);
+	const float step = (float)(((float)fr_stored - (float)fc_hz) / rate * 2.0 * M_PI);
+	for (int ind = 0; ind < K; ind++) {
+		const float ph = step * (float)ind;
+		float sn, cs;
+		sincosf(-ph, &sn, &cs);
+		wf[2 * ind] = (float)((double)(cs / (float)K) / 127.5);
+		wf[2 * ind + 1] = (float)((double)(sn / (float)K) / 127.5);
+	}
+}
+
+extern "C" void acb_build_h(float *h)
+{
+	/* msk.c:44-48: cos(2*pi*600/INTRATE/12 * (i - 66)) evaluated by cosf on the float-rounded
+	 * double argument, negative lobes clamped to zero */
+	for (int i = 0; i < 133; i++) {
+		const double arg = 2.0 * M_PI * 600.0 / ACB_INTRATE / 12 * (i - 66);
+		const float v = cosf((float)arg);
+		h[i] = v < 0 ? 0.0f : v;
+	}
+}
+
+/* ------------------------------------------------------------------ block FEC */
+
+namespace {
+
+struct FecTables {
+	uint16_t crc[256];
+	uint16_t syn[8 * 244];            /* syndrom.h:52-295 has 1936 = 8 x 242 entries; a 241-byte
+	                                     block (acars.c:319 precedes the length check) indexes just past
+	                                     that in the reference — keep the lookups in bounds here */
+	FecTables()
+	{
+		for (int b = 0; b < 256; b++) {       /* reflected CCITT, poly 0x8408 (syndrom.h:15-48) */
+			uint16_t r = (uint16_t)b;
+			for (int k = 0; k < 8; k++) r = (r & 1) ? (uint16_t)((r >> 1) ^ 0x8408) : (uint16_t)(r >> 1);
+			crc[b] = r;
+		}
+		/* syndrome of one wrong bit: CRC (init 0) of that bit followed by p zero bytes */
+		for (int bit = 0; bit < 8; bit++) {
+			uint16_t r = crc[1u << bit];
+			for (int p = 0; p < 244; p++) {
+				syn[bit + 8 * p] = r;
+				r = (uint16_t)((r >> 8) ^ crc[r & 0xff]);
+			}
+		}
+	}
+};
+
+const FecTables &tables()
+{
+	static const FecTables t;
+	return t;
+}
+
+inline bool odd_parity(unsigned char c)
+{
+	return __builtin_parity(c) != 0;      /* numbits[c] & 1, syndrom.h:4-13 */
+}
+
+inline uint16_t crc_step(const FecTables &t, uint16_t crc, unsigned char c)
+{
+	return (uint16_t)((crc >> 8) ^ t.crc[(crc ^ c) & 0xff]);      /* update_crc, syndrom.h:49 */
+}
+
+bool crc_bytes_hit(const FecTables &t, uint16_t crc)
+{
+	/* a single wrong bit inside the two BCS bytes (acars.c:57-62, 70-74): accepted, not repaired */
+	for (int i = 0; i < 16; i++)
+		if (t.syn[i] == crc) return true;
+	return false;
+}
+
+/* acars.c:39-64: try every bit of each parity-failing byte, depth-first in the reference's order */
+bool repair_parity(const FecTables &t, acb_msg_t *m, uint16_t crc, const int *pos, int npos)
+{
+	if (npos == 0) return crc == 0 || crc_bytes_hit(t, crc);
+	const int base = 8 * (m->len - pos[0] + 1);
+	for (int bit = 0; bit < 8; bit++)
+		if (repair_parity(t, m, crc ^ t.syn[bit + base], pos + 1, npos - 1)) {
+			m->txt[pos[0]] ^= (unsigned char)(1u << bit);
+			return true;
+		}
+	return false;
+}
+
+/* acars.c:66-90: no parity error but CRC fails -> two wrong bits in one byte */
+bool repair_double(const FecTables &t, acb_msg_t *m, uint16_t crc)
+{
+	if (crc_bytes_hit(t, crc)) return true;
+	for (int k = 0; k < m->len; k++) {
+		const int base = 8 * (m->len - k + 1);
+		for (int i = 0; i < 8; i++)
+			for (int j = 0; j < 8; j++)
+				if (i != j && (uint16_t)(crc ^ t.syn[i + base] ^ t.syn[j + base]) == 0) {
+					m->txt[k] ^= (unsigned char)((1u << i) | (1u << j));
+					return true;
+				}
+	}
+	return false;
+}
+
+} // namespace
+
+extern "C" uint16_t acb_crc_update(uint16_t crc, uint8_t c) { return crc_step(tables(), crc, c); }
+
+extern "C" uint16_t acb_syndrome(int index)
+{
+	return (index >= 0 && index < 8 * 242) ? tables().syn[index] : 0;
+}
+
+extern "C" int acb_block_fec(acb_msg_t *m)
+{
+	/* acars.c:123-207 */
+	const FecTables &t = tables();
+	constexpr unsigned char ETX = 0x83, STX = 0x02;
+	constexpr int MAXPERR = 3;
+	if (m->len < 13 || m->len > ACB_TXTMAX) return 0;
+	m->txt[12] = (unsigned char)((m->txt[12] & (ETX | STX)) | (ETX & STX));   /* acars.c:132-133 */
+
+	int bad[MAXPERR], nbad = 0;
+	for (int i = 0; i < m->len; i++)
+		if (!odd_parity(m->txt[i])) {
+			if (nbad < MAXPERR) bad[nbad] = i;
+			nbad++;
+		}
+	if (nbad > MAXPERR) return 0;
+	m->err = nbad;
+
+	uint16_t crc = 0;
+	for (int i = 0; i < m->len; i++) crc = crc_step(t, crc, m->txt[i]);
+	crc = crc_step(t, crc, m->crc[0]);
+	crc = crc_step(t, crc, m->crc[1]);
+
+	if (nbad) {
+		if (!repair_parity(t, m, crc, bad, nbad)) return 0;
+	} else if (crc) {
+		if (!repair_double(t, m, crc)) return 0;
+	}
+
+	int still = 0;
+	for (int i = 0; i < m->len; i++) {          /* acars.c:194-207 */
+		if (!odd_parity(m->txt[i])) still++;
+		m->txt[i] &= 0x7f;
+	}
+	return still == 0;
+}

@@ -1,0 +1,378 @@
+/*
+ * CUDA kernels of the acarsdec hot path for sm_100a.
+ *
+ *  K1  k_channelize : u8 IQ -> per-channel NCO mix x boxcar(K) -> decimate by K -> |.|
+ *                     (reference: in_callback, rtl.c:334-354).  FP32-issue bound by the
+ *                     reference's rounding sequence: every complex MAC is 4 rounded products
+ *                     and 4 rounded sums in tap order, no FMA contraction — reproduced exactly
+ *                     (packed FMUL2/FADD2 where ptxas keeps them unfused) so dm is bit-identical
+ *                     to the strict-IEEE build of the reference.
+ *  K2  k_demod      : demodMSK + putbit + decodeAcars for one channel per lane
+ *                     (reference: msk.c:67-137, acars.c:246-375), state carried in HBM between
+ *                     launches; serial recurrence per channel, parallel across channels/streams.
+ *
+ * Numerics contract: all order/rounding-sensitive arithmetic uses the
+ * explicit round-to-nearest intrinsics, which the compiler never contracts; the TU is also
+ * built with -fmad=false.
+ */
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "acb_internal.h"
+#include "frame_sm.h"
+
+namespace acb {
+
+__constant__ float c_h[FLENO];     /* matched filter, built on the host with glibc cosf (msk.c:44-48) */
+
+int upload_matched_filter(const float *h)
+{
+	return (int)cudaMemcpyToSymbol(c_h, h, sizeof(float) * FLENO);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K1: channelizer
+ * ---------------------------------------------------------------------------------------- */
+
+/* row stride of the staged IQ tile in 16-byte units: odd, so that the 8 lanes of an LDS.128
+ * phase (rows t..t+7, same column) fall in 8 distinct 16-byte bank groups */
+__host__ __device__ inline int tile_row_units(int K) { int u = K / 8; return (u & 1) ? u : u + 1; }
+
+size_t channelize_smem_bytes(int K)
+{
+	return (size_t)K * CH_GROUP * 16 + (size_t)CH_TILE * tile_row_units(K) * 16;
+}
+
+/* (float)u8 - 127.37f  (rtl.c:338-339).  The byte is planted in the mantissa of 2^23, the
+ * 2^23 removed (exact), then 127.37f subtracted — also exact: the result is a multiple of
+ * 2^-17 below 2^7, so the reference's single rounding rounds nothing either. */
+__device__ __forceinline__ float2 cvt_iq(unsigned w, int pair)
+{
+	float2 x;
+	x.x = __uint_as_float(__byte_perm(w, 0x4B000000u, pair ? 0x7542 : 0x7540));
+	x.y = __uint_as_float(__byte_perm(w, 0x4B000000u, pair ? 0x7543 : 0x7541));
+	x = __fadd2_rn(x, make_float2(-8388608.0f, -8388608.0f));
+	return __fadd2_rn(x, make_float2(-127.37f, -127.37f));
+}
+
+/* D += (a + jb) * (c + jd) with the reference's rounding: products rounded, (ac - bd) and
+ * (ad + bc) rounded, then the accumulate rounded (rtl.c:351).  w = (c, d, -d, c).
+ * Instruction shape: 2 FMUL2 + 2 FADD + 1 FADD2.  The middle sums are deliberately scalar:
+ * ptxas 12.9 contracts mul.rn.f32x2 feeding add.rn.f32x2 into FFMA2 even under -fmad=false
+ * (checked in SASS), which would skip the product rounding; it leaves FMUL2 -> FADD alone. */
+__device__ __forceinline__ void cmac(float2 &acc, float a, float b, const float4 w)
+{
+	const float2 p1 = __fmul2_rn(make_float2(a, a), make_float2(w.x, w.y));
+	const float2 p2 = __fmul2_rn(make_float2(b, b), make_float2(w.z, w.w));
+	const float2 t = make_float2(__fadd_rn(p1.x, p2.x), __fadd_rn(p1.y, p2.y));
+	acc = __fadd2_rn(acc, t);
+}
+
+/* cabsf (rtl.c:353): glibc hypotf is (float)sqrt((double)x*x + (double)y*y) for finite input */
+__device__ __forceinline__ float envelope(float2 d)
+{
+	double x = (double)d.x, y = (double)d.y;
+	return __double2float_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y))));
+}
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+	unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+/* grid = (blocks-of-1024-outputs, streams).  One CTA = one IQ block of one stream: 8 tiles of
+ * 128 outputs; thread t owns output row t of the tile and accumulates CH_GROUP channels in
+ * registers while walking its K input samples in order. */
+__global__ void __launch_bounds__(CH_TILE)
+k_channelize(const uint8_t *__restrict__ iq, size_t stream_stride, const float4 *__restrict__ wf4,
+             float *__restrict__ dm, int K, int nch, int ngrp, int nblk)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	float4 *wfs = reinterpret_cast<float4 *>(smem);
+	unsigned char *tile = smem + (size_t)K * CH_GROUP * 16;
+
+	const int t = threadIdx.x;
+	const int blk = blockIdx.x, s = blockIdx.y;
+	const int U = K / 8;                         /* 16-byte units per input row */
+	const int RU = tile_row_units(K);
+	const size_t nsamp = (size_t)nblk * OUTBLK;
+	const uint8_t *src_blk = iq + (size_t)s * stream_stride + (size_t)blk * OUTBLK * K * 2;
+
+	for (int g = 0; g < ngrp; g++) {
+		const float4 *wsrc = wf4 + ((size_t)s * ngrp + g) * K * CH_GROUP;
+		__syncthreads();
+		for (int i = t; i < K * CH_GROUP; i += CH_TILE) wfs[i] = wsrc[i];
+
+		for (int tl = 0; tl < OUTBLK / CH_TILE; tl++) {
+			const uint8_t *src = src_blk + (size_t)tl * CH_TILE * K * 2;
+			__syncthreads();                      /* previous tile fully consumed, wfs visible */
+			{
+				int row = t / U, j = t - row * U;
+				const int drow = CH_TILE / U, dj = CH_TILE - drow * U;
+				for (int u = t; u < CH_TILE * U; u += CH_TILE) {
+					cp_async16(tile + ((size_t)row * RU + j) * 16, src + (size_t)u * 16);
+					row += drow; j += dj;
+					if (j >= U) { j -= U; row++; }
+				}
+				cp_async_commit();
+				cp_async_wait_all();
+			}
+			__syncthreads();
+
+			float2 acc[CH_GROUP];
+#pragma unroll
+			for (int c = 0; c < CH_GROUP; c++) acc[c] = make_float2(0.f, 0.f);
+			const uint4 *rp = reinterpret_cast<const uint4 *>(tile + (size_t)t * RU * 16);
+			for (int j = 0; j < U; j++) {
+				const uint4 q = rp[j];
+				const unsigned wd[4] = { q.x, q.y, q.z, q.w };
+				const float4 *wj = wfs + (size_t)j * 8 * CH_GROUP;
+#pragma unroll
+				for (int e = 0; e < 4; e++) {
+					const float2 x0 = cvt_iq(wd[e], 0), x1 = cvt_iq(wd[e], 1);
+#pragma unroll
+					for (int c = 0; c < CH_GROUP; c++) cmac(acc[c], x0.x, x0.y, wj[(2 * e) * CH_GROUP + c]);
+#pragma unroll
+					for (int c = 0; c < CH_GROUP; c++) cmac(acc[c], x1.x, x1.y, wj[(2 * e + 1) * CH_GROUP + c]);
+				}
+			}
+			float *o = dm + ((size_t)s * nsamp + (size_t)blk * OUTBLK + (size_t)tl * CH_TILE + t) * nch + g * CH_GROUP;
+			const int nc = min(CH_GROUP, nch - g * CH_GROUP);
+			if (nc == CH_GROUP && (nch & 3) == 0) {
+				float4 v0 = make_float4(envelope(acc[0]), envelope(acc[1]), envelope(acc[2]), envelope(acc[3]));
+				float4 v1 = make_float4(envelope(acc[4]), envelope(acc[5]), envelope(acc[6]), envelope(acc[7]));
+				reinterpret_cast<float4 *>(o)[0] = v0;
+				reinterpret_cast<float4 *>(o)[1] = v1;
+			} else {
+#pragma unroll
+				for (int c = 0; c < CH_GROUP; c++)
+					if (c < nc) o[c] = envelope(acc[c]);
+			}
+		}
+	}
+}
+
+/* Any K (not a multiple of 8): one thread per (output, channel), straight from global memory.
+ * Same arithmetic, scalar.  Correctness path for odd rtlMult values; not tuned. */
+__global__ void __launch_bounds__(128)
+k_channelize_generic(const uint8_t *__restrict__ iq, size_t stream_stride, const float4 *__restrict__ wf4,
+                     float *__restrict__ dm, int K, int nch, int ngrp, int nblk)
+{
+	const size_t nsamp = (size_t)nblk * OUTBLK;
+	const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const int s = blockIdx.y;
+	if (gid >= nsamp * nch) return;
+	const size_t m = gid / nch;
+	const int ch = (int)(gid - m * nch);
+	const uint8_t *p = iq + (size_t)s * stream_stride + m * K * 2;
+	const float4 *w = wf4 + ((size_t)s * ngrp + ch / CH_GROUP) * K * CH_GROUP + (ch % CH_GROUP);
+	float dr = 0.f, di = 0.f;
+	for (int ind = 0; ind < K; ind++) {
+		float a = __fadd_rn((float)p[2 * ind], -127.37f), b = __fadd_rn((float)p[2 * ind + 1], -127.37f);
+		float4 ww = w[(size_t)ind * CH_GROUP];
+		float pr = __fadd_rn(__fmul_rn(a, ww.x), __fmul_rn(b, ww.z));
+		float pi = __fadd_rn(__fmul_rn(a, ww.y), __fmul_rn(b, ww.w));
+		dr = __fadd_rn(dr, pr);
+		di = __fadd_rn(di, pi);
+	}
+	dm[((size_t)s * nsamp + m) * nch + ch] = envelope(make_float2(dr, di));
+}
+
+int launch_channelize(const uint8_t *iq, size_t stream_stride, const float *wf4, float *dm,
+                      int K, int nch, int nstreams, int nblk, cudaStream_t stream)
+{
+	static int smem_set = 0;
+	const int ngrp = (nch + CH_GROUP - 1) / CH_GROUP;
+	const size_t smem = channelize_smem_bytes(K);
+	if (smem > (size_t)smem_set) {
+		cudaError_t e = cudaFuncSetAttribute(k_channelize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess) return (int)e;
+		smem_set = (int)smem;
+	}
+	dim3 grid(nblk, nstreams);
+	k_channelize<<<grid, CH_TILE, smem, stream>>>(iq, stream_stride, reinterpret_cast<const float4 *>(wf4), dm, K, nch, ngrp, nblk);
+	return (int)cudaGetLastError();
+}
+
+int launch_channelize_generic(const uint8_t *iq, size_t stream_stride, const float *wf4, float *dm,
+                              int K, int nch, int nstreams, int nblk, cudaStream_t stream)
+{
+	const int ngrp = (nch + CH_GROUP - 1) / CH_GROUP;
+	const size_t total = (size_t)nblk * OUTBLK * nch;
+	dim3 grid((unsigned)((total + 127) / 128), nstreams);
+	k_channelize_generic<<<grid, 128, 0, stream>>>(iq, stream_stride, reinterpret_cast<const float4 *>(wf4), dm, K, nch, ngrp, nblk);
+	return (int)cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K2: MSK demodulator + bit/byte framing, one channel per lane
+ * ---------------------------------------------------------------------------------------- */
+
+struct DemodRegs {
+	double phi, df, lvlsum;
+	float clk;
+	int bitcount;
+	unsigned S, idx;
+	int nbits, state;
+	unsigned outbits;
+	int blk_len, blk_err;
+	unsigned long long pos, soh_pos;
+};
+
+/* accessor for frame_sm.h: state in registers, text in the chain's HBM record */
+struct DevFrameAcc {
+	DemodRegs &r;
+	ChainState *st;
+	RawFrame *ring;
+	RingCtl *ctl;
+	unsigned cap;
+	int stream, chn;
+
+	__device__ __forceinline__ int &state() { return r.state; }
+	__device__ __forceinline__ int &nbits() { return r.nbits; }
+	__device__ __forceinline__ int &bitcount() { return r.bitcount; }
+	__device__ __forceinline__ int &blk_len() { return r.blk_len; }
+	__device__ __forceinline__ int &blk_err() { return r.blk_err; }
+	__device__ __forceinline__ unsigned &msk_s() { return r.S; }
+	__device__ __forceinline__ double &msk_df() { return r.df; }
+	__device__ __forceinline__ double &lvlsum() { return r.lvlsum; }
+	__device__ __forceinline__ void txt_put(int i, unsigned char c) { st->txt[i] = c; }
+	__device__ __forceinline__ unsigned char txt_get(int i) { return st->txt[i]; }
+	__device__ __forceinline__ void crc_put(int i, unsigned char c) { st->crc[i] = c; }
+	__device__ __forceinline__ bool frame_begin() { r.soh_pos = r.pos; return true; }   /* acars.c:283-292 */
+	__device__ __noinline__ void frame_emit()
+	{
+		/* acars.c:350-366: queue the block.  lvl = 10*log10(lvlsum/bitcount) is left to the
+		 * host (glibc log10) so the float matches the reference bit for bit. */
+		unsigned slot = atomicAdd(&ctl->count, 1u);
+		if (slot >= cap) return;                       /* overflow is reported by the host */
+		RawFrame *f = ring + slot;
+		f->stream = stream; f->chn = chn;
+		f->len = r.blk_len; f->err = r.blk_err;
+		f->lvlsum = r.lvlsum; f->bitcount = r.bitcount;
+		f->pos = r.pos; f->soh_pos = r.soh_pos;
+		f->crc[0] = st->crc[0]; f->crc[1] = st->crc[1];
+		const uint2 *src = reinterpret_cast<const uint2 *>(st->txt);
+		uint2 *dst = reinterpret_cast<uint2 *>(f->txt);
+		for (int i = 0; i < TXTCAP / 8; i++) dst[i] = src[i];
+	}
+};
+
+constexpr int DEMOD_WARPS = 1;   /* warps per CTA: one, so that chains spread over all SMs */
+
+__global__ void __launch_bounds__(32 * DEMOD_WARPS)
+k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp, int nch, int nstreams,
+        int lanes, int wps, RawFrame *__restrict__ ring, RingCtl *__restrict__ ctl, unsigned cap)
+{
+	__shared__ float s_h[FLENO + 3];
+	__shared__ float s_re[DEMOD_WARPS][FLEN][32], s_im[DEMOD_WARPS][FLEN][32];
+
+	for (int i = threadIdx.x; i < FLENO; i += blockDim.x) s_h[i] = c_h[i];
+	__syncthreads();
+
+	const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int warp = blockIdx.x * DEMOD_WARPS + wib;
+	const int s = warp / wps;
+	const int ch = (warp - s * wps) * lanes + lane;
+	if (s >= nstreams || lane >= lanes || ch >= nch) return;
+
+	ChainState *st = states + (size_t)s * nch + ch;
+	DemodRegs r;
+	r.phi = st->phi; r.df = st->df; r.lvlsum = st->lvlsum; r.clk = st->clk; r.bitcount = st->bitcount;
+	r.S = st->S; r.idx = st->idx; r.nbits = st->nbits; r.state = st->state; r.outbits = st->outbits;
+	r.blk_len = st->blk_len; r.blk_err = st->blk_err; r.pos = st->pos; r.soh_pos = st->soh_pos;
+	float (*re)[32] = s_re[wib], (*im)[32] = s_im[wib];
+#pragma unroll
+	for (int k = 0; k < FLEN; k++) { re[k][lane] = st->inb_re[k]; im[k][lane] = st->inb_im[k]; }
+
+	DevFrameAcc acc{ r, st, ring, ctl, cap, s, ch };
+
+	const double TWO_PI = 2.0 * M_PI;
+	const double S0 = 1800.0 / 12500 * 2.0 * M_PI;             /* msk.c:81 */
+	const double THR = 3 * M_PI / 2.0;                         /* msk.c:96,100 */
+	const double PLLC = (double)0.52f;                         /* msk.c:66 (float constant) */
+	const double PLLK = (1.0 - (double)0.52f) * (double)38e-4f;/* msk.c:130 (1.0-PLLC)*PLLG */
+
+	const float *in = dm + (size_t)s * nsamp * nch + ch;
+	for (int n = 0; n < nsamp; n++) {
+		/* VCO (msk.c:81-83) */
+		const double sv = __dadd_rn(S0, r.df);
+		r.phi = __dadd_rn(r.phi, sv);
+		if (r.phi >= TWO_PI) r.phi = __dadd_rn(r.phi, -TWO_PI);
+
+		/* mixer (msk.c:86-91): in * cexp(-j phi), rounded to float complex */
+		const double x = (double)in[(size_t)n * nch];
+		double sn, cs;
+		sincos(-r.phi, &sn, &cs);
+		re[r.idx][lane] = __double2float_rn(__dmul_rn(x, cs));
+		im[r.idx][lane] = __double2float_rn(__dmul_rn(x, sn));
+		r.idx = (r.idx + 1 == FLEN) ? 0 : r.idx + 1;
+
+		/* bit clock (msk.c:95-96) */
+		r.clk = __double2float_rn(__dadd_rn((double)r.clk, sv));
+		if ((double)r.clk >= __dadd_rn(THR, -__dmul_rn(sv, 0.5))) {
+			r.clk = __double2float_rn(__dadd_rn((double)r.clk, -THR));
+
+			/* matched filter (msk.c:103-107): 11 taps out of the x12 oversampled half cosine */
+			int o = __double2int_rz(__dmul_rn(12.0, __dadd_rn(__ddiv_rn((double)r.clk, sv), 0.5)));
+			o = min(max(o, 0), MFLTOVER);
+			float vr = 0.f, vi = 0.f;
+			int k = r.idx;
+#pragma unroll
+			for (int j = 0; j < FLEN; j++) {
+				const float hh = s_h[o + MFLTOVER * j];
+				vr = __fadd_rn(vr, __fmul_rn(hh, re[k][lane]));
+				vi = __fadd_rn(vi, __fmul_rn(hh, im[k][lane]));
+				k = (k + 1 == FLEN) ? 0 : k + 1;
+			}
+
+			/* normalise (msk.c:110-113) */
+			const float lvl = envelope(make_float2(vr, vi));
+			const double d = __dadd_rn((double)lvl, 1e-8);
+			vr = __double2float_rn(__ddiv_rn((double)vr, d));
+			vi = __double2float_rn(__ddiv_rn((double)vi, d));
+			r.lvlsum = __dadd_rn(r.lvlsum, (double)__fmul_rn(__fmul_rn(lvl, lvl), 0.25f));
+			r.bitcount++;
+
+			/* decision + phase error (msk.c:115-127) */
+			float vo;
+			double dphi;
+			if (r.S & 1u) { vo = vi; dphi = (vo >= 0.f) ? (double)(-vr) : (double)vr; }
+			else          { vo = vr; dphi = (vo >= 0.f) ? (double)vi : (double)(-vi); }
+			const float bitv = (r.S & 2u) ? -vo : vo;
+
+			/* putbit (msk.c:53-63) */
+			r.outbits >>= 1;
+			if (bitv > 0.f) r.outbits |= 0x80u;
+			if (--r.nbits <= 0) frame_byte(acc, (unsigned char)r.outbits);
+			r.S++;
+
+			/* PLL filter (msk.c:130) — after putbit, so a frame resync's MskDf=0 is filtered too */
+			r.df = __dadd_rn(__dmul_rn(PLLC, r.df), __dmul_rn(PLLK, dphi));
+		}
+		r.pos++;
+	}
+
+	st->phi = r.phi; st->df = r.df; st->lvlsum = r.lvlsum; st->clk = r.clk; st->bitcount = r.bitcount;
+	st->S = r.S; st->idx = r.idx; st->nbits = r.nbits; st->state = r.state; st->outbits = r.outbits;
+	st->blk_len = r.blk_len; st->blk_err = r.blk_err; st->pos = r.pos; st->soh_pos = r.soh_pos;
+#pragma unroll
+	for (int k = 0; k < FLEN; k++) { st->inb_re[k] = re[k][lane]; st->inb_im[k] = im[k][lane]; }
+}
+
+int launch_demod(ChainState *st, const float *dm, int nsamp, int nch, int nstreams,
+                 RawFrame *ring, RingCtl *ctl, unsigned cap, cudaStream_t stream)
+{
+	const int lanes = nch >= 32 ? 32 : nch;
+	const int wps = (nch + lanes - 1) / lanes;
+	const int warps = nstreams * wps;
+	const int grid = (warps + DEMOD_WARPS - 1) / DEMOD_WARPS;
+	k_demod<<<grid, 32 * DEMOD_WARPS, 0, stream>>>(st, dm, nsamp, nch, nstreams, lanes, wps, ring, ctl, cap);
+	return (int)cudaGetLastError();
+}
+
+} // namespace acb

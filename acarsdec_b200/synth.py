@@ -53,6 +53,17 @@ def frame_bytes(text: bytes, *, mode=b"2", addr=b".N123AB", ack=NAK, label=b"H1"
     return head + body + bytes([crc & 0xFF, crc >> 8, DEL])
 
 
+def corrupt_frame(frame: bytes, flips, prekey: int = 16) -> bytes:
+    """Flip bits after the BCS was computed, to exercise the block FEC (acars.c:39-215).
+    `flips` is a list of (index, xor_mask); index 0 is the first byte after SOH (the mode
+    character), negative indices count from the end of the frame (-1 = DEL, -2/-3 = BCS)."""
+    f = bytearray(frame)
+    body0 = prekey + 5
+    for idx, mask in flips:
+        f[body0 + idx if idx >= 0 else len(f) + idx] ^= mask
+    return bytes(f)
+
+
 def frame_bits(frame: bytes) -> np.ndarray:
     """LSB-first bit stream (msk.c:55-58)."""
     return np.unpackbits(np.frombuffer(frame, dtype=np.uint8), bitorder="little")

@@ -1,0 +1,170 @@
+/*
+ * acars_b200 — C ABI of the B200-native acarsdec hot path
+ * (u8 IQ -> per-channel mix+boxcar+decimate -> |.| -> demodMSK -> ACARS frame sync -> block FEC).
+ *
+ * Two layers, both plain C:
+ *
+ *  1. The context API below (acb_*): N independent IQ streams x C channels per GPU, the
+ *     superset needed beyond MAXNBCHANNELS=16 (acarsdec.h:30).  Every entry point cites the
+ *     reference interface it replaces.
+ *  2. The reference's own symbols (initMsk/demodMSK/initAcars/decodeAcars/deinitAcars and the
+ *     initRtl/runRtlSample/runRtlCancel/runRtlClose front-end trio) exported by
+ *     libacarsdec_compat.so, declared in include/acarsdec_compat.h, implemented as a thin shim
+ *     over this API so that acarsdec.c links against it unchanged.
+ *
+ * There is no CPU fallback: every processing call fails with ACB_ERR_CUDA when no sm_100
+ * device / kernel image is available.
+ */
+#ifndef ACARS_B200_H
+#define ACARS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACB_INTRATE 12500   /* acarsdec.h:31  INTRATE */
+#define ACB_OUTBLK 1024     /* rtl.c:49       RTLOUTBUFSZ: output samples per IQ block */
+#define ACB_TXTMAX 250      /* acarsdec.h:55  msgblk_t.txt */
+#define ACB_MAXK 2048       /* rtl.c:39 caps rtlMult at 320; wideband configs go beyond */
+
+enum {
+	ACB_OK = 0,
+	ACB_ERR_ARG = -1,       /* bad argument */
+	ACB_ERR_CUDA = -2,      /* CUDA runtime error / no device (see acb_last_error) */
+	ACB_ERR_NOMEM = -3,
+	ACB_ERR_OVERFLOW = -4,  /* device message ring overflowed: frames were lost */
+	ACB_ERR_PLAN = -5       /* frequency plan impossible (rtl.c:149-152) */
+};
+
+typedef struct acb_ctx acb_ctx_t;
+
+typedef struct {
+	int device;             /* CUDA ordinal */
+	int K;                  /* rtlMult: input rate = K*12500, taps == decimation (rtl.c:213-214) */
+	int nstreams;           /* independent IQ streams served by this context */
+	int nch;                /* channels per stream */
+	int max_blocks;         /* largest nblk a submit call may carry (sizes device staging) */
+	int flags;              /* ACB_FLAG_* */
+} acb_config_t;
+
+#define ACB_FLAG_NO_INPUT_STAGING 1   /* caller only uses acb_submit_device / acb_submit_dm_* */
+
+/* One decoded block, after parity/CRC repair: msgblk_t (acarsdec.h:48-57) without the queue
+ * link, plus where it came from.  `txt` is parity-stripped (acars.c:200). */
+typedef struct {
+	int stream;
+	int chn;
+	int len;
+	int err;                /* parity errors repaired (acars.c:156) */
+	float lvl;              /* 10*log10(MskLvlSum/MskBitCount), acars.c:351 */
+	uint64_t block;         /* index of the 1024-sample block in which the frame completed */
+	uint64_t pos;           /* channel sample index (12.5 kS/s) at which the frame completed */
+	uint64_t soh_pos;       /* channel sample index of the SOH byte (reference: gettimeofday, acars.c:290) */
+	unsigned char txt[ACB_TXTMAX];
+	unsigned char crc[2];
+} acb_msg_t;
+
+/* Per-channel demodulator + framing state: the persistent part of channel_t (acarsdec.h:76-89). */
+typedef struct {
+	double MskPhi, MskDf, MskLvlSum;
+	float MskClk;
+	int MskBitCount;
+	unsigned MskS, idx;
+	int nbits, Acarsstate;
+	unsigned outbits;
+	int blk_len, blk_err;
+	uint64_t pos, soh_pos;
+	float inb_re[11], inb_im[11];   /* msk.c:40 ring, FLEN=11 */
+	unsigned char blk_crc[2];
+	unsigned char blk_txt[ACB_TXTMAX];
+} acb_chan_state_t;
+
+/* ---- front-end planning: host-side, bit-identical to the reference's initRtl ---- */
+
+/* rtl.c:245-247 — "131.525" -> Hz on the 12.5 kHz raster */
+int acb_round_freq(double mhz);
+/* rtl.c:255 — the value initRtl leaves in channel[].Fr (int <- float <- unsigned) */
+int acb_stored_fr(unsigned freq_hz);
+/* rtl.c:131-168 chooseFc — 0 when the span does not fit */
+unsigned acb_choose_fc(const unsigned *freqs_hz, int n, int K);
+/* rtl.c:283-286 — wf[ind] = cexpf(-j*AMFreq*ind)/K/127.5 as 2K floats (re,im interleaved) */
+void acb_build_wf(int fr_stored, unsigned fc_hz, int K, float *wf);
+/* msk.c:44-48 — 133-tap oversampled half-cosine matched filter */
+void acb_build_h(float *h);
+
+/* ---- context ---- */
+
+int  acb_create(const acb_config_t *cfg, acb_ctx_t **out);
+void acb_destroy(acb_ctx_t *ctx);
+const char *acb_last_error(void);
+const char *acb_version(void);
+
+/* Replaces the channel part of initRtl (rtl.c:243-287) for one stream: freqs in CLI order,
+ * chooses Fc, builds and uploads the tables.  fc_out may be NULL. */
+int acb_set_plan(acb_ctx_t *ctx, int stream, const unsigned *freqs_hz, int nch, unsigned *fc_out);
+/* Same, with caller-supplied tables (nch x 2K floats), e.g. taken from channel[].wf. */
+int acb_set_wf(acb_ctx_t *ctx, int stream, const float *wf, int nch);
+/* initMsk + initAcars for every channel of every stream (msk.c:30-51, acars.c:230-234). */
+int acb_reset(acb_ctx_t *ctx);
+
+/* ---- processing ---- */
+
+/* Replaces in_callback (rtl.c:314-361) for all streams at once.  Stream s's input is
+ * `nblk` consecutive blocks of 1024*K*2 bytes (interleaved u8 I,Q) at iq + s*stream_stride.
+ * Asynchronous: host->device copy, channelizer and demod are queued; call acb_sync to
+ * collect.  `iq` should come from acb_host_alloc (pinned) for full PCIe overlap. */
+int acb_submit_host(acb_ctx_t *ctx, const uint8_t *iq, size_t stream_stride, int nblk);
+/* Same with the input already resident in device memory (no copy). */
+int acb_submit_device(acb_ctx_t *ctx, const uint8_t *iq_dev, size_t stream_stride, int nblk);
+/* Replaces demodMSK's input side (msk.c:67; soundfile.c:71-77): 12.5 kS/s envelope samples,
+ * dm[(s*nsamp + n)*nch + c], fed straight to the demodulator (no channelizer). */
+int acb_submit_dm_host(acb_ctx_t *ctx, const float *dm, int nsamp);
+/* Wait for everything queued, run the block FEC (blk_thread, acars.c:93-215) on what the
+ * device decoded, and append the survivors to the output queue in the reference's emission
+ * order (block-major, then stream, then channel, then time; rtl.c:357-360).
+ * Returns the number of messages waiting, or a negative error. */
+int acb_sync(acb_ctx_t *ctx);
+/* Pop up to `max` messages from the output queue (the outputmsg() feed, acars.c:209). */
+int acb_drain(acb_ctx_t *ctx, acb_msg_t *out, int max);
+
+/* Pinned host memory for submit_host callers. */
+void *acb_host_alloc(size_t bytes);
+void  acb_host_free(void *p);
+/* Device memory for submit_device callers (benchmarks keep the input resident in HBM). */
+void *acb_device_alloc(acb_ctx_t *ctx, size_t bytes);
+void  acb_device_free(acb_ctx_t *ctx, void *p);
+int   acb_copy_to_device(acb_ctx_t *ctx, void *dst_dev, const void *src_host, size_t bytes);
+
+/* ---- inspection (parity tests, the compat shim, bench instrumentation) ---- */
+
+/* Envelope samples the channelizer produced for the last submit: out[(s*nsamp+n)*nch + c]. */
+int acb_read_dm(acb_ctx_t *ctx, float *out, size_t nfloats);
+int acb_get_state(acb_ctx_t *ctx, int stream, int chn, acb_chan_state_t *out);
+int acb_set_state(acb_ctx_t *ctx, int stream, int chn, const acb_chan_state_t *in);
+
+typedef struct {
+	uint64_t submits;           /* submit calls */
+	uint64_t kernel_launches;   /* CUDA kernels launched by this context */
+	uint64_t blocks;            /* stream-blocks processed */
+	uint64_t raw_frames;        /* frames handed from the device to the FEC */
+	uint64_t fec_dropped;       /* frames the FEC rejected */
+	double   chan_ms;           /* accumulated device time of the channelizer kernel (CUDA events) */
+	double   demod_ms;          /* accumulated device time of the demod kernel */
+	uint64_t chan_launches, demod_launches;
+} acb_stats_t;
+int acb_get_stats(acb_ctx_t *ctx, acb_stats_t *out, int reset);
+
+/* Block FEC on one frame in place (acars.c:123-207): 1 = deliver, 0 = drop.
+ * Exposed for tests and for hosts that run their own queue. */
+int acb_block_fec(acb_msg_t *m);
+/* Tables behind it, generated rather than stored (syndrom.h:4-13, 15-49, 52-295). */
+uint16_t acb_crc_update(uint16_t crc, uint8_t c);
+uint16_t acb_syndrome(int index);      /* index = bit + 8*bytes_from_end, 0..1935 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -33,6 +33,25 @@ void ref_tap_push_sentinel(int chn)
 	pthread_mutex_unlock(&blkq_mtx);
 }
 
+/* queue an arbitrary pre-FEC block, exactly where decodeAcars would (acars.c:356-364) */
+void ref_tap_push_block(int chn, int len, const unsigned char *txt, const unsigned char *crc)
+{
+	msgblk_t *b = malloc(sizeof(msgblk_t));
+	memset(b, 0, sizeof(*b));
+	b->chn = chn;
+	b->len = len;
+	memcpy(b->txt, txt, len > 250 ? 250 : len);
+	b->crc[0] = crc[0];
+	b->crc[1] = crc[1];
+	pthread_mutex_lock(&blkq_mtx);
+	b->prev = NULL;
+	if (blkq_s) blkq_s->prev = b;
+	blkq_s = b;
+	if (blkq_e == NULL) blkq_e = blkq_s;
+	pthread_cond_signal(&blkq_wcd);
+	pthread_mutex_unlock(&blkq_mtx);
+}
+
 int ref_tab_syndrom(unsigned short *out, int max)
 {
 	int n = (int)(sizeof(syndrom) / sizeof(syndrom[0]));

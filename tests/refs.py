@@ -94,6 +94,7 @@ class RefLib:
         L.ref_tab_syndrom.argtypes = [C.c_void_p, C.c_int]
         L.ref_tab_crc.argtypes = [C.c_void_p]
         L.ref_tab_numbits.argtypes = [C.c_void_p]
+        L.ref_tap_push_block.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_char_p]
         self.K = None
 
     def open_rtl(self, K: int, freqs_mhz) -> None:
@@ -159,6 +160,10 @@ class RefLib:
                 out.append(m)
             if n < 256:
                 return out
+
+    def push_block(self, chn: int, txt: bytes, crc: bytes) -> None:
+        """Feed one pre-FEC block straight into the reference's blk_thread queue."""
+        self.lib.ref_tap_push_block(chn, len(txt), bytes(txt), bytes(crc))
 
     def tables(self):
         n = self.lib.ref_tab_syndrom(None, 0)

@@ -1,0 +1,154 @@
+"""CPU-only tests of the product's host side: the C-ABI library loads and exports every symbol
+include/acars_b200.h declares, the host planning functions and the block FEC agree with the
+oracle bit for bit, and (no GPU here) creating a context fails loudly instead of falling back."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import refs
+from acarsdec_b200 import api, synth
+from common import bits_equal
+from conftest import HAVE_GPU
+from test_oracle_vs_reference import _fec_cases
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol(native):
+    header = (ROOT / "include" / "acars_b200.h").read_text()
+    declared = set(re.findall(r"\b(acb_[a-z0-9_]+)\s*\(", header))
+    bound = {name for name, _, _ in api.ABI}
+    assert declared == bound, declared ^ bound
+    for name in declared:
+        assert hasattr(native, name)
+    assert b"sm_100a" in native.acb_version()
+
+
+def test_struct_sizes_match_header(native):
+    # acb_msg_t / acb_chan_state_t layouts as the C compiler sees them
+    import subprocess, tempfile
+    src = '#include <stdio.h>\n#include "acars_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n",sizeof(acb_msg_t),sizeof(acb_chan_state_t),sizeof(acb_stats_t),sizeof(acb_config_t));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        (Path(d) / "s.c").write_text(src)
+        subprocess.run(["gcc", "-I", str(ROOT / "include"), "-o", f"{d}/s", f"{d}/s.c"], check=True)
+        out = subprocess.run([f"{d}/s"], capture_output=True, text=True, check=True).stdout.split()
+    assert [int(x) for x in out] == [C.sizeof(api.Msg), C.sizeof(api.ChanState), C.sizeof(api.Stats), C.sizeof(api.Config)]
+
+
+@pytest.mark.parametrize("K,freqs", [
+    (160, synth.DEFAULT_FREQS_MHZ),
+    (192, (131.525, 131.725, 131.825)),
+    (200, (129.125, 130.025, 130.450, 131.125, 131.550)),
+    (160, (131.5125, 131.7375, 131.2625)),
+    (320, (118.000, 119.500, 121.000)),
+    (16, (131.525, 131.550, 131.475)),
+])
+def test_planning_matches_oracle(native, oracle, K, freqs):
+    assert api.plan(K, freqs) == oracle.plan(K, freqs)
+    assert bits_equal(api.build_wf(K, freqs), oracle.wf(K, freqs))
+
+
+def test_plan_rejects_wide_span(native, oracle):
+    f = np.array([118000000, 121000000], dtype=np.uint32)
+    assert native.acb_choose_fc(f.ctypes.data, 2, 160) == 0
+    assert oracle.lib.orc_choose_fc(f.ctypes.data, 2, 160) == 0
+
+
+def test_matched_filter_matches_oracle(native, oracle):
+    assert bits_equal(api.build_h(), oracle.h)
+
+
+def test_crc_and_syndrome_tables(native, oracle):
+    for i in range(256):
+        for crc in (0, 0x1234, 0xFFFF):
+            assert native.acb_crc_update(crc, i) == oracle.lib.orc_crc_step(crc, i)
+    for i in range(1936):
+        assert native.acb_syndrome(i) == oracle.lib.orc_syndrome(i & 7, i >> 3)
+
+
+def test_block_fec_fuzz_matches_oracle(native, oracle):
+    rng = np.random.default_rng(1234)
+    n_out = n_fixed = 0
+    for chn, txt, crc in _fec_cases(rng, 3000):
+        a, o = api.Msg(), refs.Msg()
+        for m in (a, o):
+            m.chn, m.len = chn, len(txt)
+            m.txt[:len(txt)] = txt
+            m.crc[:] = crc
+        fa, fo = api.block_fec(a), oracle.fec(o)
+        assert (fa is None) == (fo is None)
+        if fa is not None:
+            assert fa.as_tuple() == fo.as_tuple()
+            n_out += 1
+            n_fixed += fa.err > 0
+    assert n_out > 500 and n_fixed > 100
+
+
+def test_frame_state_machine_host_build(oracle):
+    """frame_sm.h compiled for the host (the compat shim's decodeAcars uses it) against the
+    restatement's orc_decode_byte on random byte streams with embedded frames."""
+    import subprocess, tempfile
+    src = r'''
+#include <stdio.h>
+#include <string.h>
+#include "frame_sm.h"
+struct Acc {
+  int st, nb, bc, len, err; unsigned S; double df, ls; unsigned char txt[256], crc[2]; int emitted; unsigned long h;
+  int &state(){return st;} int &nbits(){return nb;} int &bitcount(){return bc;} int &blk_len(){return len;} int &blk_err(){return err;}
+  unsigned &msk_s(){return S;} double &msk_df(){return df;} double &lvlsum(){return ls;}
+  void txt_put(int i,unsigned char r){txt[i]=r;} unsigned char txt_get(int i){return txt[i];} void crc_put(int i,unsigned char r){crc[i]=r;}
+  bool frame_begin(){return true;}
+  void frame_emit(){emitted++; for(int i=0;i<len;i++) h=h*131+txt[i]; h=h*131+crc[0]; h=h*131+crc[1]; h=h*131+len;}
+};
+int main(){ Acc a; memset(&a,0,sizeof(a)); a.nb=8; int c; 
+  while((c=getchar())!=EOF){ a.df=1.0; acb::frame_byte(a,(unsigned char)c); printf("%d %d %u %d %d %d %lu %d\n",a.st,a.nb,a.S,a.len,a.err,a.emitted,a.h,a.df==0.0); }
+  return 0; }
+'''
+    rng = np.random.default_rng(8)
+    stream = bytearray()
+    for i in range(300):
+        kind = i % 5
+        fr = synth.frame_bytes(synth.random_text(rng, int(rng.integers(0, 224))), prekey=0, etb=bool(i & 1))
+        fr = bytearray(fr[2:])                         # SYN SYN SOH ... BCS DEL
+        if kind == 1:
+            fr = bytearray(b ^ 0xFF for b in fr)        # inverted polarity (~SYN)
+            fr[2:] = bytes(b ^ 0xFF for b in fr[2:])    # only the SYNs inverted: decoder flips MskS
+        if kind == 2:
+            for _ in range(6):
+                fr[int(rng.integers(3, len(fr)))] ^= 1 << int(rng.integers(0, 8))
+        if kind == 3 and len(fr) > 40:
+            fr[-4] = 0x55                               # destroy ETX: the DLE path (acars.c:324)
+        stream += fr + bytes(rng.integers(0, 256, size=int(rng.integers(0, 12)), dtype=np.uint8))
+    stream += bytes([0x16, 0x16, 0x01]) + bytes([0x31] * 260)      # too long (acars.c:334)
+    with tempfile.TemporaryDirectory() as d:
+        (Path(d) / "f.cpp").write_text(src)
+        subprocess.run(["g++", "-std=c++17", "-I", str(ROOT / "acarsdec_b200" / "csrc"), "-o", f"{d}/f", f"{d}/f.cpp"], check=True)
+        out = subprocess.run([f"{d}/f"], input=bytes(stream), capture_output=True, check=True).stdout.decode().split("\n")
+    c = oracle.new_chan(0)
+    sink = refs.Sink()
+    h, emitted = 0, 0
+    for i, byte in enumerate(stream):
+        c.outbits = byte
+        c.MskDf = 1.0
+        oracle.lib.orc_decode_byte(C.byref(c), C.byref(sink.c))
+        if sink.c.nmsg > emitted:
+            m = sink.c.msgs[emitted]
+            for k in range(m.len):
+                h = (h * 131 + m.txt[k]) % 2**64
+            for v in (m.crc[0], m.crc[1], m.len):
+                h = (h * 131 + v) % 2**64
+            emitted += 1
+        st, nb, S, ln, err, em, hh, dfz = (int(x) for x in out[i].split())
+        assert (st, nb, S, em, hh, dfz) == (c.state, c.nbits, c.MskS, emitted, h, int(c.MskDf == 0.0)), i
+        if st == 3:
+            assert (ln, err) == (c.blk.len, c.blk.err), i
+    assert emitted > 150
+
+
+@pytest.mark.skipif(HAVE_GPU, reason="only meaningful without a GPU")
+def test_no_cpu_fallback(native):
+    with pytest.raises(api.AcbError):
+        api.Context(K=160, nstreams=1, nch=1, max_blocks=1)
