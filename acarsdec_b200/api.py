@@ -77,6 +77,9 @@ ABI = [
     ("acb_submit_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
     ("acb_submit_dm_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     ("acb_sync", C.c_int, [C.c_void_p]),
+    ("acb_collect", C.c_int, [C.c_void_p]),
+    ("acb_mark", C.c_int, [C.c_void_p, C.c_int]),
+    ("acb_elapsed_ms", C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     ("acb_drain", C.c_int, [C.c_void_p, C.POINTER(Msg), C.c_int]),
     ("acb_host_alloc", C.c_void_p, [C.c_size_t]),
     ("acb_host_free", None, [C.c_void_p]),
@@ -238,6 +241,17 @@ class Context:
 
     def sync(self) -> int:
         return _check(self.lib, self.lib.acb_sync(self.h))
+
+    def collect(self) -> int:
+        return _check(self.lib, self.lib.acb_collect(self.h))
+
+    def mark(self, which: int) -> None:
+        _check(self.lib, self.lib.acb_mark(self.h, which))
+
+    def elapsed_ms(self) -> float:
+        ms = C.c_float()
+        _check(self.lib, self.lib.acb_elapsed_ms(self.h, C.byref(ms)))
+        return ms.value
 
     def drain(self):
         out = []

@@ -7,9 +7,10 @@
  *
  *   host u8 IQ --copy stream--> d_iq[buf] --compute stream--> K1 k_channelize -> d_dm (HBM)
  *                                                        --> K2 k_demod      -> frame ring (HBM)
- *   acb_sync: D2H of the frames appended since the last sync -> block FEC on the host -> queue
+ *   acb_collect / acb_sync: D2H of that submit's frames -> block FEC on the host -> output queue
  *
- * Input staging is double-buffered so the H2D copy of submit i+1 overlaps the kernels of i.
+ * Up to two submits are in flight: input staging and the frame rings are double-buffered, so
+ * the H2D copy of submit i+1 overlaps the kernels of i and the read-back of i overlaps i+1.
  */
 #include <cuda_runtime.h>
 #include <math.h>
@@ -49,6 +50,13 @@ extern "C" const char *acb_version(void) { return "acars_b200 0.1 (sm_100a)"; }
 
 struct EvTriple { cudaEvent_t a, b, c; bool chan; };
 
+/* one submit in flight: which frame ring it appends to and how its frames are grouped */
+struct Ticket {
+	EvTriple ev;                                   /* a..b = channelizer, b..c = demod; c = done */
+	int ring;
+	std::vector<unsigned long long> group_starts;  /* emission-order groups (input blocks / chunks) */
+};
+
 struct acb_ctx {
 	acb_config_t cfg;
 	int ngrp;
@@ -62,17 +70,21 @@ struct acb_ctx {
 	float *d_dm;                 /* [stream][nsamp][nch] */
 	size_t dm_floats;
 	ChainState *d_state;
-	RawFrame *d_ring;
-	RingCtl *d_ctl;
+	cudaStream_t s_d2h;
+	RawFrame *d_ring[2];         /* frame rings, alternating per submit so that one can be read
+	                                back while the next submit's demod appends to the other */
+	RingCtl *d_ctl[2];
 	unsigned ring_cap;
 	RawFrame *h_ring;            /* pinned */
-	RingCtl *h_ctl;              /* pinned */
-	float *h_dm_stage;           /* pinned, for submit_dm_host */
+	RingCtl *h_ctl[2];           /* pinned */
 	int last_nsamp;
-	std::vector<unsigned long long> group_starts;   /* emission-order groups since last sync */
+	unsigned long long nsubmit;
 	unsigned long long pos;      /* envelope samples submitted so far (all chains move together) */
+	std::deque<Ticket> inflight; /* oldest first; at most 2 */
 	std::deque<acb_msg_t> outq;
-	std::vector<EvTriple> ev_inflight, ev_free;
+	std::vector<EvTriple> ev_free;
+	cudaEvent_t mark[2];
+	bool overflowed;
 	acb_stats_t stats;
 	bool use_generic;
 };
@@ -124,10 +136,10 @@ static int reset_states(acb_ctx *c)
 		s.state = 0;             /* WSYN */
 	}
 	CU(cudaMemcpy(c->d_state, init.data(), n * sizeof(ChainState), cudaMemcpyHostToDevice));
-	CU(cudaMemset(c->d_ctl, 0, sizeof(RingCtl)));
+	for (int i = 0; i < 2; i++) CU(cudaMemset(c->d_ctl[i], 0, sizeof(RingCtl)));
 	c->pos = 0;
-	c->group_starts.clear();
 	c->outq.clear();
+	c->overflowed = false;
 	return ACB_OK;
 }
 
@@ -153,11 +165,16 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 	c->use_generic = (cfg->K % 8) != 0 || channelize_smem_bytes(cfg->K) > 200 * 1024;
 	c->next_buf = 0;
 	c->last_nsamp = 0;
+	c->nsubmit = 0;
+	c->overflowed = false;
 	memset(&c->stats, 0, sizeof(c->stats));
 	*out = c;
 
 	CU(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
 	CU(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+	CU(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+	CU(cudaEventCreate(&c->mark[0]));
+	CU(cudaEventCreate(&c->mark[1]));
 	const size_t in_bytes = (size_t)cfg->nstreams * cfg->max_blocks * c->blk_bytes;
 	for (int i = 0; i < 2; i++) {
 		c->d_iq[i] = nullptr;
@@ -173,15 +190,17 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 	CU(cudaMalloc(&c->d_dm, c->dm_floats * sizeof(float)));
 	const size_t nchain = (size_t)cfg->nstreams * cfg->nch;
 	CU(cudaMalloc(&c->d_state, nchain * sizeof(ChainState)));
-	/* a frame needs >= 20 bytes on air = 833 envelope samples, so < 2 per chain per block */
-	size_t cap = nchain * (2 * (size_t)cfg->max_blocks + 4) * 2;
+	/* a frame needs >= 20 bytes on air = 833 envelope samples, so < 2 per chain per block:
+	 * one submit can never overflow its ring */
+	size_t cap = nchain * (2 * (size_t)cfg->max_blocks + 4);
 	if (cap > (1u << 22)) cap = 1u << 22;
 	c->ring_cap = (unsigned)cap;
-	CU(cudaMalloc(&c->d_ring, cap * sizeof(RawFrame)));
-	CU(cudaMalloc(&c->d_ctl, sizeof(RingCtl)));
+	for (int i = 0; i < 2; i++) {
+		CU(cudaMalloc(&c->d_ring[i], cap * sizeof(RawFrame)));
+		CU(cudaMalloc(&c->d_ctl[i], sizeof(RingCtl)));
+		CU(cudaHostAlloc(&c->h_ctl[i], sizeof(RingCtl), cudaHostAllocDefault));
+	}
 	CU(cudaHostAlloc(&c->h_ring, cap * sizeof(RawFrame), cudaHostAllocDefault));
-	CU(cudaHostAlloc(&c->h_ctl, sizeof(RingCtl), cudaHostAllocDefault));
-	c->h_dm_stage = nullptr;
 
 	float h[FLENO];
 	acb_build_h(h);
@@ -200,12 +219,13 @@ extern "C" void acb_destroy(acb_ctx_t *c)
 			cudaEventDestroy(c->ev_copied[i]);
 			cudaEventDestroy(c->ev_consumed[i]);
 		}
-		for (auto &e : c->ev_inflight) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); cudaEventDestroy(e.c); }
+		for (auto &t : c->inflight) { cudaEventDestroy(t.ev.a); cudaEventDestroy(t.ev.b); cudaEventDestroy(t.ev.c); }
 		for (auto &e : c->ev_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); cudaEventDestroy(e.c); }
-		cudaFree(c->d_wf4); cudaFree(c->d_dm); cudaFree(c->d_state); cudaFree(c->d_ring); cudaFree(c->d_ctl);
-		cudaFreeHost(c->h_ring); cudaFreeHost(c->h_ctl);
-		if (c->h_dm_stage) cudaFreeHost(c->h_dm_stage);
-		cudaStreamDestroy(c->s_copy); cudaStreamDestroy(c->s_comp);
+		cudaFree(c->d_wf4); cudaFree(c->d_dm); cudaFree(c->d_state);
+		for (int i = 0; i < 2; i++) { cudaFree(c->d_ring[i]); cudaFree(c->d_ctl[i]); cudaFreeHost(c->h_ctl[i]); }
+		cudaFreeHost(c->h_ring);
+		cudaEventDestroy(c->mark[0]); cudaEventDestroy(c->mark[1]);
+		cudaStreamDestroy(c->s_copy); cudaStreamDestroy(c->s_comp); cudaStreamDestroy(c->s_d2h);
 	}
 	delete c;
 }
@@ -263,12 +283,69 @@ static EvTriple get_events(acb_ctx *c)
 	return e;
 }
 
-/* queue K1+K2 (or K2 only) on the compute stream for `nblk` blocks / `nsamp` envelope samples */
-static int run_kernels(acb_ctx *c, const uint8_t *d_iq, size_t stride, int nblk, int nsamp)
+/* Wait for the oldest submit in flight, bring its frames back, run the block FEC (blk_thread,
+ * acars.c:93-215) and queue the survivors in the reference's emission order: per input block,
+ * channel by channel, then time (rtl.c:357-360; soundfile.c:71-77); streams are interleaved as
+ * if the reference served them in turn. */
+static int collect_oldest(acb_ctx *c)
 {
-	EvTriple ev = get_events(c);
-	ev.chan = d_iq != nullptr;
-	CU(cudaEventRecord(ev.a, c->s_comp));
+	if (c->inflight.empty()) return ACB_OK;
+	Ticket t = std::move(c->inflight.front());
+	c->inflight.pop_front();
+	CU(cudaEventSynchronize(t.ev.c));           /* the RingCtl read-back was queued before ev.c */
+	float ms = 0;
+	if (t.ev.chan && cudaEventElapsedTime(&ms, t.ev.a, t.ev.b) == cudaSuccess) c->stats.chan_ms += ms;
+	if (cudaEventElapsedTime(&ms, t.ev.b, t.ev.c) == cudaSuccess) c->stats.demod_ms += ms;
+	c->ev_free.push_back(t.ev);
+
+	unsigned count = c->h_ctl[t.ring]->count;
+	if (count > c->ring_cap) { c->overflowed = true; count = c->ring_cap; }
+	if (count) {
+		CU(cudaMemcpyAsync(c->h_ring, c->d_ring[t.ring], (size_t)count * sizeof(RawFrame), cudaMemcpyDeviceToHost, c->s_d2h));
+		CU(cudaStreamSynchronize(c->s_d2h));
+	}
+	struct Key { size_t group; int stream, chn; unsigned long long pos; unsigned idx; };
+	std::vector<Key> keys(count);
+	const auto &gs = t.group_starts;
+	for (unsigned i = 0; i < count; i++) {
+		const RawFrame &f = c->h_ring[i];
+		keys[i] = Key{ (size_t)(std::upper_bound(gs.begin(), gs.end(), f.pos) - gs.begin()), f.stream, f.chn, f.pos, i };
+	}
+	std::sort(keys.begin(), keys.end(), [](const Key &a, const Key &b) {
+		if (a.group != b.group) return a.group < b.group;
+		if (a.stream != b.stream) return a.stream < b.stream;
+		if (a.chn != b.chn) return a.chn < b.chn;
+		return a.pos < b.pos;
+	});
+	for (const Key &k : keys) {
+		const RawFrame &f = c->h_ring[k.idx];
+		acb_msg_t m;
+		memset(&m, 0, sizeof(m));
+		m.stream = f.stream; m.chn = f.chn; m.len = f.len; m.err = f.err;
+		m.lvl = (float)(10 * log10(f.lvlsum / f.bitcount));          /* acars.c:351 */
+		m.block = f.pos / OUTBLK; m.pos = f.pos; m.soh_pos = f.soh_pos;
+		memcpy(m.txt, f.txt, ACB_TXTMAX);
+		m.crc[0] = f.crc[0]; m.crc[1] = f.crc[1];
+		c->stats.raw_frames++;
+		if (acb_block_fec(&m)) c->outq.push_back(m);
+		else c->stats.fec_dropped++;
+	}
+	return ACB_OK;
+}
+
+/* queue K1+K2 (or K2 only) on the compute stream for `nblk` blocks / `nsamp` envelope samples */
+static int run_kernels(acb_ctx *c, const uint8_t *d_iq, size_t stride, int nblk, int nsamp, std::vector<unsigned long long> &&groups)
+{
+	/* the ring this submit appends to was last used two submits ago: make sure it was read back */
+	while (c->inflight.size() >= 2)
+		if (int r = collect_oldest(c)) return r;
+	Ticket t;
+	t.ring = (int)(c->nsubmit & 1);
+	t.group_starts = std::move(groups);
+	t.ev = get_events(c);
+	t.ev.chan = d_iq != nullptr;
+	CU(cudaMemsetAsync(c->d_ctl[t.ring], 0, sizeof(RingCtl), c->s_comp));
+	CU(cudaEventRecord(t.ev.a, c->s_comp));
 	if (d_iq) {
 		int r = c->use_generic
 		            ? launch_channelize_generic(d_iq, stride, c->d_wf4, c->d_dm, c->cfg.K, c->cfg.nch, c->cfg.nstreams, nblk, c->s_comp)
@@ -277,13 +354,15 @@ static int run_kernels(acb_ctx *c, const uint8_t *d_iq, size_t stride, int nblk,
 		c->stats.kernel_launches++;
 		c->stats.chan_launches++;
 	}
-	CU(cudaEventRecord(ev.b, c->s_comp));
-	int r = launch_demod(c->d_state, c->d_dm, nsamp, c->cfg.nch, c->cfg.nstreams, c->d_ring, c->d_ctl, c->ring_cap, c->s_comp);
+	CU(cudaEventRecord(t.ev.b, c->s_comp));
+	int r = launch_demod(c->d_state, c->d_dm, nsamp, c->cfg.nch, c->cfg.nstreams, c->d_ring[t.ring], c->d_ctl[t.ring], c->ring_cap, c->s_comp);
 	if (r) return fail(ACB_ERR_CUDA, "demod launch: %s", cudaGetErrorString((cudaError_t)r));
 	c->stats.kernel_launches++;
 	c->stats.demod_launches++;
-	CU(cudaEventRecord(ev.c, c->s_comp));
-	c->ev_inflight.push_back(ev);
+	CU(cudaMemcpyAsync(c->h_ctl[t.ring], c->d_ctl[t.ring], sizeof(RingCtl), cudaMemcpyDeviceToHost, c->s_comp));
+	CU(cudaEventRecord(t.ev.c, c->s_comp));
+	c->inflight.push_back(std::move(t));
+	c->nsubmit++;
 	c->stats.submits++;
 	c->last_nsamp = nsamp;
 	return ACB_OK;
@@ -298,13 +377,19 @@ static int check_blocks(acb_ctx *c, const void *p, size_t stride, int nblk)
 	return ACB_OK;
 }
 
+static std::vector<unsigned long long> block_groups(const acb_ctx *c, int nblk)
+{
+	std::vector<unsigned long long> g(nblk);
+	for (int b = 0; b < nblk; b++) g[b] = c->pos + (unsigned long long)b * OUTBLK;
+	return g;
+}
+
 extern "C" int acb_submit_device(acb_ctx_t *c, const uint8_t *iq_dev, size_t stride, int nblk)
 {
 	if (int r = check_blocks(c, iq_dev, stride, nblk)) return r;
 	if (int r = ctx_use(c)) return r;
 	if (((uintptr_t)iq_dev) % 16) return fail(ACB_ERR_ARG, "device input must be 16-byte aligned");
-	for (int b = 0; b < nblk; b++) c->group_starts.push_back(c->pos + (unsigned long long)b * OUTBLK);
-	if (int r = run_kernels(c, iq_dev, stride, nblk, nblk * OUTBLK)) return r;
+	if (int r = run_kernels(c, iq_dev, stride, nblk, nblk * OUTBLK, block_groups(c, nblk))) return r;
 	c->pos += (unsigned long long)nblk * OUTBLK;
 	c->stats.blocks += (uint64_t)nblk * c->cfg.nstreams;
 	return ACB_OK;
@@ -327,8 +412,7 @@ extern "C" int acb_submit_host(acb_ctx_t *c, const uint8_t *iq, size_t stride, i
 	}
 	CU(cudaEventRecord(c->ev_copied[b], c->s_copy));
 	CU(cudaStreamWaitEvent(c->s_comp, c->ev_copied[b], 0));
-	for (int k = 0; k < nblk; k++) c->group_starts.push_back(c->pos + (unsigned long long)k * OUTBLK);
-	if (int r = run_kernels(c, c->d_iq[b], per_stream, nblk, nblk * OUTBLK)) return r;
+	if (int r = run_kernels(c, c->d_iq[b], per_stream, nblk, nblk * OUTBLK, block_groups(c, nblk))) return r;
 	CU(cudaEventRecord(c->ev_consumed[b], c->s_comp));
 	c->buf_used[b] = true;
 	c->pos += (unsigned long long)nblk * OUTBLK;
@@ -342,70 +426,50 @@ extern "C" int acb_submit_dm_host(acb_ctx_t *c, const float *dm, int nsamp)
 	if (int r = ctx_use(c)) return r;
 	const size_t n = (size_t)c->cfg.nstreams * nsamp * c->cfg.nch;
 	if (nsamp < 1 || n > c->dm_floats) return fail(ACB_ERR_ARG, "nsamp=%d exceeds max_blocks*1024", nsamp);
-	/* d_dm may still be read by a previous demod: same stream, so the copy is ordered after it */
+	/* d_dm may still be read by the previous demod: same stream, so the copy is ordered after it.
+	 * A pageable source has been staged when the call returns; a pinned one must stay untouched
+	 * until the submit is collected. */
 	CU(cudaMemcpyAsync(c->d_dm, dm, n * sizeof(float), cudaMemcpyHostToDevice, c->s_comp));
-	c->group_starts.push_back(c->pos);
-	if (int r = run_kernels(c, nullptr, 0, 0, nsamp)) return r;
-	/* pageable source: the async copy has been staged by the time it returns; pinned sources
-	 * must stay untouched until acb_sync */
+	if (int r = run_kernels(c, nullptr, 0, 0, nsamp, std::vector<unsigned long long>{ c->pos })) return r;
 	c->pos += (unsigned long long)nsamp;
 	return ACB_OK;
+}
+
+extern "C" int acb_collect(acb_ctx_t *c)
+{
+	if (!c) return fail(ACB_ERR_ARG, "null context");
+	if (int r = ctx_use(c)) return r;
+	if (int r = collect_oldest(c)) return r;
+	if (c->overflowed) return fail(ACB_ERR_OVERFLOW, "device frame ring overflowed (%u slots)", c->ring_cap);
+	return (int)c->outq.size();
 }
 
 extern "C" int acb_sync(acb_ctx_t *c)
 {
 	if (!c) return fail(ACB_ERR_ARG, "null context");
 	if (int r = ctx_use(c)) return r;
-	CU(cudaMemcpyAsync(c->h_ctl, c->d_ctl, sizeof(RingCtl), cudaMemcpyDeviceToHost, c->s_comp));
+	while (!c->inflight.empty())
+		if (int r = collect_oldest(c)) return r;
 	CU(cudaStreamSynchronize(c->s_comp));
-	unsigned count = c->h_ctl->count;
-	const bool overflow = count > c->ring_cap;
-	if (overflow) count = c->ring_cap;
-	if (count) {
-		CU(cudaMemcpyAsync(c->h_ring, c->d_ring, (size_t)count * sizeof(RawFrame), cudaMemcpyDeviceToHost, c->s_comp));
-		CU(cudaMemsetAsync(c->d_ctl, 0, sizeof(RingCtl), c->s_comp));
-		CU(cudaStreamSynchronize(c->s_comp));
-	}
-	for (auto &e : c->ev_inflight) {
-		float ms = 0;
-		if (e.chan && cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) c->stats.chan_ms += ms;
-		if (cudaEventElapsedTime(&ms, e.b, e.c) == cudaSuccess) c->stats.demod_ms += ms;
-		c->ev_free.push_back(e);
-	}
-	c->ev_inflight.clear();
-
-	/* emission order of the reference: per input block, channel by channel, then time
-	 * (rtl.c:357-360; soundfile.c:71-77); streams are interleaved as if served in turn */
-	struct Key { unsigned long long group; int stream, chn; unsigned long long pos; unsigned idx; };
-	std::vector<Key> keys(count);
-	const auto &gs = c->group_starts;
-	for (unsigned i = 0; i < count; i++) {
-		const RawFrame &f = c->h_ring[i];
-		size_t g = std::upper_bound(gs.begin(), gs.end(), f.pos) - gs.begin();
-		keys[i] = Key{ g, f.stream, f.chn, f.pos, i };
-	}
-	std::sort(keys.begin(), keys.end(), [](const Key &a, const Key &b) {
-		if (a.group != b.group) return a.group < b.group;
-		if (a.stream != b.stream) return a.stream < b.stream;
-		if (a.chn != b.chn) return a.chn < b.chn;
-		return a.pos < b.pos;
-	});
-	for (const Key &k : keys) {
-		const RawFrame &f = c->h_ring[k.idx];
-		acb_msg_t m;
-		memset(&m, 0, sizeof(m));
-		m.stream = f.stream; m.chn = f.chn; m.len = f.len; m.err = f.err;
-		m.lvl = (float)(10 * log10(f.lvlsum / f.bitcount));          /* acars.c:351 */
-		m.block = f.pos / OUTBLK; m.pos = f.pos; m.soh_pos = f.soh_pos;
-		memcpy(m.txt, f.txt, ACB_TXTMAX);
-		m.crc[0] = f.crc[0]; m.crc[1] = f.crc[1];
-		c->stats.raw_frames++;
-		if (acb_block_fec(&m)) c->outq.push_back(m);
-		else c->stats.fec_dropped++;
-	}
-	c->group_starts.clear();
-	if (overflow) return fail(ACB_ERR_OVERFLOW, "device frame ring overflowed (%u slots): sync more often", c->ring_cap);
+	if (c->overflowed) return fail(ACB_ERR_OVERFLOW, "device frame ring overflowed (%u slots)", c->ring_cap);
 	return (int)c->outq.size();
+}
+
+extern "C" int acb_mark(acb_ctx_t *c, int which)
+{
+	if (!c || which < 0 || which > 1) return fail(ACB_ERR_ARG, "bad argument");
+	if (int r = ctx_use(c)) return r;
+	CU(cudaEventRecord(c->mark[which], c->s_comp));
+	return ACB_OK;
+}
+
+extern "C" int acb_elapsed_ms(acb_ctx_t *c, float *ms)
+{
+	if (!c || !ms) return fail(ACB_ERR_ARG, "null argument");
+	if (int r = ctx_use(c)) return r;
+	CU(cudaEventSynchronize(c->mark[1]));
+	CU(cudaEventElapsedTime(ms, c->mark[0], c->mark[1]));
+	return ACB_OK;
 }
 
 extern "C" int acb_drain(acb_ctx_t *c, acb_msg_t *out, int max)

@@ -122,6 +122,10 @@ int acb_submit_device(acb_ctx_t *ctx, const uint8_t *iq_dev, size_t stream_strid
 /* Replaces demodMSK's input side (msk.c:67; soundfile.c:71-77): 12.5 kS/s envelope samples,
  * dm[(s*nsamp + n)*nch + c], fed straight to the demodulator (no channelizer). */
 int acb_submit_dm_host(acb_ctx_t *ctx, const float *dm, int nsamp);
+/* Wait for the OLDEST submit still in flight only (at most two are), run the block FEC on its
+ * frames and queue the survivors; later submits keep running.  This is what lets the H2D copy
+ * of step i+1 overlap the kernels of step i.  Returns the number of messages waiting. */
+int acb_collect(acb_ctx_t *ctx);
 /* Wait for everything queued, run the block FEC (blk_thread, acars.c:93-215) on what the
  * device decoded, and append the survivors to the output queue in the reference's emission
  * order (block-major, then stream, then channel, then time; rtl.c:357-360).
@@ -144,6 +148,11 @@ int   acb_copy_to_device(acb_ctx_t *ctx, void *dst_dev, const void *src_host, si
 int acb_read_dm(acb_ctx_t *ctx, float *out, size_t nfloats);
 int acb_get_state(acb_ctx_t *ctx, int stream, int chn, acb_chan_state_t *out);
 int acb_set_state(acb_ctx_t *ctx, int stream, int chn, const acb_chan_state_t *in);
+
+/* CUDA-event stopwatch on the context's compute stream (the stream the kernels run on):
+ * acb_mark(ctx,0) ... submits ... acb_mark(ctx,1); acb_elapsed_ms waits for mark 1. */
+int acb_mark(acb_ctx_t *ctx, int which);
+int acb_elapsed_ms(acb_ctx_t *ctx, float *ms);
 
 typedef struct {
 	uint64_t submits;           /* submit calls */
