@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""bench.py — IQ Msamples/s through channelize + demodMSK + frame sync on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+  python bench.py --impl reference [...]                         # the reference's own CPU path
+
+One "step" is one pass of the hot path over one batch: S independent 2 MS/s uint8 IQ streams
+(configs[1] shape: K=160, 8 ACARS channels per stream) x B blocks of 1024*K complex samples per
+stream.  Per-GPU work is fixed (weak scaling): N GPUs serve N*S streams, sharded by stream index
+with no collective on the data path.
+
+Printed JSON (rank 0, one line):
+  value      device-resident throughput: inputs already in HBM, CUDA events on the library's
+             compute stream around exactly K steps, max over ranks
+  e2e        same metric through the C ABI with HOST buffers: pinned H2D copy of every step's
+             input and D2H read-back of the decoded frames inside the timed region
+  roofline   channelizer kernel: algorithmic bytes / CUDA-event duration vs measured HBM peak
+  cpu_baseline  the unmodified reference (oracle/_ref, -Ofast) on all host threads, bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+METRIC = "IQ Msamples/s through channelize+demodMSK (msgs bit-exact)"
+UNIT = "Msamples/s"
+FREQS = None  # filled from synth.DEFAULT_FREQS_MHZ
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=592, help="IQ streams per GPU")
+    ap.add_argument("--blocks", type=int, default=16, help="1024-sample output blocks per stream per step")
+    ap.add_argument("--K", type=int, default=160, help="rtlMult (160 = 2.0 MS/s)")
+    ap.add_argument("--pool", type=int, default=4, help="distinct synthetic streams generated (tiled over S)")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-worker", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--variant", default="", help=argparse.SUPPRESS)
+    ap.add_argument("--worker-blocks", type=int, default=256, help=argparse.SUPPRESS)
+    ap.add_argument("--worker-seed", type=int, default=0, help=argparse.SUPPRESS)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- synthetic input
+
+def make_pool(K: int, nblk: int, pool: int, fc: int, seed0: int = 1000):
+    """`pool` distinct streams of `nblk` blocks with injected ACARS frames (synth.py)."""
+    from acarsdec_b200 import synth
+    secs = nblk * 1024 / 12500.0
+    out = []
+    for i in range(pool):
+        plan = synth.make_plan(K, synth.DEFAULT_FREQS_MHZ, fc, seconds=secs, seed=seed0 + i)
+        out.append(synth.render_blocks(plan, 0, nblk).reshape(-1))
+    return out
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+
+def cpu_worker(args) -> None:
+    """Child process: the reference's in_callback + demodMSK + decodeAcars + blk_thread loop
+    (oracle/_ref, unmodified sources) over a small ring of synthetic blocks."""
+    import refs
+    from acarsdec_b200 import synth
+    ref = refs.RefLib(args.variant)
+    sys.stderr = open(os.devnull, "w")
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 2)                       # the reference prints its sample rate on stderr
+    ref.open_rtl(args.K, synth.DEFAULT_FREQS_MHZ)
+    bufs = np.stack(make_pool(args.K, 4, 1, ref.fc, seed0=5000 + args.worker_seed)).reshape(4, -1)
+    ref.run(bufs, 4)
+    print("READY", flush=True)
+    sys.stdin.readline()
+    t = []
+    for s in range(args.warmup + args.steps):
+        t.append(time.perf_counter())
+        ref.run(bufs, args.worker_blocks)
+    t.append(time.perf_counter())
+    nmsg = len(ref.msgs())
+    print(json.dumps({"timed_s": t[-1] - t[args.warmup], "msgs": nmsg}), flush=True)
+
+
+def run_cpu_reference(K: int, steps: int, warmup: int, blocks_per_step: int, nproc: int | None = None):
+    """All host threads, one reference instance (= one stream) per process.  Returns dict."""
+    import refs
+    variant = refs.best_fast_variant()
+    kind = "reference"
+    if not refs.ref_available(variant):
+        variant = "v3" if refs.ref_available("v3") else ("O2" if refs.ref_available("O2") else "")
+    if not variant:
+        return run_cpu_port(K, steps, warmup, blocks_per_step, nproc)
+    nproc = nproc or os.cpu_count() or 1
+    cmd = [sys.executable, str(ROOT / "bench.py"), "--cpu-worker", "--variant", variant, "--K", str(K),
+           "--steps", str(steps), "--warmup", str(warmup), "--worker-blocks", str(blocks_per_step)]
+    procs = [subprocess.Popen(cmd + ["--worker-seed", str(i)], stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True)
+             for i in range(nproc)]
+    for p in procs:
+        assert p.stdout.readline().strip() == "READY"
+    for p in procs:
+        p.stdin.write("go\n")
+        p.stdin.flush()
+    res = [json.loads(p.stdout.readline()) for p in procs]
+    for p in procs:
+        p.wait()
+    slowest = max(r["timed_s"] for r in res)
+    samples = nproc * steps * blocks_per_step * 1024 * K
+    return {"value": samples / slowest / 1e6, "unit": UNIT, "cores": nproc, "kind": kind,
+            "sample": f"{nproc} processes x 1 stream x 8 ch, {steps} steps x {blocks_per_step} blocks "
+                      f"({samples / 1e6:.0f} Msamples), oracle/_ref libacarsref_{variant}.so "
+                      f"(unmodified rtl.c/msk.c/acars.c, -Ofast -march=x86-64-{variant})",
+            "ms_per_step": slowest / steps * 1e3, "single_thread_value": None}
+
+
+def run_cpu_port(K, steps, warmup, blocks_per_step, nproc=None):
+    """Fallback when oracle/_ref is absent: the C restatement on all threads."""
+    import refs
+    refs.ensure_built()
+    orc = refs.OracleLib()
+    nproc = nproc or os.cpu_count() or 1
+    from acarsdec_b200 import synth
+    wf = orc.wf(K, synth.DEFAULT_FREQS_MHZ)
+    _, _, fc = orc.plan(K, synth.DEFAULT_FREQS_MHZ)
+    bufs = np.stack(make_pool(K, 4, 1, fc)).reshape(-1)
+    orc.lib.orc_bench_streams(nproc, K, 8, wf.ctypes.data, bufs.ctypes.data, 4, warmup * blocks_per_step)
+    secs = orc.lib.orc_bench_streams(nproc, K, 8, wf.ctypes.data, bufs.ctypes.data, 4, steps * blocks_per_step)
+    samples = nproc * steps * blocks_per_step * 1024 * K
+    return {"value": samples / secs / 1e6, "unit": UNIT, "cores": nproc, "kind": "port",
+            "sample": f"{nproc} threads x 1 stream x 8 ch, {steps * blocks_per_step} blocks each, oracle/acars_oracle.c -O2",
+            "ms_per_step": secs / steps * 1e3}
+
+
+# ----------------------------------------------------------------------------- clocks
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self, t0: float, t1: float):
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.15 and len(r) >= 8] or [r for (_, r) in self.rows[-3:] if len(r) >= 8]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons),
+                "power_w_max": max(float(r[3]) for r in rows), "samples": len(rows)}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def main():
+    args = parse_args()
+    if args.cpu_worker:
+        cpu_worker(args)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    K, S, B = args.K, args.streams, args.blocks
+    nch = 8
+    samples_per_step_rank = S * B * 1024 * K
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        blocks = 256
+        r = run_cpu_reference(K, args.steps, args.warmup, blocks)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"configs[1]: synthetic 2 MS/s uint8 IQ, 8 ACARS channels per stream (K={K}); "
+                                       f"one reference process per host thread, {blocks} blocks per step each",
+                           "K": K, "channels_per_stream": nch},
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # the CPU baseline runs first (rank 0, N=1 only), before this process touches CUDA
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        blocks = 256
+        steps = max(2, int(args.cpu_seconds / 0.4))
+        cpu = run_cpu_reference(K, steps, 1, blocks)
+
+    from acarsdec_b200 import api, build, synth
+    build.build()
+    import refs
+    from common import msg_tuple
+
+    fd, _, fc = api.plan(K, synth.DEFAULT_FREQS_MHZ)
+    pool = make_pool(K, B, args.pool, fc, seed0=1000 + 17 * rank)
+    blk_bytes = 2048 * K
+    stride = B * blk_bytes
+    ctx = api.Context(K, S, nch, B, device=local)
+    for s in range(S):
+        ctx.set_plan(s, fd)
+    pinned = api.PinnedBuffer(S * stride)
+    host = pinned.array.reshape(S, stride)
+    for s in range(S):
+        host[s] = pool[s % args.pool]
+
+    # ---- correctness of this very workload: first pass from reset state vs the CPU oracle
+    refs.ensure_built()
+    orc = refs.OracleLib()
+    wf = orc.wf(K, synth.DEFAULT_FREQS_MHZ)
+    ctx.submit_host(host, B)
+    ctx.sync()
+    got = ctx.drain()
+    checked_frames, ok = 0, True
+    for i in range(min(args.pool, S)):
+        o = refs.OracleStream(orc, K, wf)
+        o.blocks(pool[i])
+        want = [msg_tuple(m) for m in o.msgs()]
+        mine = [msg_tuple(m) for m in got if m.stream == i]
+        ok = ok and mine == want
+        checked_frames += len(want)
+    if not ok:
+        raise SystemExit("bench: GPU frames differ from the oracle on the bench workload")
+
+    # ---- device-resident throughput
+    d_in = ctx.device_alloc(S * stride)
+    ctx.copy_to_device(d_in, host)
+    for _ in range(args.warmup):
+        ctx.submit_device(d_in, B, stride)
+    ctx.sync()
+    ctx.drain()
+    ctx.stats(reset=True)
+    clk = ClockSampler(local)
+    clk.start()
+    time.sleep(0.3)
+    barrier()
+    t0 = time.perf_counter()
+    ctx.mark(0)
+    frames_dev = 0
+    for _ in range(args.steps):
+        ctx.submit_device(d_in, B, stride)
+        frames_dev += len(ctx.drain())
+    ctx.mark(1)
+    ctx.sync()
+    frames_dev += len(ctx.drain())
+    t1 = time.perf_counter()
+    ev_ms = ctx.elapsed_ms()
+    barrier()
+    st = ctx.stats(reset=True)
+    ev_ms_max = max_over_ranks(ev_ms)
+    wall_ms_max = max_over_ranks((t1 - t0) * 1e3)
+    total_samples = sum_over_ranks(float(samples_per_step_rank * args.steps))
+    value = total_samples / (ev_ms_max * 1e-3) / 1e6
+    clocks = clk.summary(t0, t1)
+    ctx.device_free(d_in)
+
+    # ---- end to end through the C ABI with host buffers (pinned H2D + frame read-back per step)
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(max(1, min(args.warmup, 2))):
+            ctx.submit_host(host, B)
+        ctx.sync()
+        ctx.drain()
+        ctx.stats(reset=True)
+        barrier()
+        e0 = time.perf_counter()
+        frames_e2e = 0
+        for _ in range(args.steps):
+            ctx.submit_host(host, B)          # queues H2D + kernels; collects the submit two back
+            frames_e2e += len(ctx.drain())    # decoded frames of completed steps, on the host
+        ctx.sync()
+        frames_e2e += len(ctx.drain())
+        e1 = time.perf_counter()
+        barrier()
+        st2 = ctx.stats(reset=True)
+        e_ms = max_over_ranks((e1 - e0) * 1e3)
+        e2e = {"value": total_samples / (e_ms * 1e-3) / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": S * stride * world,
+               "d2h_bytes_per_step": int((st2.raw_frames * 304 + 16 * st2.submits) / max(1, args.steps)) * world,
+               "ms_per_step": e_ms / args.steps, "frames_per_step": frames_e2e / args.steps,
+               "timing": "host wall clock between full device syncs, max over ranks"}
+    clk.stop()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    k1_ms = st.chan_ms / max(1, st.chan_launches)
+    k2_ms = st.demod_ms / max(1, st.demod_launches)
+    alg_bytes = S * B * (blk_bytes + 1024 * nch * 4)          # u8 IQ read once + dm written once (not fused)
+    achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "k1_traffic.json"
+    if tp.exists():
+        try:
+            tj = json.load(open(tp))
+            if tj.get("streams") == S and tj.get("blocks") == B and tj.get("K") == K:
+                traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
+    cmacs = S * B * 1024 * K * nch
+    fp32_peak_cmac = 148 * 128 * sm_mhz * 1e6 / 8.0           # 8 rounded FP32 ops per exact complex MAC
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": f"synthetic ({args.pool} distinct seeded streams per rank, tiled over {S})",
+        "config": {"workload": f"configs[1] x {S} streams per GPU: synthetic 2 MS/s uint8 IQ (K={K}), 8 ACARS channels "
+                               f"per stream, {B} blocks of 1024*K samples per stream per step",
+                   "K": K, "streams_per_gpu": S, "channels_per_stream": nch, "blocks_per_step": B,
+                   "channels_total": S * nch * world, "input_bytes_per_step_per_gpu": S * stride,
+                   "l2": "inputs larger than L2 (no flush needed)" if S * stride > 200e6 else "input smaller than L2",
+                   "sharding": "streams by index, no data-path collective", "timing": "CUDA events on the library's compute stream, max over ranks"},
+        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": int(st.kernel_launches),
+        "wall_ms_per_step": wall_ms_max / args.steps,
+        "kernels": {"k_channelize_ms": k1_ms, "k_demod_ms": k2_ms, "launches_per_step": st.kernel_launches / args.steps},
+        "roofline": {"kernel": "k_channelize", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes,
+                     "fp32_issue_frac": (cmacs / (k1_ms * 1e-3)) / fp32_peak_cmac,
+                     "note": "FP32-issue bound: the reference's rounding sequence costs 8 rounded FP32 ops per complex "
+                             "MAC per channel (4*C flop/B, C=8), see DESIGN.md"},
+        "checked": {"streams_vs_oracle": min(args.pool, S), "frames": checked_frames, "bit_exact": ok,
+                    "frames_per_step_device": frames_dev / args.steps},
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
