@@ -93,6 +93,7 @@ ABI = [
     ("acb_block_fec", C.c_int, [C.POINTER(Msg)]),
     ("acb_crc_update", C.c_uint16, [C.c_uint16, C.c_uint8]),
     ("acb_syndrome", C.c_uint16, [C.c_int]),
+    ("acb_frame_byte", None, [C.c_void_p, C.c_ubyte]),
 ]
 
 _lib = None

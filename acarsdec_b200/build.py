@@ -25,7 +25,7 @@ NVCC_FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-fmad=false", "-Xcompiler", "-f
 LIB = PKG / "libacars_b200.so"
 COMPAT = PKG / "libacarsdec_compat.so"
 LIB_SRC = [CSRC / "kernels.cu", CSRC / "context.cu", CSRC / "hostmath.cpp"]
-COMPAT_SRC = [CSRC / "compat.cpp"]
+COMPAT_SRC = [CSRC / "compat.c"]
 HEADERS = [CSRC / "acb_internal.h", CSRC / "frame_sm.h", ROOT / "include" / "acars_b200.h",
            ROOT / "include" / "acarsdec_compat.h"]
 
@@ -60,9 +60,10 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         if verbose:
             print((PKG / "build" / "libacars_b200.log").read_text())
     if all(p.exists() for p in COMPAT_SRC) and (force or _stale(COMPAT, COMPAT_SRC + HEADERS + [LIB])):
-        cmd = [nvcc(), *ARCH, "-O2", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-shared",
-               "-o", COMPAT, *COMPAT_SRC, "-I", ROOT / "include", "-L", PKG, "-lacars_b200",
-               "-Xlinker", "-rpath,$ORIGIN", "-lpthread"]
+        # plain C, the reference's language; WITH_RTL selects channel_t's layout (acarsdec.h:62-74)
+        cmd = [os.environ.get("CC", "gcc"), "-O2", "-std=gnu11", "-fPIC", "-shared", "-Wall", "-DWITH_RTL",
+               "-ffp-contract=off", "-o", COMPAT, *COMPAT_SRC, "-I", ROOT / "include", "-L", PKG, "-lacars_b200",
+               "-Wl,-rpath,$ORIGIN", "-lpthread", "-lm"]
         _run(cmd, PKG / "build" / "libacarsdec_compat.log")
     return LIB
 

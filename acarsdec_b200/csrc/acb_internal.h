@@ -66,6 +66,7 @@ int launch_channelize_generic(const uint8_t *iq, size_t stream_stride, const flo
 int launch_demod(ChainState *st, const float *dm, int nsamp, int nch, int nstreams,
                  RawFrame *ring, RingCtl *ctl, unsigned cap, CUstream_st *stream);
 int upload_matched_filter(const float *h);
+int upload_sincos_table(const double *cos_hi_lo, const double *sin_hi_lo);
 size_t channelize_smem_bytes(int K);
 } // namespace acb
 

@@ -1,0 +1,431 @@
+/*
+ * libacarsdec_compat — the reference's own symbols for the hot path, as a thin shim over the
+ * context API of libacars_b200 (include/acars_b200.h).  acarsdec.c and the untouched front-ends
+ * link against this instead of msk.c + acars.c (+ rtl.c and librtlsdr).
+ *
+ *   initMsk / demodMSK             msk.c:30, msk.c:67      -> one-channel GPU context, stateless calls
+ *   initAcars / decodeAcars /      acars.c:218, 246, 378   -> consumer thread feeding outputmsg();
+ *   deinitAcars                                               the host-side frame sync entry
+ *   initRtl / runRtlSample /       rtl.c:193, 371, 406,413 -> nbch-channel GPU context fed from a
+ *   runRtlCancel / runRtlClose                                raw u8 IQ capture instead of a dongle
+ *
+ * channel_t stays the carrier of all per-channel state, exactly like in the reference: demodMSK
+ * uploads it, runs the CUDA demodulator over ch->dm_buffer and writes the new state back, so any
+ * chunking of the stream gives the same result and the host may inspect or reset the fields.
+ * The RTL path keeps the state resident on the device between blocks (that is the fast path) and
+ * writes it back to channel[] when the run ends.
+ *
+ * Build with the same WITH_* macros as the host (channel_t's layout depends on them,
+ * acarsdec.h:62-74) and, to use the host's real header, -DACB_USE_REFERENCE_HEADER -I<acarsdec>.
+ */
+#define _GNU_SOURCE
+#include <errno.h>
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/time.h>
+#include <unistd.h>
+
+#include "../../include/acarsdec_compat.h"
+#include "../../include/acars_b200.h"
+
+#define FLEN 11                 /* msk.c:25 */
+#define RTLOUTBUFSZ 1024        /* rtl.c:49 */
+#define RTLMULTMAX 320          /* rtl.c:39 */
+
+/* ---------------------------------------------------------------- output queue + consumer */
+
+static pthread_mutex_t q_mtx = PTHREAD_MUTEX_INITIALIZER;
+static pthread_cond_t q_cnd = PTHREAD_COND_INITIALIZER;
+static msgblk_t *q_head, *q_tail;      /* FIFO through ->prev, like acars.c:30-33 */
+static pthread_t q_thread;
+static int q_running, q_shutdown;
+
+static void *consumer(void *arg)
+{
+	(void)arg;
+	for (;;) {
+		pthread_mutex_lock(&q_mtx);
+		while (!q_head && !q_shutdown) pthread_cond_wait(&q_cnd, &q_mtx);
+		msgblk_t *b = q_head;
+		if (!b) {                       /* shutdown and empty */
+			pthread_mutex_unlock(&q_mtx);
+			return NULL;
+		}
+		q_head = b->prev;
+		if (!q_head) q_tail = NULL;
+		pthread_mutex_unlock(&q_mtx);
+		outputmsg(b);                   /* acars.c:209 */
+		free(b);
+	}
+}
+
+static void q_push(msgblk_t *b)
+{
+	pthread_mutex_lock(&q_mtx);
+	b->prev = NULL;
+	if (q_tail) q_tail->prev = b; else q_head = b;
+	q_tail = b;
+	pthread_cond_signal(&q_cnd);
+	pthread_mutex_unlock(&q_mtx);
+}
+
+/* a repaired block from the library -> msgblk_t on the consumer queue */
+static void deliver(const acb_msg_t *m, int chn, const struct timeval *tv)
+{
+	msgblk_t *b = calloc(1, sizeof(*b));
+	if (!b) return;
+	b->chn = chn;
+	b->tv = *tv;
+	b->len = m->len;
+	b->err = m->err;
+	b->lvl = m->lvl;
+	memcpy(b->txt, m->txt, sizeof(b->txt));
+	b->crc[0] = m->crc[0];
+	b->crc[1] = m->crc[1];
+	q_push(b);
+}
+
+/* ---------------------------------------------------------------- initAcars / deinitAcars */
+
+int initAcars(channel_t *ch)
+{
+	if (ch->chn == 0 && !q_running) {          /* acars.c:220-228 */
+		q_shutdown = 0;
+		q_head = q_tail = NULL;
+		if (pthread_create(&q_thread, NULL, consumer, NULL)) return -1;
+		q_running = 1;
+	}
+	ch->outbits = 0;                            /* acars.c:230-234 */
+	ch->nbits = 8;
+	ch->Acarsstate = WSYN;
+	ch->blk = NULL;
+	return 0;
+}
+
+int deinitAcars(void)
+{
+	if (!q_running) return 0;
+	pthread_mutex_lock(&q_mtx);
+	q_shutdown = 1;
+	pthread_cond_signal(&q_cnd);
+	pthread_mutex_unlock(&q_mtx);
+	pthread_join(q_thread, NULL);
+	q_running = 0;
+	return 0;
+}
+
+/* ---------------------------------------------------------------- decodeAcars on the host */
+
+static int view_begin(void *u)
+{
+	channel_t *ch = u;
+	if (!ch->blk) ch->blk = malloc(sizeof(msgblk_t));      /* acars.c:283-289 */
+	if (!ch->blk) return 0;
+	gettimeofday(&ch->blk->tv, NULL);
+	ch->blk->chn = ch->chn;
+	return 1;
+}
+
+static void view_emit(void *u)
+{
+	channel_t *ch = u;
+	acb_msg_t m;
+	memset(&m, 0, sizeof(m));
+	m.chn = ch->chn;
+	m.len = ch->blk->len;
+	m.err = ch->blk->err;
+	m.lvl = (float)(10 * log10(ch->MskLvlSum / ch->MskBitCount));    /* acars.c:351 */
+	memcpy(m.txt, ch->blk->txt, sizeof(ch->blk->txt));
+	m.crc[0] = ch->blk->crc[0];
+	m.crc[1] = ch->blk->crc[1];
+	if (acb_block_fec(&m)) deliver(&m, ch->chn, &ch->blk->tv);      /* blk_thread, acars.c:123-209 */
+	free(ch->blk);
+	ch->blk = NULL;
+}
+
+/* acars.c:246 — the byte-level state machine on host-side state.  The GPU demodulator runs the
+ * same definition per channel on the device; this entry exists for API completeness (a host that
+ * assembles bits itself). */
+void decodeAcars(channel_t *ch)
+{
+	static __thread unsigned char scratch_txt[256], scratch_crc[2];
+	int st = (int)ch->Acarsstate, no_len = 0, no_err = 0;
+	acb_frame_view_t v;
+	if (st == SOH1 && ch->outbits == 0x01 && !view_begin(ch)) {   /* acars.c:285-288: no memory */
+		ch->Acarsstate = WSYN; ch->MskDf = 0; ch->nbits = 1;
+		return;
+	}
+	v.state = &st; v.nbits = &ch->nbits; v.bitcount = &ch->MskBitCount;
+	v.msk_s = &ch->MskS; v.msk_df = &ch->MskDf; v.lvlsum = &ch->MskLvlSum;
+	v.blk_len = ch->blk ? &ch->blk->len : &no_len;
+	v.blk_err = ch->blk ? &ch->blk->err : &no_err;
+	v.txt = ch->blk ? (unsigned char *)ch->blk->txt : scratch_txt;
+	v.crc = ch->blk ? ch->blk->crc : scratch_crc;
+	v.frame_begin = view_begin; v.frame_emit = view_emit; v.user = ch;
+	acb_frame_byte(&v, ch->outbits);
+	ch->Acarsstate = st;
+}
+
+/* ---------------------------------------------------------------- initMsk / demodMSK */
+
+static acb_ctx_t *one_ctx;          /* 1 stream x 1 channel, envelope input */
+static pthread_mutex_t one_mtx = PTHREAD_MUTEX_INITIALIZER;
+#define ONE_MAXBLK 4                /* 4096 samples per launch: soundfile.c's MAXNBFRAMES */
+
+static int one_ctx_get(void)
+{
+	if (one_ctx) return 0;
+	acb_config_t cfg = { 0, 160, 1, 1, ONE_MAXBLK, ACB_FLAG_NO_INPUT_STAGING };
+	const char *dev = getenv("ACARSDEC_B200_DEVICE");
+	if (dev) cfg.device = atoi(dev);
+	if (acb_create(&cfg, &one_ctx) != ACB_OK) {
+		fprintf(stderr, "acarsdec_b200: %s\n", acb_last_error());
+		if (one_ctx) acb_destroy(one_ctx);
+		one_ctx = NULL;
+		return -1;
+	}
+	return 0;
+}
+
+int initMsk(channel_t *ch)
+{
+	ch->MskPhi = ch->MskClk = 0;            /* msk.c:34-40 */
+	ch->MskS = 0;
+	ch->MskDf = 0;
+	ch->idx = 0;
+	ch->inb = calloc(FLEN, sizeof(float complex));
+	if (ch->inb == NULL) return -1;
+	pthread_mutex_lock(&one_mtx);
+	int r = one_ctx_get();                  /* fails loudly when there is no B200: no CPU fallback */
+	pthread_mutex_unlock(&one_mtx);
+	return r;
+}
+
+static void state_pack(const channel_t *ch, acb_chan_state_t *s)
+{
+	memset(s, 0, sizeof(*s));
+	s->MskPhi = ch->MskPhi; s->MskDf = ch->MskDf; s->MskLvlSum = ch->MskLvlSum; s->MskClk = ch->MskClk;
+	s->MskBitCount = ch->MskBitCount; s->MskS = ch->MskS; s->idx = ch->idx;
+	s->nbits = ch->nbits; s->Acarsstate = (int)ch->Acarsstate; s->outbits = ch->outbits;
+	for (int i = 0; i < FLEN; i++) { s->inb_re[i] = crealf(ch->inb[i]); s->inb_im[i] = cimagf(ch->inb[i]); }
+	if (ch->blk) {
+		s->blk_len = ch->blk->len; s->blk_err = ch->blk->err;
+		memcpy(s->blk_txt, ch->blk->txt, sizeof(ch->blk->txt));
+		s->blk_crc[0] = ch->blk->crc[0]; s->blk_crc[1] = ch->blk->crc[1];
+	}
+}
+
+static void state_unpack(const acb_chan_state_t *s, channel_t *ch)
+{
+	ch->MskPhi = s->MskPhi; ch->MskDf = s->MskDf; ch->MskLvlSum = s->MskLvlSum; ch->MskClk = s->MskClk;
+	ch->MskBitCount = s->MskBitCount; ch->MskS = s->MskS; ch->idx = s->idx;
+	ch->nbits = s->nbits; ch->Acarsstate = s->Acarsstate; ch->outbits = (unsigned char)s->outbits;
+	for (int i = 0; i < FLEN; i++) ch->inb[i] = s->inb_re[i] + s->inb_im[i] * I;
+	if (s->Acarsstate >= TXT && s->Acarsstate <= CRC2) {      /* a frame is being assembled */
+		if (!ch->blk) {
+			ch->blk = calloc(1, sizeof(msgblk_t));
+			if (ch->blk) { gettimeofday(&ch->blk->tv, NULL); ch->blk->chn = ch->chn; }
+		}
+		if (ch->blk) {
+			ch->blk->len = s->blk_len; ch->blk->err = s->blk_err;
+			memcpy(ch->blk->txt, s->blk_txt, sizeof(ch->blk->txt));
+			ch->blk->crc[0] = s->blk_crc[0]; ch->blk->crc[1] = s->blk_crc[1];
+		}
+	}
+}
+
+void demodMSK(channel_t *ch, int len)
+{
+	struct timeval now;
+	acb_chan_state_t st;
+	acb_msg_t out[8];
+	pthread_mutex_lock(&one_mtx);
+	if (one_ctx_get()) { pthread_mutex_unlock(&one_mtx); return; }
+	gettimeofday(&now, NULL);
+	state_pack(ch, &st);
+	int rc = acb_set_state(one_ctx, 0, 0, &st);
+	for (int off = 0; rc == ACB_OK && off < len; off += ONE_MAXBLK * RTLOUTBUFSZ) {
+		int n = len - off < ONE_MAXBLK * RTLOUTBUFSZ ? len - off : ONE_MAXBLK * RTLOUTBUFSZ;
+		rc = acb_submit_dm_host(one_ctx, ch->dm_buffer + off, n);
+		if (rc == ACB_OK) rc = acb_sync(one_ctx);
+		if (rc > 0) rc = ACB_OK;
+	}
+	if (rc == ACB_OK) rc = acb_get_state(one_ctx, 0, 0, &st);
+	if (rc != ACB_OK) {
+		fprintf(stderr, "acarsdec_b200: demodMSK: %s\n", acb_last_error());
+		pthread_mutex_unlock(&one_mtx);
+		return;
+	}
+	int had_blk = ch->blk != NULL;
+	struct timeval tv = had_blk ? ch->blk->tv : now;
+	state_unpack(&st, ch);
+	if (!(st.Acarsstate >= TXT && st.Acarsstate <= CRC2) && ch->blk) {   /* frame finished or dropped */
+		free(ch->blk);
+		ch->blk = NULL;
+	}
+	for (int n; (n = acb_drain(one_ctx, out, 8)) > 0;)
+		for (int i = 0; i < n; i++) deliver(&out[i], ch->chn, &tv);
+	pthread_mutex_unlock(&one_mtx);
+}
+
+/* ---------------------------------------------------------------- RTL front-end on a capture file */
+
+#ifdef WITH_RTL
+
+static acb_ctx_t *rtl_ctx;
+static FILE *rtl_src;
+static int rtl_batch = 16;              /* blocks per submit; ACARSDEC_B200_BLOCKS */
+static volatile int rtl_cancel;
+static size_t rtl_inbufsize;
+
+int initRtl(char **argv, int optind)
+{
+	unsigned Fd[MAXNBCHANNELS];
+	char *argF;
+	if (argv[optind] == NULL) {
+		fprintf(stderr, "Need a raw u8 IQ capture file (or - for stdin) after -r\n");
+		exit(1);
+	}
+	const char *path = argv[optind++];
+	if (rtlMult > RTLMULTMAX || rtlMult < 1) {          /* rtl.c:208-211 */
+		fprintf(stderr, "rtlMult can't be larger than 360\n");
+		return 1;
+	}
+	rtl_inbufsize = (size_t)RTLOUTBUFSZ * rtlMult * 2;   /* rtl.c:213 */
+	rtl_src = strcmp(path, "-") ? fopen(path, "rb") : stdin;
+	if (!rtl_src) {
+		fprintf(stderr, "Failed to open IQ capture %s: %s\n", path, strerror(errno));
+		return -1;
+	}
+	nbch = 0;
+	while ((argF = argv[optind]) && nbch < MAXNBCHANNELS) {      /* rtl.c:243-257 */
+		Fd[nbch] = (unsigned)acb_round_freq(atof(argF));
+		optind++;
+		if (Fd[nbch] < 118000000 || Fd[nbch] > 138000000) {
+			fprintf(stderr, "WARNING: Invalid frequency %d\n", Fd[nbch]);
+			continue;
+		}
+		channel[nbch].chn = nbch;
+		channel[nbch].Fr = acb_stored_fr(Fd[nbch]);
+		nbch++;
+	}
+	if (nbch == 0) {
+		fprintf(stderr, "Need a least one frequency\n");
+		return 1;
+	}
+	unsigned Fc = acb_choose_fc(Fd, nbch, rtlMult);              /* rtl.c:268-270 */
+	if (Fc == 0) {
+		fprintf(stderr, "Frequencies too far apart\n");
+		return 1;
+	}
+	const char *e = getenv("ACARSDEC_B200_BLOCKS");
+	if (e && atoi(e) > 0) rtl_batch = atoi(e);
+	acb_config_t cfg = { 0, rtlMult, 1, (int)nbch, rtl_batch, 0 };
+	if ((e = getenv("ACARSDEC_B200_DEVICE"))) cfg.device = atoi(e);
+	if (acb_create(&cfg, &rtl_ctx) != ACB_OK) {
+		fprintf(stderr, "acarsdec_b200: %s\n", acb_last_error());
+		if (rtl_ctx) acb_destroy(rtl_ctx);
+		rtl_ctx = NULL;
+		return 1;
+	}
+	float *wf = malloc(sizeof(float) * 2 * rtlMult * nbch);
+	if (!wf) return 1;
+	for (unsigned n = 0; n < nbch; n++) {                        /* rtl.c:272-287 */
+		channel_t *ch = &channel[n];
+		ch->wf = malloc(rtlMult * sizeof(float complex));
+		ch->dm_buffer = malloc(RTLOUTBUFSZ * sizeof(float));
+		if (ch->wf == NULL || ch->dm_buffer == NULL) {
+			fprintf(stderr, "ERROR : malloc\n");
+			return 1;
+		}
+		acb_build_wf(ch->Fr, Fc, rtlMult, wf + (size_t)n * 2 * rtlMult);
+		for (int i = 0; i < rtlMult; i++)
+			ch->wf[i] = wf[((size_t)n * rtlMult + i) * 2] + wf[((size_t)n * rtlMult + i) * 2 + 1] * I;
+	}
+	int rc = acb_set_wf(rtl_ctx, 0, wf, (int)nbch);
+	free(wf);
+	if (rc != ACB_OK) {
+		fprintf(stderr, "acarsdec_b200: %s\n", acb_last_error());
+		return 1;
+	}
+	if (verbose) fprintf(stderr, "Set center freq. to %dHz\n", (int)Fc);
+	fprintf(stderr, "Setting sample rate: %.4f MS/s\n", INTRATE * rtlMult / 1e6);    /* rtl.c:298 */
+	return 0;
+}
+
+static void rtl_deliver_ready(const struct timeval *tv)
+{
+	acb_msg_t out[16];
+	for (int n; (n = acb_drain(rtl_ctx, out, 16)) > 0;)
+		for (int i = 0; i < n; i++) deliver(&out[i], out[i].chn, tv);
+}
+
+int runRtlSample(void)
+{
+	if (!rtl_ctx || !rtl_src) return 1;
+	uint8_t *buf[2];
+	for (int i = 0; i < 2; i++) {
+		buf[i] = acb_host_alloc(rtl_inbufsize * rtl_batch);
+		if (!buf[i]) { fprintf(stderr, "acarsdec_b200: %s\n", acb_last_error()); return 1; }
+	}
+	/* demodulator state as the host initialised it (initMsk/initAcars) goes to the device */
+	acb_chan_state_t st;
+	for (unsigned n = 0; n < nbch; n++) {
+		state_pack(&channel[n], &st);
+		acb_set_state(rtl_ctx, 0, (int)n, &st);
+	}
+	int which = 0, rc = ACB_OK, inflight = 0;
+	struct timeval tv_prev;
+	gettimeofday(&tv_prev, NULL);
+	while (!signalExit && !rtl_cancel) {
+		if (inflight == 2) {
+			/* buf[which] was the source of the submit two back: it must have been consumed */
+			rc = acb_collect(rtl_ctx);
+			if (rc < 0) break;
+			inflight--;
+			rtl_deliver_ready(&tv_prev);
+		}
+		size_t got = fread(buf[which], 1, rtl_inbufsize * rtl_batch, rtl_src);
+		int nblk = (int)(got / rtl_inbufsize);
+		if (got % rtl_inbufsize) fprintf(stderr, "warning: partial read\n");     /* rtl.c:322-326 */
+		if (nblk == 0) break;
+		struct timeval tv;
+		gettimeofday(&tv, NULL);
+		rc = acb_submit_host(rtl_ctx, buf[which], rtl_inbufsize * nblk, nblk);
+		if (rc != ACB_OK) break;
+		which ^= 1;
+		inflight++;
+		tv_prev = tv;
+		if (nblk < rtl_batch) break;
+	}
+	if (rc >= 0) rc = acb_sync(rtl_ctx);
+	if (rc < 0) fprintf(stderr, "acarsdec_b200: %s\n", acb_last_error());
+	struct timeval tv;
+	gettimeofday(&tv, NULL);
+	rtl_deliver_ready(&tv);
+	for (unsigned n = 0; n < nbch; n++)
+		if (acb_get_state(rtl_ctx, 0, (int)n, &st) == ACB_OK) state_unpack(&st, &channel[n]);
+	for (int i = 0; i < 2; i++) acb_host_free(buf[i]);
+	signalExit = 1;                                     /* rtl.c:366: the reader thread ended */
+	return rc < 0 ? 1 : 0;
+}
+
+int runRtlCancel(void)
+{
+	rtl_cancel = 1;
+	return 0;
+}
+
+int runRtlClose(void)
+{
+	if (rtl_ctx) { acb_destroy(rtl_ctx); rtl_ctx = NULL; }
+	if (rtl_src && rtl_src != stdin) fclose(rtl_src);
+	rtl_src = NULL;
+	return 0;
+}
+
+#endif /* WITH_RTL */

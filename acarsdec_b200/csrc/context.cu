@@ -205,6 +205,22 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 	float h[FLENO];
 	acb_build_h(h);
 	CU((cudaError_t)upload_matched_filter(h));
+	{
+		/* cos/sin(k*pi/32) as double-double for the demod kernel's VCO sincos; long double (64-bit
+		 * mantissa) is ample for the non-zero entries, the multiples of pi/2 are set exactly */
+		double tc[128], ts[128];
+		const long double pi = 3.14159265358979323846264338327950288L;
+		for (int k = 0; k < 64; k++) {
+			const long double c = cosl(k * pi / 32), s = sinl(k * pi / 32);
+			tc[2 * k] = (double)c; tc[2 * k + 1] = (double)(c - (long double)tc[2 * k]);
+			ts[2 * k] = (double)s; ts[2 * k + 1] = (double)(s - (long double)ts[2 * k]);
+			if (k % 16 == 0) {
+				static const double qc[4] = { 1, 0, -1, 0 }, qs[4] = { 0, 1, 0, -1 };
+				tc[2 * k] = qc[k / 16]; tc[2 * k + 1] = 0; ts[2 * k] = qs[k / 16]; ts[2 * k + 1] = 0;
+			}
+		}
+		CU((cudaError_t)upload_sincos_table(tc, ts));
+	}
 	if (int r = reset_states(c)) return r;
 	return ACB_OK;
 }

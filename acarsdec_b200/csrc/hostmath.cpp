@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "../../include/acars_b200.h"
+#include "frame_sm.h"
 
 /* ------------------------------------------------------------------ front-end planning */
 
@@ -214,4 +215,31 @@ extern "C" int acb_block_fec(acb_msg_t *m)
 		m->txt[i] &= 0x7f;
 	}
 	return still == 0;
+}
+
+/* ------------------------------------------------------------------ frame sync on the host */
+
+namespace {
+struct ViewAcc {
+	acb_frame_view_t *v;
+	int &state() { return *v->state; }
+	int &nbits() { return *v->nbits; }
+	int &bitcount() { return *v->bitcount; }
+	int &blk_len() { return *v->blk_len; }
+	int &blk_err() { return *v->blk_err; }
+	unsigned &msk_s() { return *v->msk_s; }
+	double &msk_df() { return *v->msk_df; }
+	double &lvlsum() { return *v->lvlsum; }
+	void txt_put(int i, unsigned char r) { v->txt[i] = r; }
+	unsigned char txt_get(int i) { return v->txt[i]; }
+	void crc_put(int i, unsigned char r) { v->crc[i] = r; }
+	bool frame_begin() { return v->frame_begin ? v->frame_begin(v->user) != 0 : true; }
+	void frame_emit() { if (v->frame_emit) v->frame_emit(v->user); }
+};
+} // namespace
+
+extern "C" void acb_frame_byte(acb_frame_view_t *v, unsigned char r)
+{
+	ViewAcc a{ v };
+	acb::frame_byte(a, r);
 }

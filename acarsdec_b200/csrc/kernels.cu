@@ -210,6 +210,13 @@ int launch_channelize_generic(const uint8_t *iq, size_t stream_stride, const flo
 
 /* ------------------------------------------------------------------------------------------
  * K2: MSK demodulator + bit/byte framing, one channel per lane
+ *
+ * The recurrence is serial per channel (VCO phase -> ring -> matched filter -> PLL -> VCO step,
+ * with the frame synchroniser resetting the PLL), so the kernel is latency bound; what it can
+ * do is (a) never diverge: every lane runs "up to 6 samples, then one bit" per outer iteration
+ * (the bit clock fires every 5.2 samples), (b) expose the 6 independent sincos evaluations of an
+ * iteration to the scheduler at once, (c) use a branch-free table sincos (20 FP64 ops) instead
+ * of the library one (~45 + slow path), (d) prefetch the 6 envelope samples.
  * ---------------------------------------------------------------------------------------- */
 
 struct DemodRegs {
@@ -262,20 +269,61 @@ struct DevFrameAcc {
 	}
 };
 
-constexpr int DEMOD_WARPS = 1;   /* warps per CTA: one, so that chains spread over all SMs */
+/* cos/sin of k*pi/32 as double-double (hi, lo), built on the host in long double */
+__device__ double2 g_sc_cos[64], g_sc_sin[64];
 
-__global__ void __launch_bounds__(32 * DEMOD_WARPS)
+int upload_sincos_table(const double *cos_hi_lo, const double *sin_hi_lo)
+{
+	cudaError_t e = cudaMemcpyToSymbol(g_sc_cos, cos_hi_lo, sizeof(double) * 128);
+	if (e != cudaSuccess) return (int)e;
+	return (int)cudaMemcpyToSymbol(g_sc_sin, sin_hi_lo, sizeof(double) * 128);
+}
+
+/* cos(p), sin(p) for p in [0, 2*pi] — the VCO phase after msk.c:82-83.  p = k*pi/32 + r with
+ * |r| <= pi/64 (three-part pi/32, so r keeps full relative accuracy next to the zeros of sin and
+ * cos, which are table points with exact entries); short Taylor polynomials for sin r and
+ * cos r - 1; angle addition against the double-double table.  Max error measured against 80-bit
+ * references: 1.7 ulp (typ. < 0.6), i.e. the class of CUDA's own sincos; see DESIGN.md for why
+ * ~1 ulp here is invisible after the (float) rounding of in*cexp(-j p) (msk.c:90). */
+__device__ __forceinline__ void sincos_vco(double p, const double2 *tcos, const double2 *tsin, double &sn, double &cs)
+{
+	const double MAGIC = 6755399441055744.0;                 /* 1.5 * 2^52 */
+	const double t = fma(p, 0x1.45f306dc9c883p+3, MAGIC);    /* p * 32/pi, rounded to integer */
+	const int k = __double2loint(t) & 63;
+	const double kd = t - MAGIC;
+	double r = fma(-kd, 0x1.921fb54442d18p-4, p);
+	r = fma(-kd, 0x1.1a62633145c07p-58, r);
+	r = fma(-kd, -0x1.f1976b7ed8fbcp-114, r);
+	const double r2 = r * r;
+	double sp = fma(r2, 1.0 / 362880, -1.0 / 5040);
+	sp = fma(sp, r2, 1.0 / 120);
+	sp = fma(sp, r2, -1.0 / 6);
+	const double sr = fma(r * r2, sp, r);                    /* sin r */
+	double cp = fma(r2, 1.0 / 40320, -1.0 / 720);
+	cp = fma(cp, r2, 1.0 / 24);
+	cp = fma(cp, r2, -0.5);
+	const double cm = r2 * cp;                               /* cos r - 1 */
+	const double2 C = tcos[k], S = tsin[k];
+	cs = C.x + fma(-S.x, sr, fma(C.x, cm, C.y));
+	sn = S.x + fma(C.x, sr, fma(S.x, cm, S.y));
+}
+
+constexpr int DEMOD_LOOK = 6;    /* samples examined per outer iteration (bit period = 5.17..5.25) */
+
+__global__ void __launch_bounds__(32)
 k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp, int nch, int nstreams,
         int lanes, int wps, RawFrame *__restrict__ ring, RingCtl *__restrict__ ctl, unsigned cap)
 {
 	__shared__ float s_h[FLENO + 3];
-	__shared__ float s_re[DEMOD_WARPS][FLEN][32], s_im[DEMOD_WARPS][FLEN][32];
+	__shared__ float s_re[FLEN][32], s_im[FLEN][32];
+	__shared__ double2 s_cos[64], s_sin[64];
 
-	for (int i = threadIdx.x; i < FLENO; i += blockDim.x) s_h[i] = c_h[i];
-	__syncthreads();
+	for (int i = threadIdx.x; i < FLENO; i += 32) s_h[i] = c_h[i];
+	for (int i = threadIdx.x; i < 64; i += 32) { s_cos[i] = g_sc_cos[i]; s_sin[i] = g_sc_sin[i]; }
+	__syncwarp();
 
-	const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int warp = blockIdx.x * DEMOD_WARPS + wib;
+	const int lane = threadIdx.x;
+	const int warp = blockIdx.x;
 	const int s = warp / wps;
 	const int ch = (warp - s * wps) * lanes + lane;
 	if (s >= nstreams || lane >= lanes || ch >= nch) return;
@@ -285,9 +333,8 @@ k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp
 	r.phi = st->phi; r.df = st->df; r.lvlsum = st->lvlsum; r.clk = st->clk; r.bitcount = st->bitcount;
 	r.S = st->S; r.idx = st->idx; r.nbits = st->nbits; r.state = st->state; r.outbits = st->outbits;
 	r.blk_len = st->blk_len; r.blk_err = st->blk_err; r.pos = st->pos; r.soh_pos = st->soh_pos;
-	float (*re)[32] = s_re[wib], (*im)[32] = s_im[wib];
 #pragma unroll
-	for (int k = 0; k < FLEN; k++) { re[k][lane] = st->inb_re[k]; im[k][lane] = st->inb_im[k]; }
+	for (int k = 0; k < FLEN; k++) { s_re[k][lane] = st->inb_re[k]; s_im[k][lane] = st->inb_im[k]; }
 
 	DevFrameAcc acc{ r, st, ring, ctl, cap, s, ch };
 
@@ -298,23 +345,59 @@ k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp
 	const double PLLK = (1.0 - (double)0.52f) * (double)38e-4f;/* msk.c:130 (1.0-PLLC)*PLLG */
 
 	const float *in = dm + (size_t)s * nsamp * nch + ch;
-	for (int n = 0; n < nsamp; n++) {
-		/* VCO (msk.c:81-83) */
+	const unsigned long long pos0 = r.pos;
+	int n = 0;
+	while (n < nsamp) {
+		const int m = min(DEMOD_LOOK, nsamp - n);
+		float x[DEMOD_LOOK];
+#pragma unroll
+		for (int k = 0; k < DEMOD_LOOK; k++) x[k] = (k < m) ? in[(size_t)(n + k) * nch] : 0.f;
+
+		/* VCO step is constant until the next bit (msk.c:81): MskDf only changes in the bit path */
 		const double sv = __dadd_rn(S0, r.df);
-		r.phi = __dadd_rn(r.phi, sv);
-		if (r.phi >= TWO_PI) r.phi = __dadd_rn(r.phi, -TWO_PI);
+		const double fire_at = __dadd_rn(THR, -__dmul_rn(sv, 0.5));
 
-		/* mixer (msk.c:86-91): in * cexp(-j phi), rounded to float complex */
-		const double x = (double)in[(size_t)n * nch];
-		double sn, cs;
-		sincos(-r.phi, &sn, &cs);
-		re[r.idx][lane] = __double2float_rn(__dmul_rn(x, cs));
-		im[r.idx][lane] = __double2float_rn(__dmul_rn(x, sn));
-		r.idx = (r.idx + 1 == FLEN) ? 0 : r.idx + 1;
+		/* the two cheap serial chains of the next samples: phase (msk.c:82-83) and bit clock
+		 * (msk.c:95-96), each rounded step by step exactly like the reference's loop */
+		double pk[DEMOD_LOOK];
+		double p = r.phi;
+		float clk = r.clk;
+		int cnt = m;                 /* samples consumed this iteration */
+		bool fired = false;
+#pragma unroll
+		for (int k = 0; k < DEMOD_LOOK; k++) {
+			double pn = __dadd_rn(p, sv);
+			pn = (pn >= TWO_PI) ? __dadd_rn(pn, -TWO_PI) : pn;
+			const float cn = __double2float_rn(__dadd_rn((double)clk, sv));
+			const bool live = (k < m) && !fired;
+			pk[k] = pn;              /* beyond the consumed range: harmless finite values */
+			if (live) {
+				p = pn;
+				clk = cn;
+				if ((double)cn >= fire_at) { fired = true; cnt = k + 1; }
+			}
+		}
 
-		/* bit clock (msk.c:95-96) */
-		r.clk = __double2float_rn(__dadd_rn((double)r.clk, sv));
-		if ((double)r.clk >= __dadd_rn(THR, -__dmul_rn(sv, 0.5))) {
+		/* mixer (msk.c:86-91): in * cexp(-j phi) for every candidate sample; the 6 sincos are
+		 * independent, which is what hides their latency */
+		{
+			unsigned slot = r.idx;
+#pragma unroll
+			for (int k = 0; k < DEMOD_LOOK; k++) {
+				double sn, cs;
+				sincos_vco(pk[k], s_cos, s_sin, sn, cs);
+				const float vre = __double2float_rn(__dmul_rn((double)x[k], cs));
+				const float vim = __double2float_rn(__dmul_rn((double)x[k], -sn));
+				if (k < cnt) { s_re[slot][lane] = vre; s_im[slot][lane] = vim; }
+				slot = (slot + 1 == FLEN) ? 0 : slot + 1;
+			}
+		}
+		r.idx = (r.idx + cnt) % FLEN;
+		r.phi = p;
+		r.clk = clk;
+		r.pos = pos0 + (unsigned long long)(n + cnt - 1);       /* the sample that fired the bit */
+
+		if (fired) {
 			r.clk = __double2float_rn(__dadd_rn((double)r.clk, -THR));
 
 			/* matched filter (msk.c:103-107): 11 taps out of the x12 oversampled half cosine */
@@ -325,8 +408,8 @@ k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp
 #pragma unroll
 			for (int j = 0; j < FLEN; j++) {
 				const float hh = s_h[o + MFLTOVER * j];
-				vr = __fadd_rn(vr, __fmul_rn(hh, re[k][lane]));
-				vi = __fadd_rn(vi, __fmul_rn(hh, im[k][lane]));
+				vr = __fadd_rn(vr, __fmul_rn(hh, s_re[k][lane]));
+				vi = __fadd_rn(vi, __fmul_rn(hh, s_im[k][lane]));
 				k = (k + 1 == FLEN) ? 0 : k + 1;
 			}
 
@@ -354,14 +437,15 @@ k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp
 			/* PLL filter (msk.c:130) — after putbit, so a frame resync's MskDf=0 is filtered too */
 			r.df = __dadd_rn(__dmul_rn(PLLC, r.df), __dmul_rn(PLLK, dphi));
 		}
-		r.pos++;
+		n += cnt;
 	}
+	r.pos = pos0 + (unsigned long long)nsamp;
 
 	st->phi = r.phi; st->df = r.df; st->lvlsum = r.lvlsum; st->clk = r.clk; st->bitcount = r.bitcount;
 	st->S = r.S; st->idx = r.idx; st->nbits = r.nbits; st->state = r.state; st->outbits = r.outbits;
 	st->blk_len = r.blk_len; st->blk_err = r.blk_err; st->pos = r.pos; st->soh_pos = r.soh_pos;
 #pragma unroll
-	for (int k = 0; k < FLEN; k++) { st->inb_re[k] = re[k][lane]; st->inb_im[k] = im[k][lane]; }
+	for (int k = 0; k < FLEN; k++) { st->inb_re[k] = s_re[k][lane]; st->inb_im[k] = s_im[k][lane]; }
 }
 
 int launch_demod(ChainState *st, const float *dm, int nsamp, int nch, int nstreams,
@@ -369,9 +453,8 @@ int launch_demod(ChainState *st, const float *dm, int nsamp, int nch, int nstrea
 {
 	const int lanes = nch >= 32 ? 32 : nch;
 	const int wps = (nch + lanes - 1) / lanes;
-	const int warps = nstreams * wps;
-	const int grid = (warps + DEMOD_WARPS - 1) / DEMOD_WARPS;
-	k_demod<<<grid, 32 * DEMOD_WARPS, 0, stream>>>(st, dm, nsamp, nch, nstreams, lanes, wps, ring, ctl, cap);
+	const int grid = nstreams * wps;             /* one warp per CTA so that chains spread over all SMs */
+	k_demod<<<grid, 32, 0, stream>>>(st, dm, nsamp, nch, nstreams, lanes, wps, ring, ctl, cap);
 	return (int)cudaGetLastError();
 }
 

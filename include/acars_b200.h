@@ -173,6 +173,21 @@ int acb_block_fec(acb_msg_t *m);
 uint16_t acb_crc_update(uint16_t crc, uint8_t c);
 uint16_t acb_syndrome(int index);      /* index = bit + 8*bytes_from_end, 0..1935 */
 
+/* The bit/byte frame synchroniser (decodeAcars, acars.c:246-375) as a host call, over caller-owned
+ * state: the same definition (csrc/frame_sm.h) the demod kernel runs per channel on the device.
+ * Used by the compat shim's decodeAcars(channel_t*).  Integer-only. */
+typedef struct {
+	int *state, *nbits, *bitcount, *blk_len, *blk_err;
+	unsigned *msk_s;
+	double *msk_df, *lvlsum;
+	unsigned char *txt;                 /* >= 250 bytes */
+	unsigned char *crc;                 /* 2 bytes */
+	int (*frame_begin)(void *user);     /* SOH seen; return 0 to refuse (no storage) */
+	void (*frame_emit)(void *user);     /* frame complete */
+	void *user;
+} acb_frame_view_t;
+void acb_frame_byte(acb_frame_view_t *v, unsigned char r);
+
 #ifdef __cplusplus
 }
 #endif
