@@ -230,6 +230,26 @@ struct DemodRegs {
 	unsigned long long pos, soh_pos;
 };
 
+/* acars.c:350-366: queue the finished block.  lvl = 10*log10(lvlsum/bitcount) is left to the host
+ * (glibc log10) so the float matches the reference bit for bit.  Out of line and by value: it
+ * runs once per frame, and keeping it away from the loop keeps the loop's state in registers. */
+static __device__ __noinline__ void emit_frame(const ChainState *st, RawFrame *ring, RingCtl *ctl, unsigned cap,
+                                               int stream, int chn, int len, int err, double lvlsum, int bitcount,
+                                               unsigned long long pos, unsigned long long soh_pos)
+{
+	const unsigned slot = atomicAdd(&ctl->count, 1u);
+	if (slot >= cap) return;                       /* overflow is reported by the host */
+	RawFrame *f = ring + slot;
+	f->stream = stream; f->chn = chn;
+	f->len = len; f->err = err;
+	f->lvlsum = lvlsum; f->bitcount = bitcount;
+	f->pos = pos; f->soh_pos = soh_pos;
+	f->crc[0] = st->crc[0]; f->crc[1] = st->crc[1];
+	const uint2 *src = reinterpret_cast<const uint2 *>(st->txt);
+	uint2 *dst = reinterpret_cast<uint2 *>(f->txt);
+	for (int i = 0; i < TXTCAP / 8; i++) dst[i] = src[i];
+}
+
 /* accessor for frame_sm.h: state in registers, text in the chain's HBM record */
 struct DevFrameAcc {
 	DemodRegs &r;
@@ -251,21 +271,9 @@ struct DevFrameAcc {
 	__device__ __forceinline__ unsigned char txt_get(int i) { return st->txt[i]; }
 	__device__ __forceinline__ void crc_put(int i, unsigned char c) { st->crc[i] = c; }
 	__device__ __forceinline__ bool frame_begin() { r.soh_pos = r.pos; return true; }   /* acars.c:283-292 */
-	__device__ __noinline__ void frame_emit()
+	__device__ __forceinline__ void frame_emit()
 	{
-		/* acars.c:350-366: queue the block.  lvl = 10*log10(lvlsum/bitcount) is left to the
-		 * host (glibc log10) so the float matches the reference bit for bit. */
-		unsigned slot = atomicAdd(&ctl->count, 1u);
-		if (slot >= cap) return;                       /* overflow is reported by the host */
-		RawFrame *f = ring + slot;
-		f->stream = stream; f->chn = chn;
-		f->len = r.blk_len; f->err = r.blk_err;
-		f->lvlsum = r.lvlsum; f->bitcount = r.bitcount;
-		f->pos = r.pos; f->soh_pos = r.soh_pos;
-		f->crc[0] = st->crc[0]; f->crc[1] = st->crc[1];
-		const uint2 *src = reinterpret_cast<const uint2 *>(st->txt);
-		uint2 *dst = reinterpret_cast<uint2 *>(f->txt);
-		for (int i = 0; i < TXTCAP / 8; i++) dst[i] = src[i];
+		emit_frame(st, ring, ctl, cap, stream, chn, r.blk_len, r.blk_err, r.lvlsum, r.bitcount, r.pos, r.soh_pos);
 	}
 };
 
@@ -308,6 +316,20 @@ __device__ __forceinline__ void sincos_vco(double p, const double2 *tcos, const 
 	sn = S.x + fma(C.x, sr, fma(S.x, cm, S.y));
 }
 
+/* Round a double to float precision, result kept as a double: bit-identical to
+ * (double)(float)x (round to nearest even) for zero and for every x whose float image is a normal
+ * number.  MskClk lives in [-0.5, 5.3]; differences of such values are zero or >= 2^-52 in
+ * magnitude, so the float-denormal range (< 2^-126) cannot occur.  Integer ops on the bit pattern
+ * instead of two F2F conversions: the bit clock (msk.c:95) is a serial chain of these, six per
+ * bit, and it must stay branch-free to be scheduled among the sincos evaluations. */
+__device__ __forceinline__ double round_to_f32(double x)
+{
+	unsigned long long u = (unsigned long long)__double_as_longlong(x);
+	u += 0x0FFFFFFFull + ((u >> 29) & 1ull);
+	u &= ~0x1FFFFFFFull;
+	return __longlong_as_double((long long)u);
+}
+
 constexpr int DEMOD_LOOK = 6;    /* samples examined per outer iteration (bit period = 5.17..5.25) */
 
 __global__ void __launch_bounds__(32)
@@ -315,7 +337,7 @@ k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp
         int lanes, int wps, RawFrame *__restrict__ ring, RingCtl *__restrict__ ctl, unsigned cap)
 {
 	__shared__ float s_h[FLENO + 3];
-	__shared__ float s_re[FLEN][32], s_im[FLEN][32];
+	__shared__ float s_re[FLEN + 1][32], s_im[FLEN + 1][32];     /* row FLEN: scratch */
 	__shared__ double2 s_cos[64], s_sin[64];
 
 	for (int i = threadIdx.x; i < FLENO; i += 32) s_h[i] = c_h[i];
@@ -346,62 +368,67 @@ k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp
 
 	const float *in = dm + (size_t)s * nsamp * nch + ch;
 	const unsigned long long pos0 = r.pos;
+	double clkd = (double)r.clk;             /* MskClk: a float value carried in a double register */
 	int n = 0;
 	while (n < nsamp) {
 		const int m = min(DEMOD_LOOK, nsamp - n);
 		float x[DEMOD_LOOK];
 #pragma unroll
-		for (int k = 0; k < DEMOD_LOOK; k++) x[k] = (k < m) ? in[(size_t)(n + k) * nch] : 0.f;
+		for (int k = 0; k < DEMOD_LOOK; k++) x[k] = in[(size_t)min(n + k, nsamp - 1) * nch];
+		if (n + 2 * DEMOD_LOOK < nsamp) asm volatile("prefetch.global.L1 [%0];" ::"l"(in + (size_t)(n + 2 * DEMOD_LOOK) * nch));
 
 		/* VCO step is constant until the next bit (msk.c:81): MskDf only changes in the bit path */
 		const double sv = __dadd_rn(S0, r.df);
 		const double fire_at = __dadd_rn(THR, -__dmul_rn(sv, 0.5));
 
 		/* the two cheap serial chains of the next samples: phase (msk.c:82-83) and bit clock
-		 * (msk.c:95-96), each rounded step by step exactly like the reference's loop */
+		 * (msk.c:95-96), each rounded step by step exactly like the reference's loop; straight-line
+		 * code (selects, no branches) so that it can be scheduled among the sincos below */
 		double pk[DEMOD_LOOK];
 		double p = r.phi;
-		float clk = r.clk;
 		int cnt = m;                 /* samples consumed this iteration */
 		bool fired = false;
 #pragma unroll
 		for (int k = 0; k < DEMOD_LOOK; k++) {
 			double pn = __dadd_rn(p, sv);
 			pn = (pn >= TWO_PI) ? __dadd_rn(pn, -TWO_PI) : pn;
-			const float cn = __double2float_rn(__dadd_rn((double)clk, sv));
-			const bool live = (k < m) && !fired;
+			const double cn = round_to_f32(__dadd_rn(clkd, sv));
+			const bool live = (k < m) & !fired;
+			const bool fire = live & (cn >= fire_at);
 			pk[k] = pn;              /* beyond the consumed range: harmless finite values */
-			if (live) {
-				p = pn;
-				clk = cn;
-				if ((double)cn >= fire_at) { fired = true; cnt = k + 1; }
-			}
+			p = live ? pn : p;
+			clkd = live ? cn : clkd;
+			cnt = fire ? k + 1 : cnt;
+			fired = fired | fire;
 		}
 
 		/* mixer (msk.c:86-91): in * cexp(-j phi) for every candidate sample; the 6 sincos are
-		 * independent, which is what hides their latency */
+		 * independent, which is what hides their latency.  Samples beyond `cnt` land in a spare
+		 * ring row instead of being branched around. */
 		{
 			unsigned slot = r.idx;
 #pragma unroll
 			for (int k = 0; k < DEMOD_LOOK; k++) {
 				double sn, cs;
 				sincos_vco(pk[k], s_cos, s_sin, sn, cs);
-				const float vre = __double2float_rn(__dmul_rn((double)x[k], cs));
-				const float vim = __double2float_rn(__dmul_rn((double)x[k], -sn));
-				if (k < cnt) { s_re[slot][lane] = vre; s_im[slot][lane] = vim; }
+				const double xd = (double)x[k];
+				const float vre = __double2float_rn(__dmul_rn(xd, cs));
+				const float vim = __double2float_rn(__dmul_rn(xd, -sn));
+				const unsigned row = (k < cnt) ? slot : FLEN;
+				s_re[row][lane] = vre;
+				s_im[row][lane] = vim;
 				slot = (slot + 1 == FLEN) ? 0 : slot + 1;
 			}
 		}
 		r.idx = (r.idx + cnt) % FLEN;
 		r.phi = p;
-		r.clk = clk;
 		r.pos = pos0 + (unsigned long long)(n + cnt - 1);       /* the sample that fired the bit */
 
 		if (fired) {
-			r.clk = __double2float_rn(__dadd_rn((double)r.clk, -THR));
+			clkd = round_to_f32(__dadd_rn(clkd, -THR));
 
 			/* matched filter (msk.c:103-107): 11 taps out of the x12 oversampled half cosine */
-			int o = __double2int_rz(__dmul_rn(12.0, __dadd_rn(__ddiv_rn((double)r.clk, sv), 0.5)));
+			int o = __double2int_rz(__dmul_rn(12.0, __dadd_rn(__ddiv_rn(clkd, sv), 0.5)));
 			o = min(max(o, 0), MFLTOVER);
 			float vr = 0.f, vi = 0.f;
 			int k = r.idx;
@@ -440,6 +467,7 @@ k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp
 		n += cnt;
 	}
 	r.pos = pos0 + (unsigned long long)nsamp;
+	r.clk = (float)clkd;
 
 	st->phi = r.phi; st->df = r.df; st->lvlsum = r.lvlsum; st->clk = r.clk; st->bitcount = r.bitcount;
 	st->S = r.S; st->idx = r.idx; st->nbits = r.nbits; st->state = r.state; st->outbits = r.outbits;
