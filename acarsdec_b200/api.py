@@ -37,6 +37,13 @@ class Msg(C.Structure):
         return self.as_tuple() + (np.float32(self.lvl).tobytes(),)
 
 
+# acb_msg_t as a numpy record (same layout as the ctypes Msg above; checked at import)
+MSG_DTYPE = np.dtype([("stream", "<i4"), ("chn", "<i4"), ("len", "<i4"), ("err", "<i4"), ("lvl", "<f4"),
+                      ("block", "<u8"), ("pos", "<u8"), ("soh_pos", "<u8"), ("txt", "u1", (TXTMAX,)), ("crc", "u1", (2,))],
+                     align=True)
+assert MSG_DTYPE.itemsize == C.sizeof(Msg)
+
+
 class ChanState(C.Structure):
     _fields_ = [("MskPhi", C.c_double), ("MskDf", C.c_double), ("MskLvlSum", C.c_double), ("MskClk", C.c_float),
                 ("MskBitCount", C.c_int), ("MskS", C.c_uint), ("idx", C.c_uint), ("nbits", C.c_int),
@@ -265,6 +272,17 @@ class Context:
                 out.append(m)
             if n < 256:
                 return out
+
+    def drain_records(self, chunk: int = 65536) -> np.ndarray:
+        """All queued messages as one numpy record array (MSG_DTYPE): one C call per `chunk`."""
+        parts = []
+        while True:
+            buf = np.empty(chunk, dtype=MSG_DTYPE)
+            n = self.lib.acb_drain(self.h, buf.ctypes.data_as(C.POINTER(Msg)), chunk)
+            parts.append(buf[:n])
+            if n < chunk:
+                break
+        return parts[0] if len(parts) == 1 else np.concatenate(parts)
 
     def read_dm(self, nsamp: int) -> np.ndarray:
         out = np.empty((self.nstreams, nsamp, self.nch), dtype=np.float32)

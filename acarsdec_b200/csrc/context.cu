@@ -5,8 +5,10 @@
  * input thread (in_callback rtl.c:314-361 -> demodMSK msk.c:67 -> decodeAcars acars.c:246) and
  * on its blk_thread (acars.c:93-215).  Data flow per submit:
  *
- *   host u8 IQ --copy stream--> d_iq[buf] --compute stream--> K1 k_channelize -> d_dm (HBM)
- *                                                        --> K2 k_demod      -> frame ring (HBM)
+ *   host u8 IQ --copy stream--> d_iq[buf] --channelizer stream--> K1 k_channelize -> d_dm[b] (HBM)
+ *                                           --demod stream-------> K2 k_demod    -> frame ring[b]
+ *   K2 of submit i (latency bound: one serial recurrence per channel) runs concurrently with K1
+ *   of submit i+1 (FP32-issue bound); envelope buffers are double-buffered between them.
  *   acb_collect / acb_sync: D2H of that submit's frames -> block FEC on the host -> output queue
  *
  * Up to two submits are in flight: input staging and the frame rings are double-buffered, so
@@ -48,7 +50,7 @@ static int fail(int code, const char *fmt, ...)
 extern "C" const char *acb_last_error(void) { return g_err; }
 extern "C" const char *acb_version(void) { return "acars_b200 0.1 (sm_100a)"; }
 
-struct EvTriple { cudaEvent_t a, b, c; bool chan; };
+struct EvTriple { cudaEvent_t a, b, b2, c; bool chan; };   /* a..b = K1 on s_comp, b2..c = K2 on s_dem */
 
 /* one submit in flight: which frame ring it appends to and how its frames are grouped */
 struct Ticket {
@@ -61,13 +63,16 @@ struct acb_ctx {
 	acb_config_t cfg;
 	int ngrp;
 	size_t blk_bytes;            /* 1024*K*2 */
-	cudaStream_t s_copy, s_comp;
+	cudaStream_t s_copy, s_comp, s_dem;   /* H2D copies | channelizer (K1) | demod (K2) */
 	uint8_t *d_iq[2];
 	cudaEvent_t ev_copied[2], ev_consumed[2];
 	bool buf_used[2];
 	int next_buf;
 	float *d_wf4;                /* [stream][grp][K][8] float4 (c, d, -d, c) */
-	float *d_dm;                 /* [stream][nsamp][nch] */
+	float *d_dm[2];              /* [stream][nsamp][nch], alternating per submit */
+	cudaEvent_t ev_k1_done[2], ev_dm_free[2];
+	bool dm_used[2];
+	int last_dm;
 	size_t dm_floats;
 	ChainState *d_state;
 	cudaStream_t s_d2h;
@@ -126,6 +131,13 @@ extern "C" int acb_copy_to_device(acb_ctx_t *c, void *dst, const void *src, size
 	return ACB_OK;
 }
 
+static int sync_streams(acb_ctx *c)
+{
+	CU(cudaStreamSynchronize(c->s_comp));
+	CU(cudaStreamSynchronize(c->s_dem));
+	return ACB_OK;
+}
+
 static int reset_states(acb_ctx *c)
 {
 	const size_t n = (size_t)c->cfg.nstreams * c->cfg.nch;
@@ -172,6 +184,7 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 
 	CU(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
 	CU(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+	CU(cudaStreamCreateWithFlags(&c->s_dem, cudaStreamNonBlocking));
 	CU(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
 	CU(cudaEventCreate(&c->mark[0]));
 	CU(cudaEventCreate(&c->mark[1]));
@@ -187,7 +200,13 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 	CU(cudaMalloc(&c->d_wf4, wf_floats * sizeof(float)));
 	CU(cudaMemset(c->d_wf4, 0, wf_floats * sizeof(float)));
 	c->dm_floats = (size_t)cfg->nstreams * cfg->max_blocks * OUTBLK * cfg->nch;
-	CU(cudaMalloc(&c->d_dm, c->dm_floats * sizeof(float)));
+	for (int i = 0; i < 2; i++) {
+		CU(cudaMalloc(&c->d_dm[i], c->dm_floats * sizeof(float)));
+		CU(cudaEventCreateWithFlags(&c->ev_k1_done[i], cudaEventDisableTiming));
+		CU(cudaEventCreateWithFlags(&c->ev_dm_free[i], cudaEventDisableTiming));
+		c->dm_used[i] = false;
+	}
+	c->last_dm = 0;
 	const size_t nchain = (size_t)cfg->nstreams * cfg->nch;
 	CU(cudaMalloc(&c->d_state, nchain * sizeof(ChainState)));
 	/* a frame needs >= 20 bytes on air = 833 envelope samples, so < 2 per chain per block:
@@ -235,13 +254,14 @@ extern "C" void acb_destroy(acb_ctx_t *c)
 			cudaEventDestroy(c->ev_copied[i]);
 			cudaEventDestroy(c->ev_consumed[i]);
 		}
-		for (auto &t : c->inflight) { cudaEventDestroy(t.ev.a); cudaEventDestroy(t.ev.b); cudaEventDestroy(t.ev.c); }
-		for (auto &e : c->ev_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); cudaEventDestroy(e.c); }
-		cudaFree(c->d_wf4); cudaFree(c->d_dm); cudaFree(c->d_state);
+		for (auto &t : c->inflight) { cudaEventDestroy(t.ev.a); cudaEventDestroy(t.ev.b); cudaEventDestroy(t.ev.b2); cudaEventDestroy(t.ev.c); }
+		for (auto &e : c->ev_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); cudaEventDestroy(e.b2); cudaEventDestroy(e.c); }
+		cudaFree(c->d_wf4); cudaFree(c->d_state);
+		for (int i = 0; i < 2; i++) { cudaFree(c->d_dm[i]); cudaEventDestroy(c->ev_k1_done[i]); cudaEventDestroy(c->ev_dm_free[i]); }
 		for (int i = 0; i < 2; i++) { cudaFree(c->d_ring[i]); cudaFree(c->d_ctl[i]); cudaFreeHost(c->h_ctl[i]); }
 		cudaFreeHost(c->h_ring);
 		cudaEventDestroy(c->mark[0]); cudaEventDestroy(c->mark[1]);
-		cudaStreamDestroy(c->s_copy); cudaStreamDestroy(c->s_comp); cudaStreamDestroy(c->s_d2h);
+		cudaStreamDestroy(c->s_copy); cudaStreamDestroy(c->s_comp); cudaStreamDestroy(c->s_dem); cudaStreamDestroy(c->s_d2h);
 	}
 	delete c;
 }
@@ -269,7 +289,7 @@ extern "C" int acb_set_wf(acb_ctx_t *c, int stream, const float *wf, int nch)
 			o[0] = re; o[1] = im; o[2] = -im; o[3] = re;      /* (c, d, -d, c): see cmac() */
 		}
 	}
-	CU(cudaStreamSynchronize(c->s_comp));
+	if (int r = sync_streams(c)) return r;
 	CU(cudaMemcpy(c->d_wf4 + (size_t)stream * t.size(), t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
 	return ACB_OK;
 }
@@ -294,7 +314,7 @@ static EvTriple get_events(acb_ctx *c)
 		e = c->ev_free.back();
 		c->ev_free.pop_back();
 	} else {
-		cudaEventCreate(&e.a); cudaEventCreate(&e.b); cudaEventCreate(&e.c);
+		cudaEventCreate(&e.a); cudaEventCreate(&e.b); cudaEventCreate(&e.b2); cudaEventCreate(&e.c);
 	}
 	return e;
 }
@@ -311,7 +331,7 @@ static int collect_oldest(acb_ctx *c)
 	CU(cudaEventSynchronize(t.ev.c));           /* the RingCtl read-back was queued before ev.c */
 	float ms = 0;
 	if (t.ev.chan && cudaEventElapsedTime(&ms, t.ev.a, t.ev.b) == cudaSuccess) c->stats.chan_ms += ms;
-	if (cudaEventElapsedTime(&ms, t.ev.b, t.ev.c) == cudaSuccess) c->stats.demod_ms += ms;
+	if (cudaEventElapsedTime(&ms, t.ev.b2, t.ev.c) == cudaSuccess) c->stats.demod_ms += ms;
 	c->ev_free.push_back(t.ev);
 
 	unsigned count = c->h_ctl[t.ring]->count;
@@ -350,7 +370,8 @@ static int collect_oldest(acb_ctx *c)
 }
 
 /* queue K1+K2 (or K2 only) on the compute stream for `nblk` blocks / `nsamp` envelope samples */
-static int run_kernels(acb_ctx *c, const uint8_t *d_iq, size_t stride, int nblk, int nsamp, std::vector<unsigned long long> &&groups)
+static int run_kernels(acb_ctx *c, const uint8_t *d_iq, size_t stride, int nblk, int nsamp, const float *dm_host,
+                       std::vector<unsigned long long> &&groups)
 {
 	/* the ring this submit appends to was last used two submits ago: make sure it was read back */
 	while (c->inflight.size() >= 2)
@@ -360,23 +381,37 @@ static int run_kernels(acb_ctx *c, const uint8_t *d_iq, size_t stride, int nblk,
 	t.group_starts = std::move(groups);
 	t.ev = get_events(c);
 	t.ev.chan = d_iq != nullptr;
-	CU(cudaMemsetAsync(c->d_ctl[t.ring], 0, sizeof(RingCtl), c->s_comp));
-	CU(cudaEventRecord(t.ev.a, c->s_comp));
+	const int b = t.ring;                          /* envelope buffer and frame ring of this submit */
+	float *dmbuf = c->d_dm[b];
 	if (d_iq) {
+		/* K1 may overwrite d_dm[b] only after the demod of two submits ago has read it */
+		if (c->dm_used[b]) CU(cudaStreamWaitEvent(c->s_comp, c->ev_dm_free[b], 0));
+		CU(cudaEventRecord(t.ev.a, c->s_comp));
 		int r = c->use_generic
-		            ? launch_channelize_generic(d_iq, stride, c->d_wf4, c->d_dm, c->cfg.K, c->cfg.nch, c->cfg.nstreams, nblk, c->s_comp)
-		            : launch_channelize(d_iq, stride, c->d_wf4, c->d_dm, c->cfg.K, c->cfg.nch, c->cfg.nstreams, nblk, c->s_comp);
+		            ? launch_channelize_generic(d_iq, stride, c->d_wf4, dmbuf, c->cfg.K, c->cfg.nch, c->cfg.nstreams, nblk, c->s_comp)
+		            : launch_channelize(d_iq, stride, c->d_wf4, dmbuf, c->cfg.K, c->cfg.nch, c->cfg.nstreams, nblk, c->s_comp);
 		if (r) return fail(ACB_ERR_CUDA, "channelizer launch: %s", cudaGetErrorString((cudaError_t)r));
 		c->stats.kernel_launches++;
 		c->stats.chan_launches++;
+		CU(cudaEventRecord(t.ev.b, c->s_comp));
+		CU(cudaEventRecord(c->ev_k1_done[b], c->s_comp));
+		CU(cudaStreamWaitEvent(c->s_dem, c->ev_k1_done[b], 0));
+	} else if (dm_host) {
+		/* envelope input: the copy is ordered behind the previous demod on the same stream, and
+		 * behind any channelizer launch that still targets the other buffer only */
+		CU(cudaMemcpyAsync(dmbuf, dm_host, (size_t)c->cfg.nstreams * nsamp * c->cfg.nch * sizeof(float), cudaMemcpyHostToDevice, c->s_dem));
 	}
-	CU(cudaEventRecord(t.ev.b, c->s_comp));
-	int r = launch_demod(c->d_state, c->d_dm, nsamp, c->cfg.nch, c->cfg.nstreams, c->d_ring[t.ring], c->d_ctl[t.ring], c->ring_cap, c->s_comp);
+	CU(cudaMemsetAsync(c->d_ctl[b], 0, sizeof(RingCtl), c->s_dem));
+	CU(cudaEventRecord(t.ev.b2, c->s_dem));
+	int r = launch_demod(c->d_state, dmbuf, nsamp, c->cfg.nch, c->cfg.nstreams, c->d_ring[b], c->d_ctl[b], c->ring_cap, c->s_dem);
 	if (r) return fail(ACB_ERR_CUDA, "demod launch: %s", cudaGetErrorString((cudaError_t)r));
 	c->stats.kernel_launches++;
 	c->stats.demod_launches++;
-	CU(cudaMemcpyAsync(c->h_ctl[t.ring], c->d_ctl[t.ring], sizeof(RingCtl), cudaMemcpyDeviceToHost, c->s_comp));
-	CU(cudaEventRecord(t.ev.c, c->s_comp));
+	CU(cudaMemcpyAsync(c->h_ctl[b], c->d_ctl[b], sizeof(RingCtl), cudaMemcpyDeviceToHost, c->s_dem));
+	CU(cudaEventRecord(t.ev.c, c->s_dem));
+	CU(cudaEventRecord(c->ev_dm_free[b], c->s_dem));
+	c->dm_used[b] = true;
+	c->last_dm = b;
 	c->inflight.push_back(std::move(t));
 	c->nsubmit++;
 	c->stats.submits++;
@@ -405,7 +440,7 @@ extern "C" int acb_submit_device(acb_ctx_t *c, const uint8_t *iq_dev, size_t str
 	if (int r = check_blocks(c, iq_dev, stride, nblk)) return r;
 	if (int r = ctx_use(c)) return r;
 	if (((uintptr_t)iq_dev) % 16) return fail(ACB_ERR_ARG, "device input must be 16-byte aligned");
-	if (int r = run_kernels(c, iq_dev, stride, nblk, nblk * OUTBLK, block_groups(c, nblk))) return r;
+	if (int r = run_kernels(c, iq_dev, stride, nblk, nblk * OUTBLK, nullptr, block_groups(c, nblk))) return r;
 	c->pos += (unsigned long long)nblk * OUTBLK;
 	c->stats.blocks += (uint64_t)nblk * c->cfg.nstreams;
 	return ACB_OK;
@@ -428,8 +463,8 @@ extern "C" int acb_submit_host(acb_ctx_t *c, const uint8_t *iq, size_t stride, i
 	}
 	CU(cudaEventRecord(c->ev_copied[b], c->s_copy));
 	CU(cudaStreamWaitEvent(c->s_comp, c->ev_copied[b], 0));
-	if (int r = run_kernels(c, c->d_iq[b], per_stream, nblk, nblk * OUTBLK, block_groups(c, nblk))) return r;
-	CU(cudaEventRecord(c->ev_consumed[b], c->s_comp));
+	if (int r = run_kernels(c, c->d_iq[b], per_stream, nblk, nblk * OUTBLK, nullptr, block_groups(c, nblk))) return r;
+	CU(cudaEventRecord(c->ev_consumed[b], c->s_comp));      /* staging buffer is free once K1 has read it */
 	c->buf_used[b] = true;
 	c->pos += (unsigned long long)nblk * OUTBLK;
 	c->stats.blocks += (uint64_t)nblk * c->cfg.nstreams;
@@ -442,11 +477,9 @@ extern "C" int acb_submit_dm_host(acb_ctx_t *c, const float *dm, int nsamp)
 	if (int r = ctx_use(c)) return r;
 	const size_t n = (size_t)c->cfg.nstreams * nsamp * c->cfg.nch;
 	if (nsamp < 1 || n > c->dm_floats) return fail(ACB_ERR_ARG, "nsamp=%d exceeds max_blocks*1024", nsamp);
-	/* d_dm may still be read by the previous demod: same stream, so the copy is ordered after it.
-	 * A pageable source has been staged when the call returns; a pinned one must stay untouched
+	/* A pageable source has been staged when the call returns; a pinned one must stay untouched
 	 * until the submit is collected. */
-	CU(cudaMemcpyAsync(c->d_dm, dm, n * sizeof(float), cudaMemcpyHostToDevice, c->s_comp));
-	if (int r = run_kernels(c, nullptr, 0, 0, nsamp, std::vector<unsigned long long>{ c->pos })) return r;
+	if (int r = run_kernels(c, nullptr, 0, 0, nsamp, dm, std::vector<unsigned long long>{ c->pos })) return r;
 	c->pos += (unsigned long long)nsamp;
 	return ACB_OK;
 }
@@ -467,6 +500,7 @@ extern "C" int acb_sync(acb_ctx_t *c)
 	while (!c->inflight.empty())
 		if (int r = collect_oldest(c)) return r;
 	CU(cudaStreamSynchronize(c->s_comp));
+	CU(cudaStreamSynchronize(c->s_dem));
 	if (c->overflowed) return fail(ACB_ERR_OVERFLOW, "device frame ring overflowed (%u slots)", c->ring_cap);
 	return (int)c->outq.size();
 }
@@ -475,7 +509,8 @@ extern "C" int acb_mark(acb_ctx_t *c, int which)
 {
 	if (!c || which < 0 || which > 1) return fail(ACB_ERR_ARG, "bad argument");
 	if (int r = ctx_use(c)) return r;
-	CU(cudaEventRecord(c->mark[which], c->s_comp));
+	/* a timed region starts on the channelizer stream and ends behind the last demod */
+	CU(cudaEventRecord(c->mark[which], which == 0 ? c->s_comp : c->s_dem));
 	return ACB_OK;
 }
 
@@ -506,7 +541,8 @@ extern "C" int acb_read_dm(acb_ctx_t *c, float *out, size_t nfloats)
 	const size_t have = (size_t)c->cfg.nstreams * c->last_nsamp * c->cfg.nch;
 	if (nfloats > have) return fail(ACB_ERR_ARG, "asked for %zu floats, last submit produced %zu", nfloats, have);
 	CU(cudaStreamSynchronize(c->s_comp));
-	CU(cudaMemcpy(out, c->d_dm, nfloats * sizeof(float), cudaMemcpyDeviceToHost));
+	CU(cudaStreamSynchronize(c->s_dem));
+	CU(cudaMemcpy(out, c->d_dm[c->last_dm], nfloats * sizeof(float), cudaMemcpyDeviceToHost));
 	return ACB_OK;
 }
 
@@ -542,7 +578,7 @@ extern "C" int acb_get_state(acb_ctx_t *c, int stream, int chn, acb_chan_state_t
 	if (stream < 0 || stream >= c->cfg.nstreams || chn < 0 || chn >= c->cfg.nch) return fail(ACB_ERR_ARG, "stream/chn out of range");
 	if (int r = ctx_use(c)) return r;
 	ChainState s;
-	CU(cudaStreamSynchronize(c->s_comp));
+	if (int r = sync_streams(c)) return r;
 	CU(cudaMemcpy(&s, c->d_state + (size_t)stream * c->cfg.nch + chn, sizeof(s), cudaMemcpyDeviceToHost));
 	to_api(s, out);
 	return ACB_OK;
@@ -556,7 +592,7 @@ extern "C" int acb_set_state(acb_ctx_t *c, int stream, int chn, const acb_chan_s
 	if (int r = ctx_use(c)) return r;
 	ChainState s;
 	from_api(in, s);
-	CU(cudaStreamSynchronize(c->s_comp));
+	if (int r = sync_streams(c)) return r;
 	CU(cudaMemcpy(c->d_state + (size_t)stream * c->cfg.nch + chn, &s, sizeof(s), cudaMemcpyHostToDevice));
 	return ACB_OK;
 }

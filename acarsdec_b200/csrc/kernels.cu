@@ -185,14 +185,15 @@ k_channelize_generic(const uint8_t *__restrict__ iq, size_t stream_stride, const
 int launch_channelize(const uint8_t *iq, size_t stream_stride, const float *wf4, float *dm,
                       int K, int nch, int nstreams, int nblk, cudaStream_t stream)
 {
-	static int smem_set = 0;
 	const int ngrp = (nch + CH_GROUP - 1) / CH_GROUP;
 	const size_t smem = channelize_smem_bytes(K);
-	if (smem > (size_t)smem_set) {
-		cudaError_t e = cudaFuncSetAttribute(k_channelize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (e != cudaSuccess) return (int)e;
-		smem_set = (int)smem;
-	}
+	cudaError_t e = cudaFuncSetAttribute(k_channelize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) return (int)e;
+	/* both kernels ask for the largest shared-memory carve-out: an SM's L1/shared split only
+	 * changes when the SM is idle, so kernels that prefer different splits cannot be co-resident
+	 * — and the demod of submit i is meant to run underneath the channelizer of submit i+1 */
+	e = cudaFuncSetAttribute(k_channelize, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+	if (e != cudaSuccess) return (int)e;
 	dim3 grid(nblk, nstreams);
 	k_channelize<<<grid, CH_TILE, smem, stream>>>(iq, stream_stride, reinterpret_cast<const float4 *>(wf4), dm, K, nch, ngrp, nblk);
 	return (int)cudaGetLastError();
@@ -482,6 +483,8 @@ int launch_demod(ChainState *st, const float *dm, int nsamp, int nch, int nstrea
 	const int lanes = nch >= 32 ? 32 : nch;
 	const int wps = (nch + lanes - 1) / lanes;
 	const int grid = nstreams * wps;             /* one warp per CTA so that chains spread over all SMs */
+	cudaError_t e = cudaFuncSetAttribute(k_demod, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+	if (e != cudaSuccess) return (int)e;
 	k_demod<<<grid, 32, 0, stream>>>(st, dm, nsamp, nch, nstreams, lanes, wps, ring, ctl, cap);
 	return (int)cudaGetLastError();
 }

@@ -306,7 +306,7 @@ def main():
     for _ in range(args.warmup):
         ctx.submit_device(d_in, B, stride)
     ctx.sync()
-    ctx.drain()
+    ctx.drain_records()
     ctx.stats(reset=True)
     clk = ClockSampler(local)
     clk.start()
@@ -317,10 +317,10 @@ def main():
     frames_dev = 0
     for _ in range(args.steps):
         ctx.submit_device(d_in, B, stride)
-        frames_dev += len(ctx.drain())
+        frames_dev += len(ctx.drain_records())
     ctx.mark(1)
     ctx.sync()
-    frames_dev += len(ctx.drain())
+    frames_dev += len(ctx.drain_records())
     t1 = time.perf_counter()
     ev_ms = ctx.elapsed_ms()
     barrier()
@@ -338,16 +338,16 @@ def main():
         for _ in range(max(1, min(args.warmup, 2))):
             ctx.submit_host(host, B)
         ctx.sync()
-        ctx.drain()
+        ctx.drain_records()
         ctx.stats(reset=True)
         barrier()
         e0 = time.perf_counter()
         frames_e2e = 0
         for _ in range(args.steps):
             ctx.submit_host(host, B)          # queues H2D + kernels; collects the submit two back
-            frames_e2e += len(ctx.drain())    # decoded frames of completed steps, on the host
+            frames_e2e += len(ctx.drain_records())    # decoded frames of completed steps, on the host
         ctx.sync()
-        frames_e2e += len(ctx.drain())
+        frames_e2e += len(ctx.drain_records())
         e1 = time.perf_counter()
         barrier()
         st2 = ctx.stats(reset=True)
