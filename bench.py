@@ -74,6 +74,19 @@ def make_pool(K: int, nblk: int, pool: int, fc: int, seed0: int = 1000):
 
 # ----------------------------------------------------------------------------- CPU reference arm
 
+def effective_cpus() -> int:
+    """Host threads this process may actually use: affinity mask capped by the cgroup CPU quota
+    (the GPU boxes show 128 CPUs but run the container under a 16-CPU quota)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, -(-int(quota) // int(period))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 def cpu_worker(args) -> None:
     """Child process: the reference's in_callback + demodMSK + decodeAcars + blk_thread loop
     (oracle/_ref, unmodified sources) over a small ring of synthetic blocks."""
@@ -106,7 +119,7 @@ def run_cpu_reference(K: int, steps: int, warmup: int, blocks_per_step: int, npr
         variant = "v3" if refs.ref_available("v3") else ("O2" if refs.ref_available("O2") else "")
     if not variant:
         return run_cpu_port(K, steps, warmup, blocks_per_step, nproc)
-    nproc = nproc or os.cpu_count() or 1
+    nproc = nproc or effective_cpus()
     cmd = [sys.executable, str(ROOT / "bench.py"), "--cpu-worker", "--variant", variant, "--K", str(K),
            "--steps", str(steps), "--warmup", str(warmup), "--worker-blocks", str(blocks_per_step)]
     procs = [subprocess.Popen(cmd + ["--worker-seed", str(i)], stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True)
@@ -122,7 +135,8 @@ def run_cpu_reference(K: int, steps: int, warmup: int, blocks_per_step: int, npr
     slowest = max(r["timed_s"] for r in res)
     samples = nproc * steps * blocks_per_step * 1024 * K
     return {"value": samples / slowest / 1e6, "unit": UNIT, "cores": nproc, "kind": kind,
-            "sample": f"{nproc} processes x 1 stream x 8 ch, {steps} steps x {blocks_per_step} blocks "
+            "sample": f"{nproc} processes (= usable host threads; {os.cpu_count()} visible) x 1 stream x 8 ch, "
+                      f"{steps} steps x {blocks_per_step} blocks "
                       f"({samples / 1e6:.0f} Msamples), oracle/_ref libacarsref_{variant}.so "
                       f"(unmodified rtl.c/msk.c/acars.c, -Ofast -march=x86-64-{variant})",
             "ms_per_step": slowest / steps * 1e3, "single_thread_value": None}
@@ -133,7 +147,7 @@ def run_cpu_port(K, steps, warmup, blocks_per_step, nproc=None):
     import refs
     refs.ensure_built()
     orc = refs.OracleLib()
-    nproc = nproc or os.cpu_count() or 1
+    nproc = nproc or effective_cpus()
     from acarsdec_b200 import synth
     wf = orc.wf(K, synth.DEFAULT_FREQS_MHZ)
     _, _, fc = orc.plan(K, synth.DEFAULT_FREQS_MHZ)
@@ -231,32 +245,19 @@ def main():
         print(json.dumps(line))
         return
 
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from acarsdec_b200 import sharding
+    dist, rank, world, local = sharding.init_process_group()      # NCCL rendezvous only: no data-path collective
+    dev = f"cuda:{local}" if dist is not None else None
 
     def barrier():
         if dist is not None:
             dist.barrier()
 
     def max_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return sharding.reduce_scalar(dist, x, "max", dev)
 
     def sum_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return sharding.reduce_scalar(dist, x, "sum", dev)
 
     # the CPU baseline runs first (rank 0, N=1 only), before this process touches CUDA
     cpu = None
