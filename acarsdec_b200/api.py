@@ -88,6 +88,7 @@ ABI = [
     ("acb_mark", C.c_int, [C.c_void_p, C.c_int]),
     ("acb_elapsed_ms", C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     ("acb_drain", C.c_int, [C.c_void_p, C.POINTER(Msg), C.c_int]),
+    ("acb_pending", C.c_int, [C.c_void_p]),
     ("acb_host_alloc", C.c_void_p, [C.c_size_t]),
     ("acb_host_free", None, [C.c_void_p]),
     ("acb_device_alloc", C.c_void_p, [C.c_void_p, C.c_size_t]),
@@ -273,16 +274,17 @@ class Context:
             if n < 256:
                 return out
 
-    def drain_records(self, chunk: int = 65536) -> np.ndarray:
-        """All queued messages as one numpy record array (MSG_DTYPE): one C call per `chunk`."""
-        parts = []
-        while True:
-            buf = np.empty(chunk, dtype=MSG_DTYPE)
-            n = self.lib.acb_drain(self.h, buf.ctypes.data_as(C.POINTER(Msg)), chunk)
-            parts.append(buf[:n])
-            if n < chunk:
-                break
-        return parts[0] if len(parts) == 1 else np.concatenate(parts)
+    def pending(self) -> int:
+        return self.lib.acb_pending(self.h)
+
+    def drain_records(self) -> np.ndarray:
+        """All queued messages as one numpy record array (MSG_DTYPE), one C call."""
+        n = self.lib.acb_pending(self.h)
+        buf = np.empty(n, dtype=MSG_DTYPE)
+        if n:
+            got = self.lib.acb_drain(self.h, buf.ctypes.data_as(C.POINTER(Msg)), n)
+            buf = buf[:got]
+        return buf
 
     def read_dm(self, nsamp: int) -> np.ndarray:
         out = np.empty((self.nstreams, nsamp, self.nch), dtype=np.float32)

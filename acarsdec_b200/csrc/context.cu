@@ -70,7 +70,8 @@ struct acb_ctx {
 	int next_buf;
 	float *d_wf4;                /* [stream][grp][K][8] float4 (c, d, -d, c) */
 	float *d_dm[2];              /* [stream][nsamp][nch], alternating per submit */
-	cudaEvent_t ev_k1_done[2], ev_dm_free[2];
+	cudaEvent_t ev_k1_done[2], ev_dm_free[2], ev_ring_read[2];
+	bool ring_read_pending[2];
 	bool dm_used[2];
 	int last_dm;
 	size_t dm_floats;
@@ -204,6 +205,8 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 		CU(cudaMalloc(&c->d_dm[i], c->dm_floats * sizeof(float)));
 		CU(cudaEventCreateWithFlags(&c->ev_k1_done[i], cudaEventDisableTiming));
 		CU(cudaEventCreateWithFlags(&c->ev_dm_free[i], cudaEventDisableTiming));
+		CU(cudaEventCreateWithFlags(&c->ev_ring_read[i], cudaEventDisableTiming));
+		c->ring_read_pending[i] = false;
 		c->dm_used[i] = false;
 	}
 	c->last_dm = 0;
@@ -257,7 +260,7 @@ extern "C" void acb_destroy(acb_ctx_t *c)
 		for (auto &t : c->inflight) { cudaEventDestroy(t.ev.a); cudaEventDestroy(t.ev.b); cudaEventDestroy(t.ev.b2); cudaEventDestroy(t.ev.c); }
 		for (auto &e : c->ev_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); cudaEventDestroy(e.b2); cudaEventDestroy(e.c); }
 		cudaFree(c->d_wf4); cudaFree(c->d_state);
-		for (int i = 0; i < 2; i++) { cudaFree(c->d_dm[i]); cudaEventDestroy(c->ev_k1_done[i]); cudaEventDestroy(c->ev_dm_free[i]); }
+		for (int i = 0; i < 2; i++) { cudaFree(c->d_dm[i]); cudaEventDestroy(c->ev_k1_done[i]); cudaEventDestroy(c->ev_dm_free[i]); cudaEventDestroy(c->ev_ring_read[i]); }
 		for (int i = 0; i < 2; i++) { cudaFree(c->d_ring[i]); cudaFree(c->d_ctl[i]); cudaFreeHost(c->h_ctl[i]); }
 		cudaFreeHost(c->h_ring);
 		cudaEventDestroy(c->mark[0]); cudaEventDestroy(c->mark[1]);
@@ -319,30 +322,51 @@ static EvTriple get_events(acb_ctx *c)
 	return e;
 }
 
-/* Wait for the oldest submit in flight, bring its frames back, run the block FEC (blk_thread,
- * acars.c:93-215) and queue the survivors in the reference's emission order: per input block,
- * channel by channel, then time (rtl.c:357-360; soundfile.c:71-77); streams are interleaved as
- * if the reference served them in turn. */
-static int collect_oldest(acb_ctx *c)
-{
-	if (c->inflight.empty()) return ACB_OK;
-	Ticket t = std::move(c->inflight.front());
-	c->inflight.pop_front();
-	CU(cudaEventSynchronize(t.ev.c));           /* the RingCtl read-back was queued before ev.c */
-	float ms = 0;
-	if (t.ev.chan && cudaEventElapsedTime(&ms, t.ev.a, t.ev.b) == cudaSuccess) c->stats.chan_ms += ms;
-	if (cudaEventElapsedTime(&ms, t.ev.b2, t.ev.c) == cudaSuccess) c->stats.demod_ms += ms;
-	c->ev_free.push_back(t.ev);
+/* Collecting a submit has a device half and a host half:
+ *   harvest_begin  waits until its demod kernel is done, reads the frame count and queues the D2H
+ *                  copy of its frames (copy stream s_d2h, event ev_ring_read[ring]);
+ *   harvest_finish waits for that copy, runs the block FEC (blk_thread, acars.c:93-215) and queues
+ *                  the survivors in the reference's emission order: per input block, channel by
+ *                  channel, then time (rtl.c:357-360; soundfile.c:71-77); streams are interleaved as
+ *                  if the reference served them in turn.
+ * A new submit is launched BETWEEN the two halves, so the host-side FEC of submit i-1 never delays
+ * the channelizer of submit i+1. */
+struct Harvest {
+	Ticket t;
+	unsigned count;
+	bool active;
+};
 
-	unsigned count = c->h_ctl[t.ring]->count;
-	if (count > c->ring_cap) { c->overflowed = true; count = c->ring_cap; }
-	if (count) {
-		CU(cudaMemcpyAsync(c->h_ring, c->d_ring[t.ring], (size_t)count * sizeof(RawFrame), cudaMemcpyDeviceToHost, c->s_d2h));
-		CU(cudaStreamSynchronize(c->s_d2h));
-	}
+static int harvest_begin(acb_ctx *c, Harvest &h)
+{
+	h.active = false;
+	if (c->inflight.empty()) return ACB_OK;
+	h.t = std::move(c->inflight.front());
+	c->inflight.pop_front();
+	h.active = true;
+	CU(cudaEventSynchronize(h.t.ev.c));           /* the RingCtl read-back was queued before ev.c */
+	float ms = 0;
+	if (h.t.ev.chan && cudaEventElapsedTime(&ms, h.t.ev.a, h.t.ev.b) == cudaSuccess) c->stats.chan_ms += ms;
+	if (cudaEventElapsedTime(&ms, h.t.ev.b2, h.t.ev.c) == cudaSuccess) c->stats.demod_ms += ms;
+	c->ev_free.push_back(h.t.ev);
+	h.count = c->h_ctl[h.t.ring]->count;
+	if (h.count > c->ring_cap) { c->overflowed = true; h.count = c->ring_cap; }
+	if (h.count)
+		CU(cudaMemcpyAsync(c->h_ring, c->d_ring[h.t.ring], (size_t)h.count * sizeof(RawFrame), cudaMemcpyDeviceToHost, c->s_d2h));
+	CU(cudaEventRecord(c->ev_ring_read[h.t.ring], c->s_d2h));
+	c->ring_read_pending[h.t.ring] = true;
+	return ACB_OK;
+}
+
+static int harvest_finish(acb_ctx *c, Harvest &h)
+{
+	if (!h.active) return ACB_OK;
+	h.active = false;
+	CU(cudaStreamSynchronize(c->s_d2h));
+	const unsigned count = h.count;
 	struct Key { size_t group; int stream, chn; unsigned long long pos; unsigned idx; };
 	std::vector<Key> keys(count);
-	const auto &gs = t.group_starts;
+	const auto &gs = h.t.group_starts;
 	for (unsigned i = 0; i < count; i++) {
 		const RawFrame &f = c->h_ring[i];
 		keys[i] = Key{ (size_t)(std::upper_bound(gs.begin(), gs.end(), f.pos) - gs.begin()), f.stream, f.chn, f.pos, i };
@@ -369,13 +393,26 @@ static int collect_oldest(acb_ctx *c)
 	return ACB_OK;
 }
 
+static int collect_oldest(acb_ctx *c)
+{
+	Harvest h;
+	if (int r = harvest_begin(c, h)) return r;
+	return harvest_finish(c, h);
+}
+
 /* queue K1+K2 (or K2 only) on the compute stream for `nblk` blocks / `nsamp` envelope samples */
 static int run_kernels(acb_ctx *c, const uint8_t *d_iq, size_t stride, int nblk, int nsamp, const float *dm_host,
                        std::vector<unsigned long long> &&groups)
 {
-	/* the ring this submit appends to was last used two submits ago: make sure it was read back */
-	while (c->inflight.size() >= 2)
+	/* the ring this submit appends to was last used two submits ago: its frames must be on their
+	 * way back before the new demod may clear it — but the host-side FEC of those frames waits
+	 * until the new kernels have been launched */
+	while (c->inflight.size() > 2)
 		if (int r = collect_oldest(c)) return r;
+	Harvest old;
+	old.active = false;
+	if (c->inflight.size() == 2)
+		if (int r = harvest_begin(c, old)) return r;
 	Ticket t;
 	t.ring = (int)(c->nsubmit & 1);
 	t.group_starts = std::move(groups);
@@ -401,6 +438,10 @@ static int run_kernels(acb_ctx *c, const uint8_t *d_iq, size_t stride, int nblk,
 		 * behind any channelizer launch that still targets the other buffer only */
 		CU(cudaMemcpyAsync(dmbuf, dm_host, (size_t)c->cfg.nstreams * nsamp * c->cfg.nch * sizeof(float), cudaMemcpyHostToDevice, c->s_dem));
 	}
+	if (c->ring_read_pending[b]) {
+		CU(cudaStreamWaitEvent(c->s_dem, c->ev_ring_read[b], 0));
+		c->ring_read_pending[b] = false;
+	}
 	CU(cudaMemsetAsync(c->d_ctl[b], 0, sizeof(RingCtl), c->s_dem));
 	CU(cudaEventRecord(t.ev.b2, c->s_dem));
 	int r = launch_demod(c->d_state, dmbuf, nsamp, c->cfg.nch, c->cfg.nstreams, c->d_ring[b], c->d_ctl[b], c->ring_cap, c->s_dem);
@@ -416,7 +457,7 @@ static int run_kernels(acb_ctx *c, const uint8_t *d_iq, size_t stride, int nblk,
 	c->nsubmit++;
 	c->stats.submits++;
 	c->last_nsamp = nsamp;
-	return ACB_OK;
+	return harvest_finish(c, old);
 }
 
 static int check_blocks(acb_ctx *c, const void *p, size_t stride, int nblk)
@@ -532,6 +573,12 @@ extern "C" int acb_drain(acb_ctx_t *c, acb_msg_t *out, int max)
 		c->outq.pop_front();
 	}
 	return n;
+}
+
+extern "C" int acb_pending(acb_ctx_t *c)
+{
+	if (!c) return fail(ACB_ERR_ARG, "null context");
+	return (int)c->outq.size();
 }
 
 extern "C" int acb_read_dm(acb_ctx_t *c, float *out, size_t nfloats)

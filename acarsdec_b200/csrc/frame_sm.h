@@ -59,8 +59,9 @@ template <class A> ACB_HD void frame_finish(A &a)
 /* acars.c:246-375 — called by putbit when nbits reaches 0 with the assembled byte r */
 template <class A> ACB_HD void frame_byte(A &a, unsigned char r)
 {
-	switch (a.state()) {
-	case F_WSYN:                            /* sliding one bit at a time */
+	/* WSYN first and without the switch: while hunting for SYN this runs once per BIT inside the
+	 * demodulator's serial loop, and a 7-way switch compiles to an indirect branch there */
+	if (a.state() == F_WSYN) {              /* sliding one bit at a time */
 		if (r == C_SYN || r == C_NSYN) {
 			if (r == C_NSYN) a.msk_s() ^= 2u;   /* inverted polarity */
 			a.state() = F_SYN2;
@@ -69,6 +70,8 @@ template <class A> ACB_HD void frame_byte(A &a, unsigned char r)
 			a.nbits() = 1;
 		}
 		return;
+	}
+	switch (a.state()) {
 	case F_SYN2:
 		if (r == C_SYN) { a.state() = F_SOH1; a.nbits() = 8; return; }
 		if (r == C_NSYN) { a.msk_s() ^= 2u; a.nbits() = 8; return; }

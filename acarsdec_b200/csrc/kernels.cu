@@ -259,6 +259,7 @@ struct DevFrameAcc {
 	RingCtl *ctl;
 	unsigned cap;
 	int stream, chn;
+	bool leader;             /* the lane of the channel's group that owns the HBM side effects */
 
 	__device__ __forceinline__ int &state() { return r.state; }
 	__device__ __forceinline__ int &nbits() { return r.nbits; }
@@ -268,13 +269,14 @@ struct DevFrameAcc {
 	__device__ __forceinline__ unsigned &msk_s() { return r.S; }
 	__device__ __forceinline__ double &msk_df() { return r.df; }
 	__device__ __forceinline__ double &lvlsum() { return r.lvlsum; }
-	__device__ __forceinline__ void txt_put(int i, unsigned char c) { st->txt[i] = c; }
-	__device__ __forceinline__ unsigned char txt_get(int i) { return st->txt[i]; }
-	__device__ __forceinline__ void crc_put(int i, unsigned char c) { st->crc[i] = c; }
+	__device__ __forceinline__ void txt_put(int i, unsigned char c) { if (leader) st->txt[i] = c; }
+	/* only the leader's value is ever stored (crc_put); the shadows' reads are don't-cares */
+	__device__ __forceinline__ unsigned char txt_get(int i) { return leader ? st->txt[i] : (unsigned char)0; }
+	__device__ __forceinline__ void crc_put(int i, unsigned char c) { if (leader) st->crc[i] = c; }
 	__device__ __forceinline__ bool frame_begin() { r.soh_pos = r.pos; return true; }   /* acars.c:283-292 */
 	__device__ __forceinline__ void frame_emit()
 	{
-		emit_frame(st, ring, ctl, cap, stream, chn, r.blk_len, r.blk_err, r.lvlsum, r.bitcount, r.pos, r.soh_pos);
+		if (leader) emit_frame(st, ring, ctl, cap, stream, chn, r.blk_len, r.blk_err, r.lvlsum, r.bitcount, r.pos, r.soh_pos);
 	}
 };
 
@@ -294,23 +296,24 @@ int upload_sincos_table(const double *cos_hi_lo, const double *sin_hi_lo)
  * cos r - 1; angle addition against the double-double table.  Max error measured against 80-bit
  * references: 1.7 ulp (typ. < 0.6), i.e. the class of CUDA's own sincos; see DESIGN.md for why
  * ~1 ulp here is invisible after the (float) rounding of in*cexp(-j p) (msk.c:90). */
+constexpr double SC_MAGIC = 6755399441055744.0;     /* 1.5 * 2^52 */
+
 __device__ __forceinline__ void sincos_vco(double p, const double2 *tcos, const double2 *tsin, double &sn, double &cs)
 {
-	const double MAGIC = 6755399441055744.0;                 /* 1.5 * 2^52 */
-	const double t = fma(p, 0x1.45f306dc9c883p+3, MAGIC);    /* p * 32/pi, rounded to integer */
+	const double t = fma(p, 0x1.45f306dc9c883p+3, SC_MAGIC);               /* p * 32/pi, rounded to integer */
 	const int k = __double2loint(t) & 63;
-	const double kd = t - MAGIC;
+	const double kd = t - SC_MAGIC;
 	double r = fma(-kd, 0x1.921fb54442d18p-4, p);
 	r = fma(-kd, 0x1.1a62633145c07p-58, r);
 	r = fma(-kd, -0x1.f1976b7ed8fbcp-114, r);
 	const double r2 = r * r;
-	double sp = fma(r2, 1.0 / 362880, -1.0 / 5040);
-	sp = fma(sp, r2, 1.0 / 120);
-	sp = fma(sp, r2, -1.0 / 6);
+	double sp = fma(r2, (1.0 / 362880), (-1.0 / 5040));
+	sp = fma(sp, r2, (1.0 / 120));
+	sp = fma(sp, r2, (-1.0 / 6));
 	const double sr = fma(r * r2, sp, r);                    /* sin r */
-	double cp = fma(r2, 1.0 / 40320, -1.0 / 720);
-	cp = fma(cp, r2, 1.0 / 24);
-	cp = fma(cp, r2, -0.5);
+	double cp = fma(r2, (1.0 / 40320), (-1.0 / 720));
+	cp = fma(cp, r2, (1.0 / 24));
+	cp = fma(cp, r2, (-0.5));
 	const double cm = r2 * cp;                               /* cos r - 1 */
 	const double2 C = tcos[k], S = tsin[k];
 	cs = C.x + fma(-S.x, sr, fma(C.x, cm, C.y));
@@ -333,37 +336,50 @@ __device__ __forceinline__ double round_to_f32(double x)
 
 constexpr int DEMOD_LOOK = 6;    /* samples examined per outer iteration (bit period = 5.17..5.25) */
 
+constexpr int DEMOD_GROUP = 4;                       /* lanes per channel (8 is faster alone, slower under the channelizer) */
+constexpr int DEMOD_CPW = 32 / DEMOD_GROUP;          /* channels per warp */
+
+/* One warp = 8 channels of one stream x 4 lanes per channel.  The 4 lanes of a channel run the
+ * SAME recurrence on the same inputs (identical registers, no communication needed) except for
+ * the mixer: lane `sub` evaluates in*cexp(-j phi) for candidate samples sub and 4+sub and drops
+ * the result into the channel's ring in shared memory.  SIMT lanes are the one way to get the
+ * independent sincos evaluations of a bit period executed side by side: as straight-line code of
+ * one lane, ptxas schedules them back to back (6 x 16 dependent FP64 ops x 8 cycles).  Only the
+ * group leader touches HBM state (frame text, frame ring, state write-back). */
 __global__ void __launch_bounds__(32)
 k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp, int nch, int nstreams,
-        int lanes, int wps, RawFrame *__restrict__ ring, RingCtl *__restrict__ ctl, unsigned cap)
+        int wps, RawFrame *__restrict__ ring, RingCtl *__restrict__ ctl, unsigned cap)
 {
 	__shared__ float s_h[FLENO + 3];
-	__shared__ float s_re[FLEN + 1][32], s_im[FLEN + 1][32];     /* row FLEN: scratch */
+	__shared__ float s_re[FLEN + 1][DEMOD_CPW], s_im[FLEN + 1][DEMOD_CPW];     /* row FLEN: scratch */
 	__shared__ double2 s_cos[64], s_sin[64];
 
 	for (int i = threadIdx.x; i < FLENO; i += 32) s_h[i] = c_h[i];
 	for (int i = threadIdx.x; i < 64; i += 32) { s_cos[i] = g_sc_cos[i]; s_sin[i] = g_sc_sin[i]; }
-	__syncwarp();
 
 	const int lane = threadIdx.x;
+	const int grp = lane / DEMOD_GROUP, sub = lane % DEMOD_GROUP;
 	const int warp = blockIdx.x;
 	const int s = warp / wps;
-	const int ch = (warp - s * wps) * lanes + lane;
-	if (s >= nstreams || lane >= lanes || ch >= nch) return;
+	const int ch_raw = (warp - s * wps) * DEMOD_CPW + grp;
+	const bool valid = ch_raw < nch;                 /* surplus groups shadow the last channel, silently */
+	const int ch = valid ? ch_raw : nch - 1;
+	const bool leader = valid && sub == 0;
 
 	ChainState *st = states + (size_t)s * nch + ch;
 	DemodRegs r;
 	r.phi = st->phi; r.df = st->df; r.lvlsum = st->lvlsum; r.clk = st->clk; r.bitcount = st->bitcount;
 	r.S = st->S; r.idx = st->idx; r.nbits = st->nbits; r.state = st->state; r.outbits = st->outbits;
 	r.blk_len = st->blk_len; r.blk_err = st->blk_err; r.pos = st->pos; r.soh_pos = st->soh_pos;
-#pragma unroll
-	for (int k = 0; k < FLEN; k++) { s_re[k][lane] = st->inb_re[k]; s_im[k][lane] = st->inb_im[k]; }
+	for (int k = sub; k < FLEN; k += DEMOD_GROUP) { s_re[k][grp] = st->inb_re[k]; s_im[k][grp] = st->inb_im[k]; }
+	__syncwarp();
 
-	DevFrameAcc acc{ r, st, ring, ctl, cap, s, ch };
+	DevFrameAcc acc{ r, st, ring, ctl, cap, s, ch, leader };
 
 	const double TWO_PI = 2.0 * M_PI;
 	const double S0 = 1800.0 / 12500 * 2.0 * M_PI;             /* msk.c:81 */
 	const double THR = 3 * M_PI / 2.0;                         /* msk.c:96,100 */
+	const double INV_S0 = 1.0 / (1800.0 / 12500 * 2.0 * M_PI);
 	const double PLLC = (double)0.52f;                         /* msk.c:66 (float constant) */
 	const double PLLK = (1.0 - (double)0.52f) * (double)38e-4f;/* msk.c:130 (1.0-PLLC)*PLLG */
 
@@ -371,55 +387,83 @@ k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp
 	const unsigned long long pos0 = r.pos;
 	double clkd = (double)r.clk;             /* MskClk: a float value carried in a double register */
 	int n = 0;
-	while (n < nsamp) {
-		const int m = min(DEMOD_LOOK, nsamp - n);
-		float x[DEMOD_LOOK];
-#pragma unroll
-		for (int k = 0; k < DEMOD_LOOK; k++) x[k] = in[(size_t)min(n + k, nsamp - 1) * nch];
+	/* channels of a warp consume 5 or 6 samples per iteration each, so they finish a few
+	 * iterations apart: finished groups idle through empty iterations (m = 0) */
+	while (__any_sync(0xffffffffu, n < nsamp)) {
+		const int m = max(0, min(DEMOD_LOOK, nsamp - n));
+		/* this lane's two candidate samples */
+		const int k1 = sub, k2 = DEMOD_GROUP + sub;
+		const float x1 = in[(size_t)min(n + k1, nsamp - 1) * nch];
+		const float x2 = in[(size_t)min(n + k2, nsamp - 1) * nch];
 		if (n + 2 * DEMOD_LOOK < nsamp) asm volatile("prefetch.global.L1 [%0];" ::"l"(in + (size_t)(n + 2 * DEMOD_LOOK) * nch));
 
 		/* VCO step is constant until the next bit (msk.c:81): MskDf only changes in the bit path */
 		const double sv = __dadd_rn(S0, r.df);
 		const double fire_at = __dadd_rn(THR, -__dmul_rn(sv, 0.5));
+		/* 1/sv for the phase-index fast path below: three Newton steps from 1/S0 (|sv/S0 - 1| < 2e-2),
+		 * off the critical path */
+		double inv_s = INV_S0;
+		inv_s = fma(inv_s, fma(-sv, inv_s, 1.0), inv_s);
+		inv_s = fma(inv_s, fma(-sv, inv_s, 1.0), inv_s);
+		inv_s = fma(inv_s, fma(-sv, inv_s, 1.0), inv_s);
 
 		/* the two cheap serial chains of the next samples: phase (msk.c:82-83) and bit clock
 		 * (msk.c:95-96), each rounded step by step exactly like the reference's loop; straight-line
-		 * code (selects, no branches) so that it can be scheduled among the sincos below */
-		double pk[DEMOD_LOOK];
-		double p = r.phi;
+		 * code (selects, no branches) */
+		double pk[DEMOD_LOOK], ck[DEMOD_LOOK];
+		{
+			double p = r.phi, c = clkd;
+#pragma unroll
+			for (int k = 0; k < DEMOD_LOOK; k++) {
+				p = __dadd_rn(p, sv);
+				p = (p >= TWO_PI) ? __dadd_rn(p, -TWO_PI) : p;
+				c = round_to_f32(__dadd_rn(c, sv));
+				pk[k] = p;
+				ck[k] = c;
+			}
+		}
+		/* first of the m available samples at which the clock fires (msk.c:96), if any; the state
+		 * after `cnt` samples is picked with bit masks (a select chain on the index would be
+		 * turned into a local-memory array by the compiler) */
 		int cnt = m;                 /* samples consumed this iteration */
 		bool fired = false;
 #pragma unroll
-		for (int k = 0; k < DEMOD_LOOK; k++) {
-			double pn = __dadd_rn(p, sv);
-			pn = (pn >= TWO_PI) ? __dadd_rn(pn, -TWO_PI) : pn;
-			const double cn = round_to_f32(__dadd_rn(clkd, sv));
-			const bool live = (k < m) & !fired;
-			const bool fire = live & (cn >= fire_at);
-			pk[k] = pn;              /* beyond the consumed range: harmless finite values */
-			p = live ? pn : p;
-			clkd = live ? cn : clkd;
-			cnt = fire ? k + 1 : cnt;
-			fired = fired | fire;
+		for (int k = DEMOD_LOOK - 1; k >= 0; k--) {
+			const bool f = (k < m) & (ck[k] >= fire_at);
+			cnt = f ? k + 1 : cnt;
+			fired = fired | f;
 		}
-
-		/* mixer (msk.c:86-91): in * cexp(-j phi) for every candidate sample; the 6 sincos are
-		 * independent, which is what hides their latency.  Samples beyond `cnt` land in a spare
-		 * ring row instead of being branched around. */
+		double p;
 		{
-			unsigned slot = r.idx;
+			long long pb = (cnt == 0) ? __double_as_longlong(r.phi) : 0, cb = (cnt == 0) ? __double_as_longlong(clkd) : 0;
 #pragma unroll
 			for (int k = 0; k < DEMOD_LOOK; k++) {
-				double sn, cs;
-				sincos_vco(pk[k], s_cos, s_sin, sn, cs);
-				const double xd = (double)x[k];
-				const float vre = __double2float_rn(__dmul_rn(xd, cs));
-				const float vim = __double2float_rn(__dmul_rn(xd, -sn));
-				const unsigned row = (k < cnt) ? slot : FLEN;
-				s_re[row][lane] = vre;
-				s_im[row][lane] = vim;
-				slot = (slot + 1 == FLEN) ? 0 : slot + 1;
+				const long long mk = -(long long)(cnt == k + 1);
+				pb |= __double_as_longlong(pk[k]) & mk;
+				cb |= __double_as_longlong(ck[k]) & mk;
 			}
+			p = __longlong_as_double(pb);
+			clkd = __longlong_as_double(cb);
+		}
+		/* mixer (msk.c:86-91): in * cexp(-j phi), this lane's share */
+		{
+			const double p1 = (sub == 0) ? pk[0] : (sub == 1) ? pk[1] : (sub == 2) ? pk[2] : pk[3];
+			const double p2 = (sub & 1) ? pk[5] : pk[4];
+			double sn1, cs1, sn2, cs2;
+			sincos_vco(p1, s_cos, s_sin, sn1, cs1);
+			sincos_vco(p2, s_cos, s_sin, sn2, cs2);
+			const double xd1 = (double)x1, xd2 = (double)x2;
+			const float re1 = __double2float_rn(__dmul_rn(xd1, cs1)), im1 = __double2float_rn(__dmul_rn(xd1, -sn1));
+			const float re2 = __double2float_rn(__dmul_rn(xd2, cs2)), im2 = __double2float_rn(__dmul_rn(xd2, -sn2));
+			unsigned row1 = r.idx + k1, row2 = r.idx + k2;
+			row1 = (row1 >= FLEN) ? row1 - FLEN : row1;
+			row2 = (row2 >= FLEN) ? row2 - FLEN : row2;
+			row1 = (k1 < cnt) ? row1 : FLEN;                       /* past the bit instant: scratch row */
+			row2 = (k2 < cnt && k2 < DEMOD_LOOK) ? row2 : FLEN;
+			__syncwarp();          /* the previous bit's matched filter has read the rows being replaced */
+			s_re[row1][grp] = re1; s_im[row1][grp] = im1;
+			s_re[row2][grp] = re2; s_im[row2][grp] = im2;
+			__syncwarp();
 		}
 		r.idx = (r.idx + cnt) % FLEN;
 		r.phi = p;
@@ -428,19 +472,24 @@ k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp
 		if (fired) {
 			clkd = round_to_f32(__dadd_rn(clkd, -THR));
 
-			/* matched filter (msk.c:103-107): 11 taps out of the x12 oversampled half cosine */
-			int o = __double2int_rz(__dmul_rn(12.0, __dadd_rn(__ddiv_rn(clkd, sv), 0.5)));
+			/* matched filter (msk.c:103-107): 11 taps out of the x12 oversampled half cosine.
+			 * Phase index o = (int)(12*(MskClk/s + 0.5)): with inv_s good to 1e-15 the product gives
+			 * the value to ~1e-14; only when that lands within 1e-9 of an integer (where the
+			 * truncation could differ) is the reference's exact division sequence replayed. */
+			double u = fma(__dmul_rn(clkd, inv_s), 12.0, 6.0);
+			if (fabs(u - rint(u)) < 1e-9) u = __dmul_rn(12.0, __dadd_rn(__ddiv_rn(clkd, sv), 0.5));
+			int o = __double2int_rz(u);
 			o = min(max(o, 0), MFLTOVER);
 			float vr = 0.f, vi = 0.f;
-			int k = r.idx;
+			const float *hp = s_h + o;
+			int kk = r.idx;
 #pragma unroll
 			for (int j = 0; j < FLEN; j++) {
-				const float hh = s_h[o + MFLTOVER * j];
-				vr = __fadd_rn(vr, __fmul_rn(hh, s_re[k][lane]));
-				vi = __fadd_rn(vi, __fmul_rn(hh, s_im[k][lane]));
-				k = (k + 1 == FLEN) ? 0 : k + 1;
+				const float hh = hp[MFLTOVER * j];
+				vr = __fadd_rn(vr, __fmul_rn(hh, s_re[kk][grp]));
+				vi = __fadd_rn(vi, __fmul_rn(hh, s_im[kk][grp]));
+				kk = (kk + 1 == FLEN) ? 0 : kk + 1;
 			}
-
 			/* normalise (msk.c:110-113) */
 			const float lvl = envelope(make_float2(vr, vi));
 			const double d = __dadd_rn((double)lvl, 1e-8);
@@ -467,6 +516,7 @@ k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp
 		}
 		n += cnt;
 	}
+	if (!leader) return;
 	r.pos = pos0 + (unsigned long long)nsamp;
 	r.clk = (float)clkd;
 
@@ -474,18 +524,17 @@ k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp
 	st->S = r.S; st->idx = r.idx; st->nbits = r.nbits; st->state = r.state; st->outbits = r.outbits;
 	st->blk_len = r.blk_len; st->blk_err = r.blk_err; st->pos = r.pos; st->soh_pos = r.soh_pos;
 #pragma unroll
-	for (int k = 0; k < FLEN; k++) { st->inb_re[k] = s_re[k][lane]; st->inb_im[k] = s_im[k][lane]; }
+	for (int k = 0; k < FLEN; k++) { st->inb_re[k] = s_re[k][grp]; st->inb_im[k] = s_im[k][grp]; }
 }
 
 int launch_demod(ChainState *st, const float *dm, int nsamp, int nch, int nstreams,
                  RawFrame *ring, RingCtl *ctl, unsigned cap, cudaStream_t stream)
 {
-	const int lanes = nch >= 32 ? 32 : nch;
-	const int wps = (nch + lanes - 1) / lanes;
+	const int wps = (nch + DEMOD_CPW - 1) / DEMOD_CPW;
 	const int grid = nstreams * wps;             /* one warp per CTA so that chains spread over all SMs */
 	cudaError_t e = cudaFuncSetAttribute(k_demod, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 	if (e != cudaSuccess) return (int)e;
-	k_demod<<<grid, 32, 0, stream>>>(st, dm, nsamp, nch, nstreams, lanes, wps, ring, ctl, cap);
+	k_demod<<<grid, 32, 0, stream>>>(st, dm, nsamp, nch, nstreams, wps, ring, ctl, cap);
 	return (int)cudaGetLastError();
 }
 

@@ -133,6 +133,8 @@ int acb_collect(acb_ctx_t *ctx);
 int acb_sync(acb_ctx_t *ctx);
 /* Pop up to `max` messages from the output queue (the outputmsg() feed, acars.c:209). */
 int acb_drain(acb_ctx_t *ctx, acb_msg_t *out, int max);
+/* Messages currently waiting in the output queue. */
+int acb_pending(acb_ctx_t *ctx);
 
 /* Pinned host memory for submit_host callers. */
 void *acb_host_alloc(size_t bytes);
