@@ -51,7 +51,7 @@ struct RingCtl {
 };
 
 /* channelizer tile geometry */
-constexpr int CH_TILE = 128;          /* outputs per tile = threads per CTA */
+constexpr int CH_TILE = 128;          /* threads per channelizer CTA (2 output rows each) */
 constexpr int CH_GROUP = 8;           /* channels accumulated per pass */
 
 } // namespace acb
@@ -63,11 +63,13 @@ int launch_channelize(const uint8_t *iq, size_t stream_stride, const float *wf4,
                       int K, int nch, int nstreams, int nblk, CUstream_st *stream);
 int launch_channelize_generic(const uint8_t *iq, size_t stream_stride, const float *wf4, float *dm,
                               int K, int nch, int nstreams, int nblk, CUstream_st *stream);
+int launch_channelize_real(const float *samples, size_t stream_stride_bytes, const float *wf2, float *dm,
+                           int K, int nch, int nstreams, int nblk, CUstream_st *stream);
 int launch_demod(ChainState *st, const float *dm, int nsamp, int nch, int nstreams,
                  RawFrame *ring, RingCtl *ctl, unsigned cap, CUstream_st *stream);
 int upload_matched_filter(const float *h);
 int upload_sincos_table(const double *cos_hi_lo, const double *sin_hi_lo);
-size_t channelize_smem_bytes(int K);
+size_t channelize_smem_bytes(bool real);
 } // namespace acb
 
 #endif

@@ -18,6 +18,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -175,7 +176,7 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 	c->cfg = *cfg;
 	c->ngrp = (cfg->nch + CH_GROUP - 1) / CH_GROUP;
 	c->blk_bytes = (size_t)OUTBLK * cfg->K * 2;
-	c->use_generic = (cfg->K % 8) != 0 || channelize_smem_bytes(cfg->K) > 200 * 1024;
+	c->use_generic = (cfg->K % 8) != 0;
 	c->next_buf = 0;
 	c->last_nsamp = 0;
 	c->nsubmit = 0;

@@ -1,8 +1,9 @@
 /*
  * CUDA kernels of the acarsdec hot path for sm_100a.
  *
- *  K1  k_channelize : u8 IQ -> per-channel NCO mix x boxcar(K) -> decimate by K -> |.|
- *                     (reference: in_callback, rtl.c:334-354).  FP32-issue bound by the
+ *  K1  k_channelize<REAL> : u8 IQ (or float32 real samples) -> per-channel NCO mix x boxcar(K)
+ *                     -> decimate by K -> |.|  (reference: in_callback, rtl.c:334-354; REAL:
+ *                     rx_callback, air.c:291-341).  FP32-issue bound by the
  *                     reference's rounding sequence: every complex MAC is 4 rounded products
  *                     and 4 rounded sums in tap order, no FMA contraction — reproduced exactly
  *                     (packed FMUL2/FADD2 where ptxas keeps them unfused) so dm is bit-identical
@@ -34,15 +35,6 @@ int upload_matched_filter(const float *h)
 /* ------------------------------------------------------------------------------------------
  * K1: channelizer
  * ---------------------------------------------------------------------------------------- */
-
-/* row stride of the staged IQ tile in 16-byte units: odd, so that the 8 lanes of an LDS.128
- * phase (rows t..t+7, same column) fall in 8 distinct 16-byte bank groups */
-__host__ __device__ inline int tile_row_units(int K) { int u = K / 8; return (u & 1) ? u : u + 1; }
-
-size_t channelize_smem_bytes(int K)
-{
-	return (size_t)K * CH_GROUP * 16 + (size_t)CH_TILE * tile_row_units(K) * 16;
-}
 
 /* (float)u8 - 127.37f  (rtl.c:338-339).  The byte is planted in the mantissa of 2^23, the
  * 2^23 removed (exact), then 127.37f subtracted — also exact: the result is a multiple of
@@ -84,76 +76,178 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-/* grid = (blocks-of-1024-outputs, streams).  One CTA = one IQ block of one stream: 8 tiles of
- * 128 outputs; thread t owns output row t of the tile and accumulates CH_GROUP channels in
- * registers while walking its K input samples in order. */
-__global__ void __launch_bounds__(CH_TILE)
-k_channelize(const uint8_t *__restrict__ iq, size_t stream_stride, const float4 *__restrict__ wf4,
-             float *__restrict__ dm, int K, int nch, int ngrp, int nblk)
-{
-	extern __shared__ __align__(16) unsigned char smem[];
-	float4 *wfs = reinterpret_cast<float4 *>(smem);
-	unsigned char *tile = smem + (size_t)K * CH_GROUP * 16;
+/* ------------------------------------------------------------------------------------------
+ * K1 pipeline.  One CTA = one 1024-output block; 128 threads, two
+ * output rows per thread (rows t and t+128 of a 256-row tile) so every broadcast table load
+ * feeds two complex MACs; the K taps are walked in chunks of 5 sixteen-byte units per row
+ * (5 is odd: the strided LDS.128 row reads are conflict free without padding) staged by
+ * cp.async into a 2-deep ring together with the matching slice of the table, so the copy of
+ * chunk i+1 runs under the arithmetic of chunk i.  Any K that keeps rows 16-byte aligned, up to
+ * ACB_MAXK.  REAL selects the air.c front-end arithmetic: float32 real samples, D += wf[i]*S
+ * (air.c:314-333), table entries (c, d); otherwise u8 IQ, entries (c, d, -d, c) (rtl.c:334-354).
+ * ---------------------------------------------------------------------------------------- */
 
+constexpr int C2_ROWS = 256;
+constexpr int C2_UNITS = 5;
+constexpr int C2_STAGES = 2;
+
+template <bool REAL> struct C2 {
+	static constexpr int TAP_BYTES = REAL ? 4 : 2;               /* input bytes per tap */
+	static constexpr int TAPS_PER_UNIT = 16 / TAP_BYTES;
+	static constexpr int W_BYTES = REAL ? 8 : 16;                /* table bytes per (tap, channel) */
+	static constexpr int CHUNK_TAPS = C2_UNITS * TAPS_PER_UNIT;
+	static constexpr int TILE_BYTES = C2_ROWS * C2_UNITS * 16;
+	static constexpr int WF_BYTES = CHUNK_TAPS * CH_GROUP * W_BYTES;
+	static constexpr int STAGE_BYTES = TILE_BYTES + WF_BYTES;
+};
+
+/* air.c:317-318: D += wf[i] * S — (c*S, d*S) rounded, then the accumulate rounded.  Scalar
+ * products + packed add: ptxas leaves that pair unfused (it contracts FMUL2 -> FADD2). */
+__device__ __forceinline__ void rmac(float2 &acc, float sv, const float2 w)
+{
+	acc = __fadd2_rn(acc, make_float2(__fmul_rn(w.x, sv), __fmul_rn(w.y, sv)));
+}
+
+template <bool REAL>
+__global__ void __launch_bounds__(CH_TILE)
+k_channelize(const uint8_t *__restrict__ in, size_t stream_stride, const uint8_t *__restrict__ wf,
+              float *__restrict__ dm, int K, int nch, int ngrp, int nblk)
+{
+	using T = C2<REAL>;
+	extern __shared__ __align__(16) unsigned char smem[];
 	const int t = threadIdx.x;
 	const int blk = blockIdx.x, s = blockIdx.y;
-	const int U = K / 8;                         /* 16-byte units per input row */
-	const int RU = tile_row_units(K);
+	const size_t rowbytes = (size_t)K * T::TAP_BYTES;
+	const int U = (int)(rowbytes / 16);                              /* units per row */
+	const int nchunk = (U + C2_UNITS - 1) / C2_UNITS;
 	const size_t nsamp = (size_t)nblk * OUTBLK;
-	const uint8_t *src_blk = iq + (size_t)s * stream_stride + (size_t)blk * OUTBLK * K * 2;
+	const uint8_t *src_blk = in + (size_t)s * stream_stride + (size_t)blk * OUTBLK * rowbytes;
+	constexpr int NTILE = OUTBLK / C2_ROWS;
+	const int nstep = NTILE * nchunk;
 
 	for (int g = 0; g < ngrp; g++) {
-		const float4 *wsrc = wf4 + ((size_t)s * ngrp + g) * K * CH_GROUP;
-		__syncthreads();
-		for (int i = t; i < K * CH_GROUP; i += CH_TILE) wfs[i] = wsrc[i];
+		const uint8_t *wsrc = wf + ((size_t)s * ngrp + g) * K * CH_GROUP * T::W_BYTES;
 
-		for (int tl = 0; tl < OUTBLK / CH_TILE; tl++) {
-			const uint8_t *src = src_blk + (size_t)tl * CH_TILE * K * 2;
-			__syncthreads();                      /* previous tile fully consumed, wfs visible */
-			{
-				int row = t / U, j = t - row * U;
-				const int drow = CH_TILE / U, dj = CH_TILE - drow * U;
-				for (int u = t; u < CH_TILE * U; u += CH_TILE) {
-					cp_async16(tile + ((size_t)row * RU + j) * 16, src + (size_t)u * 16);
-					row += drow; j += dj;
-					if (j >= U) { j -= U; row++; }
-				}
-				cp_async_commit();
-				cp_async_wait_all();
+		auto issue = [&](int step) {
+			const int tile = step / nchunk, ck = step - tile * nchunk;
+			unsigned char *st = smem + (size_t)(step % C2_STAGES) * T::STAGE_BYTES;
+			const int uc = min(C2_UNITS, U - ck * C2_UNITS);         /* units of this chunk */
+			const uint8_t *tsrc = src_blk + (size_t)tile * C2_ROWS * rowbytes + (size_t)ck * C2_UNITS * 16;
+			for (int u = t; u < C2_ROWS * uc; u += CH_TILE) {
+				const int row = u / uc, j = u - row * uc;
+				cp_async16(st + ((size_t)row * C2_UNITS + j) * 16, tsrc + (size_t)row * rowbytes + (size_t)j * 16);
 			}
-			__syncthreads();
+			const int wunits = uc * T::TAPS_PER_UNIT * CH_GROUP * T::W_BYTES / 16;
+			const uint8_t *ws = wsrc + (size_t)ck * T::CHUNK_TAPS * CH_GROUP * T::W_BYTES;
+			for (int u = t; u < wunits; u += CH_TILE) cp_async16(st + T::TILE_BYTES + (size_t)u * 16, ws + (size_t)u * 16);
+			cp_async_commit();
+		};
 
-			float2 acc[CH_GROUP];
+		float2 accA[CH_GROUP], accB[CH_GROUP];
 #pragma unroll
-			for (int c = 0; c < CH_GROUP; c++) acc[c] = make_float2(0.f, 0.f);
-			const uint4 *rp = reinterpret_cast<const uint4 *>(tile + (size_t)t * RU * 16);
-			for (int j = 0; j < U; j++) {
-				const uint4 q = rp[j];
-				const unsigned wd[4] = { q.x, q.y, q.z, q.w };
-				const float4 *wj = wfs + (size_t)j * 8 * CH_GROUP;
-#pragma unroll
-				for (int e = 0; e < 4; e++) {
-					const float2 x0 = cvt_iq(wd[e], 0), x1 = cvt_iq(wd[e], 1);
-#pragma unroll
-					for (int c = 0; c < CH_GROUP; c++) cmac(acc[c], x0.x, x0.y, wj[(2 * e) * CH_GROUP + c]);
-#pragma unroll
-					for (int c = 0; c < CH_GROUP; c++) cmac(acc[c], x1.x, x1.y, wj[(2 * e + 1) * CH_GROUP + c]);
-				}
-			}
-			float *o = dm + ((size_t)s * nsamp + (size_t)blk * OUTBLK + (size_t)tl * CH_TILE + t) * nch + g * CH_GROUP;
-			const int nc = min(CH_GROUP, nch - g * CH_GROUP);
-			if (nc == CH_GROUP && (nch & 3) == 0) {
-				float4 v0 = make_float4(envelope(acc[0]), envelope(acc[1]), envelope(acc[2]), envelope(acc[3]));
-				float4 v1 = make_float4(envelope(acc[4]), envelope(acc[5]), envelope(acc[6]), envelope(acc[7]));
-				reinterpret_cast<float4 *>(o)[0] = v0;
-				reinterpret_cast<float4 *>(o)[1] = v1;
+		for (int c = 0; c < CH_GROUP; c++) accA[c] = accB[c] = make_float2(0.f, 0.f);
+
+		__syncthreads();                                             /* previous group done with the ring */
+		issue(0);
+		for (int step = 0; step < nstep; step++) {
+			if (step + 1 < nstep) {
+				issue(step + 1);
+				asm volatile("cp.async.wait_group 1;" ::: "memory");
 			} else {
-#pragma unroll
-				for (int c = 0; c < CH_GROUP; c++)
-					if (c < nc) o[c] = envelope(acc[c]);
+				asm volatile("cp.async.wait_group 0;" ::: "memory");
 			}
+			__syncthreads();                                         /* chunk `step` visible to all */
+			const int tile = step / nchunk, ck = step - tile * nchunk;
+			const unsigned char *st = smem + (size_t)(step % C2_STAGES) * T::STAGE_BYTES;
+			const int uc = min(C2_UNITS, U - ck * C2_UNITS);
+			const uint4 *rowA = reinterpret_cast<const uint4 *>(st) + (size_t)t * C2_UNITS;
+			const uint4 *rowB = reinterpret_cast<const uint4 *>(st) + (size_t)(t + CH_TILE) * C2_UNITS;
+			for (int j = 0; j < uc; j++) {
+				const uint4 qa = rowA[j], qb = rowB[j];
+				const unsigned wa[4] = { qa.x, qa.y, qa.z, qa.w }, wb[4] = { qb.x, qb.y, qb.z, qb.w };
+				if (REAL) {
+					const float2 *wj = reinterpret_cast<const float2 *>(st + T::TILE_BYTES) + (size_t)j * 4 * CH_GROUP;
+#pragma unroll
+					for (int e = 0; e < 4; e++) {
+						const float sa = __uint_as_float(wa[e]), sb = __uint_as_float(wb[e]);
+#pragma unroll
+						for (int c = 0; c < CH_GROUP; c++) {
+							const float2 w = wj[e * CH_GROUP + c];
+							rmac(accA[c], sa, w);
+							rmac(accB[c], sb, w);
+						}
+					}
+				} else {
+					const float4 *wj = reinterpret_cast<const float4 *>(st + T::TILE_BYTES) + (size_t)j * 8 * CH_GROUP;
+#pragma unroll
+					for (int e = 0; e < 4; e++) {
+#pragma unroll
+						for (int h = 0; h < 2; h++) {
+							const float2 xa = cvt_iq(wa[e], h), xb = cvt_iq(wb[e], h);
+#pragma unroll
+							for (int c = 0; c < CH_GROUP; c++) {
+								const float4 w = wj[(2 * e + h) * CH_GROUP + c];
+								cmac(accA[c], xa.x, xa.y, w);
+								cmac(accB[c], xb.x, xb.y, w);
+							}
+						}
+					}
+				}
+			}
+			if (ck == nchunk - 1) {                                  /* row complete: |D| out, restart */
+				const int nc = min(CH_GROUP, nch - g * CH_GROUP);
+#pragma unroll
+				for (int half = 0; half < 2; half++) {
+					float2 *acc = half ? accB : accA;
+					const size_t m = (size_t)blk * OUTBLK + (size_t)tile * C2_ROWS + t + half * CH_TILE;
+					float *o = dm + ((size_t)s * nsamp + m) * nch + g * CH_GROUP;
+					if (nc == CH_GROUP && (nch & 3) == 0) {
+						reinterpret_cast<float4 *>(o)[0] = make_float4(envelope(acc[0]), envelope(acc[1]), envelope(acc[2]), envelope(acc[3]));
+						reinterpret_cast<float4 *>(o)[1] = make_float4(envelope(acc[4]), envelope(acc[5]), envelope(acc[6]), envelope(acc[7]));
+					} else {
+#pragma unroll
+						for (int c = 0; c < CH_GROUP; c++)
+							if (c < nc) o[c] = envelope(acc[c]);
+					}
+#pragma unroll
+					for (int c = 0; c < CH_GROUP; c++) acc[c] = make_float2(0.f, 0.f);
+				}
+			}
+			__syncthreads();                                         /* stage may be refilled by issue(step+2) */
 		}
 	}
+}
+
+size_t channelize_smem_bytes(bool real)
+{
+	return (size_t)C2_STAGES * (real ? C2<true>::STAGE_BYTES : C2<false>::STAGE_BYTES);
+}
+
+template <bool REAL>
+static int launch_channelize_t(const uint8_t *in, size_t stream_stride, const void *wf, float *dm,
+                                int K, int nch, int nstreams, int nblk, cudaStream_t stream)
+{
+	const int ngrp = (nch + CH_GROUP - 1) / CH_GROUP;
+	const size_t smem = channelize_smem_bytes(REAL);
+	cudaError_t e = cudaFuncSetAttribute(k_channelize<REAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) return (int)e;
+	e = cudaFuncSetAttribute(k_channelize<REAL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+	if (e != cudaSuccess) return (int)e;
+	dim3 grid(nblk, nstreams);
+	k_channelize<REAL><<<grid, CH_TILE, smem, stream>>>(in, stream_stride, reinterpret_cast<const uint8_t *>(wf), dm, K, nch, ngrp, nblk);
+	return (int)cudaGetLastError();
+}
+
+int launch_channelize(const uint8_t *iq, size_t stream_stride, const float *wf4, float *dm,
+                       int K, int nch, int nstreams, int nblk, cudaStream_t stream)
+{
+	return launch_channelize_t<false>(iq, stream_stride, wf4, dm, K, nch, nstreams, nblk, stream);
+}
+
+int launch_channelize_real(const float *samples, size_t stream_stride_bytes, const float *wf2, float *dm,
+                           int K, int nch, int nstreams, int nblk, cudaStream_t stream)
+{
+	return launch_channelize_t<true>(reinterpret_cast<const uint8_t *>(samples), stream_stride_bytes, wf2, dm, K, nch, nstreams, nblk, stream);
 }
 
 /* Any K (not a multiple of 8): one thread per (output, channel), straight from global memory.
@@ -180,23 +274,6 @@ k_channelize_generic(const uint8_t *__restrict__ iq, size_t stream_stride, const
 		di = __fadd_rn(di, pi);
 	}
 	dm[((size_t)s * nsamp + m) * nch + ch] = envelope(make_float2(dr, di));
-}
-
-int launch_channelize(const uint8_t *iq, size_t stream_stride, const float *wf4, float *dm,
-                      int K, int nch, int nstreams, int nblk, cudaStream_t stream)
-{
-	const int ngrp = (nch + CH_GROUP - 1) / CH_GROUP;
-	const size_t smem = channelize_smem_bytes(K);
-	cudaError_t e = cudaFuncSetAttribute(k_channelize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	if (e != cudaSuccess) return (int)e;
-	/* both kernels ask for the largest shared-memory carve-out: an SM's L1/shared split only
-	 * changes when the SM is idle, so kernels that prefer different splits cannot be co-resident
-	 * — and the demod of submit i is meant to run underneath the channelizer of submit i+1 */
-	e = cudaFuncSetAttribute(k_channelize, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-	if (e != cudaSuccess) return (int)e;
-	dim3 grid(nblk, nstreams);
-	k_channelize<<<grid, CH_TILE, smem, stream>>>(iq, stream_stride, reinterpret_cast<const float4 *>(wf4), dm, K, nch, ngrp, nblk);
-	return (int)cudaGetLastError();
 }
 
 int launch_channelize_generic(const uint8_t *iq, size_t stream_stride, const float *wf4, float *dm,
