@@ -72,16 +72,20 @@ ABI = [
     ("acb_stored_fr", C.c_int, [C.c_uint]),
     ("acb_choose_fc", C.c_uint, [C.c_void_p, C.c_int, C.c_int]),
     ("acb_build_wf", None, [C.c_int, C.c_uint, C.c_int, C.c_void_p]),
+    ("acb_air_choose_fc", C.c_uint, [C.c_uint, C.c_uint]),
+    ("acb_air_build_wf", None, [C.c_int, C.c_int, C.c_uint, C.c_void_p]),
     ("acb_build_h", None, [C.c_void_p]),
     ("acb_create", C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
     ("acb_destroy", None, [C.c_void_p]),
     ("acb_last_error", C.c_char_p, []),
     ("acb_version", C.c_char_p, []),
     ("acb_set_plan", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_uint)]),
+    ("acb_set_plan_air", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_uint)]),
     ("acb_set_wf", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     ("acb_reset", C.c_int, [C.c_void_p]),
     ("acb_submit_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
     ("acb_submit_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
+    ("acb_submit_real_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     ("acb_submit_dm_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     ("acb_sync", C.c_int, [C.c_void_p]),
     ("acb_collect", C.c_int, [C.c_void_p]),
@@ -149,6 +153,22 @@ def build_wf(K: int, freqs_mhz) -> np.ndarray:
     out = np.empty((len(fr), 2 * K), dtype=np.float32)
     for i, f in enumerate(fr):
         lib.acb_build_wf(f, fc, K, out[i].ctypes.data)
+    return out
+
+
+def air_plan(rate: int, freqs_mhz):
+    """(freqs_hz, Fc, K) as initAirspy derives them (air.c:165-242, no-filter rates)."""
+    lib = load()
+    fd = [lib.acb_round_freq(float(f)) for f in freqs_mhz]
+    return fd, int(lib.acb_air_choose_fc(min(fd), max(fd))), rate // 12500
+
+
+def build_wf_air(rate: int, freqs_mhz) -> np.ndarray:
+    lib = load()
+    fd, fc, K = air_plan(rate, freqs_mhz)
+    out = np.empty((len(fd), 2 * K), dtype=np.float32)
+    for i, f in enumerate(fd):
+        lib.acb_air_build_wf(f, fc, rate, out[i].ctypes.data)
     return out
 
 
@@ -241,6 +261,17 @@ class Context:
 
     def submit_device(self, dev_ptr: int, nblk: int, stream_stride: int) -> None:
         _check(self.lib, self.lib.acb_submit_device(self.h, dev_ptr, stream_stride, nblk))
+
+    def set_plan_air(self, stream: int, freqs_hz) -> int:
+        f = np.asarray(freqs_hz, dtype=np.uint32)
+        fc = C.c_uint()
+        _check(self.lib, self.lib.acb_set_plan_air(self.h, stream, f.ctypes.data, len(f), C.byref(fc)))
+        return fc.value
+
+    def submit_real(self, x: np.ndarray) -> int:
+        """x: float32 (nstreams, nsamples) real samples; returns envelope samples produced per channel."""
+        assert x.dtype == np.float32 and x.ndim == 2 and x.shape[0] == self.nstreams and x.strides[1] == 4
+        return _check(self.lib, self.lib.acb_submit_real_host(self.h, x.ctypes.data, x.strides[0] // 4, x.shape[1]))
 
     def submit_dm(self, dm: np.ndarray) -> None:
         """dm: float32 (nstreams, nsamp, nch)."""

@@ -94,6 +94,11 @@ struct acb_ctx {
 	bool overflowed;
 	acb_stats_t stats;
 	bool use_generic;
+	bool real_input;             /* ACB_FLAG_REAL_INPUT: float32 real samples (air.c front-end) */
+	float *d_real[2];            /* per stream: [carry + new samples], alternating per submit */
+	size_t real_cap;             /* floats per stream in d_real */
+	size_t carry;                /* samples of every stream not yet consumed (< K) */
+	int real_buf;
 };
 
 static int ctx_use(acb_ctx *c)
@@ -152,6 +157,7 @@ static int reset_states(acb_ctx *c)
 	CU(cudaMemcpy(c->d_state, init.data(), n * sizeof(ChainState), cudaMemcpyHostToDevice));
 	for (int i = 0; i < 2; i++) CU(cudaMemset(c->d_ctl[i], 0, sizeof(RingCtl)));
 	c->pos = 0;
+	c->carry = 0;
 	c->outq.clear();
 	c->overflowed = false;
 	return ACB_OK;
@@ -176,7 +182,11 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 	c->cfg = *cfg;
 	c->ngrp = (cfg->nch + CH_GROUP - 1) / CH_GROUP;
 	c->blk_bytes = (size_t)OUTBLK * cfg->K * 2;
-	c->use_generic = (cfg->K % 8) != 0;
+	c->real_input = (cfg->flags & ACB_FLAG_REAL_INPUT) != 0;
+	c->use_generic = c->real_input ? (cfg->K % 4) != 0 : (cfg->K % 8) != 0;
+	c->d_real[0] = c->d_real[1] = nullptr;
+	c->carry = 0;
+	c->real_buf = 0;
 	c->next_buf = 0;
 	c->last_nsamp = 0;
 	c->nsubmit = 0;
@@ -194,11 +204,16 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 	for (int i = 0; i < 2; i++) {
 		c->d_iq[i] = nullptr;
 		c->buf_used[i] = false;
-		if (!(cfg->flags & ACB_FLAG_NO_INPUT_STAGING)) CU(cudaMalloc(&c->d_iq[i], in_bytes));
+		if (!(cfg->flags & ACB_FLAG_NO_INPUT_STAGING) && !c->real_input) CU(cudaMalloc(&c->d_iq[i], in_bytes));
+		if (c->real_input) {
+			/* room for the carried remainder (< K) plus one submit, rounded so streams stay 16-B aligned */
+			c->real_cap = (((size_t)cfg->max_blocks * OUTBLK + 1) * cfg->K + 3) & ~(size_t)3;
+			CU(cudaMalloc(&c->d_real[i], (size_t)cfg->nstreams * c->real_cap * sizeof(float)));
+		}
 		CU(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
 		CU(cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
 	}
-	const size_t wf_floats = (size_t)cfg->nstreams * c->ngrp * cfg->K * CH_GROUP * 4;
+	const size_t wf_floats = (size_t)cfg->nstreams * c->ngrp * cfg->K * CH_GROUP * (c->real_input ? 2 : 4);
 	CU(cudaMalloc(&c->d_wf4, wf_floats * sizeof(float)));
 	CU(cudaMemset(c->d_wf4, 0, wf_floats * sizeof(float)));
 	c->dm_floats = (size_t)cfg->nstreams * cfg->max_blocks * OUTBLK * cfg->nch;
@@ -255,6 +270,7 @@ extern "C" void acb_destroy(acb_ctx_t *c)
 		cudaDeviceSynchronize();
 		for (int i = 0; i < 2; i++) {
 			if (c->d_iq[i]) cudaFree(c->d_iq[i]);
+			if (c->d_real[i]) cudaFree(c->d_real[i]);
 			cudaEventDestroy(c->ev_copied[i]);
 			cudaEventDestroy(c->ev_consumed[i]);
 		}
@@ -284,13 +300,15 @@ extern "C" int acb_set_wf(acb_ctx_t *c, int stream, const float *wf, int nch)
 	if (stream < 0 || stream >= c->cfg.nstreams || nch != c->cfg.nch) return fail(ACB_ERR_ARG, "stream/nch mismatch");
 	if (int r = ctx_use(c)) return r;
 	const int K = c->cfg.K;
-	std::vector<float> t((size_t)c->ngrp * K * CH_GROUP * 4, 0.0f);
+	const int W = c->real_input ? 2 : 4;
+	std::vector<float> t((size_t)c->ngrp * K * CH_GROUP * W, 0.0f);
 	for (int ch = 0; ch < nch; ch++) {
 		const int g = ch / CH_GROUP, cc = ch % CH_GROUP;
 		for (int ind = 0; ind < K; ind++) {
 			const float re = wf[((size_t)ch * K + ind) * 2], im = wf[((size_t)ch * K + ind) * 2 + 1];
-			float *o = &t[(((size_t)g * K + ind) * CH_GROUP + cc) * 4];
-			o[0] = re; o[1] = im; o[2] = -im; o[3] = re;      /* (c, d, -d, c): see cmac() */
+			float *o = &t[(((size_t)g * K + ind) * CH_GROUP + cc) * W];
+			o[0] = re; o[1] = im;
+			if (!c->real_input) { o[2] = -im; o[3] = re; }    /* (c, d, -d, c): see cmac() */
 		}
 	}
 	if (int r = sync_streams(c)) return r;
@@ -302,6 +320,7 @@ extern "C" int acb_set_plan(acb_ctx_t *c, int stream, const unsigned *freqs_hz, 
 {
 	if (!c || !freqs_hz) return fail(ACB_ERR_ARG, "null argument");
 	if (nch != c->cfg.nch) return fail(ACB_ERR_ARG, "nch mismatch");
+	if (c->real_input) return fail(ACB_ERR_ARG, "real-input context: use acb_set_plan_air");
 	const unsigned fc = acb_choose_fc(freqs_hz, nch, c->cfg.K);
 	if (fc == 0) return fail(ACB_ERR_PLAN, "Frequencies too far apart");    /* rtl.c:149-152 */
 	std::vector<float> wf((size_t)nch * c->cfg.K * 2);
@@ -425,11 +444,27 @@ static int run_kernels(acb_ctx *c, const uint8_t *d_iq, size_t stride, int nblk,
 		/* K1 may overwrite d_dm[b] only after the demod of two submits ago has read it */
 		if (c->dm_used[b]) CU(cudaStreamWaitEvent(c->s_comp, c->ev_dm_free[b], 0));
 		CU(cudaEventRecord(t.ev.a, c->s_comp));
-		int r = c->use_generic
-		            ? launch_channelize_generic(d_iq, stride, c->d_wf4, dmbuf, c->cfg.K, c->cfg.nch, c->cfg.nstreams, nblk, c->s_comp)
-		            : launch_channelize(d_iq, stride, c->d_wf4, dmbuf, c->cfg.K, c->cfg.nch, c->cfg.nstreams, nblk, c->s_comp);
+		int r = 0;
+		if (c->real_input) {
+			/* whole 1024-row blocks through the pipeline kernel, the remaining rows (a real-input
+			 * submit may carry any number of samples) through the generic one */
+			const int fast = c->use_generic ? 0 : nsamp / OUTBLK;
+			if (fast) {
+				r = launch_channelize_real((const float *)d_iq, stride, c->d_wf4, dmbuf, c->cfg.K, c->cfg.nch, c->cfg.nstreams, fast, (size_t)nsamp, c->s_comp);
+				c->stats.kernel_launches++;
+			}
+			if (!r && nsamp > fast * OUTBLK) {
+				r = launch_channelize_generic(true, d_iq, stride, c->d_wf4, dmbuf, c->cfg.K, c->cfg.nch, c->cfg.nstreams,
+				                              (size_t)fast * OUTBLK, (size_t)nsamp - (size_t)fast * OUTBLK, (size_t)nsamp, c->s_comp);
+				c->stats.kernel_launches++;
+			}
+		} else {
+			r = c->use_generic
+			        ? launch_channelize_generic(false, d_iq, stride, c->d_wf4, dmbuf, c->cfg.K, c->cfg.nch, c->cfg.nstreams, 0, (size_t)nsamp, (size_t)nsamp, c->s_comp)
+			        : launch_channelize(d_iq, stride, c->d_wf4, dmbuf, c->cfg.K, c->cfg.nch, c->cfg.nstreams, nblk, c->s_comp);
+			c->stats.kernel_launches++;
+		}
 		if (r) return fail(ACB_ERR_CUDA, "channelizer launch: %s", cudaGetErrorString((cudaError_t)r));
-		c->stats.kernel_launches++;
 		c->stats.chan_launches++;
 		CU(cudaEventRecord(t.ev.b, c->s_comp));
 		CU(cudaEventRecord(c->ev_k1_done[b], c->s_comp));
@@ -464,6 +499,7 @@ static int run_kernels(acb_ctx *c, const uint8_t *d_iq, size_t stride, int nblk,
 static int check_blocks(acb_ctx *c, const void *p, size_t stride, int nblk)
 {
 	if (!c || !p) return fail(ACB_ERR_ARG, "null argument");
+	if (c->real_input) return fail(ACB_ERR_ARG, "real-input context: use acb_submit_real_host");
 	if (nblk < 1 || nblk > c->cfg.max_blocks) return fail(ACB_ERR_ARG, "nblk=%d outside 1..%d", nblk, c->cfg.max_blocks);
 	if (c->cfg.nstreams > 1 && stride < (size_t)nblk * c->blk_bytes) return fail(ACB_ERR_ARG, "stream_stride smaller than one stream's input");
 	if (stride % 16) return fail(ACB_ERR_ARG, "stream_stride must be a multiple of 16 bytes");
@@ -511,6 +547,53 @@ extern "C" int acb_submit_host(acb_ctx_t *c, const uint8_t *iq, size_t stride, i
 	c->pos += (unsigned long long)nblk * OUTBLK;
 	c->stats.blocks += (uint64_t)nblk * c->cfg.nstreams;
 	return ACB_OK;
+}
+
+extern "C" int acb_submit_real_host(acb_ctx_t *c, const float *x, size_t stride_samples, size_t nsamples)
+{
+	if (!c || !x) return fail(ACB_ERR_ARG, "null argument");
+	if (!c->real_input) return fail(ACB_ERR_ARG, "context was not created with ACB_FLAG_REAL_INPUT");
+	if (int r = ctx_use(c)) return r;
+	const size_t K = (size_t)c->cfg.K, total = c->carry + nsamples;
+	const size_t nout = total / K;
+	if (nsamples == 0 || total > c->real_cap || nout > (size_t)c->cfg.max_blocks * OUTBLK)
+		return fail(ACB_ERR_ARG, "nsamples=%zu exceeds max_blocks*1024*K", nsamples);
+	if (c->cfg.nstreams > 1 && stride_samples < nsamples) return fail(ACB_ERR_ARG, "stream stride smaller than one stream's input");
+	const int b = c->real_buf;
+	/* d_real[b] was last read by the channelizer two submits ago (its carry has been copied on);
+	 * everything below is stream-ordered on the channelizer stream, the copy included */
+	float *buf = c->d_real[b];
+	CU(cudaMemcpy2DAsync(buf + c->carry, c->real_cap * sizeof(float), x, stride_samples * sizeof(float),
+	                     nsamples * sizeof(float), c->cfg.nstreams, cudaMemcpyHostToDevice, c->s_comp));
+	const size_t rem = total - nout * K;
+	if (nout) {
+		if (int r = run_kernels(c, (const uint8_t *)buf, c->real_cap * sizeof(float), 0, (int)nout, nullptr,
+		                        std::vector<unsigned long long>{ c->pos }))
+			return r;
+		c->pos += nout;
+		/* the unconsumed tail (air.c:329-334 keeps a partial sum instead: same arithmetic order)
+		 * moves to the front of the other buffer */
+		if (rem)
+			CU(cudaMemcpy2DAsync(c->d_real[b ^ 1], c->real_cap * sizeof(float), buf + nout * K, c->real_cap * sizeof(float),
+			                     rem * sizeof(float), c->cfg.nstreams, cudaMemcpyDeviceToDevice, c->s_comp));
+		c->real_buf = b ^ 1;
+	}
+	c->carry = rem;          /* nout == 0: the samples simply stay behind the previous carry */
+	return (int)nout;
+}
+
+extern "C" int acb_set_plan_air(acb_ctx_t *c, int stream, const unsigned *freqs_hz, int nch, unsigned *fc_out)
+{
+	if (!c || !freqs_hz) return fail(ACB_ERR_ARG, "null argument");
+	if (!c->real_input || nch != c->cfg.nch) return fail(ACB_ERR_ARG, "not a real-input context / nch mismatch");
+	unsigned lo = freqs_hz[0], hi = freqs_hz[0];
+	for (int i = 1; i < nch; i++) { lo = std::min(lo, freqs_hz[i]); hi = std::max(hi, freqs_hz[i]); }
+	const unsigned rate = (unsigned)c->cfg.K * ACB_INTRATE;
+	const unsigned fc = acb_air_choose_fc(lo, hi);
+	std::vector<float> wf((size_t)nch * c->cfg.K * 2);
+	for (int ch = 0; ch < nch; ch++) acb_air_build_wf((int)freqs_hz[ch], (int)fc, rate, &wf[(size_t)ch * c->cfg.K * 2]);
+	if (fc_out) *fc_out = fc;
+	return acb_set_wf(c, stream, wf.data(), nch);
 }
 
 extern "C" int acb_submit_dm_host(acb_ctx_t *c, const float *dm, int nsamp)

@@ -80,6 +80,32 @@ extern "C" void acb_build_wf(int fr_stored, unsigned fc_hz, int K, float *wf)
 	}
 }
 
+extern "C" unsigned acb_air_choose_fc(unsigned min_hz, unsigned max_hz)
+{
+	/* air.c:42-64 with filter == 0 (all Airspy rates except 5 MS/s, where the reference also
+	 * programs the R820T IF filters — a device matter with no file-replay equivalent) */
+	return ((max_hz + min_hz) / 2 + ACB_INTRATE / 2) / ACB_INTRATE * ACB_INTRATE;
+}
+
+extern "C" void acb_air_build_wf(int fr_hz, int fc_hz, unsigned rate, float *wf)
+{
+	/* air.c:263-285: IF = rate/4 above (Fc - Fr); the phase is a double accumulator kept inside
+	 * +-2*pi; the unit vector is cexpf of the float-rounded phase (= sincosf); "/AIRMULT" divides
+	 * by the float image of the unsigned tap count */
+	const unsigned K = rate / ACB_INTRATE;
+	const double step = 2.0 * M_PI * (double)(unsigned)(fc_hz - fr_hz + rate / 4) / (double)rate;
+	double ph = 0;
+	for (unsigned i = 0; i < K; i++) {
+		float sn, cs;
+		sincosf((float)-ph, &sn, &cs);
+		wf[2 * i] = cs / (float)K;
+		wf[2 * i + 1] = sn / (float)K;
+		ph += step;
+		if (ph > 2.0 * M_PI) ph -= 2.0 * M_PI;
+		if (ph < -2.0 * M_PI) ph += 2.0 * M_PI;
+	}
+}
+
 extern "C" void acb_build_h(float *h)
 {
 	/* msk.c:44-48: cos(2*pi*600/INTRATE/12 * (i - 66)) evaluated by cosf on the float-rounded

@@ -191,3 +191,34 @@ def make_plan(K: int = 160, freqs_mhz=DEFAULT_FREQS_MHZ, fc_hz: int | None = Non
 
 def blocks_for_seconds(K: int, seconds: float) -> int:
     return int(np.ceil(seconds * INTRATE / OUTBLK))
+
+
+# ----------------------------------------------------------------------------- Airspy-style input
+
+def render_real(plan: StreamPlan, n0: int, nsamples: int, *, scale: float = 1.0 / 256) -> np.ndarray:
+    """float32 REAL samples [n0, n0+nsamples) at plan.rate for the air.c front-end: every channel
+    sits at the intermediate frequency Fc - Fr + rate/4 (air.c:278), AM-modulated like the IQ
+    case; noise from (seed, n0) so any range renders reproducibly when cut at the same points."""
+    fs = plan.rate
+    x = np.zeros(nsamples, dtype=np.float64)
+    n = np.arange(n0, n0 + nsamples, dtype=np.float64)
+    for b in plan.bursts:
+        bits = frame_bits(b.frame)
+        dur = len(bits) / BAUD
+        guard = 0.002
+        lo = max(n0, int(np.floor((b.t0 - guard) * fs)))
+        hi = min(n0 + nsamples, int(np.ceil((b.t0 + dur + guard) * fs)))
+        if lo >= hi:
+            continue
+        nn = n[lo - n0:hi - n0]
+        t = nn / fs - b.t0
+        theta0, f = msk_audio_phase(bits)
+        k = np.floor(t * BAUD).astype(np.int64)
+        inside = (k >= 0) & (k < len(bits))
+        kc = np.clip(k, 0, len(bits) - 1)
+        audio = np.where(inside, np.cos(theta0[kc] + 2 * np.pi * f[kc] * (t - kc / BAUD)), 0.0)
+        f_if = float(plan.fc_hz - plan.freqs_hz[b.chan] + fs // 4)
+        x[lo - n0:hi - n0] += b.amp * (1.0 + b.depth * audio) * np.cos(2 * np.pi * f_if * (nn / fs) + b.phase)
+    rng = np.random.default_rng([plan.seed, 0xA1, n0])
+    x += rng.standard_normal(nsamples) * plan.noise_sigma
+    return (x * scale).astype(np.float32)

@@ -51,6 +51,8 @@ typedef struct {
 } acb_config_t;
 
 #define ACB_FLAG_NO_INPUT_STAGING 1   /* caller only uses acb_submit_device / acb_submit_dm_* */
+#define ACB_FLAG_REAL_INPUT 2         /* Airspy front-end (air.c): float32 REAL samples at IF = rate/4,
+                                         rate = K*12500; use acb_set_plan_air / acb_submit_real_host */
 
 /* One decoded block, after parity/CRC repair: msgblk_t (acarsdec.h:48-57) without the queue
  * link, plus where it came from.  `txt` is parity-stripped (acars.c:200). */
@@ -92,6 +94,10 @@ int acb_stored_fr(unsigned freq_hz);
 unsigned acb_choose_fc(const unsigned *freqs_hz, int n, int K);
 /* rtl.c:283-286 — wf[ind] = cexpf(-j*AMFreq*ind)/K/127.5 as 2K floats (re,im interleaved) */
 void acb_build_wf(int fr_stored, unsigned fc_hz, int K, float *wf);
+/* air.c:42-64 (filter == 0) — Airspy tuner centre for the span [min,max] */
+unsigned acb_air_choose_fc(unsigned min_hz, unsigned max_hz);
+/* air.c:263-285 — wf[i] = cexpf(-j*Ph_i)/AIRMULT with the reference's double phase accumulator */
+void acb_air_build_wf(int fr_hz, int fc_hz, unsigned rate, float *wf);
 /* msk.c:44-48 — 133-tap oversampled half-cosine matched filter */
 void acb_build_h(float *h);
 
@@ -105,6 +111,8 @@ const char *acb_version(void);
 /* Replaces the channel part of initRtl (rtl.c:243-287) for one stream: freqs in CLI order,
  * chooses Fc, builds and uploads the tables.  fc_out may be NULL. */
 int acb_set_plan(acb_ctx_t *ctx, int stream, const unsigned *freqs_hz, int nch, unsigned *fc_out);
+/* The channel part of initAirspy (air.c:165-285) for a real-input context. */
+int acb_set_plan_air(acb_ctx_t *ctx, int stream, const unsigned *freqs_hz, int nch, unsigned *fc_out);
 /* Same, with caller-supplied tables (nch x 2K floats), e.g. taken from channel[].wf. */
 int acb_set_wf(acb_ctx_t *ctx, int stream, const float *wf, int nch);
 /* initMsk + initAcars for every channel of every stream (msk.c:30-51, acars.c:230-234). */
@@ -119,6 +127,11 @@ int acb_reset(acb_ctx_t *ctx);
 int acb_submit_host(acb_ctx_t *ctx, const uint8_t *iq, size_t stream_stride, int nblk);
 /* Same with the input already resident in device memory (no copy). */
 int acb_submit_device(acb_ctx_t *ctx, const uint8_t *iq_dev, size_t stream_stride, int nblk);
+/* Replaces rx_callback (air.c:291-341): `nsamples` float32 real samples per stream (stream s at
+ * x + s*stream_stride_samples), ANY count per call — what does not fill a K-sample output row is
+ * carried to the next call, the equivalent of the reference's carried partial sum ch->D / ind.
+ * Returns the number of envelope samples produced per channel (>= 0) or a negative error. */
+int acb_submit_real_host(acb_ctx_t *ctx, const float *x, size_t stream_stride_samples, size_t nsamples);
 /* Replaces demodMSK's input side (msk.c:67; soundfile.c:71-77): 12.5 kS/s envelope samples,
  * dm[(s*nsamp + n)*nch + c], fed straight to the demodulator (no channelizer). */
 int acb_submit_dm_host(acb_ctx_t *ctx, const float *dm, int nsamp);

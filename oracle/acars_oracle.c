@@ -123,6 +123,52 @@ void orc_channelize(const uint8_t *iq, int nout, int K, int nch, const float *wf
 	}
 }
 
+/* ------------------------------------------------------------------ Airspy front-end (air.c) */
+
+/* air.c:42-64 with filter == 0 (every rate but 5 MS/s): centre of the span on the 12.5 kHz raster */
+unsigned orc_air_choose_fc(unsigned minf, unsigned maxf)
+{
+	return ((maxf + minf) / 2 + ORC_INTRATE / 2) / ORC_INTRATE * ORC_INTRATE;
+}
+
+/* air.c:263-285 — the mixer table is generated by a double phase accumulator, the IF offset is
+ * rate/4, and the unit vector is cexpf of the float-rounded phase */
+void orc_air_build_wf(int fr, int fc, unsigned rate, float *wf)
+{
+	const unsigned K = rate / ORC_INTRATE;
+	const double step = 2.0 * M_PI * (double)(unsigned)(fc - fr + rate / 4) / (double)rate;
+	double ph = 0;
+	for (unsigned i = 0; i < K; i++) {
+		float sn, cs;
+		sincosf((float)-ph, &sn, &cs);
+		wf[2 * i] = cs / (float)K;
+		wf[2 * i + 1] = sn / (float)K;
+		ph += step;
+		if (ph > 2.0 * M_PI) ph -= 2.0 * M_PI;
+		if (ph < -2.0 * M_PI) ph += 2.0 * M_PI;
+	}
+}
+
+/* air.c:291-341 — D += wf[i]*S over K consecutive REAL samples per output; the reference carries
+ * D and the tap index across transfers of arbitrary size, which is the same sequence of rounded
+ * operations as walking the concatenated stream row by row */
+void orc_channelize_real(const float *x, int nout, int K, int nch, const float *wf, float *dm)
+{
+	for (int m = 0; m < nout; m++) {
+		const float *p = x + (size_t)m * K;
+		for (int ch = 0; ch < nch; ch++) {
+			const float *w = wf + (size_t)ch * 2 * K;
+			float dr = 0, di = 0;
+			for (int i = 0; i < K; i++) {
+				float pr = w[2 * i] * p[i], pi = w[2 * i + 1] * p[i];
+				dr = dr + pr;
+				di = di + pi;
+			}
+			dm[(size_t)ch * nout + m] = hypotf(dr, di);
+		}
+	}
+}
+
 /* ------------------------------------------------------------------ frame sync (acars.c) */
 
 #define SYN 0x16

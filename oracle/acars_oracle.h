@@ -63,6 +63,12 @@ void orc_build_wf(int fr_stored, unsigned fc, int K, float *wf /*2K, re/im inter
 void orc_channelize(const uint8_t *iq, int nout, int K, int nch,
                     const float *wf /*nch x 2K*/, float *dm /*nch x nout*/);              /* rtl.c:334-354 */
 
+/* Airspy front-end (air.c): float32 real samples at IF = rate/4 */
+unsigned orc_air_choose_fc(unsigned minf, unsigned maxf);                 /* air.c:42-64, no-filter branch */
+void orc_air_build_wf(int fr, int fc, unsigned rate, float *wf /*2K*/);    /* air.c:263-285 */
+void orc_channelize_real(const float *x, int nout, int K, int nch,
+                         const float *wf /*nch x 2K*/, float *dm /*nch x nout*/);      /* air.c:291-341 */
+
 /* demod + framing (msk.c, acars.c) */
 void orc_chan_init(orc_chan_t *c, int chn);                           /* msk.c:30-51, acars.c:230-234 */
 void orc_demod(orc_chan_t *c, const float *h, const float *dm, int len, orc_sink_t *sink); /* msk.c:67-137 */

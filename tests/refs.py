@@ -179,6 +179,68 @@ class RefLib:
         self.lib.ref_close()
 
 
+class RefAirLib:
+    """oracle/_ref/libacarsref_air_O2.so: the reference's air.c front-end compiled in place."""
+
+    def __init__(self):
+        self.lib = C.CDLL(str(ORACLE_DIR / "_ref" / "libacarsref_air_O2.so"))
+        L = self.lib
+        L.ref_air_open.argtypes = [C.c_uint, C.c_int, C.POINTER(C.c_char_p)]
+        L.ref_air_transfer.argtypes = [C.c_void_p, C.c_int]
+        L.ref_get_wf.argtypes = [C.c_int, C.c_void_p]
+        L.ref_get_dm.argtypes = [C.c_int, C.c_void_p, C.c_int]
+        L.ref_state.argtypes = [C.c_int, C.POINTER(RefState)]
+        L.ref_msgs.argtypes = [C.POINTER(Msg), C.c_int]
+        L.ref_air_fc.restype = C.c_uint
+        L.ref_air_mult.restype = C.c_uint
+
+    def open(self, rate: int, freqs_mhz) -> None:
+        strs = [("%.4f" % f).encode() for f in freqs_mhz]
+        arr = (C.c_char_p * len(strs))(*strs)
+        if self.lib.ref_air_open(rate, len(strs), arr):
+            raise RuntimeError("ref_air_open failed")
+        self.K = self.lib.ref_air_mult()
+
+    @property
+    def fc(self) -> int:
+        return self.lib.ref_air_fc()
+
+    def wf(self, ch: int) -> np.ndarray:
+        out = np.empty(2 * self.K, dtype=np.float32)
+        self.lib.ref_get_wf(ch, out.ctypes.data)
+        return out
+
+    def transfer(self, x: np.ndarray) -> int:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        return self.lib.ref_air_transfer(x.ctypes.data, len(x))
+
+    def dm(self, ch: int, n: int) -> np.ndarray:
+        out = np.empty(n, dtype=np.float32)
+        self.lib.ref_get_dm(ch, out.ctypes.data, n)
+        return out
+
+    def state(self, ch: int) -> RefState:
+        s = RefState()
+        self.lib.ref_state(ch, C.byref(s))
+        return s
+
+    def msgs(self):
+        self.lib.ref_flush()
+        out = []
+        buf = (Msg * 256)()
+        while True:
+            n = self.lib.ref_msgs(buf, 256)
+            for i in range(n):
+                m = Msg()
+                C.memmove(C.byref(m), C.byref(buf[i]), C.sizeof(Msg))
+                out.append(m)
+            if n < 256:
+                return out
+
+    def close(self) -> None:
+        self.lib.ref_close()
+
+
 class OracleLib:
     def __init__(self):
         self.lib = C.CDLL(str(ORACLE_DIR / "libacars_oracle.so"))
@@ -195,6 +257,10 @@ class OracleLib:
         L.orc_stored_fr.argtypes = [C.c_uint]
         L.orc_build_wf.argtypes = [C.c_int, C.c_uint, C.c_int, C.c_void_p]
         L.orc_channelize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_air_choose_fc.argtypes = [C.c_uint, C.c_uint]
+        L.orc_air_choose_fc.restype = C.c_uint
+        L.orc_air_build_wf.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_void_p]
+        L.orc_channelize_real.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_chan_init.argtypes = [C.POINTER(OrcChan), C.c_int]
         L.orc_demod.argtypes = [C.POINTER(OrcChan), C.c_void_p, C.c_void_p, C.c_int, C.POINTER(OrcSink)]
         L.orc_block_fec.argtypes = [C.POINTER(Msg)]
@@ -237,6 +303,26 @@ class OracleLib:
         dm = np.empty((nch, nout), dtype=np.float32)
         wf = np.ascontiguousarray(wf, dtype=np.float32)
         self.lib.orc_channelize(iq.ctypes.data, nout, K, nch, wf.ctypes.data, dm.ctypes.data)
+        return dm
+
+    def air_plan(self, rate: int, freqs_mhz):
+        """(freqs_hz, Fc, K) the way initAirspy derives them (air.c:165-242, no-filter rates)."""
+        fd = [self.lib.orc_round_freq(float(f)) for f in freqs_mhz]
+        return fd, int(self.lib.orc_air_choose_fc(min(fd), max(fd))), rate // 12500
+
+    def air_wf(self, rate: int, freqs_mhz) -> np.ndarray:
+        fd, fc, K = self.air_plan(rate, freqs_mhz)
+        out = np.empty((len(fd), 2 * K), dtype=np.float32)
+        for i, f in enumerate(fd):
+            self.lib.orc_air_build_wf(f, fc, rate, out[i].ctypes.data)
+        return out
+
+    def channelize_real(self, x: np.ndarray, K: int, wf: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
+        nout = x.size // K
+        dm = np.empty((wf.shape[0], nout), dtype=np.float32)
+        wf = np.ascontiguousarray(wf, dtype=np.float32)
+        self.lib.orc_channelize_real(x.ctypes.data, nout, K, wf.shape[0], wf.ctypes.data, dm.ctypes.data)
         return dm
 
     def new_chan(self, chn: int) -> OrcChan:

@@ -152,3 +152,14 @@ int main(){ Acc a; memset(&a,0,sizeof(a)); a.nb=8; int c;
 def test_no_cpu_fallback(native):
     with pytest.raises(api.AcbError):
         api.Context(K=160, nstreams=1, nch=1, max_blocks=1)
+
+
+@pytest.mark.parametrize("rate,freqs", [
+    (2500000, (131.525, 131.725, 131.825)),
+    (3000000, synth.DEFAULT_FREQS_MHZ),
+    (6000000, (129.125, 130.025, 131.550, 131.725)),
+    (10000000, (131.525, 136.900)),
+])
+def test_air_planning_matches_oracle(native, oracle, rate, freqs):
+    assert api.air_plan(rate, freqs) == oracle.air_plan(rate, freqs)
+    assert bits_equal(api.build_wf_air(rate, freqs), oracle.air_wf(rate, freqs))
