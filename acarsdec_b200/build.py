@@ -24,6 +24,7 @@ NVCC_FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-fmad=false", "-Xcompiler", "-f
 
 LIB = PKG / "libacars_b200.so"
 COMPAT = PKG / "libacarsdec_compat.so"
+COMPAT_AIR = PKG / "libacarsdec_compat_air.so"      # same shim built for -DWITH_AIR hosts (channel_t differs)
 LIB_SRC = [CSRC / "kernels.cu", CSRC / "context.cu", CSRC / "hostmath.cpp"]
 COMPAT_SRC = [CSRC / "compat.c"]
 HEADERS = [CSRC / "acb_internal.h", CSRC / "frame_sm.h", ROOT / "include" / "acars_b200.h",
@@ -65,6 +66,10 @@ def build(force: bool = False, verbose: bool = False) -> Path:
                "-ffp-contract=off", "-o", COMPAT, *COMPAT_SRC, "-I", ROOT / "include", "-L", PKG, "-lacars_b200",
                "-Wl,-rpath,$ORIGIN", "-lpthread", "-lm"]
         _run(cmd, PKG / "build" / "libacarsdec_compat.log")
+        cmd = [os.environ.get("CC", "gcc"), "-O2", "-std=gnu11", "-fPIC", "-shared", "-Wall", "-DWITH_AIR",
+               "-ffp-contract=off", "-o", COMPAT_AIR, *COMPAT_SRC, "-I", ROOT / "include", "-L", PKG, "-lacars_b200",
+               "-Wl,-rpath,$ORIGIN", "-lpthread", "-lm"]
+        _run(cmd, PKG / "build" / "libacarsdec_compat_air.log")
     return LIB
 
 

@@ -429,3 +429,113 @@ int runRtlClose(void)
 }
 
 #endif /* WITH_RTL */
+
+/* ---------------------------------------------------------------- Airspy front-end on a capture file */
+
+#ifdef WITH_AIR
+
+static acb_ctx_t *air_ctx;
+static FILE *air_src;
+static unsigned air_rate, air_mult;
+static volatile int air_cancel;
+#define AIR_TRANSFER 65536          /* samples per read: libairspy's float32-real transfer size */
+
+/* air.c:66 initAirspy — argv[optind] names a raw float32 capture of REAL samples (what libairspy
+ * delivers with AIRSPY_SAMPLE_FLOAT32_REAL); its rate comes from ACARSDEC_B200_AIRRATE (default
+ * 2500000; the reference takes the first device rate <= 10 MS/s that is a multiple of 12500). */
+int initAirspy(char **argv, int optind)
+{
+	unsigned Fd[MAXNBCHANNELS];
+	char *argF;
+	if (argv[optind] == NULL) { fprintf(stderr, "Need a float32 capture file after -s\n"); return -1; }
+	const char *path = argv[optind++];
+	const char *e = getenv("ACARSDEC_B200_AIRRATE");
+	air_rate = e ? (unsigned)atoi(e) : 2500000u;
+	air_mult = air_rate / INTRATE;
+	if (air_rate > 10000000 || air_mult * INTRATE != air_rate) {          /* air.c:211-216 */
+		fprintf(stderr, "did not find needed sampling rate\n");
+		return -1;
+	}
+	air_src = strcmp(path, "-") ? fopen(path, "rb") : stdin;
+	if (!air_src) { fprintf(stderr, "Failed to open capture %s: %s\n", path, strerror(errno)); return -1; }
+	nbch = 0;
+	while ((argF = argv[optind]) && nbch < MAXNBCHANNELS) {               /* air.c:165-183 */
+		Fd[nbch] = (unsigned)acb_round_freq(atof(argF));
+		optind++;
+		if (Fd[nbch] < 118000000 || Fd[nbch] > 138000000) {
+			fprintf(stderr, "WARNING: Invalid frequency %d\n", Fd[nbch]);
+			continue;
+		}
+		channel[nbch].chn = nbch;
+		channel[nbch].Fr = (int)Fd[nbch];
+		nbch++;
+	}
+	if (nbch == 0) { fprintf(stderr, "Need a least one frequency\n"); return 1; }
+	if (air_rate == 5000000) { fprintf(stderr, "5 MS/s needs the R820T IF filter path (air.c:47-61): not available on a capture\n"); return 1; }
+	unsigned lo = Fd[0], hi = Fd[0];
+	for (unsigned n = 1; n < nbch; n++) { if (Fd[n] < lo) lo = Fd[n]; if (Fd[n] > hi) hi = Fd[n]; }
+	const unsigned Fc = acb_air_choose_fc(lo, hi);
+	if (Fc == 0) { fprintf(stderr, "Frequencies too far apart\n"); return 1; }
+	if (verbose) fprintf(stderr, "Using %d sampling rate\nSet freq. to %d hz\n", air_rate, Fc);
+	const int maxblk = (AIR_TRANSFER * 8 / (int)air_mult) / RTLOUTBUFSZ + 2;
+	acb_config_t cfg = { 0, (int)air_mult, 1, (int)nbch, maxblk, ACB_FLAG_REAL_INPUT };
+	if ((e = getenv("ACARSDEC_B200_DEVICE"))) cfg.device = atoi(e);
+	if (acb_create(&cfg, &air_ctx) != ACB_OK) {
+		fprintf(stderr, "acarsdec_b200: %s\n", acb_last_error());
+		if (air_ctx) acb_destroy(air_ctx);
+		air_ctx = NULL;
+		return -1;
+	}
+	float *wf = malloc(sizeof(float) * 2 * air_mult * nbch);
+	if (!wf) return -1;
+	for (unsigned n = 0; n < nbch; n++) {                                 /* air.c:263-285 */
+		channel_t *ch = &channel[n];
+		ch->wf = malloc(air_mult * sizeof(float complex));
+		ch->dm_buffer = malloc(512 * sizeof(double));
+		if (ch->wf == NULL || ch->dm_buffer == NULL) { fprintf(stderr, "malloc error\n"); return -1; }
+		ch->D = 0;
+		acb_air_build_wf(ch->Fr, (int)Fc, air_rate, wf + (size_t)n * 2 * air_mult);
+		for (unsigned i = 0; i < air_mult; i++)
+			ch->wf[i] = wf[((size_t)n * air_mult + i) * 2] + wf[((size_t)n * air_mult + i) * 2 + 1] * I;
+	}
+	int rc = acb_set_wf(air_ctx, 0, wf, (int)nbch);
+	free(wf);
+	if (rc != ACB_OK) { fprintf(stderr, "acarsdec_b200: %s\n", acb_last_error()); return -1; }
+	return 0;
+}
+
+/* air.c:344 runAirspySample — batches of 8 transfers per submit; any length is fine, the library
+ * carries what does not fill an output row (the reference carries ch->D / ind) */
+int runAirspySample(void)
+{
+	if (!air_ctx || !air_src) return -1;
+	const size_t cap = (size_t)AIR_TRANSFER * 8;
+	float *buf = acb_host_alloc(cap * sizeof(float));
+	if (!buf) { fprintf(stderr, "acarsdec_b200: %s\n", acb_last_error()); return -1; }
+	acb_chan_state_t st;
+	acb_msg_t out[16];
+	for (unsigned n = 0; n < nbch; n++) { state_pack(&channel[n], &st); acb_set_state(air_ctx, 0, (int)n, &st); }
+	int rc = ACB_OK;
+	while (!signalExit && !air_cancel) {
+		size_t got = fread(buf, sizeof(float), cap, air_src);
+		if (got == 0) break;
+		struct timeval tv;
+		gettimeofday(&tv, NULL);
+		rc = acb_submit_real_host(air_ctx, buf, got, got);
+		if (rc < 0) break;
+		rc = acb_sync(air_ctx);          /* the one pinned buffer is refilled next */
+		if (rc < 0) break;
+		for (int n; (n = acb_drain(air_ctx, out, 16)) > 0;)
+			for (int i = 0; i < n; i++) deliver(&out[i], out[i].chn, &tv);
+		if (got < cap) break;
+	}
+	if (rc < 0) fprintf(stderr, "acarsdec_b200: %s\n", acb_last_error());
+	for (unsigned n = 0; n < nbch; n++)
+		if (acb_get_state(air_ctx, 0, (int)n, &st) == ACB_OK) state_unpack(&st, &channel[n]);
+	acb_host_free(buf);
+	acb_destroy(air_ctx);
+	air_ctx = NULL;
+	return rc < 0 ? -1 : 0;
+}
+
+#endif /* WITH_AIR */

@@ -74,6 +74,9 @@ extern int signalExit;
 #ifdef WITH_RTL
 extern int gain, ppm, rtlMult;
 #endif
+#ifdef WITH_AIR
+extern int gain;
+#endif
 
 /* callback OUT of the library: every repaired block, from one consumer thread (acars.c:209) */
 extern void outputmsg(const msgblk_t *);
@@ -104,6 +107,13 @@ int initRtl(char **argv, int optind);
 int runRtlSample(void);
 int runRtlCancel(void);
 int runRtlClose(void);
+#endif
+
+#ifdef WITH_AIR
+/* air.c:66 / 344 (acarsdec.h:168-169).  argv[optind] names a raw float32 capture of REAL samples at
+ * IF = rate/4 (AIRSPY_SAMPLE_FLOAT32_REAL); rate from ACARSDEC_B200_AIRRATE (default 2500000). */
+int initAirspy(char **argv, int optind);
+int runAirspySample(void);
 #endif
 
 #ifdef __cplusplus
