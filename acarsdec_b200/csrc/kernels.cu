@@ -336,9 +336,10 @@ static __device__ __noinline__ void emit_frame(const ChainState *st, RawFrame *r
 	RawFrame *f = ring + slot;
 	f->stream = stream; f->chn = chn;
 	f->len = len; f->err = err;
-	f->lvlsum = lvlsum; f->bitcount = bitcount;
+	f->lvlsum = lvlsum; f->bitcount = bitcount; f->pad0 = 0;
 	f->pos = pos; f->soh_pos = soh_pos;
 	f->crc[0] = st->crc[0]; f->crc[1] = st->crc[1];
+	for (int i = 0; i < 6; i++) f->pad1[i] = 0;            /* the record goes to the host as a whole */
 	const uint2 *src = reinterpret_cast<const uint2 *>(st->txt);
 	uint2 *dst = reinterpret_cast<uint2 *>(f->txt);
 	for (int i = 0; i < TXTCAP / 8; i++) dst[i] = src[i];
@@ -444,7 +445,8 @@ k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp
         int wps, RawFrame *__restrict__ ring, RingCtl *__restrict__ ctl, unsigned cap)
 {
 	__shared__ float s_h[FLENO + 3];
-	__shared__ float s_re[FLEN + 1][DEMOD_CPW], s_im[FLEN + 1][DEMOD_CPW];     /* row FLEN: scratch */
+	/* rows FLEN.. : one scratch row per lane of the group, for mixer outputs past the bit instant */
+	__shared__ float s_re[FLEN + DEMOD_GROUP][DEMOD_CPW], s_im[FLEN + DEMOD_GROUP][DEMOD_CPW];
 	__shared__ double2 s_cos[64], s_sin[64];
 
 	for (int i = threadIdx.x; i < FLENO; i += 32) s_h[i] = c_h[i];
@@ -551,8 +553,8 @@ k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp
 			unsigned row1 = r.idx + k1, row2 = r.idx + k2;
 			row1 = (row1 >= FLEN) ? row1 - FLEN : row1;
 			row2 = (row2 >= FLEN) ? row2 - FLEN : row2;
-			row1 = (k1 < cnt) ? row1 : FLEN;                       /* past the bit instant: scratch row */
-			row2 = (k2 < cnt && k2 < DEMOD_LOOK) ? row2 : FLEN;
+			row1 = (k1 < cnt) ? row1 : FLEN + sub;                 /* past the bit instant: scratch row */
+			row2 = (k2 < cnt && k2 < DEMOD_LOOK) ? row2 : FLEN + sub;
 			__syncwarp();          /* the previous bit's matched filter has read the rows being replaced */
 			s_re[row1][grp] = re1; s_im[row1][grp] = im1;
 			s_re[row2][grp] = re2; s_im[row2][grp] = im2;

