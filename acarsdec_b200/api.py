@@ -21,7 +21,7 @@ TXTMAX = 250
 
 class Config(C.Structure):
     _fields_ = [("device", C.c_int), ("K", C.c_int), ("nstreams", C.c_int), ("nch", C.c_int),
-                ("max_blocks", C.c_int), ("flags", C.c_int)]
+                ("max_blocks", C.c_int), ("flags", C.c_int), ("taps", C.c_int)]
 
 
 class Msg(C.Structure):
@@ -207,11 +207,11 @@ class PinnedBuffer:
 class Context:
     """N streams x C channels on one GPU (acb_ctx_t)."""
 
-    def __init__(self, K: int, nstreams: int, nch: int, max_blocks: int, device: int = 0, flags: int = 0):
+    def __init__(self, K: int, nstreams: int, nch: int, max_blocks: int, device: int = 0, flags: int = 0, taps: int = 0):
         self.lib = load()
         self.K, self.nstreams, self.nch, self.max_blocks = K, nstreams, nch, max_blocks
         self.block_bytes = OUTBLK * K * 2
-        cfg = Config(device, K, nstreams, nch, max_blocks, flags)
+        cfg = Config(device, K, nstreams, nch, max_blocks, flags, taps)
         h = C.c_void_p()
         rc = self.lib.acb_create(C.byref(cfg), C.byref(h))
         if rc < 0:

@@ -179,7 +179,7 @@ static pthread_mutex_t one_mtx = PTHREAD_MUTEX_INITIALIZER;
 static int one_ctx_get(void)
 {
 	if (one_ctx) return 0;
-	acb_config_t cfg = { 0, 160, 1, 1, ONE_MAXBLK, ACB_FLAG_NO_INPUT_STAGING };
+	acb_config_t cfg = { 0, 160, 1, 1, ONE_MAXBLK, ACB_FLAG_NO_INPUT_STAGING, 0 };
 	const char *dev = getenv("ACARSDEC_B200_DEVICE");
 	if (dev) cfg.device = atoi(dev);
 	if (acb_create(&cfg, &one_ctx) != ACB_OK) {
@@ -324,7 +324,7 @@ int initRtl(char **argv, int optind)
 	}
 	const char *e = getenv("ACARSDEC_B200_BLOCKS");
 	if (e && atoi(e) > 0) rtl_batch = atoi(e);
-	acb_config_t cfg = { 0, rtlMult, 1, (int)nbch, rtl_batch, 0 };
+	acb_config_t cfg = { 0, rtlMult, 1, (int)nbch, rtl_batch, 0, 0 };
 	if ((e = getenv("ACARSDEC_B200_DEVICE"))) cfg.device = atoi(e);
 	if (acb_create(&cfg, &rtl_ctx) != ACB_OK) {
 		fprintf(stderr, "acarsdec_b200: %s\n", acb_last_error());
@@ -478,7 +478,7 @@ int initAirspy(char **argv, int optind)
 	if (Fc == 0) { fprintf(stderr, "Frequencies too far apart\n"); return 1; }
 	if (verbose) fprintf(stderr, "Using %d sampling rate\nSet freq. to %d hz\n", air_rate, Fc);
 	const int maxblk = (AIR_TRANSFER * 8 / (int)air_mult) / RTLOUTBUFSZ + 2;
-	acb_config_t cfg = { 0, (int)air_mult, 1, (int)nbch, maxblk, ACB_FLAG_REAL_INPUT };
+	acb_config_t cfg = { 0, (int)air_mult, 1, (int)nbch, maxblk, ACB_FLAG_REAL_INPUT, 0 };
 	if ((e = getenv("ACARSDEC_B200_DEVICE"))) cfg.device = atoi(e);
 	if (acb_create(&cfg, &air_ctx) != ACB_OK) {
 		fprintf(stderr, "acarsdec_b200: %s\n", acb_last_error());

@@ -94,6 +94,8 @@ struct acb_ctx {
 	bool overflowed;
 	acb_stats_t stats;
 	bool use_generic;
+	int taps;                    /* FIR length actually applied per output row (<= K) */
+	int taps_pad;                /* taps rounded up to whole 16-byte units of input (zero weights) */
 	bool real_input;             /* ACB_FLAG_REAL_INPUT: float32 real samples (air.c front-end) */
 	float *d_real[2];            /* per stream: [carry + new samples], alternating per submit */
 	size_t real_cap;             /* floats per stream in d_real */
@@ -168,6 +170,7 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 	if (!cfg || !out) return fail(ACB_ERR_ARG, "null argument");
 	if (cfg->K < 1 || cfg->K > ACB_MAXK) return fail(ACB_ERR_ARG, "K=%d out of range 1..%d", cfg->K, ACB_MAXK);
 	if (cfg->nstreams < 1 || cfg->nch < 1 || cfg->max_blocks < 1) return fail(ACB_ERR_ARG, "nstreams/nch/max_blocks must be >= 1");
+	if (cfg->taps < 0 || cfg->taps > cfg->K) return fail(ACB_ERR_ARG, "taps=%d must be 0 (= K) or 1..K=%d", cfg->taps, cfg->K);
 	int ndev = 0;
 	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
 		return fail(ACB_ERR_CUDA, "no CUDA device: libacars_b200 has no CPU fallback");
@@ -184,6 +187,12 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 	c->blk_bytes = (size_t)OUTBLK * cfg->K * 2;
 	c->real_input = (cfg->flags & ACB_FLAG_REAL_INPUT) != 0;
 	c->use_generic = c->real_input ? (cfg->K % 4) != 0 : (cfg->K % 8) != 0;
+	c->taps = cfg->taps ? cfg->taps : cfg->K;
+	{
+		const int per_unit = c->real_input ? 4 : 8;          /* taps per 16 bytes of input */
+		c->taps_pad = c->use_generic ? c->taps : (c->taps + per_unit - 1) / per_unit * per_unit;
+		if (c->taps_pad > cfg->K) c->taps_pad = cfg->K;      /* K itself is a multiple of per_unit here */
+	}
 	c->d_real[0] = c->d_real[1] = nullptr;
 	c->carry = 0;
 	c->real_buf = 0;
@@ -213,7 +222,7 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 		CU(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
 		CU(cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
 	}
-	const size_t wf_floats = (size_t)cfg->nstreams * c->ngrp * cfg->K * CH_GROUP * (c->real_input ? 2 : 4);
+	const size_t wf_floats = (size_t)cfg->nstreams * c->ngrp * c->taps_pad * CH_GROUP * (c->real_input ? 2 : 4);
 	CU(cudaMalloc(&c->d_wf4, wf_floats * sizeof(float)));
 	CU(cudaMemset(c->d_wf4, 0, wf_floats * sizeof(float)));
 	c->dm_floats = (size_t)cfg->nstreams * cfg->max_blocks * OUTBLK * cfg->nch;
@@ -299,14 +308,14 @@ extern "C" int acb_set_wf(acb_ctx_t *c, int stream, const float *wf, int nch)
 	if (!c || !wf) return fail(ACB_ERR_ARG, "null argument");
 	if (stream < 0 || stream >= c->cfg.nstreams || nch != c->cfg.nch) return fail(ACB_ERR_ARG, "stream/nch mismatch");
 	if (int r = ctx_use(c)) return r;
-	const int K = c->cfg.K;
+	const int T = c->taps, TP = c->taps_pad;      /* taps beyond T keep zero weights: D + (+0) = D */
 	const int W = c->real_input ? 2 : 4;
-	std::vector<float> t((size_t)c->ngrp * K * CH_GROUP * W, 0.0f);
+	std::vector<float> t((size_t)c->ngrp * TP * CH_GROUP * W, 0.0f);
 	for (int ch = 0; ch < nch; ch++) {
 		const int g = ch / CH_GROUP, cc = ch % CH_GROUP;
-		for (int ind = 0; ind < K; ind++) {
-			const float re = wf[((size_t)ch * K + ind) * 2], im = wf[((size_t)ch * K + ind) * 2 + 1];
-			float *o = &t[(((size_t)g * K + ind) * CH_GROUP + cc) * W];
+		for (int ind = 0; ind < T; ind++) {
+			const float re = wf[((size_t)ch * T + ind) * 2], im = wf[((size_t)ch * T + ind) * 2 + 1];
+			float *o = &t[(((size_t)g * TP + ind) * CH_GROUP + cc) * W];
 			o[0] = re; o[1] = im;
 			if (!c->real_input) { o[2] = -im; o[3] = re; }    /* (c, d, -d, c): see cmac() */
 		}
@@ -321,6 +330,7 @@ extern "C" int acb_set_plan(acb_ctx_t *c, int stream, const unsigned *freqs_hz, 
 	if (!c || !freqs_hz) return fail(ACB_ERR_ARG, "null argument");
 	if (nch != c->cfg.nch) return fail(ACB_ERR_ARG, "nch mismatch");
 	if (c->real_input) return fail(ACB_ERR_ARG, "real-input context: use acb_set_plan_air");
+	if (c->taps != c->cfg.K) return fail(ACB_ERR_ARG, "taps != K: the reference planner builds K-tap tables; supply yours with acb_set_wf");
 	const unsigned fc = acb_choose_fc(freqs_hz, nch, c->cfg.K);
 	if (fc == 0) return fail(ACB_ERR_PLAN, "Frequencies too far apart");    /* rtl.c:149-152 */
 	std::vector<float> wf((size_t)nch * c->cfg.K * 2);
@@ -450,18 +460,18 @@ static int run_kernels(acb_ctx *c, const uint8_t *d_iq, size_t stride, int nblk,
 			 * submit may carry any number of samples) through the generic one */
 			const int fast = c->use_generic ? 0 : nsamp / OUTBLK;
 			if (fast) {
-				r = launch_channelize_real((const float *)d_iq, stride, c->d_wf4, dmbuf, c->cfg.K, c->cfg.nch, c->cfg.nstreams, fast, (size_t)nsamp, c->s_comp);
+				r = launch_channelize_real((const float *)d_iq, stride, c->d_wf4, dmbuf, c->cfg.K, c->taps_pad, c->cfg.nch, c->cfg.nstreams, fast, (size_t)nsamp, c->s_comp);
 				c->stats.kernel_launches++;
 			}
 			if (!r && nsamp > fast * OUTBLK) {
-				r = launch_channelize_generic(true, d_iq, stride, c->d_wf4, dmbuf, c->cfg.K, c->cfg.nch, c->cfg.nstreams,
+				r = launch_channelize_generic(true, d_iq, stride, c->d_wf4, dmbuf, c->cfg.K, c->taps_pad, c->cfg.nch, c->cfg.nstreams,
 				                              (size_t)fast * OUTBLK, (size_t)nsamp - (size_t)fast * OUTBLK, (size_t)nsamp, c->s_comp);
 				c->stats.kernel_launches++;
 			}
 		} else {
 			r = c->use_generic
-			        ? launch_channelize_generic(false, d_iq, stride, c->d_wf4, dmbuf, c->cfg.K, c->cfg.nch, c->cfg.nstreams, 0, (size_t)nsamp, (size_t)nsamp, c->s_comp)
-			        : launch_channelize(d_iq, stride, c->d_wf4, dmbuf, c->cfg.K, c->cfg.nch, c->cfg.nstreams, nblk, c->s_comp);
+			        ? launch_channelize_generic(false, d_iq, stride, c->d_wf4, dmbuf, c->cfg.K, c->taps_pad, c->cfg.nch, c->cfg.nstreams, 0, (size_t)nsamp, (size_t)nsamp, c->s_comp)
+			        : launch_channelize(d_iq, stride, c->d_wf4, dmbuf, c->cfg.K, c->taps_pad, c->cfg.nch, c->cfg.nstreams, nblk, c->s_comp);
 			c->stats.kernel_launches++;
 		}
 		if (r) return fail(ACB_ERR_CUDA, "channelizer launch: %s", cudaGetErrorString((cudaError_t)r));
@@ -586,6 +596,7 @@ extern "C" int acb_set_plan_air(acb_ctx_t *c, int stream, const unsigned *freqs_
 {
 	if (!c || !freqs_hz) return fail(ACB_ERR_ARG, "null argument");
 	if (!c->real_input || nch != c->cfg.nch) return fail(ACB_ERR_ARG, "not a real-input context / nch mismatch");
+	if (c->taps != c->cfg.K) return fail(ACB_ERR_ARG, "taps != K: supply the tables with acb_set_wf");
 	unsigned lo = freqs_hz[0], hi = freqs_hz[0];
 	for (int i = 1; i < nch; i++) { lo = std::min(lo, freqs_hz[i]); hi = std::max(hi, freqs_hz[i]); }
 	const unsigned rate = (unsigned)c->cfg.K * ACB_INTRATE;

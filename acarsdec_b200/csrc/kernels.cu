@@ -111,21 +111,21 @@ __device__ __forceinline__ void rmac(float2 &acc, float sv, const float2 w)
 template <bool REAL>
 __global__ void __launch_bounds__(CH_TILE)
 k_channelize(const uint8_t *__restrict__ in, size_t stream_stride, const uint8_t *__restrict__ wf,
-              float *__restrict__ dm, int K, int nch, int ngrp, size_t nsamp)
+              float *__restrict__ dm, int K, int taps, int nch, int ngrp, size_t nsamp)
 {
 	using T = C2<REAL>;
 	extern __shared__ __align__(16) unsigned char smem[];
 	const int t = threadIdx.x;
 	const int blk = blockIdx.x, s = blockIdx.y;
 	const size_t rowbytes = (size_t)K * T::TAP_BYTES;
-	const int U = (int)(rowbytes / 16);                              /* units per row */
+	const int U = taps * T::TAP_BYTES / 16;                          /* units of each row that carry taps (taps <= K) */
 	const int nchunk = (U + C2_UNITS - 1) / C2_UNITS;
 	const uint8_t *src_blk = in + (size_t)s * stream_stride + (size_t)blk * OUTBLK * rowbytes;
 	constexpr int NTILE = OUTBLK / C2_ROWS;
 	const int nstep = NTILE * nchunk;
 
 	for (int g = 0; g < ngrp; g++) {
-		const uint8_t *wsrc = wf + ((size_t)s * ngrp + g) * K * CH_GROUP * T::W_BYTES;
+		const uint8_t *wsrc = wf + ((size_t)s * ngrp + g) * taps * CH_GROUP * T::W_BYTES;
 
 		auto issue = [&](int step) {
 			const int tile = step / nchunk, ck = step - tile * nchunk;
@@ -224,7 +224,7 @@ size_t channelize_smem_bytes(bool real)
 
 template <bool REAL>
 static int launch_channelize_t(const uint8_t *in, size_t stream_stride, const void *wf, float *dm,
-                                int K, int nch, int nstreams, int nblk, size_t nsamp, cudaStream_t stream)
+                                int K, int taps, int nch, int nstreams, int nblk, size_t nsamp, cudaStream_t stream)
 {
 	if (nblk == 0) return 0;
 	const int ngrp = (nch + CH_GROUP - 1) / CH_GROUP;
@@ -234,21 +234,21 @@ static int launch_channelize_t(const uint8_t *in, size_t stream_stride, const vo
 	e = cudaFuncSetAttribute(k_channelize<REAL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 	if (e != cudaSuccess) return (int)e;
 	dim3 grid(nblk, nstreams);
-	k_channelize<REAL><<<grid, CH_TILE, smem, stream>>>(in, stream_stride, reinterpret_cast<const uint8_t *>(wf), dm, K, nch, ngrp, nsamp);
+	k_channelize<REAL><<<grid, CH_TILE, smem, stream>>>(in, stream_stride, reinterpret_cast<const uint8_t *>(wf), dm, K, taps, nch, ngrp, nsamp);
 	return (int)cudaGetLastError();
 }
 
 int launch_channelize(const uint8_t *iq, size_t stream_stride, const float *wf4, float *dm,
-                      int K, int nch, int nstreams, int nblk, cudaStream_t stream)
+                      int K, int taps, int nch, int nstreams, int nblk, cudaStream_t stream)
 {
-	return launch_channelize_t<false>(iq, stream_stride, wf4, dm, K, nch, nstreams, nblk, (size_t)nblk * OUTBLK, stream);
+	return launch_channelize_t<false>(iq, stream_stride, wf4, dm, K, taps, nch, nstreams, nblk, (size_t)nblk * OUTBLK, stream);
 }
 
 /* float32 real input: whole 1024-row blocks here, the caller sends the remaining rows to the generic kernel */
 int launch_channelize_real(const float *samples, size_t stream_stride_bytes, const float *wf2, float *dm,
-                           int K, int nch, int nstreams, int nblk, size_t nsamp, cudaStream_t stream)
+                           int K, int taps, int nch, int nstreams, int nblk, size_t nsamp, cudaStream_t stream)
 {
-	return launch_channelize_t<true>(reinterpret_cast<const uint8_t *>(samples), stream_stride_bytes, wf2, dm, K, nch, nstreams, nblk, nsamp, stream);
+	return launch_channelize_t<true>(reinterpret_cast<const uint8_t *>(samples), stream_stride_bytes, wf2, dm, K, taps, nch, nstreams, nblk, nsamp, stream);
 }
 
 /* Rows the pipeline kernel does not take (K that breaks 16-byte row alignment; the < 1024 rows
@@ -257,7 +257,7 @@ int launch_channelize_real(const float *samples, size_t stream_stride_bytes, con
 template <bool REAL>
 __global__ void __launch_bounds__(128)
 k_channelize_generic(const uint8_t *__restrict__ in, size_t stream_stride, const uint8_t *__restrict__ wf,
-                     float *__restrict__ dm, int K, int nch, int ngrp, size_t row0, size_t nrows, size_t nsamp)
+                     float *__restrict__ dm, int K, int taps, int nch, int ngrp, size_t row0, size_t nrows, size_t nsamp)
 {
 	const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const int s = blockIdx.y;
@@ -267,16 +267,16 @@ k_channelize_generic(const uint8_t *__restrict__ in, size_t stream_stride, const
 	float dr = 0.f, di = 0.f;
 	if (REAL) {
 		const float *p = reinterpret_cast<const float *>(in + (size_t)s * stream_stride) + m * K;
-		const float2 *w = reinterpret_cast<const float2 *>(wf) + ((size_t)s * ngrp + ch / CH_GROUP) * K * CH_GROUP + (ch % CH_GROUP);
-		for (int i = 0; i < K; i++) {
+		const float2 *w = reinterpret_cast<const float2 *>(wf) + ((size_t)s * ngrp + ch / CH_GROUP) * taps * CH_GROUP + (ch % CH_GROUP);
+		for (int i = 0; i < taps; i++) {
 			const float2 ww = w[(size_t)i * CH_GROUP];
 			dr = __fadd_rn(dr, __fmul_rn(ww.x, p[i]));
 			di = __fadd_rn(di, __fmul_rn(ww.y, p[i]));
 		}
 	} else {
 		const uint8_t *p = in + (size_t)s * stream_stride + m * K * 2;
-		const float4 *w = reinterpret_cast<const float4 *>(wf) + ((size_t)s * ngrp + ch / CH_GROUP) * K * CH_GROUP + (ch % CH_GROUP);
-		for (int ind = 0; ind < K; ind++) {
+		const float4 *w = reinterpret_cast<const float4 *>(wf) + ((size_t)s * ngrp + ch / CH_GROUP) * taps * CH_GROUP + (ch % CH_GROUP);
+		for (int ind = 0; ind < taps; ind++) {
 			float a = __fadd_rn((float)p[2 * ind], -127.37f), b = __fadd_rn((float)p[2 * ind + 1], -127.37f);
 			float4 ww = w[(size_t)ind * CH_GROUP];
 			float pr = __fadd_rn(__fmul_rn(a, ww.x), __fmul_rn(b, ww.z));
@@ -289,16 +289,16 @@ k_channelize_generic(const uint8_t *__restrict__ in, size_t stream_stride, const
 }
 
 int launch_channelize_generic(bool real, const void *in, size_t stream_stride, const void *wf, float *dm,
-                              int K, int nch, int nstreams, size_t row0, size_t nrows, size_t nsamp, cudaStream_t stream)
+                              int K, int taps, int nch, int nstreams, size_t row0, size_t nrows, size_t nsamp, cudaStream_t stream)
 {
 	if (nrows == 0) return 0;
 	const int ngrp = (nch + CH_GROUP - 1) / CH_GROUP;
 	const size_t total = nrows * nch;
 	dim3 grid((unsigned)((total + 127) / 128), nstreams);
 	if (real)
-		k_channelize_generic<true><<<grid, 128, 0, stream>>>((const uint8_t *)in, stream_stride, (const uint8_t *)wf, dm, K, nch, ngrp, row0, nrows, nsamp);
+		k_channelize_generic<true><<<grid, 128, 0, stream>>>((const uint8_t *)in, stream_stride, (const uint8_t *)wf, dm, K, taps, nch, ngrp, row0, nrows, nsamp);
 	else
-		k_channelize_generic<false><<<grid, 128, 0, stream>>>((const uint8_t *)in, stream_stride, (const uint8_t *)wf, dm, K, nch, ngrp, row0, nrows, nsamp);
+		k_channelize_generic<false><<<grid, 128, 0, stream>>>((const uint8_t *)in, stream_stride, (const uint8_t *)wf, dm, K, taps, nch, ngrp, row0, nrows, nsamp);
 	return (int)cudaGetLastError();
 }
 

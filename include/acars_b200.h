@@ -48,6 +48,10 @@ typedef struct {
 	int nch;                /* channels per stream */
 	int max_blocks;         /* largest nblk a submit call may carry (sizes device staging) */
 	int flags;              /* ACB_FLAG_* */
+	int taps;               /* FIR length per output: 0 = K (the reference: boxcar x NCO over the whole
+	                           decimation period, rtl.c:283-286).  1..K selects the generalised case of
+	                           BASELINE configs 3/5: only the first `taps` samples of every K-sample row
+	                           are weighted (tables from acb_set_wf, nch x 2*taps floats), same arithmetic */
 } acb_config_t;
 
 #define ACB_FLAG_NO_INPUT_STAGING 1   /* caller only uses acb_submit_device / acb_submit_dm_* */

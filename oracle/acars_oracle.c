@@ -123,6 +123,30 @@ void orc_channelize(const uint8_t *iq, int nout, int K, int nch, const float *wf
 	}
 }
 
+/* Generalisation used by BASELINE configs 3 and 5 ("FIR taps=165", "tap sweep 65-513"): the
+ * reference only has taps == K; with taps < K the first `taps` samples of every K-sample row are
+ * weighted by an arbitrary complex table, in the same rounded operation order (rtl.c:350-353).
+ * This restatement IS the definition (parity unpinned beyond taps == K, where it reduces to
+ * orc_channelize). */
+void orc_channelize_fir(const uint8_t *iq, int nout, int K, int taps, int nch, const float *wf, float *dm)
+{
+	for (int m = 0; m < nout; m++) {
+		const uint8_t *p = iq + (size_t)m * K * 2;
+		for (int ch = 0; ch < nch; ch++) {
+			const float *w = wf + (size_t)ch * 2 * taps;
+			float dr = 0, di = 0;
+			for (int ind = 0; ind < taps; ind++) {
+				float a = (float)p[2 * ind] - 127.37f, b = (float)p[2 * ind + 1] - 127.37f;
+				float c = w[2 * ind], d = w[2 * ind + 1];
+				float pr = a * c - b * d, pi = a * d + b * c;
+				dr = dr + pr;
+				di = di + pi;
+			}
+			dm[(size_t)ch * nout + m] = hypotf(dr, di);
+		}
+	}
+}
+
 /* ------------------------------------------------------------------ Airspy front-end (air.c) */
 
 /* air.c:42-64 with filter == 0 (every rate but 5 MS/s): centre of the span on the 12.5 kHz raster */

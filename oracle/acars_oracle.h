@@ -63,6 +63,11 @@ void orc_build_wf(int fr_stored, unsigned fc, int K, float *wf /*2K, re/im inter
 void orc_channelize(const uint8_t *iq, int nout, int K, int nch,
                     const float *wf /*nch x 2K*/, float *dm /*nch x nout*/);              /* rtl.c:334-354 */
 
+/* generalised FIR of BASELINE configs 3/5 (no reference implementation: taps < K weight only the
+ * first `taps` samples of each K-sample row; same complex-float arithmetic as orc_channelize) */
+void orc_channelize_fir(const uint8_t *iq, int nout, int K, int taps, int nch,
+                        const float *wf /*nch x 2*taps*/, float *dm /*nch x nout*/);
+
 /* Airspy front-end (air.c): float32 real samples at IF = rate/4 */
 unsigned orc_air_choose_fc(unsigned minf, unsigned maxf);                 /* air.c:42-64, no-filter branch */
 void orc_air_build_wf(int fr, int fc, unsigned rate, float *wf /*2K*/);    /* air.c:263-285 */

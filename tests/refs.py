@@ -261,6 +261,7 @@ class OracleLib:
         L.orc_air_choose_fc.restype = C.c_uint
         L.orc_air_build_wf.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_void_p]
         L.orc_channelize_real.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_channelize_fir.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_chan_init.argtypes = [C.POINTER(OrcChan), C.c_int]
         L.orc_demod.argtypes = [C.POINTER(OrcChan), C.c_void_p, C.c_void_p, C.c_int, C.POINTER(OrcSink)]
         L.orc_block_fec.argtypes = [C.POINTER(Msg)]
@@ -323,6 +324,15 @@ class OracleLib:
         dm = np.empty((wf.shape[0], nout), dtype=np.float32)
         wf = np.ascontiguousarray(wf, dtype=np.float32)
         self.lib.orc_channelize_real(x.ctypes.data, nout, K, wf.shape[0], wf.ctypes.data, dm.ctypes.data)
+        return dm
+
+    def channelize_fir(self, iq: np.ndarray, K: int, taps: int, wf: np.ndarray) -> np.ndarray:
+        iq = np.ascontiguousarray(iq, dtype=np.uint8).reshape(-1)
+        nout = iq.size // (2 * K)
+        dm = np.empty((wf.shape[0], nout), dtype=np.float32)
+        wf = np.ascontiguousarray(wf, dtype=np.float32)
+        assert wf.shape[1] == 2 * taps
+        self.lib.orc_channelize_fir(iq.ctypes.data, nout, K, taps, wf.shape[0], wf.ctypes.data, dm.ctypes.data)
         return dm
 
     def new_chan(self, chn: int) -> OrcChan:

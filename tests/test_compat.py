@@ -66,8 +66,13 @@ def test_compat_library_exports_reference_symbols(tmp_path):
     hdr = (ROOT / "include" / "acarsdec_compat.h").read_text()
     tail = re.sub(r"/\*.*?\*/", "", hdr[hdr.index('extern "C" {'):], flags=re.S)
     declared = set(re.findall(r"^\s*(?:int|void)\s+(\w+)\s*\(", tail, flags=re.M))
-    assert declared == {"initMsk", "demodMSK", "initAcars", "decodeAcars", "deinitAcars", "initRtl", "runRtlSample", "runRtlCancel", "runRtlClose"}
-    assert declared <= defined
+    common = {"initMsk", "demodMSK", "initAcars", "decodeAcars", "deinitAcars"}
+    rtl = {"initRtl", "runRtlSample", "runRtlCancel", "runRtlClose"}
+    air = {"initAirspy", "runAirspySample"}
+    assert declared == common | rtl | air
+    assert common | rtl <= defined
+    out = subprocess.run(["nm", "-D", "--defined-only", str(PKG / "libacarsdec_compat_air.so")], capture_output=True, text=True, check=True).stdout
+    assert common | air <= set(re.findall(r" T (\w+)", out))
     # and it links into a host that supplies acarsdec.c's globals
     assert _host(tmp_path).exists()
 
