@@ -77,7 +77,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 /* ------------------------------------------------------------------------------------------
- * K1 pipeline.  One CTA = one 1024-output block; 128 threads, two
+ * K1 pipeline.  One CTA = one 1024-output block x one group of 8 channels; 128 threads, two
  * output rows per thread (rows t and t+128 of a 256-row tile) so every broadcast table load
  * feeds two complex MACs; the K taps are walked in chunks of 5 sixteen-byte units per row
  * (5 is odd: the strided LDS.128 row reads are conflict free without padding) staged by
@@ -124,7 +124,8 @@ k_channelize(const uint8_t *__restrict__ in, size_t stream_stride, const uint8_t
 	constexpr int NTILE = OUTBLK / C2_ROWS;
 	const int nstep = NTILE * nchunk;
 
-	for (int g = 0; g < ngrp; g++) {
+	{
+		const int g = blockIdx.z;                                    /* channel group of 8: one CTA each */
 		const uint8_t *wsrc = wf + ((size_t)s * ngrp + g) * taps * CH_GROUP * T::W_BYTES;
 
 		auto issue = [&](int step) {
@@ -146,7 +147,6 @@ k_channelize(const uint8_t *__restrict__ in, size_t stream_stride, const uint8_t
 #pragma unroll
 		for (int c = 0; c < CH_GROUP; c++) accA[c] = accB[c] = make_float2(0.f, 0.f);
 
-		__syncthreads();                                             /* previous group done with the ring */
 		issue(0);
 		for (int step = 0; step < nstep; step++) {
 			if (step + 1 < nstep) {
@@ -233,7 +233,7 @@ static int launch_channelize_t(const uint8_t *in, size_t stream_stride, const vo
 	if (e != cudaSuccess) return (int)e;
 	e = cudaFuncSetAttribute(k_channelize<REAL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 	if (e != cudaSuccess) return (int)e;
-	dim3 grid(nblk, nstreams);
+	dim3 grid(nblk, nstreams, ngrp);
 	k_channelize<REAL><<<grid, CH_TILE, smem, stream>>>(in, stream_stride, reinterpret_cast<const uint8_t *>(wf), dm, K, taps, nch, ngrp, nsamp);
 	return (int)cudaGetLastError();
 }
