@@ -378,3 +378,24 @@ def test_config4_128_streams(native, oracle):
         assert per.get(s, []) == want, s
         total += len(want)
     assert total > 300
+
+
+def test_wide_stream_channel_sharding(native):
+    """One stream, channels sharded over the visible GPUs with a single NCCL broadcast of the raw
+    block (world size 1 when only one GPU is visible: same code path minus the collective)."""
+    import json as _json
+    import subprocess
+    import sys as _sys
+    import torch
+    n = min(torch.cuda.device_count(), 2)
+    worker = str(__import__("pathlib").Path(__file__).resolve().parent / "wide_stream_worker.py")
+    if n >= 2:
+        cmd = [_sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+               "--master-addr", "127.0.0.1", "--master-port", "29533", worker]
+    else:
+        cmd = [_sys.executable, worker]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    res = _json.loads(line)
+    assert res["match"] and res["world"] == max(n, 1) and res["frames"] >= 8
