@@ -88,15 +88,21 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
  * ---------------------------------------------------------------------------------------- */
 
 constexpr int C2_ROWS = 256;
-constexpr int C2_UNITS = 5;
-constexpr int C2_STAGES = 2;
+#ifndef C2_REAL_UNITS
+#define C2_REAL_UNITS 5
+#endif
+#ifndef C2_REAL_STAGES
+#define C2_REAL_STAGES 2
+#endif
 
 template <bool REAL> struct C2 {
+	static constexpr int UNITS = REAL ? C2_REAL_UNITS : 5;      /* 16-byte units of a row per chunk: odd */
+	static constexpr int STAGES = REAL ? C2_REAL_STAGES : 2;     /* cp.async ring depth */
 	static constexpr int TAP_BYTES = REAL ? 4 : 2;               /* input bytes per tap */
 	static constexpr int TAPS_PER_UNIT = 16 / TAP_BYTES;
 	static constexpr int W_BYTES = REAL ? 8 : 16;                /* table bytes per (tap, channel) */
-	static constexpr int CHUNK_TAPS = C2_UNITS * TAPS_PER_UNIT;
-	static constexpr int TILE_BYTES = C2_ROWS * C2_UNITS * 16;
+	static constexpr int CHUNK_TAPS = UNITS * TAPS_PER_UNIT;
+	static constexpr int TILE_BYTES = C2_ROWS * UNITS * 16;
 	static constexpr int WF_BYTES = CHUNK_TAPS * CH_GROUP * W_BYTES;
 	static constexpr int STAGE_BYTES = TILE_BYTES + WF_BYTES;
 };
@@ -119,7 +125,7 @@ k_channelize(const uint8_t *__restrict__ in, size_t stream_stride, const uint8_t
 	const int blk = blockIdx.x, s = blockIdx.y;
 	const size_t rowbytes = (size_t)K * T::TAP_BYTES;
 	const int U = taps * T::TAP_BYTES / 16;                          /* units of each row that carry taps (taps <= K) */
-	const int nchunk = (U + C2_UNITS - 1) / C2_UNITS;
+	const int nchunk = (U + T::UNITS - 1) / T::UNITS;
 	const uint8_t *src_blk = in + (size_t)s * stream_stride + (size_t)blk * OUTBLK * rowbytes;
 	constexpr int NTILE = OUTBLK / C2_ROWS;
 	const int nstep = NTILE * nchunk;
@@ -130,12 +136,24 @@ k_channelize(const uint8_t *__restrict__ in, size_t stream_stride, const uint8_t
 
 		auto issue = [&](int step) {
 			const int tile = step / nchunk, ck = step - tile * nchunk;
-			unsigned char *st = smem + (size_t)(step % C2_STAGES) * T::STAGE_BYTES;
-			const int uc = min(C2_UNITS, U - ck * C2_UNITS);         /* units of this chunk */
-			const uint8_t *tsrc = src_blk + (size_t)tile * C2_ROWS * rowbytes + (size_t)ck * C2_UNITS * 16;
-			for (int u = t; u < C2_ROWS * uc; u += CH_TILE) {
-				const int row = u / uc, j = u - row * uc;
-				cp_async16(st + ((size_t)row * C2_UNITS + j) * 16, tsrc + (size_t)row * rowbytes + (size_t)j * 16);
+			unsigned char *st = smem + (size_t)(step % T::STAGES) * T::STAGE_BYTES;
+			const int uc = min(T::UNITS, U - ck * T::UNITS);         /* units of this chunk */
+			const uint8_t *tsrc = src_blk + (size_t)tile * C2_ROWS * rowbytes + (size_t)ck * T::UNITS * 16;
+			{
+				/* unit u = t + 128*i of the chunk tile lives at (row u/uc, column u%uc): one division
+				 * per chunk, then incremental (the address arithmetic is a fifth of the kernel's
+				 * instructions otherwise) */
+				int row = t / uc, j = t - row * uc;
+				const int drow = CH_TILE / uc, dj = CH_TILE - drow * uc;
+				unsigned char *dst = st + ((size_t)row * T::UNITS + j) * 16;
+				const uint8_t *src = tsrc + (size_t)row * rowbytes + (size_t)j * 16;
+				const size_t dstep = ((size_t)drow * T::UNITS + dj) * 16, sstep = (size_t)drow * rowbytes + (size_t)dj * 16;
+				const size_t dwrap = (size_t)(T::UNITS - uc) * 16, swrap = rowbytes - (size_t)uc * 16;
+				for (int u = t; u < C2_ROWS * uc; u += CH_TILE) {
+					cp_async16(dst, src);
+					dst += dstep; src += sstep; j += dj;
+					if (j >= uc) { j -= uc; dst += dwrap; src += swrap; }
+				}
 			}
 			const int wunits = uc * T::TAPS_PER_UNIT * CH_GROUP * T::W_BYTES / 16;
 			const uint8_t *ws = wsrc + (size_t)ck * T::CHUNK_TAPS * CH_GROUP * T::W_BYTES;
@@ -147,20 +165,21 @@ k_channelize(const uint8_t *__restrict__ in, size_t stream_stride, const uint8_t
 #pragma unroll
 		for (int c = 0; c < CH_GROUP; c++) accA[c] = accB[c] = make_float2(0.f, 0.f);
 
-		issue(0);
+		/* prologue: STAGES-1 chunks in flight; every iteration commits exactly one group (possibly
+		 * empty) so that "all but the newest STAGES-1 groups" always means "chunk `step` landed" */
+#pragma unroll
+		for (int i = 0; i < T::STAGES - 1; i++) {
+			if (i < nstep) issue(i); else cp_async_commit();
+		}
 		for (int step = 0; step < nstep; step++) {
-			if (step + 1 < nstep) {
-				issue(step + 1);
-				asm volatile("cp.async.wait_group 1;" ::: "memory");
-			} else {
-				asm volatile("cp.async.wait_group 0;" ::: "memory");
-			}
+			if (step + T::STAGES - 1 < nstep) issue(step + T::STAGES - 1); else cp_async_commit();
+			asm volatile("cp.async.wait_group %0;" ::"n"(T::STAGES - 1) : "memory");
 			__syncthreads();                                         /* chunk `step` visible to all */
 			const int tile = step / nchunk, ck = step - tile * nchunk;
-			const unsigned char *st = smem + (size_t)(step % C2_STAGES) * T::STAGE_BYTES;
-			const int uc = min(C2_UNITS, U - ck * C2_UNITS);
-			const uint4 *rowA = reinterpret_cast<const uint4 *>(st) + (size_t)t * C2_UNITS;
-			const uint4 *rowB = reinterpret_cast<const uint4 *>(st) + (size_t)(t + CH_TILE) * C2_UNITS;
+			const unsigned char *st = smem + (size_t)(step % T::STAGES) * T::STAGE_BYTES;
+			const int uc = min(T::UNITS, U - ck * T::UNITS);
+			const uint4 *rowA = reinterpret_cast<const uint4 *>(st) + (size_t)t * T::UNITS;
+			const uint4 *rowB = reinterpret_cast<const uint4 *>(st) + (size_t)(t + CH_TILE) * T::UNITS;
 			for (int j = 0; j < uc; j++) {
 				const uint4 qa = rowA[j], qb = rowB[j];
 				const unsigned wa[4] = { qa.x, qa.y, qa.z, qa.w }, wb[4] = { qb.x, qb.y, qb.z, qb.w };
@@ -219,7 +238,7 @@ k_channelize(const uint8_t *__restrict__ in, size_t stream_stride, const uint8_t
 
 size_t channelize_smem_bytes(bool real)
 {
-	return (size_t)C2_STAGES * (real ? C2<true>::STAGE_BYTES : C2<false>::STAGE_BYTES);
+	return real ? (size_t)C2<true>::STAGES * C2<true>::STAGE_BYTES : (size_t)C2<false>::STAGES * C2<false>::STAGE_BYTES;
 }
 
 template <bool REAL>

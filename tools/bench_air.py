@@ -5,8 +5,9 @@ import json, sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
-import numpy as np
+import numpy as np, os
 from acarsdec_b200 import api, synth
+if os.environ.get('ACB_LIB'): api.LIB_PATH = Path(os.environ['ACB_LIB'])
 import refs
 
 rate = int(sys.argv[1]) if len(sys.argv) > 1 else 2500000
