@@ -74,6 +74,7 @@ ABI = [
     ("acb_build_wf", None, [C.c_int, C.c_uint, C.c_int, C.c_void_p]),
     ("acb_air_choose_fc", C.c_uint, [C.c_uint, C.c_uint]),
     ("acb_air_build_wf", None, [C.c_int, C.c_int, C.c_uint, C.c_void_p]),
+    ("acb_cs16_build_wf", None, [C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_void_p]),
     ("acb_build_h", None, [C.c_void_p]),
     ("acb_create", C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
     ("acb_destroy", None, [C.c_void_p]),
@@ -81,11 +82,14 @@ ABI = [
     ("acb_version", C.c_char_p, []),
     ("acb_set_plan", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_uint)]),
     ("acb_set_plan_air", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_uint)]),
+    ("acb_set_plan_cs16", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.POINTER(C.c_uint)]),
     ("acb_set_wf", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     ("acb_reset", C.c_int, [C.c_void_p]),
     ("acb_submit_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
     ("acb_submit_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
     ("acb_submit_real_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    ("acb_submit_cs16_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    ("acb_submit_cs16_planar_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     ("acb_submit_dm_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     ("acb_sync", C.c_int, [C.c_void_p]),
     ("acb_collect", C.c_int, [C.c_void_p]),
@@ -169,6 +173,14 @@ def build_wf_air(rate: int, freqs_mhz) -> np.ndarray:
     out = np.empty((len(fd), 2 * K), dtype=np.float32)
     for i, f in enumerate(fd):
         lib.acb_air_build_wf(f, fc, rate, out[i].ctypes.data)
+    return out
+
+
+def build_wf_cs16(variant: int, K: int, freqs_hz, fc_hz: int) -> np.ndarray:
+    lib = load()
+    out = np.empty((len(freqs_hz), 2 * K), dtype=np.float32)
+    for i, f in enumerate(freqs_hz):
+        lib.acb_cs16_build_wf(variant, int(f), int(fc_hz), K, out[i].ctypes.data)
     return out
 
 
@@ -272,6 +284,22 @@ class Context:
         """x: float32 (nstreams, nsamples) real samples; returns envelope samples produced per channel."""
         assert x.dtype == np.float32 and x.ndim == 2 and x.shape[0] == self.nstreams and x.strides[1] == 4
         return _check(self.lib, self.lib.acb_submit_real_host(self.h, x.ctypes.data, x.strides[0] // 4, x.shape[1]))
+
+    def set_plan_cs16(self, stream: int, freqs_hz, variant: int, fc_hz: int = 0) -> int:
+        f = np.asarray(freqs_hz, dtype=np.uint32)
+        fc = C.c_uint()
+        _check(self.lib, self.lib.acb_set_plan_cs16(self.h, stream, f.ctypes.data, len(f), variant, fc_hz, C.byref(fc)))
+        return fc.value
+
+    def submit_cs16(self, iq: np.ndarray) -> int:
+        """iq: int16 (nstreams, nsamples, 2) interleaved I,Q."""
+        assert iq.dtype == np.int16 and iq.ndim == 3 and iq.shape[0] == self.nstreams and iq.shape[2] == 2 and iq.flags.c_contiguous
+        return _check(self.lib, self.lib.acb_submit_cs16_host(self.h, iq.ctypes.data, iq.shape[1], iq.shape[1]))
+
+    def submit_cs16_planar(self, xi: np.ndarray, xq: np.ndarray) -> int:
+        """xi, xq: int16 (nstreams, nsamples) separate I and Q planes (the SDRplay callback's layout)."""
+        assert xi.dtype == np.int16 and xq.dtype == np.int16 and xi.shape == xq.shape and xi.flags.c_contiguous and xq.flags.c_contiguous
+        return _check(self.lib, self.lib.acb_submit_cs16_planar_host(self.h, xi.ctypes.data, xq.ctypes.data, xi.shape[1], xi.shape[1]))
 
     def submit_dm(self, dm: np.ndarray) -> None:
         """dm: float32 (nstreams, nsamp, nch)."""

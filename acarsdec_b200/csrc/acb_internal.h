@@ -59,17 +59,16 @@ constexpr int CH_GROUP = 8;           /* channels accumulated per pass */
 /* kernels.cu entry points (host-callable launchers) */
 struct CUstream_st;
 namespace acb {
-int launch_channelize(const uint8_t *iq, size_t stream_stride, const float *wf4, float *dm,
-                      int K, int taps, int nch, int nstreams, int nblk, CUstream_st *stream);
-int launch_channelize_real(const float *samples, size_t stream_stride_bytes, const float *wf2, float *dm,
-                           int K, int taps, int nch, int nstreams, int nblk, size_t nsamp, CUstream_st *stream);
-int launch_channelize_generic(bool real, const void *in, size_t stream_stride, const void *wf, float *dm,
+enum InputKind { IN_KIND_U8IQ = 0, IN_KIND_F32REAL = 1, IN_KIND_CS16IQ = 2 };
+int launch_channelize(int mode, const void *in, size_t stream_stride_bytes, const float *wf, float *dm,
+                      int K, int taps, int nch, int nstreams, int nblk, size_t nsamp, CUstream_st *stream);
+int launch_channelize_generic(int mode, const void *in, size_t stream_stride, const void *wf, float *dm,
                               int K, int taps, int nch, int nstreams, size_t row0, size_t nrows, size_t nsamp, CUstream_st *stream);
 int launch_demod(ChainState *st, const float *dm, int nsamp, int nch, int nstreams,
                  RawFrame *ring, RingCtl *ctl, unsigned cap, CUstream_st *stream);
 int upload_matched_filter(const float *h);
 int upload_sincos_table(const double *cos_hi_lo, const double *sin_hi_lo);
-size_t channelize_smem_bytes(bool real);
+size_t channelize_smem_bytes(int mode);
 } // namespace acb
 
 #endif

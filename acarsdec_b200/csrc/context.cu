@@ -96,7 +96,8 @@ struct acb_ctx {
 	bool use_generic;
 	int taps;                    /* FIR length actually applied per output row (<= K) */
 	int taps_pad;                /* taps rounded up to whole 16-byte units of input (zero weights) */
-	bool real_input;             /* ACB_FLAG_REAL_INPUT: float32 real samples (air.c front-end) */
+	int in_kind;                 /* IN_KIND_*: u8 IQ blocks | float32 real (air.c) | CS16 IQ (soapy.c, sdrplay.c) */
+	bool real_input;             /* in_kind != u8: 4-byte input elements, arbitrary submit lengths, carried remainder */
 	float *d_real[2];            /* per stream: [carry + new samples], alternating per submit */
 	size_t real_cap;             /* floats per stream in d_real */
 	size_t carry;                /* samples of every stream not yet consumed (< K) */
@@ -185,11 +186,13 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 	c->cfg = *cfg;
 	c->ngrp = (cfg->nch + CH_GROUP - 1) / CH_GROUP;
 	c->blk_bytes = (size_t)OUTBLK * cfg->K * 2;
-	c->real_input = (cfg->flags & ACB_FLAG_REAL_INPUT) != 0;
+	if ((cfg->flags & ACB_FLAG_REAL_INPUT) && (cfg->flags & ACB_FLAG_CS16_INPUT)) return fail(ACB_ERR_ARG, "REAL_INPUT and CS16_INPUT are exclusive");
+	c->in_kind = (cfg->flags & ACB_FLAG_REAL_INPUT) ? IN_KIND_F32REAL : (cfg->flags & ACB_FLAG_CS16_INPUT) ? IN_KIND_CS16IQ : IN_KIND_U8IQ;
+	c->real_input = c->in_kind != IN_KIND_U8IQ;
 	c->use_generic = c->real_input ? (cfg->K % 4) != 0 : (cfg->K % 8) != 0;
 	c->taps = cfg->taps ? cfg->taps : cfg->K;
 	{
-		const int per_unit = c->real_input ? 4 : 8;          /* taps per 16 bytes of input */
+		const int per_unit = c->real_input ? 4 : 8;          /* taps per 16 bytes of input (4-byte vs 2-byte taps) */
 		c->taps_pad = c->use_generic ? c->taps : (c->taps + per_unit - 1) / per_unit * per_unit;
 		if (c->taps_pad > cfg->K) c->taps_pad = cfg->K;      /* K itself is a multiple of per_unit here */
 	}
@@ -222,7 +225,7 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 		CU(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
 		CU(cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
 	}
-	const size_t wf_floats = (size_t)cfg->nstreams * c->ngrp * c->taps_pad * CH_GROUP * (c->real_input ? 2 : 4);
+	const size_t wf_floats = (size_t)cfg->nstreams * c->ngrp * c->taps_pad * CH_GROUP * (c->in_kind == IN_KIND_F32REAL ? 2 : 4);
 	CU(cudaMalloc(&c->d_wf4, wf_floats * sizeof(float)));
 	CU(cudaMemset(c->d_wf4, 0, wf_floats * sizeof(float)));
 	c->dm_floats = (size_t)cfg->nstreams * cfg->max_blocks * OUTBLK * cfg->nch;
@@ -309,7 +312,7 @@ extern "C" int acb_set_wf(acb_ctx_t *c, int stream, const float *wf, int nch)
 	if (stream < 0 || stream >= c->cfg.nstreams || nch != c->cfg.nch) return fail(ACB_ERR_ARG, "stream/nch mismatch");
 	if (int r = ctx_use(c)) return r;
 	const int T = c->taps, TP = c->taps_pad;      /* taps beyond T keep zero weights: D + (+0) = D */
-	const int W = c->real_input ? 2 : 4;
+	const int W = c->in_kind == IN_KIND_F32REAL ? 2 : 4;
 	std::vector<float> t((size_t)c->ngrp * TP * CH_GROUP * W, 0.0f);
 	for (int ch = 0; ch < nch; ch++) {
 		const int g = ch / CH_GROUP, cc = ch % CH_GROUP;
@@ -317,7 +320,7 @@ extern "C" int acb_set_wf(acb_ctx_t *c, int stream, const float *wf, int nch)
 			const float re = wf[((size_t)ch * T + ind) * 2], im = wf[((size_t)ch * T + ind) * 2 + 1];
 			float *o = &t[(((size_t)g * TP + ind) * CH_GROUP + cc) * W];
 			o[0] = re; o[1] = im;
-			if (!c->real_input) { o[2] = -im; o[3] = re; }    /* (c, d, -d, c): see cmac() */
+			if (W == 4) { o[2] = -im; o[3] = re; }            /* (c, d, -d, c): see cmac() */
 		}
 	}
 	if (int r = sync_streams(c)) return r;
@@ -329,7 +332,7 @@ extern "C" int acb_set_plan(acb_ctx_t *c, int stream, const unsigned *freqs_hz, 
 {
 	if (!c || !freqs_hz) return fail(ACB_ERR_ARG, "null argument");
 	if (nch != c->cfg.nch) return fail(ACB_ERR_ARG, "nch mismatch");
-	if (c->real_input) return fail(ACB_ERR_ARG, "real-input context: use acb_set_plan_air");
+	if (c->real_input) return fail(ACB_ERR_ARG, "not a u8-IQ context: use acb_set_plan_air / acb_set_plan_cs16");
 	if (c->taps != c->cfg.K) return fail(ACB_ERR_ARG, "taps != K: the reference planner builds K-tap tables; supply yours with acb_set_wf");
 	const unsigned fc = acb_choose_fc(freqs_hz, nch, c->cfg.K);
 	if (fc == 0) return fail(ACB_ERR_PLAN, "Frequencies too far apart");    /* rtl.c:149-152 */
@@ -455,23 +458,16 @@ static int run_kernels(acb_ctx *c, const uint8_t *d_iq, size_t stride, int nblk,
 		if (c->dm_used[b]) CU(cudaStreamWaitEvent(c->s_comp, c->ev_dm_free[b], 0));
 		CU(cudaEventRecord(t.ev.a, c->s_comp));
 		int r = 0;
-		if (c->real_input) {
-			/* whole 1024-row blocks through the pipeline kernel, the remaining rows (a real-input
-			 * submit may carry any number of samples) through the generic one */
-			const int fast = c->use_generic ? 0 : nsamp / OUTBLK;
-			if (fast) {
-				r = launch_channelize_real((const float *)d_iq, stride, c->d_wf4, dmbuf, c->cfg.K, c->taps_pad, c->cfg.nch, c->cfg.nstreams, fast, (size_t)nsamp, c->s_comp);
-				c->stats.kernel_launches++;
-			}
-			if (!r && nsamp > fast * OUTBLK) {
-				r = launch_channelize_generic(true, d_iq, stride, c->d_wf4, dmbuf, c->cfg.K, c->taps_pad, c->cfg.nch, c->cfg.nstreams,
-				                              (size_t)fast * OUTBLK, (size_t)nsamp - (size_t)fast * OUTBLK, (size_t)nsamp, c->s_comp);
-				c->stats.kernel_launches++;
-			}
-		} else {
-			r = c->use_generic
-			        ? launch_channelize_generic(false, d_iq, stride, c->d_wf4, dmbuf, c->cfg.K, c->taps_pad, c->cfg.nch, c->cfg.nstreams, 0, (size_t)nsamp, (size_t)nsamp, c->s_comp)
-			        : launch_channelize(d_iq, stride, c->d_wf4, dmbuf, c->cfg.K, c->taps_pad, c->cfg.nch, c->cfg.nstreams, nblk, c->s_comp);
+		/* whole 1024-row blocks through the pipeline kernel, the remaining rows (submits of 4-byte
+		 * samples may carry any count) and unaligned K through the generic one */
+		const int fast = c->use_generic ? 0 : nsamp / OUTBLK;
+		if (fast) {
+			r = launch_channelize(c->in_kind, d_iq, stride, c->d_wf4, dmbuf, c->cfg.K, c->taps_pad, c->cfg.nch, c->cfg.nstreams, fast, (size_t)nsamp, c->s_comp);
+			c->stats.kernel_launches++;
+		}
+		if (!r && nsamp > fast * OUTBLK) {
+			r = launch_channelize_generic(c->in_kind, d_iq, stride, c->d_wf4, dmbuf, c->cfg.K, c->taps_pad, c->cfg.nch, c->cfg.nstreams,
+			                              (size_t)fast * OUTBLK, (size_t)nsamp - (size_t)fast * OUTBLK, (size_t)nsamp, c->s_comp);
 			c->stats.kernel_launches++;
 		}
 		if (r) return fail(ACB_ERR_CUDA, "channelizer launch: %s", cudaGetErrorString((cudaError_t)r));
@@ -509,7 +505,7 @@ static int run_kernels(acb_ctx *c, const uint8_t *d_iq, size_t stride, int nblk,
 static int check_blocks(acb_ctx *c, const void *p, size_t stride, int nblk)
 {
 	if (!c || !p) return fail(ACB_ERR_ARG, "null argument");
-	if (c->real_input) return fail(ACB_ERR_ARG, "real-input context: use acb_submit_real_host");
+	if (c->real_input) return fail(ACB_ERR_ARG, "not a u8-IQ context: use acb_submit_real_host / acb_submit_cs16_host");
 	if (nblk < 1 || nblk > c->cfg.max_blocks) return fail(ACB_ERR_ARG, "nblk=%d outside 1..%d", nblk, c->cfg.max_blocks);
 	if (c->cfg.nstreams > 1 && stride < (size_t)nblk * c->blk_bytes) return fail(ACB_ERR_ARG, "stream_stride smaller than one stream's input");
 	if (stride % 16) return fail(ACB_ERR_ARG, "stream_stride must be a multiple of 16 bytes");
@@ -559,10 +555,11 @@ extern "C" int acb_submit_host(acb_ctx_t *c, const uint8_t *iq, size_t stride, i
 	return ACB_OK;
 }
 
-extern "C" int acb_submit_real_host(acb_ctx_t *c, const float *x, size_t stride_samples, size_t nsamples)
+/* 4-byte samples (float32 real or int16 I,Q) of arbitrary count: appended behind the carried
+ * remainder in d_real[b]; `x2` != NULL means planar int16 input (x = I plane, x2 = Q plane), which
+ * two strided copies interleave on the way to the device */
+static int submit4(acb_ctx *c, const void *x, const void *x2, size_t stride_samples, size_t nsamples)
 {
-	if (!c || !x) return fail(ACB_ERR_ARG, "null argument");
-	if (!c->real_input) return fail(ACB_ERR_ARG, "context was not created with ACB_FLAG_REAL_INPUT");
 	if (int r = ctx_use(c)) return r;
 	const size_t K = (size_t)c->cfg.K, total = c->carry + nsamples;
 	const size_t nout = total / K;
@@ -571,18 +568,26 @@ extern "C" int acb_submit_real_host(acb_ctx_t *c, const float *x, size_t stride_
 	if (c->cfg.nstreams > 1 && stride_samples < nsamples) return fail(ACB_ERR_ARG, "stream stride smaller than one stream's input");
 	const int b = c->real_buf;
 	/* d_real[b] was last read by the channelizer two submits ago (its carry has been copied on);
-	 * everything below is stream-ordered on the channelizer stream, the copy included */
+	 * everything below is stream-ordered on the channelizer stream, the copies included */
 	float *buf = c->d_real[b];
-	CU(cudaMemcpy2DAsync(buf + c->carry, c->real_cap * sizeof(float), x, stride_samples * sizeof(float),
-	                     nsamples * sizeof(float), c->cfg.nstreams, cudaMemcpyHostToDevice, c->s_comp));
+	if (!x2) {
+		CU(cudaMemcpy2DAsync(buf + c->carry, c->real_cap * sizeof(float), x, stride_samples * sizeof(float),
+		                     nsamples * sizeof(float), c->cfg.nstreams, cudaMemcpyHostToDevice, c->s_comp));
+	} else {
+		for (int s = 0; s < c->cfg.nstreams; s++) {
+			char *dst = (char *)(buf + (size_t)s * c->real_cap + c->carry);
+			CU(cudaMemcpy2DAsync(dst, 4, (const char *)x + (size_t)s * stride_samples * 2, 2, 2, nsamples, cudaMemcpyHostToDevice, c->s_comp));
+			CU(cudaMemcpy2DAsync(dst + 2, 4, (const char *)x2 + (size_t)s * stride_samples * 2, 2, 2, nsamples, cudaMemcpyHostToDevice, c->s_comp));
+		}
+	}
 	const size_t rem = total - nout * K;
 	if (nout) {
 		if (int r = run_kernels(c, (const uint8_t *)buf, c->real_cap * sizeof(float), 0, (int)nout, nullptr,
 		                        std::vector<unsigned long long>{ c->pos }))
 			return r;
 		c->pos += nout;
-		/* the unconsumed tail (air.c:329-334 keeps a partial sum instead: same arithmetic order)
-		 * moves to the front of the other buffer */
+		/* the unconsumed tail (air.c:329-334 / soapy.c:238-252 keep a partial sum instead: same
+		 * arithmetic order) moves to the front of the other buffer */
 		if (rem)
 			CU(cudaMemcpy2DAsync(c->d_real[b ^ 1], c->real_cap * sizeof(float), buf + nout * K, c->real_cap * sizeof(float),
 			                     rem * sizeof(float), c->cfg.nstreams, cudaMemcpyDeviceToDevice, c->s_comp));
@@ -592,10 +597,45 @@ extern "C" int acb_submit_real_host(acb_ctx_t *c, const float *x, size_t stride_
 	return (int)nout;
 }
 
+extern "C" int acb_submit_real_host(acb_ctx_t *c, const float *x, size_t stride_samples, size_t nsamples)
+{
+	if (!c || !x) return fail(ACB_ERR_ARG, "null argument");
+	if (c->in_kind != IN_KIND_F32REAL) return fail(ACB_ERR_ARG, "context was not created with ACB_FLAG_REAL_INPUT");
+	return submit4(c, x, nullptr, stride_samples, nsamples);
+}
+
+extern "C" int acb_submit_cs16_host(acb_ctx_t *c, const int16_t *iq, size_t stride_samples, size_t nsamples)
+{
+	if (!c || !iq) return fail(ACB_ERR_ARG, "null argument");
+	if (c->in_kind != IN_KIND_CS16IQ) return fail(ACB_ERR_ARG, "context was not created with ACB_FLAG_CS16_INPUT");
+	return submit4(c, iq, nullptr, stride_samples, nsamples);
+}
+
+extern "C" int acb_submit_cs16_planar_host(acb_ctx_t *c, const int16_t *xi, const int16_t *xq, size_t stride_samples, size_t nsamples)
+{
+	if (!c || !xi || !xq) return fail(ACB_ERR_ARG, "null argument");
+	if (c->in_kind != IN_KIND_CS16IQ) return fail(ACB_ERR_ARG, "context was not created with ACB_FLAG_CS16_INPUT");
+	return submit4(c, xi, xq, stride_samples, nsamples);
+}
+
+extern "C" int acb_set_plan_cs16(acb_ctx_t *c, int stream, const unsigned *freqs_hz, int nch, int variant, unsigned fc_hz, unsigned *fc_out)
+{
+	if (!c || !freqs_hz) return fail(ACB_ERR_ARG, "null argument");
+	if (c->in_kind != IN_KIND_CS16IQ || nch != c->cfg.nch) return fail(ACB_ERR_ARG, "not a CS16 context / nch mismatch");
+	if (c->taps != c->cfg.K) return fail(ACB_ERR_ARG, "taps != K: supply the tables with acb_set_wf");
+	if (variant != ACB_CS16_SOAPY && variant != ACB_CS16_SDRPLAY) return fail(ACB_ERR_ARG, "unknown CS16 variant");
+	const unsigned fc = fc_hz ? fc_hz : acb_choose_fc(freqs_hz, nch, c->cfg.K);      /* soapy.c:132-136, sdrplay.c:124 */
+	if (fc == 0) return fail(ACB_ERR_PLAN, "Frequencies too far apart");
+	std::vector<float> wf((size_t)nch * c->cfg.K * 2);
+	for (int ch = 0; ch < nch; ch++) acb_cs16_build_wf(variant, freqs_hz[ch], fc, c->cfg.K, &wf[(size_t)ch * c->cfg.K * 2]);
+	if (fc_out) *fc_out = fc;
+	return acb_set_wf(c, stream, wf.data(), nch);
+}
+
 extern "C" int acb_set_plan_air(acb_ctx_t *c, int stream, const unsigned *freqs_hz, int nch, unsigned *fc_out)
 {
 	if (!c || !freqs_hz) return fail(ACB_ERR_ARG, "null argument");
-	if (!c->real_input || nch != c->cfg.nch) return fail(ACB_ERR_ARG, "not a real-input context / nch mismatch");
+	if (c->in_kind != IN_KIND_F32REAL || nch != c->cfg.nch) return fail(ACB_ERR_ARG, "not a real-input context / nch mismatch");
 	if (c->taps != c->cfg.K) return fail(ACB_ERR_ARG, "taps != K: supply the tables with acb_set_wf");
 	unsigned lo = freqs_hz[0], hi = freqs_hz[0];
 	for (int i = 1; i < nch; i++) { lo = std::min(lo, freqs_hz[i]); hi = std::max(hi, freqs_hz[i]); }

@@ -106,6 +106,28 @@ extern "C" void acb_air_build_wf(int fr_hz, int fc_hz, unsigned rate, float *wf)
 	}
 }
 
+extern "C" void acb_cs16_build_wf(int variant, unsigned freq_hz, unsigned fc_hz, int K, float *wf)
+{
+	/* soapy.c:159-162 / sdrplay.c:133-137: oscillator[ind] = cexpf(-j*phase*ind)/K, where the
+	 * per-tap phase is a FLOAT product in soapy.c (float AMFreq) and a DOUBLE product rounded to
+	 * float by cexpf's argument conversion in sdrplay.c (double correctionPhase); channel[].Fr is a
+	 * float in both.  What the kernel needs on top is folded in exactly (powers of two commute with
+	 * every rounding here): soapy.c:242 divides each product by 32768.0 before accumulating, and
+	 * sdrplay.c:225 divides the envelope by 4. */
+	const float fr = (float)freq_hz;
+	const float rate = (float)(ACB_INTRATE * K);
+	const double dstep = (fr - (float)fc_hz) / rate * 2.0 * M_PI;
+	const float fstep = (float)dstep;
+	const float scale = variant == ACB_CS16_SOAPY ? 1.0f / 32768.0f : 0.25f;
+	for (int ind = 0; ind < K; ind++) {
+		const float ph = variant == ACB_CS16_SOAPY ? fstep * (float)ind : (float)(dstep * ind);
+		float sn, cs;
+		sincosf(-ph, &sn, &cs);
+		wf[2 * ind] = cs / (float)K * scale;
+		wf[2 * ind + 1] = sn / (float)K * scale;
+	}
+}
+
 extern "C" void acb_build_h(float *h)
 {
 	/* msk.c:44-48: cos(2*pi*600/INTRATE/12 * (i - 66)) evaluated by cosf on the float-rounded

@@ -1,9 +1,9 @@
 /*
  * CUDA kernels of the acarsdec hot path for sm_100a.
  *
- *  K1  k_channelize<REAL> : u8 IQ (or float32 real samples) -> per-channel NCO mix x boxcar(K)
- *                     -> decimate by K -> |.|  (reference: in_callback, rtl.c:334-354; REAL:
- *                     rx_callback, air.c:291-341).  FP32-issue bound by the
+ *  K1  k_channelize<MODE> : u8 IQ / float32 real / CS16 IQ samples -> per-channel NCO mix x
+ *                     boxcar(K) -> decimate by K -> |.|  (reference: in_callback rtl.c:334-354;
+ *                     rx_callback air.c:291-341; soapy.c:232-254, sdrplay.c:215-236).  FP32-issue bound by the
  *                     reference's rounding sequence: every complex MAC is 4 rounded products
  *                     and 4 rounded sums in tap order, no FMA contraction — reproduced exactly
  *                     (packed FMUL2/FADD2 where ptxas keeps them unfused) so dm is bit-identical
@@ -83,29 +83,36 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
  * (5 is odd: the strided LDS.128 row reads are conflict free without padding) staged by
  * cp.async into a 2-deep ring together with the matching slice of the table, so the copy of
  * chunk i+1 runs under the arithmetic of chunk i.  Any K that keeps rows 16-byte aligned, up to
- * ACB_MAXK.  REAL selects the air.c front-end arithmetic: float32 real samples, D += wf[i]*S
- * (air.c:314-333), table entries (c, d); otherwise u8 IQ, entries (c, d, -d, c) (rtl.c:334-354).
+ * ACB_MAXK.  MODE: u8 IQ with table entries (c, d, -d, c) (rtl.c:334-354); float32 real samples,
+ * D += wf[i]*S, entries (c, d) (air.c:314-333); CS16 IQ, same complex MAC as u8 on (float)int16
+ * (soapy.c:239-242 with the /32768.0 folded into the table, sdrplay.c:218-222).
  * ---------------------------------------------------------------------------------------- */
 
 constexpr int C2_ROWS = 256;
-#ifndef C2_REAL_UNITS
-#define C2_REAL_UNITS 5
-#endif
-#ifndef C2_REAL_STAGES
-#define C2_REAL_STAGES 2
-#endif
+enum { IN_U8IQ = 0, IN_F32REAL = 1, IN_CS16IQ = 2 };   /* input sample formats (acb_internal.h: InputKind) */
 
-template <bool REAL> struct C2 {
-	static constexpr int UNITS = REAL ? C2_REAL_UNITS : 5;      /* 16-byte units of a row per chunk: odd */
-	static constexpr int STAGES = REAL ? C2_REAL_STAGES : 2;     /* cp.async ring depth */
-	static constexpr int TAP_BYTES = REAL ? 4 : 2;               /* input bytes per tap */
+template <int MODE> struct C2 {
+	static constexpr int UNITS = 5;                              /* 16-byte units of a row per chunk: odd */
+	static constexpr int STAGES = 2;                             /* cp.async ring depth */
+	static constexpr int TAP_BYTES = MODE == IN_U8IQ ? 2 : 4;    /* input bytes per tap */
 	static constexpr int TAPS_PER_UNIT = 16 / TAP_BYTES;
-	static constexpr int W_BYTES = REAL ? 8 : 16;                /* table bytes per (tap, channel) */
+	static constexpr int W_BYTES = MODE == IN_F32REAL ? 8 : 16;  /* table bytes per (tap, channel) */
 	static constexpr int CHUNK_TAPS = UNITS * TAPS_PER_UNIT;
 	static constexpr int TILE_BYTES = C2_ROWS * UNITS * 16;
 	static constexpr int WF_BYTES = CHUNK_TAPS * CH_GROUP * W_BYTES;
 	static constexpr int STAGE_BYTES = TILE_BYTES + WF_BYTES;
 };
+
+/* (float)int16 for both halves of a CS16 sample (soapy.c:239-240, sdrplay.c:218-219): x ^ 0x8000
+ * planted in the mantissa of 2^23, then 2^23 + 2^15 removed — exact */
+__device__ __forceinline__ float2 cvt_cs16(unsigned w)
+{
+	const unsigned v = w ^ 0x80008000u;
+	float2 x;
+	x.x = __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7410));
+	x.y = __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7432));
+	return __fadd2_rn(x, make_float2(-8421376.0f, -8421376.0f));
+}
 
 /* air.c:317-318: D += wf[i] * S — (c*S, d*S) rounded, then the accumulate rounded.  Scalar
  * products + packed add: ptxas leaves that pair unfused (it contracts FMUL2 -> FADD2). */
@@ -114,12 +121,12 @@ __device__ __forceinline__ void rmac(float2 &acc, float sv, const float2 w)
 	acc = __fadd2_rn(acc, make_float2(__fmul_rn(w.x, sv), __fmul_rn(w.y, sv)));
 }
 
-template <bool REAL>
+template <int MODE>
 __global__ void __launch_bounds__(CH_TILE)
 k_channelize(const uint8_t *__restrict__ in, size_t stream_stride, const uint8_t *__restrict__ wf,
               float *__restrict__ dm, int K, int taps, int nch, int ngrp, size_t nsamp)
 {
-	using T = C2<REAL>;
+	using T = C2<MODE>;
 	extern __shared__ __align__(16) unsigned char smem[];
 	const int t = threadIdx.x;
 	const int blk = blockIdx.x, s = blockIdx.y;
@@ -183,7 +190,7 @@ k_channelize(const uint8_t *__restrict__ in, size_t stream_stride, const uint8_t
 			for (int j = 0; j < uc; j++) {
 				const uint4 qa = rowA[j], qb = rowB[j];
 				const unsigned wa[4] = { qa.x, qa.y, qa.z, qa.w }, wb[4] = { qb.x, qb.y, qb.z, qb.w };
-				if (REAL) {
+				if (MODE == IN_F32REAL) {
 					const float2 *wj = reinterpret_cast<const float2 *>(st + T::TILE_BYTES) + (size_t)j * 4 * CH_GROUP;
 #pragma unroll
 					for (int e = 0; e < 4; e++) {
@@ -193,6 +200,18 @@ k_channelize(const uint8_t *__restrict__ in, size_t stream_stride, const uint8_t
 							const float2 w = wj[e * CH_GROUP + c];
 							rmac(accA[c], sa, w);
 							rmac(accB[c], sb, w);
+						}
+					}
+				} else if (MODE == IN_CS16IQ) {
+					const float4 *wj = reinterpret_cast<const float4 *>(st + T::TILE_BYTES) + (size_t)j * 4 * CH_GROUP;
+#pragma unroll
+					for (int e = 0; e < 4; e++) {
+						const float2 xa = cvt_cs16(wa[e]), xb = cvt_cs16(wb[e]);
+#pragma unroll
+						for (int c = 0; c < CH_GROUP; c++) {
+							const float4 w = wj[e * CH_GROUP + c];
+							cmac(accA[c], xa.x, xa.y, w);
+							cmac(accB[c], xb.x, xb.y, w);
 						}
 					}
 				} else {
@@ -236,44 +255,47 @@ k_channelize(const uint8_t *__restrict__ in, size_t stream_stride, const uint8_t
 	}
 }
 
-size_t channelize_smem_bytes(bool real)
+size_t channelize_smem_bytes(int mode)
 {
-	return real ? (size_t)C2<true>::STAGES * C2<true>::STAGE_BYTES : (size_t)C2<false>::STAGES * C2<false>::STAGE_BYTES;
+	return mode == IN_F32REAL ? (size_t)C2<IN_F32REAL>::STAGES * C2<IN_F32REAL>::STAGE_BYTES
+	                          : (size_t)C2<IN_U8IQ>::STAGES * C2<IN_U8IQ>::STAGE_BYTES;    /* cs16 == u8 layout */
 }
 
-template <bool REAL>
-static int launch_channelize_t(const uint8_t *in, size_t stream_stride, const void *wf, float *dm,
-                                int K, int taps, int nch, int nstreams, int nblk, size_t nsamp, cudaStream_t stream)
+template <int MODE>
+static int launch_channelize_t(const void *in, size_t stream_stride, const void *wf, float *dm,
+                               int K, int taps, int nch, int nstreams, int nblk, size_t nsamp, cudaStream_t stream)
 {
 	if (nblk == 0) return 0;
 	const int ngrp = (nch + CH_GROUP - 1) / CH_GROUP;
-	const size_t smem = channelize_smem_bytes(REAL);
-	cudaError_t e = cudaFuncSetAttribute(k_channelize<REAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	const size_t smem = (size_t)C2<MODE>::STAGES * C2<MODE>::STAGE_BYTES;
+	cudaError_t e = cudaFuncSetAttribute(k_channelize<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return (int)e;
-	e = cudaFuncSetAttribute(k_channelize<REAL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+	/* both kernels ask for the largest shared-memory carve-out: an SM's L1/shared split only
+	 * changes when the SM is idle, so kernels that prefer different splits cannot be co-resident
+	 * — and the demod of submit i is meant to run underneath the channelizer of submit i+1 */
+	e = cudaFuncSetAttribute(k_channelize<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 	if (e != cudaSuccess) return (int)e;
 	dim3 grid(nblk, nstreams, ngrp);
-	k_channelize<REAL><<<grid, CH_TILE, smem, stream>>>(in, stream_stride, reinterpret_cast<const uint8_t *>(wf), dm, K, taps, nch, ngrp, nsamp);
+	k_channelize<MODE><<<grid, CH_TILE, smem, stream>>>(reinterpret_cast<const uint8_t *>(in), stream_stride,
+	                                                    reinterpret_cast<const uint8_t *>(wf), dm, K, taps, nch, ngrp, nsamp);
 	return (int)cudaGetLastError();
 }
 
-int launch_channelize(const uint8_t *iq, size_t stream_stride, const float *wf4, float *dm,
-                      int K, int taps, int nch, int nstreams, int nblk, cudaStream_t stream)
+/* whole 1024-row blocks of any input kind; the caller sends remaining rows to the generic kernel */
+int launch_channelize(int mode, const void *in, size_t stream_stride_bytes, const float *wf, float *dm,
+                      int K, int taps, int nch, int nstreams, int nblk, size_t nsamp, cudaStream_t stream)
 {
-	return launch_channelize_t<false>(iq, stream_stride, wf4, dm, K, taps, nch, nstreams, nblk, (size_t)nblk * OUTBLK, stream);
-}
-
-/* float32 real input: whole 1024-row blocks here, the caller sends the remaining rows to the generic kernel */
-int launch_channelize_real(const float *samples, size_t stream_stride_bytes, const float *wf2, float *dm,
-                           int K, int taps, int nch, int nstreams, int nblk, size_t nsamp, cudaStream_t stream)
-{
-	return launch_channelize_t<true>(reinterpret_cast<const uint8_t *>(samples), stream_stride_bytes, wf2, dm, K, taps, nch, nstreams, nblk, nsamp, stream);
+	switch (mode) {
+	case IN_F32REAL: return launch_channelize_t<IN_F32REAL>(in, stream_stride_bytes, wf, dm, K, taps, nch, nstreams, nblk, nsamp, stream);
+	case IN_CS16IQ: return launch_channelize_t<IN_CS16IQ>(in, stream_stride_bytes, wf, dm, K, taps, nch, nstreams, nblk, nsamp, stream);
+	default: return launch_channelize_t<IN_U8IQ>(in, stream_stride_bytes, wf, dm, K, taps, nch, nstreams, nblk, nsamp, stream);
+	}
 }
 
 /* Rows the pipeline kernel does not take (K that breaks 16-byte row alignment; the < 1024 rows
  * left over by a real-input submit of arbitrary length): one thread per (output, channel),
  * straight from global memory, same arithmetic.  Correctness path, not tuned. */
-template <bool REAL>
+template <int MODE>
 __global__ void __launch_bounds__(128)
 k_channelize_generic(const uint8_t *__restrict__ in, size_t stream_stride, const uint8_t *__restrict__ wf,
                      float *__restrict__ dm, int K, int taps, int nch, int ngrp, size_t row0, size_t nrows, size_t nsamp)
@@ -284,13 +306,22 @@ k_channelize_generic(const uint8_t *__restrict__ in, size_t stream_stride, const
 	const size_t m = row0 + gid / nch;
 	const int ch = (int)(gid % nch);
 	float dr = 0.f, di = 0.f;
-	if (REAL) {
+	if (MODE == IN_F32REAL) {
 		const float *p = reinterpret_cast<const float *>(in + (size_t)s * stream_stride) + m * K;
 		const float2 *w = reinterpret_cast<const float2 *>(wf) + ((size_t)s * ngrp + ch / CH_GROUP) * taps * CH_GROUP + (ch % CH_GROUP);
 		for (int i = 0; i < taps; i++) {
 			const float2 ww = w[(size_t)i * CH_GROUP];
 			dr = __fadd_rn(dr, __fmul_rn(ww.x, p[i]));
 			di = __fadd_rn(di, __fmul_rn(ww.y, p[i]));
+		}
+	} else if (MODE == IN_CS16IQ) {
+		const short *p = reinterpret_cast<const short *>(in + (size_t)s * stream_stride) + m * K * 2;
+		const float4 *w = reinterpret_cast<const float4 *>(wf) + ((size_t)s * ngrp + ch / CH_GROUP) * taps * CH_GROUP + (ch % CH_GROUP);
+		for (int ind = 0; ind < taps; ind++) {
+			const float a = (float)p[2 * ind], b = (float)p[2 * ind + 1];
+			const float4 ww = w[(size_t)ind * CH_GROUP];
+			dr = __fadd_rn(dr, __fadd_rn(__fmul_rn(a, ww.x), __fmul_rn(b, ww.z)));
+			di = __fadd_rn(di, __fadd_rn(__fmul_rn(a, ww.y), __fmul_rn(b, ww.w)));
 		}
 	} else {
 		const uint8_t *p = in + (size_t)s * stream_stride + m * K * 2;
@@ -307,17 +338,17 @@ k_channelize_generic(const uint8_t *__restrict__ in, size_t stream_stride, const
 	dm[((size_t)s * nsamp + m) * nch + ch] = envelope(make_float2(dr, di));
 }
 
-int launch_channelize_generic(bool real, const void *in, size_t stream_stride, const void *wf, float *dm,
+int launch_channelize_generic(int mode, const void *in, size_t stream_stride, const void *wf, float *dm,
                               int K, int taps, int nch, int nstreams, size_t row0, size_t nrows, size_t nsamp, cudaStream_t stream)
 {
 	if (nrows == 0) return 0;
 	const int ngrp = (nch + CH_GROUP - 1) / CH_GROUP;
 	const size_t total = nrows * nch;
 	dim3 grid((unsigned)((total + 127) / 128), nstreams);
-	if (real)
-		k_channelize_generic<true><<<grid, 128, 0, stream>>>((const uint8_t *)in, stream_stride, (const uint8_t *)wf, dm, K, taps, nch, ngrp, row0, nrows, nsamp);
-	else
-		k_channelize_generic<false><<<grid, 128, 0, stream>>>((const uint8_t *)in, stream_stride, (const uint8_t *)wf, dm, K, taps, nch, ngrp, row0, nrows, nsamp);
+	const uint8_t *i8 = (const uint8_t *)in, *w8 = (const uint8_t *)wf;
+	if (mode == IN_F32REAL) k_channelize_generic<IN_F32REAL><<<grid, 128, 0, stream>>>(i8, stream_stride, w8, dm, K, taps, nch, ngrp, row0, nrows, nsamp);
+	else if (mode == IN_CS16IQ) k_channelize_generic<IN_CS16IQ><<<grid, 128, 0, stream>>>(i8, stream_stride, w8, dm, K, taps, nch, ngrp, row0, nrows, nsamp);
+	else k_channelize_generic<IN_U8IQ><<<grid, 128, 0, stream>>>(i8, stream_stride, w8, dm, K, taps, nch, ngrp, row0, nrows, nsamp);
 	return (int)cudaGetLastError();
 }
 

@@ -222,3 +222,21 @@ def render_real(plan: StreamPlan, n0: int, nsamples: int, *, scale: float = 1.0 
     rng = np.random.default_rng([plan.seed, 0xA1, n0])
     x += rng.standard_normal(nsamples) * plan.noise_sigma
     return (x * scale).astype(np.float32)
+
+
+def render_cs16(plan: StreamPlan, n0: int, nsamples: int, *, gain: float = 64.0) -> np.ndarray:
+    """int16 (nsamples, 2) I,Q for the SoapySDR / SDRplay front-ends: the same complex baseband as
+    render_blocks (before u8 quantisation), scaled by `gain` LSB per unit and rounded."""
+    fs = plan.rate
+    x = np.zeros(nsamples, dtype=np.complex128)
+    for b in plan.bursts:
+        r = burst_samples(plan, b, n0, n0 + nsamples)
+        if r is not None:
+            lo, hi, v = r
+            x[lo - n0:hi - n0] += v
+    rng = np.random.default_rng([plan.seed, 0xC5, n0])
+    g = rng.standard_normal(2 * nsamples) * plan.noise_sigma
+    out = np.empty((nsamples, 2), dtype=np.float64)
+    out[:, 0] = x.real + g[0::2]
+    out[:, 1] = x.imag + g[1::2]
+    return np.clip(np.floor(out * gain + 0.5), -32768, 32767).astype(np.int16)

@@ -55,6 +55,8 @@ typedef struct {
 } acb_config_t;
 
 #define ACB_FLAG_NO_INPUT_STAGING 1   /* caller only uses acb_submit_device / acb_submit_dm_* */
+#define ACB_FLAG_CS16_INPUT 4         /* SoapySDR / SDRplay front-ends (soapy.c, sdrplay.c): int16 I,Q samples;
+                                         use acb_set_plan_cs16 / acb_submit_cs16_host (or _planar_host) */
 #define ACB_FLAG_REAL_INPUT 2         /* Airspy front-end (air.c): float32 REAL samples at IF = rate/4,
                                          rate = K*12500; use acb_set_plan_air / acb_submit_real_host */
 
@@ -102,6 +104,11 @@ void acb_build_wf(int fr_stored, unsigned fc_hz, int K, float *wf);
 unsigned acb_air_choose_fc(unsigned min_hz, unsigned max_hz);
 /* air.c:263-285 — wf[i] = cexpf(-j*Ph_i)/AIRMULT with the reference's double phase accumulator */
 void acb_air_build_wf(int fr_hz, int fc_hz, unsigned rate, float *wf);
+/* soapy.c:159-162 (variant ACB_CS16_SOAPY, with soapy.c:242's /32768.0 folded in) and
+ * sdrplay.c:133-137 (ACB_CS16_SDRPLAY, with sdrplay.c:225's /4 folded in): effective mixer tables */
+#define ACB_CS16_SOAPY 0
+#define ACB_CS16_SDRPLAY 1
+void acb_cs16_build_wf(int variant, unsigned freq_hz, unsigned fc_hz, int K, float *wf);
 /* msk.c:44-48 — 133-tap oversampled half-cosine matched filter */
 void acb_build_h(float *h);
 
@@ -117,6 +124,9 @@ const char *acb_version(void);
 int acb_set_plan(acb_ctx_t *ctx, int stream, const unsigned *freqs_hz, int nch, unsigned *fc_out);
 /* The channel part of initAirspy (air.c:165-285) for a real-input context. */
 int acb_set_plan_air(acb_ctx_t *ctx, int stream, const unsigned *freqs_hz, int nch, unsigned *fc_out);
+/* The channel part of initSoapy (soapy.c:112-163) / initSdrplay (sdrplay.c:95-138) for a CS16
+ * context; fc_hz = 0 lets chooseFc pick the centre (soapy.c:132-133 honours a user frequency). */
+int acb_set_plan_cs16(acb_ctx_t *ctx, int stream, const unsigned *freqs_hz, int nch, int variant, unsigned fc_hz, unsigned *fc_out);
 /* Same, with caller-supplied tables (nch x 2K floats), e.g. taken from channel[].wf. */
 int acb_set_wf(acb_ctx_t *ctx, int stream, const float *wf, int nch);
 /* initMsk + initAcars for every channel of every stream (msk.c:30-51, acars.c:230-234). */
@@ -136,6 +146,11 @@ int acb_submit_device(acb_ctx_t *ctx, const uint8_t *iq_dev, size_t stream_strid
  * carried to the next call, the equivalent of the reference's carried partial sum ch->D / ind.
  * Returns the number of envelope samples produced per channel (>= 0) or a negative error. */
 int acb_submit_real_host(acb_ctx_t *ctx, const float *x, size_t stream_stride_samples, size_t nsamples);
+/* Replaces the channelizer loops of soapy.c:232-254 (interleaved CS16) and sdrplay.c:215-236
+ * (planar xi/xq): `nsamples` complex int16 samples per stream, any count per call, remainder
+ * carried (the reference carries ch->D and the tap index).  Returns envelope samples produced. */
+int acb_submit_cs16_host(acb_ctx_t *ctx, const int16_t *iq, size_t stream_stride_samples, size_t nsamples);
+int acb_submit_cs16_planar_host(acb_ctx_t *ctx, const int16_t *xi, const int16_t *xq, size_t stream_stride_samples, size_t nsamples);
 /* Replaces demodMSK's input side (msk.c:67; soundfile.c:71-77): 12.5 kS/s envelope samples,
  * dm[(s*nsamp + n)*nch + c], fed straight to the demodulator (no channelizer). */
 int acb_submit_dm_host(acb_ctx_t *ctx, const float *dm, int nsamp);

@@ -193,6 +193,53 @@ void orc_channelize_real(const float *x, int nout, int K, int nch, const float *
 	}
 }
 
+/* ------------------------------------------------------------------ CS16 front-ends */
+
+/* soapy.c:159-162 (float per-tap phase) / sdrplay.c:133-137 (double per-tap phase, rounded to
+ * float by cexpf's argument); channel[].Fr is a float in both */
+void orc_cs16_build_osc(int variant, unsigned freq_hz, unsigned fc, int K, float *osc)
+{
+	float fr = (float)freq_hz;
+	double dstep = (fr - (float)fc) / (float)(ORC_INTRATE * K) * 2.0 * M_PI;
+	float fstep = (float)dstep;
+	for (int ind = 0; ind < K; ind++) {
+		float sn, cs;
+		if (variant == 0) sincosf(-(fstep * ind), &sn, &cs);
+		else sincosf((float)-(dstep * ind), &sn, &cs);
+		osc[2 * ind] = cs / (float)K;
+		osc[2 * ind + 1] = sn / (float)K;
+	}
+}
+
+/* soapy.c:238-243: D += v * osc[ind] / 32768.0 — the float complex product is widened to double,
+ * divided, added to D in double and the sum stored back to float.  sdrplay.c:218-225: D += v*osc in
+ * float, envelope cabsf(D)/4.  The references carry D and ind across reads: same operation order. */
+void orc_channelize_cs16(int variant, const int16_t *iq, int nout, int K, int nch, const float *osc, float *dm)
+{
+	for (int m = 0; m < nout; m++) {
+		const int16_t *p = iq + (size_t)m * K * 2;
+		for (int ch = 0; ch < nch; ch++) {
+			const float *w = osc + (size_t)ch * 2 * K;
+			float dr = 0, di = 0;
+			for (int ind = 0; ind < K; ind++) {
+				float a = (float)p[2 * ind], b = (float)p[2 * ind + 1];
+				float c = w[2 * ind], d = w[2 * ind + 1];
+				float pr = a * c - b * d, pi = a * d + b * c;
+				if (variant == 0) {
+					dr = (float)((double)dr + (double)pr / 32768.0);
+					di = (float)((double)di + (double)pi / 32768.0);
+				} else {
+					dr = dr + pr;
+					di = di + pi;
+				}
+			}
+			float e = hypotf(dr, di);
+			dm[(size_t)ch * nout + m] = variant == 1 ? e / 4 : e;   /* variant 2: plain D += v*w, |D| (what the
+			                                                           product computes with folded tables) */
+		}
+	}
+}
+
 /* ------------------------------------------------------------------ frame sync (acars.c) */
 
 #define SYN 0x16

@@ -74,6 +74,11 @@ void orc_air_build_wf(int fr, int fc, unsigned rate, float *wf /*2K*/);    /* ai
 void orc_channelize_real(const float *x, int nout, int K, int nch,
                          const float *wf /*nch x 2K*/, float *dm /*nch x nout*/);      /* air.c:291-341 */
 
+/* CS16 front-ends: variant 0 = soapy.c, 1 = sdrplay.c */
+void orc_cs16_build_osc(int variant, unsigned freq_hz, unsigned fc, int K, float *osc /*2K*/); /* soapy.c:159-162, sdrplay.c:133-137 */
+void orc_channelize_cs16(int variant, const int16_t *iq /*interleaved I,Q*/, int nout, int K, int nch,
+                         const float *osc /*nch x 2K*/, float *dm /*nch x nout*/);          /* soapy.c:232-254, sdrplay.c:215-236 */
+
 /* demod + framing (msk.c, acars.c) */
 void orc_chan_init(orc_chan_t *c, int chn);                           /* msk.c:30-51, acars.c:230-234 */
 void orc_demod(orc_chan_t *c, const float *h, const float *dm, int len, orc_sink_t *sink); /* msk.c:67-137 */

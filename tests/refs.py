@@ -241,6 +241,95 @@ class RefAirLib:
         self.lib.ref_close()
 
 
+class RefCs16Lib:
+    """oracle/_ref/libacarsref_{soapy,sdrplay}_O2.so: the reference's CS16 front-ends in place."""
+
+    def __init__(self, which: str):
+        self.which = which
+        self.lib = C.CDLL(str(ORACLE_DIR / "_ref" / f"libacarsref_{which}_O2.so"))
+        L = self.lib
+        L.ref_get_osc.argtypes = [C.c_int, C.c_void_p, C.c_int]
+        L.ref_get_dm.argtypes = [C.c_int, C.c_void_p, C.c_int]
+        L.ref_get_carry.argtypes = [C.c_int, C.c_void_p]
+        L.ref_state.argtypes = [C.c_int, C.POINTER(RefState)]
+        L.ref_msgs.argtypes = [C.POINTER(Msg), C.c_int]
+        if which == "soapy":
+            L.ref_soapy_open.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_char_p)]
+            L.ref_soapy_feed.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+        else:
+            L.ref_sdrplay_open.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+            L.ref_sdrplay_packet.argtypes = [C.c_void_p, C.c_void_p, C.c_uint]
+            L.ref_sdrplay_fc.restype = C.c_uint
+
+    def open(self, freqs_mhz, K: int = 160, user_freq: int = 0) -> None:
+        strs = [("%.4f" % f).encode() for f in freqs_mhz]
+        arr = (C.c_char_p * len(strs))(*strs)
+        r = self.lib.ref_soapy_open(K, user_freq, len(strs), arr) if self.which == "soapy" else self.lib.ref_sdrplay_open(len(strs), arr)
+        if r:
+            raise RuntimeError(f"open failed: {r}")
+        self.K = K if self.which == "soapy" else 160
+
+    @property
+    def fc(self) -> int:
+        return self.lib.ref_soapy_fc() if self.which == "soapy" else self.lib.ref_sdrplay_fc()
+
+    def osc(self, ch: int) -> np.ndarray:
+        out = np.empty(2 * self.K, dtype=np.float32)
+        self.lib.ref_get_osc(ch, out.ctypes.data, self.K)
+        return out
+
+    def feed(self, iq: np.ndarray, sizes) -> None:
+        """iq: int16 (n, 2).  soapy: one run of the read loop with the given read sizes (cycled);
+        sdrplay: one callback per size, planar xi/xq."""
+        iq = np.ascontiguousarray(iq, dtype=np.int16)
+        if self.which == "soapy":
+            sz = np.asarray(sizes, dtype=np.int32)
+            self.lib.ref_soapy_feed(iq.ctypes.data, len(iq), sz.ctypes.data, len(sz))
+        else:
+            pos, i = 0, 0
+            while pos < len(iq):
+                n = min(int(sizes[i % len(sizes)]), len(iq) - pos)
+                xi = np.ascontiguousarray(iq[pos:pos + n, 0])
+                xq = np.ascontiguousarray(iq[pos:pos + n, 1])
+                self.lib.ref_sdrplay_packet(xi.ctypes.data, xq.ctypes.data, n)
+                pos += n
+                i += 1
+
+    def counter(self, ch: int) -> int:
+        return self.lib.ref_counter(ch)
+
+    def dm(self, ch: int, n: int) -> np.ndarray:
+        out = np.empty(n, dtype=np.float32)
+        self.lib.ref_get_dm(ch, out.ctypes.data, n)
+        return out
+
+    def carry(self, ch: int) -> np.ndarray:
+        out = np.empty(2, dtype=np.float32)
+        self.lib.ref_get_carry(ch, out.ctypes.data)
+        return out
+
+    def state(self, ch: int) -> RefState:
+        s = RefState()
+        self.lib.ref_state(ch, C.byref(s))
+        return s
+
+    def msgs(self):
+        self.lib.ref_flush()
+        out = []
+        buf = (Msg * 256)()
+        while True:
+            n = self.lib.ref_msgs(buf, 256)
+            for i in range(n):
+                m = Msg()
+                C.memmove(C.byref(m), C.byref(buf[i]), C.sizeof(Msg))
+                out.append(m)
+            if n < 256:
+                return out
+
+    def close(self) -> None:
+        self.lib.ref_close()
+
+
 class OracleLib:
     def __init__(self):
         self.lib = C.CDLL(str(ORACLE_DIR / "libacars_oracle.so"))
@@ -262,6 +351,8 @@ class OracleLib:
         L.orc_air_build_wf.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_void_p]
         L.orc_channelize_real.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_channelize_fir.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_cs16_build_osc.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_void_p]
+        L.orc_channelize_cs16.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_chan_init.argtypes = [C.POINTER(OrcChan), C.c_int]
         L.orc_demod.argtypes = [C.POINTER(OrcChan), C.c_void_p, C.c_void_p, C.c_int, C.POINTER(OrcSink)]
         L.orc_block_fec.argtypes = [C.POINTER(Msg)]
@@ -333,6 +424,20 @@ class OracleLib:
         wf = np.ascontiguousarray(wf, dtype=np.float32)
         assert wf.shape[1] == 2 * taps
         self.lib.orc_channelize_fir(iq.ctypes.data, nout, K, taps, wf.shape[0], wf.ctypes.data, dm.ctypes.data)
+        return dm
+
+    def cs16_osc(self, variant: int, K: int, freqs_hz, fc: int) -> np.ndarray:
+        out = np.empty((len(freqs_hz), 2 * K), dtype=np.float32)
+        for i, f in enumerate(freqs_hz):
+            self.lib.orc_cs16_build_osc(variant, int(f), int(fc), K, out[i].ctypes.data)
+        return out
+
+    def channelize_cs16(self, variant: int, iq: np.ndarray, K: int, osc: np.ndarray) -> np.ndarray:
+        iq = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1)
+        nout = iq.size // (2 * K)
+        dm = np.empty((osc.shape[0], nout), dtype=np.float32)
+        osc = np.ascontiguousarray(osc, dtype=np.float32)
+        self.lib.orc_channelize_cs16(variant, iq.ctypes.data, nout, K, osc.shape[0], osc.ctypes.data, dm.ctypes.data)
         return dm
 
     def new_chan(self, chn: int) -> OrcChan:
