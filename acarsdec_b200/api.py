@@ -107,6 +107,7 @@ ABI = [
     ("acb_set_state", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(ChanState)]),
     ("acb_get_stats", C.c_int, [C.c_void_p, C.POINTER(Stats), C.c_int]),
     ("acb_block_fec", C.c_int, [C.POINTER(Msg)]),
+    ("acb_block_fec_batch", C.c_int, [C.c_void_p, C.POINTER(Msg), C.c_int, C.POINTER(C.c_int)]),
     ("acb_crc_update", C.c_uint16, [C.c_uint16, C.c_uint8]),
     ("acb_syndrome", C.c_uint16, [C.c_int]),
     ("acb_frame_byte", None, [C.c_void_p, C.c_ubyte]),
@@ -344,6 +345,24 @@ class Context:
             got = self.lib.acb_drain(self.h, buf.ctypes.data_as(C.POINTER(Msg)), n)
             buf = buf[:got]
         return buf
+
+    def block_fec_batch(self, msgs):
+        """Device block FEC over a list of raw Msg (parity-bearing txt): returns [fixed Msg or None]."""
+        n = len(msgs)
+        arr = (Msg * n)()
+        for i, m in enumerate(msgs):
+            C.memmove(C.byref(arr[i]), C.byref(m), C.sizeof(Msg))
+        keep = (C.c_int * n)()
+        _check(self.lib, self.lib.acb_block_fec_batch(self.h, arr, n, keep))
+        out = []
+        for i in range(n):
+            if keep[i]:
+                m = Msg()
+                C.memmove(C.byref(m), C.byref(arr[i]), C.sizeof(Msg))
+                out.append(m)
+            else:
+                out.append(None)
+        return out
 
     def read_dm(self, nsamp: int) -> np.ndarray:
         out = np.empty((self.nstreams, nsamp, self.nch), dtype=np.float32)

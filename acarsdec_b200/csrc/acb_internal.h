@@ -38,7 +38,7 @@ struct RawFrame {
 	int stream, chn, len, err;
 	double lvlsum;
 	int bitcount;
-	int pad0;
+	int pad0;                         /* block-FEC status: 0 = not processed, 1 = deliver, 2 = drop */
 	unsigned long long pos, soh_pos;
 	unsigned char crc[2];
 	unsigned char pad1[6];
@@ -66,6 +66,7 @@ int launch_channelize_generic(int mode, const void *in, size_t stream_stride, co
                               int K, int taps, int nch, int nstreams, size_t row0, size_t nrows, size_t nsamp, CUstream_st *stream);
 int launch_demod(ChainState *st, const float *dm, int nsamp, int nch, int nstreams,
                  RawFrame *ring, RingCtl *ctl, unsigned cap, CUstream_st *stream);
+int launch_block_fec(RawFrame *ring, const RingCtl *ctl, unsigned cap, CUstream_st *stream);
 int upload_matched_filter(const float *h);
 int upload_sincos_table(const double *cos_hi_lo, const double *sin_hi_lo);
 size_t channelize_smem_bytes(int mode);

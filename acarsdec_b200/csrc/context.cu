@@ -358,12 +358,12 @@ static EvTriple get_events(acb_ctx *c)
 /* Collecting a submit has a device half and a host half:
  *   harvest_begin  waits until its demod kernel is done, reads the frame count and queues the D2H
  *                  copy of its frames (copy stream s_d2h, event ev_ring_read[ring]);
- *   harvest_finish waits for that copy, runs the block FEC (blk_thread, acars.c:93-215) and queues
- *                  the survivors in the reference's emission order: per input block, channel by
+ *   harvest_finish waits for that copy and queues the frames the device block FEC (k_block_fec, the
+ *                  blk_thread role, acars.c:93-215) kept, in the reference's emission order: per input block, channel by
  *                  channel, then time (rtl.c:357-360; soundfile.c:71-77); streams are interleaved as
  *                  if the reference served them in turn.
- * A new submit is launched BETWEEN the two halves, so the host-side FEC of submit i-1 never delays
- * the channelizer of submit i+1. */
+ * A new submit is launched BETWEEN the two halves, so the host-side sort/copy of submit i-1 never
+ * delays the channelizer of submit i+1. */
 struct Harvest {
 	Ticket t;
 	unsigned count;
@@ -420,7 +420,7 @@ static int harvest_finish(acb_ctx *c, Harvest &h)
 		memcpy(m.txt, f.txt, ACB_TXTMAX);
 		m.crc[0] = f.crc[0]; m.crc[1] = f.crc[1];
 		c->stats.raw_frames++;
-		if (acb_block_fec(&m)) c->outq.push_back(m);
+		if (f.pad0 == 1) c->outq.push_back(m);          /* repaired and parity-stripped on the device (k_block_fec) */
 		else c->stats.fec_dropped++;
 	}
 	return ACB_OK;
@@ -490,6 +490,10 @@ static int run_kernels(acb_ctx *c, const uint8_t *d_iq, size_t stride, int nblk,
 	if (r) return fail(ACB_ERR_CUDA, "demod launch: %s", cudaGetErrorString((cudaError_t)r));
 	c->stats.kernel_launches++;
 	c->stats.demod_launches++;
+	/* block FEC on the frames this submit appended (blk_thread's job, acars.c:93-215), in place */
+	r = launch_block_fec(c->d_ring[b], c->d_ctl[b], c->ring_cap, c->s_dem);
+	if (r) return fail(ACB_ERR_CUDA, "block FEC launch: %s", cudaGetErrorString((cudaError_t)r));
+	c->stats.kernel_launches++;
 	CU(cudaMemcpyAsync(c->h_ctl[b], c->d_ctl[b], sizeof(RingCtl), cudaMemcpyDeviceToHost, c->s_dem));
 	CU(cudaEventRecord(t.ev.c, c->s_dem));
 	CU(cudaEventRecord(c->ev_dm_free[b], c->s_dem));
@@ -708,6 +712,44 @@ extern "C" int acb_drain(acb_ctx_t *c, acb_msg_t *out, int max)
 		c->outq.pop_front();
 	}
 	return n;
+}
+
+extern "C" int acb_block_fec_batch(acb_ctx_t *c, acb_msg_t *msgs, int n, int *keep)
+{
+	if (!c || !msgs || !keep || n < 0) return fail(ACB_ERR_ARG, "bad argument");
+	if (int r = ctx_use(c)) return r;
+	if (n == 0) return 0;
+	std::vector<RawFrame> raw(n);
+	memset(raw.data(), 0, (size_t)n * sizeof(RawFrame));
+	for (int i = 0; i < n; i++) {
+		raw[i].len = msgs[i].len; raw[i].err = msgs[i].err; raw[i].chn = msgs[i].chn;
+		memcpy(raw[i].txt, msgs[i].txt, ACB_TXTMAX);
+		raw[i].crc[0] = msgs[i].crc[0]; raw[i].crc[1] = msgs[i].crc[1];
+	}
+	RawFrame *d = nullptr;
+	RingCtl *dc = nullptr, hc;
+	memset(&hc, 0, sizeof(hc));
+	hc.count = (unsigned)n;
+	CU(cudaMalloc(&d, (size_t)n * sizeof(RawFrame)));
+	CU(cudaMalloc(&dc, sizeof(RingCtl)));
+	CU(cudaMemcpy(d, raw.data(), (size_t)n * sizeof(RawFrame), cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(dc, &hc, sizeof(hc), cudaMemcpyHostToDevice));
+	int r = launch_block_fec(d, dc, (unsigned)n, c->s_d2h);
+	if (r) return fail(ACB_ERR_CUDA, "block FEC launch: %s", cudaGetErrorString((cudaError_t)r));
+	CU(cudaMemcpyAsync(raw.data(), d, (size_t)n * sizeof(RawFrame), cudaMemcpyDeviceToHost, c->s_d2h));
+	CU(cudaStreamSynchronize(c->s_d2h));
+	cudaFree(d);
+	cudaFree(dc);
+	int kept = 0;
+	for (int i = 0; i < n; i++) {
+		keep[i] = raw[i].pad0 == 1;
+		kept += keep[i];
+		if (keep[i]) {
+			msgs[i].err = raw[i].err;
+			memcpy(msgs[i].txt, raw[i].txt, ACB_TXTMAX);
+		}
+	}
+	return kept;
 }
 
 extern "C" int acb_pending(acb_ctx_t *c)

@@ -145,7 +145,7 @@ namespace {
 
 struct FecTables {
 	uint16_t crc[256];
-	uint16_t syn[8 * 244];            /* syndrom.h:52-295 has 1936 = 8 x 242 entries; a 241-byte
+	uint16_t syn[8 * 252];            /* syndrom.h:52-295 has 1936 = 8 x 242 entries; a 241-byte
 	                                     block (acars.c:319 precedes the length check) indexes just past
 	                                     that in the reference — keep the lookups in bounds here */
 	FecTables()
@@ -158,7 +158,7 @@ struct FecTables {
 		/* syndrome of one wrong bit: CRC (init 0) of that bit followed by p zero bytes */
 		for (int bit = 0; bit < 8; bit++) {
 			uint16_t r = crc[1u << bit];
-			for (int p = 0; p < 244; p++) {
+			for (int p = 0; p < 252; p++) {
 				syn[bit + 8 * p] = r;
 				r = (uint16_t)((r >> 8) ^ crc[r & 0xff]);
 			}

@@ -386,7 +386,7 @@ static __device__ __noinline__ void emit_frame(const ChainState *st, RawFrame *r
 	RawFrame *f = ring + slot;
 	f->stream = stream; f->chn = chn;
 	f->len = len; f->err = err;
-	f->lvlsum = lvlsum; f->bitcount = bitcount; f->pad0 = 0;
+	f->lvlsum = lvlsum; f->bitcount = bitcount; f->pad0 = 0;          /* pad0: FEC status, set by k_block_fec */
 	f->pos = pos; f->soh_pos = soh_pos;
 	f->crc[0] = st->crc[0]; f->crc[1] = st->crc[1];
 	for (int i = 0; i < 6; i++) f->pad1[i] = 0;            /* the record goes to the host as a whole */
@@ -680,6 +680,130 @@ int launch_demod(ChainState *st, const float *dm, int nsamp, int nch, int nstrea
 	cudaError_t e = cudaFuncSetAttribute(k_demod, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 	if (e != cudaSuccess) return (int)e;
 	k_demod<<<grid, 32, 0, stream>>>(st, dm, nsamp, nch, nstreams, wps, ring, ctl, cap);
+	return (int)cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K3: block FEC, one thread per finished frame (blk_thread, acars.c:123-207; fixprerr acars.c:39-64;
+ * fixdberr acars.c:66-90).  Integer only.  Works in place on the frame ring right behind the demod:
+ * status in RawFrame::pad0 (1 = deliver, 2 = drop), err = parity errors found, txt repaired and
+ * parity-stripped.  CRC and syndrome tables are generated in shared memory per CTA (syndrom.h:15-48,
+ * 52-295) rather than stored.
+ * ---------------------------------------------------------------------------------------- */
+
+constexpr int FEC_SYN_BYTES = 252;      /* covers len <= 250 (the reference table has 242 rows; a
+                                           241-byte block indexes past it there, see hostmath.cpp) */
+
+__device__ __forceinline__ unsigned fec_crc_step(const unsigned short *tab, unsigned crc, unsigned c)
+{
+	return ((crc >> 8) ^ tab[(crc ^ c) & 0xffu]) & 0xffffu;               /* update_crc, syndrom.h:49 */
+}
+
+__device__ __forceinline__ bool fec_crc_bytes_hit(const unsigned short *syn, unsigned crc)
+{
+	bool hit = false;
+#pragma unroll
+	for (int i = 0; i < 16; i++) hit |= (syn[i] == crc);                  /* acars.c:57-62, 70-74 */
+	return hit;
+}
+
+__global__ void __launch_bounds__(128)
+k_block_fec(RawFrame *__restrict__ ring, const RingCtl *__restrict__ ctl, unsigned cap)
+{
+	__shared__ unsigned short s_crc[256];
+	__shared__ unsigned short s_syn[8 * FEC_SYN_BYTES];
+	for (int b = threadIdx.x; b < 256; b += blockDim.x) {
+		unsigned r = b;
+		for (int k = 0; k < 8; k++) r = (r & 1u) ? (r >> 1) ^ 0x8408u : r >> 1;
+		s_crc[b] = (unsigned short)r;
+	}
+	__syncthreads();
+	if (threadIdx.x < 8) {                                                /* one bit position per thread */
+		unsigned r = s_crc[1u << threadIdx.x];
+		for (int p = 0; p < FEC_SYN_BYTES; p++) {
+			s_syn[threadIdx.x + 8 * p] = (unsigned short)r;
+			r = fec_crc_step(s_crc, r, 0);
+		}
+	}
+	__syncthreads();
+
+	const unsigned count = min(ctl->count, cap);
+	for (unsigned f = blockIdx.x * blockDim.x + threadIdx.x; f < count; f += gridDim.x * blockDim.x) {
+		RawFrame *fr = ring + f;
+		unsigned char *txt = fr->txt;
+		const int len = fr->len;
+		int status = 2;
+		do {
+			if (len < 13 || len > 250) break;                                 /* acars.c:124-129 */
+			txt[12] = (unsigned char)((txt[12] & 0x83u) | 0x02u);             /* force STX/ETX, acars.c:132-133 */
+			int bad[3], nbad = 0;
+			unsigned crc = 0;
+			for (int i = 0; i < len; i++) {
+				const unsigned c = txt[i];
+				if ((__popc(c) & 1) == 0) { if (nbad < 3) bad[nbad] = i; nbad++; }
+				crc = fec_crc_step(s_crc, crc, c);
+			}
+			if (nbad > 3) break;                                              /* acars.c:145-152 */
+			crc = fec_crc_step(s_crc, crc, fr->crc[0]);
+			crc = fec_crc_step(s_crc, crc, fr->crc[1]);
+			fr->err = nbad;
+			bool ok = true;
+			if (nbad) {
+				/* fixprerr, depth first in the reference's order: bit of the first bad byte outermost */
+				ok = false;
+				const int p0 = 8 * (len - bad[0] + 1), p1 = nbad > 1 ? 8 * (len - bad[1] + 1) : 0, p2 = nbad > 2 ? 8 * (len - bad[2] + 1) : 0;
+				for (int i0 = 0; i0 < 8 && !ok; i0++) {
+					const unsigned c0 = crc ^ s_syn[i0 + p0];
+					if (nbad == 1) {
+						if (c0 == 0 || fec_crc_bytes_hit(s_syn, c0)) { txt[bad[0]] ^= (unsigned char)(1u << i0); ok = true; }
+						continue;
+					}
+					for (int i1 = 0; i1 < 8 && !ok; i1++) {
+						const unsigned c1 = c0 ^ s_syn[i1 + p1];
+						if (nbad == 2) {
+							if (c1 == 0 || fec_crc_bytes_hit(s_syn, c1)) {
+								txt[bad[1]] ^= (unsigned char)(1u << i1); txt[bad[0]] ^= (unsigned char)(1u << i0); ok = true;
+							}
+							continue;
+						}
+						for (int i2 = 0; i2 < 8 && !ok; i2++) {
+							const unsigned c2 = c1 ^ s_syn[i2 + p2];
+							if (c2 == 0 || fec_crc_bytes_hit(s_syn, c2)) {
+								txt[bad[2]] ^= (unsigned char)(1u << i2); txt[bad[1]] ^= (unsigned char)(1u << i1);
+								txt[bad[0]] ^= (unsigned char)(1u << i0); ok = true;
+							}
+						}
+					}
+				}
+			} else if (crc) {
+				/* fixdberr: single wrong bit in the BCS, else two wrong bits in one byte */
+				ok = fec_crc_bytes_hit(s_syn, crc);
+				for (int k = 0; k < len && !ok; k++) {
+					const int base = 8 * (len - k + 1);
+					for (int i = 0; i < 8 && !ok; i++)
+						for (int j = 0; j < 8 && !ok; j++)
+							if (i != j && (crc ^ s_syn[i + base] ^ s_syn[j + base]) == 0) {
+								txt[k] ^= (unsigned char)((1u << i) | (1u << j));
+								ok = true;
+							}
+				}
+			}
+			if (!ok) break;
+			int still = 0;                                                    /* acars.c:194-207 */
+			for (int i = 0; i < len; i++) {
+				const unsigned c = txt[i];
+				still += ((__popc(c) & 1) == 0);
+				txt[i] = (unsigned char)(c & 0x7fu);
+			}
+			status = still ? 2 : 1;
+		} while (0);
+		fr->pad0 = status;
+	}
+}
+
+int launch_block_fec(RawFrame *ring, const RingCtl *ctl, unsigned cap, cudaStream_t stream)
+{
+	k_block_fec<<<64, 128, 0, stream>>>(ring, ctl, cap);
 	return (int)cudaGetLastError();
 }
 

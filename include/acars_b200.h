@@ -200,9 +200,14 @@ typedef struct {
 } acb_stats_t;
 int acb_get_stats(acb_ctx_t *ctx, acb_stats_t *out, int reset);
 
-/* Block FEC on one frame in place (acars.c:123-207): 1 = deliver, 0 = drop.
- * Exposed for tests and for hosts that run their own queue. */
+/* Block FEC on one frame in place on the HOST (acars.c:123-207): 1 = deliver, 0 = drop.  The
+ * processing path runs the same repair on the device (k_block_fec, one thread per frame, right
+ * behind the demod); this entry serves the shim's host-side decodeAcars and callers with their own
+ * queue. */
 int acb_block_fec(acb_msg_t *m);
+/* The device block FEC on a batch of raw frames (len, txt with parity bits, crc): repairs msgs[i]
+ * in place, keep[i] = 1 where the reference would call outputmsg().  Returns the number kept. */
+int acb_block_fec_batch(acb_ctx_t *ctx, acb_msg_t *msgs, int n, int *keep);
 /* Tables behind it, generated rather than stored (syndrom.h:4-13, 15-49, 52-295). */
 uint16_t acb_crc_update(uint16_t crc, uint8_t c);
 uint16_t acb_syndrome(int index);      /* index = bit + 8*bytes_from_end, 0..1935 */

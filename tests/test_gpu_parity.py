@@ -234,7 +234,7 @@ def test_full_path_synthetic_vs_oracle(native, oracle, K, seed, nstreams):
         dm_tail = ctx.read_dm((nblk - half) * 1024)
         states = [[ctx.get_state(s, c).vec() for c in range(len(fm))] for s in range(nstreams)]
         st = ctx.stats()
-    assert st.kernel_launches == 4 and st.chan_launches == 2 and st.demod_launches == 2
+    assert st.kernel_launches == 6 and st.chan_launches == 2 and st.demod_launches == 2   # K1+K2+K3 per submit
     total = 0
     for s in range(nstreams):
         o = refs.OracleStream(oracle, K, wf)
@@ -399,3 +399,29 @@ def test_wide_stream_channel_sharding(native):
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     res = _json.loads(line)
     assert res["match"] and res["world"] == max(n, 1) and res["frames"] >= 8
+
+
+def test_device_block_fec_fuzz_matches_oracle(native, oracle):
+    """k_block_fec (one thread per frame) against the restatement's blk_thread on 6000 fuzzed
+    frames: clean, 1-3 parity errors, double-bit errors, BCS errors, hopeless ones, short ones."""
+    from test_oracle_vs_reference import _fec_cases
+    rng = np.random.default_rng(4321)
+    raw, want = [], []
+    for chn, txt, crc in _fec_cases(rng, 6000):
+        a, o = api.Msg(), refs.Msg()
+        for m in (a, o):
+            m.chn, m.len = chn, len(txt)
+            m.txt[:len(txt)] = txt
+            m.crc[:] = crc
+        raw.append(a)
+        want.append(oracle.fec(o))
+    with api.Context(160, 1, 1, 1) as ctx:
+        got = ctx.block_fec_batch(raw)
+    n_out = n_fixed = 0
+    for g, w in zip(got, want):
+        assert (g is None) == (w is None)
+        if g is not None:
+            assert (g.len, g.err, bytes(g.txt[:g.len])) == (w.len, w.err, bytes(w.txt[:w.len]))
+            n_out += 1
+            n_fixed += g.err > 0
+    assert n_out > 1000 and n_fixed > 200
