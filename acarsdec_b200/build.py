@@ -25,6 +25,9 @@ NVCC_FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-fmad=false", "-Xcompiler", "-f
 LIB = PKG / "libacars_b200.so"
 COMPAT = PKG / "libacarsdec_compat.so"
 COMPAT_AIR = PKG / "libacarsdec_compat_air.so"      # same shim built for -DWITH_AIR hosts (channel_t differs)
+COMPAT_VARIANTS = [("WITH_RTL", COMPAT), ("WITH_AIR", COMPAT_AIR),
+                   ("WITH_SOAPY", PKG / "libacarsdec_compat_soapy.so"),
+                   ("WITH_SDRPLAY", PKG / "libacarsdec_compat_sdrplay.so")]
 LIB_SRC = [CSRC / "kernels.cu", CSRC / "context.cu", CSRC / "hostmath.cpp"]
 COMPAT_SRC = [CSRC / "compat.c"]
 HEADERS = [CSRC / "acb_internal.h", CSRC / "frame_sm.h", ROOT / "include" / "acars_b200.h",
@@ -60,16 +63,15 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         _run(cmd, PKG / "build" / "libacars_b200.log")
         if verbose:
             print((PKG / "build" / "libacars_b200.log").read_text())
-    if all(p.exists() for p in COMPAT_SRC) and (force or _stale(COMPAT, COMPAT_SRC + HEADERS + [LIB])):
-        # plain C, the reference's language; WITH_RTL selects channel_t's layout (acarsdec.h:62-74)
-        cmd = [os.environ.get("CC", "gcc"), "-O2", "-std=gnu11", "-fPIC", "-shared", "-Wall", "-DWITH_RTL",
-               "-ffp-contract=off", "-o", COMPAT, *COMPAT_SRC, "-I", ROOT / "include", "-L", PKG, "-lacars_b200",
-               "-Wl,-rpath,$ORIGIN", "-lpthread", "-lm"]
-        _run(cmd, PKG / "build" / "libacarsdec_compat.log")
-        cmd = [os.environ.get("CC", "gcc"), "-O2", "-std=gnu11", "-fPIC", "-shared", "-Wall", "-DWITH_AIR",
-               "-ffp-contract=off", "-o", COMPAT_AIR, *COMPAT_SRC, "-I", ROOT / "include", "-L", PKG, "-lacars_b200",
-               "-Wl,-rpath,$ORIGIN", "-lpthread", "-lm"]
-        _run(cmd, PKG / "build" / "libacarsdec_compat_air.log")
+    if all(p.exists() for p in COMPAT_SRC) and (
+            force or any(_stale(t, COMPAT_SRC + HEADERS + [LIB]) for _, t in COMPAT_VARIANTS)):
+        # plain C, the reference's language; the host's WITH_* macro selects channel_t's layout
+        # (acarsdec.h:62-74) and the front-end symbols, so there is one shim per front-end
+        for macro, target in COMPAT_VARIANTS:
+            cmd = [os.environ.get("CC", "gcc"), "-O2", "-std=gnu11", "-fPIC", "-shared", "-Wall", "-D" + macro,
+                   "-ffp-contract=off", "-o", target, *COMPAT_SRC, "-I", ROOT / "include", "-L", PKG, "-lacars_b200",
+                   "-Wl,-rpath,$ORIGIN", "-lpthread", "-lm"]
+            _run(cmd, PKG / "build" / (target.stem + ".log"))
     return LIB
 
 

@@ -539,3 +539,164 @@ int runAirspySample(void)
 }
 
 #endif /* WITH_AIR */
+
+/* ---------------------------------------------------------------- CS16 front-ends on a capture file */
+
+#if defined(WITH_SOAPY) || defined(WITH_SDRPLAY)
+
+static acb_ctx_t *cs_ctx;
+static FILE *cs_src;
+static int cs_mult;
+#define CS_BATCH 8                  /* blocks of 1024*mult complex samples per submit */
+
+/* the channel part shared by initSoapy (soapy.c:112-163) and initSdrplay (sdrplay.c:95-138) */
+static int cs16_setup(const char *path, char **argv, int optind, int mult, int variant, unsigned fc_user, const char *range_fmt)
+{
+	unsigned Fd[MAXNBCHANNELS];
+	char *argF;
+	cs_mult = mult;
+	cs_src = strcmp(path, "-") ? fopen(path, "rb") : stdin;
+	if (!cs_src) { fprintf(stderr, "Failed to open CS16 capture %s: %s\n", path, strerror(errno)); return -1; }
+	nbch = 0;
+	while ((argF = argv[optind]) && nbch < MAXNBCHANNELS) {
+		Fd[nbch] = (unsigned)acb_round_freq(atof(argF));
+		optind++;
+		if (Fd[nbch] < 118000000 || Fd[nbch] > 138000000) {
+			fprintf(stderr, range_fmt, Fd[nbch]);
+			continue;
+		}
+		channel[nbch].chn = nbch;
+		channel[nbch].Fr = (float)Fd[nbch];
+		nbch++;
+	}
+	if (nbch == 0) { fprintf(stderr, "Need a least one frequency\n"); return 1; }
+	acb_config_t cfg = { 0, mult, 1, (int)nbch, CS_BATCH, ACB_FLAG_CS16_INPUT, 0 };
+	const char *e = getenv("ACARSDEC_B200_DEVICE");
+	if (e) cfg.device = atoi(e);
+	if (acb_create(&cfg, &cs_ctx) != ACB_OK) {
+		fprintf(stderr, "acarsdec_b200: %s\n", acb_last_error());
+		if (cs_ctx) acb_destroy(cs_ctx);
+		cs_ctx = NULL;
+		return -1;
+	}
+	unsigned Fc = 0;
+	if (acb_set_plan_cs16(cs_ctx, 0, Fd, (int)nbch, variant, fc_user, &Fc) != ACB_OK) {
+		fprintf(stderr, "%s\n", acb_last_error());            /* "Frequencies too far apart" */
+		return 1;
+	}
+	/* channel[] as the reference leaves it: the unscaled oscillator (the library's table carries an
+	 * exact power-of-two factor on top, see acb_cs16_build_wf) */
+	const float unscale = variant == ACB_CS16_SOAPY ? 32768.0f : 4.0f;
+	float *wf = malloc(sizeof(float) * 2 * mult);
+	if (!wf) return -1;
+	for (unsigned n = 0; n < nbch; n++) {
+		channel_t *ch = &channel[n];
+		ch->counter = 0;
+		ch->D = 0;
+		ch->oscillator = malloc(mult * sizeof(float complex));
+		ch->dm_buffer = malloc(RTLOUTBUFSZ * sizeof(float));
+		if (!ch->oscillator || !ch->dm_buffer) { fprintf(stderr, "ERROR : malloc\n"); free(wf); return -1; }
+		acb_cs16_build_wf(variant, (unsigned)ch->Fr, Fc, mult, wf);
+		for (int i = 0; i < mult; i++) ch->oscillator[i] = wf[2 * i] * unscale + wf[2 * i + 1] * unscale * I;
+	}
+	free(wf);
+	return (int)-(long)Fc;                                   /* <= -1: success, the centre frequency negated */
+}
+
+static int cs16_run(void)
+{
+	if (!cs_ctx || !cs_src) return -1;
+	const size_t cap = (size_t)RTLOUTBUFSZ * cs_mult * CS_BATCH;          /* complex samples per submit */
+	int16_t *buf = acb_host_alloc(cap * 2 * sizeof(int16_t));
+	if (!buf) { fprintf(stderr, "acarsdec_b200: %s\n", acb_last_error()); return -1; }
+	acb_chan_state_t st;
+	acb_msg_t out[16];
+	for (unsigned n = 0; n < nbch; n++) { state_pack(&channel[n], &st); acb_set_state(cs_ctx, 0, (int)n, &st); }
+	int rc = ACB_OK;
+	while (!signalExit) {
+		size_t got = fread(buf, 2 * sizeof(int16_t), cap, cs_src);
+		if (got == 0) break;
+		struct timeval tv;
+		gettimeofday(&tv, NULL);
+		rc = acb_submit_cs16_host(cs_ctx, buf, got, got);      /* any count: the remainder is carried */
+		if (rc < 0) break;
+		rc = acb_sync(cs_ctx);
+		if (rc < 0) break;
+		for (int n; (n = acb_drain(cs_ctx, out, 16)) > 0;)
+			for (int i = 0; i < n; i++) deliver(&out[i], out[i].chn, &tv);
+		if (got < cap) break;
+	}
+	if (rc < 0) fprintf(stderr, "acarsdec_b200: %s\n", acb_last_error());
+	for (unsigned n = 0; n < nbch; n++)
+		if (acb_get_state(cs_ctx, 0, (int)n, &st) == ACB_OK) state_unpack(&st, &channel[n]);
+	acb_host_free(buf);
+	signalExit = 1;
+	return rc < 0 ? -1 : 0;
+}
+
+static void cs16_close(void)
+{
+	if (cs_ctx) { acb_destroy(cs_ctx); cs_ctx = NULL; }
+	if (cs_src && cs_src != stdin) fclose(cs_src);
+	cs_src = NULL;
+}
+#endif
+
+#ifdef WITH_SOAPY
+/* soapy.c:69 initSoapy — argv[optind] (the "device string" after -d) names a raw interleaved CS16
+ * capture sampled at rateMult*12500 Hz; -c freq is honoured, -g/-p/--antenna are accepted. */
+int initSoapy(char **argv, int optind)
+{
+	if (argv[optind] == NULL) {
+		fprintf(stderr, "Need a CS16 capture file after -d\n");
+		exit(1);                                             /* soapy.c:76-79 */
+	}
+	const char *path = argv[optind++];
+	int r = cs16_setup(path, argv, optind, rateMult, ACB_CS16_SOAPY, (unsigned)freq,
+	                   "WARNING: frequency not in range 118-138 MHz: %d\n");
+	if (r >= 0 || r == -1) return r;
+	freq = -r;                                               /* soapy.c:132-133 */
+	const int rate = INTRATE * rateMult;
+	for (unsigned n = 0; n < nbch; n++) {                    /* soapy.c:138-144 */
+		const int f = (int)channel[n].Fr;
+		if (f < freq - rate / 2 || f > freq + rate / 2)
+			fprintf(stderr, "WARNING: frequency not in tuned range %d-%d: %d\n", freq - rate / 2, freq + rate / 2, f);
+	}
+	if (verbose) fprintf(stderr, "Set center freq. to %dHz\nSetting sample rate: %.4f MS/s\n", freq, rate / 1e6);
+	return 0;
+}
+
+int soapySetAntenna(const char *antenna)
+{
+	if (cs_ctx == NULL) { fprintf(stderr, "soapySetAntenna: SoapySDR not init'd\n"); return 1; }    /* soapy.c:183-186 */
+	if (antenna == NULL) { fprintf(stderr, "soapySetAntenna: antenna is NULL\n"); return 1; }
+	return 0;                                                /* nothing to switch on a capture */
+}
+
+int runSoapySample(void) { return cs16_run() < 0 ? 1 : 0; }   /* soapy.c:263 */
+
+int runSoapyClose(void) { cs16_close(); return 0; }           /* soapy.c:297 */
+#endif /* WITH_SOAPY */
+
+#ifdef WITH_SDRPLAY
+/* sdrplay.c:95 initSdrplay — the reference takes no device argument (-s f1 f2 ...), so the capture
+ * (raw interleaved CS16 at 2 MS/s) is named by ACARSDEC_B200_CAPTURE. */
+int initSdrplay(char **argv, int optind)
+{
+	const char *path = getenv("ACARSDEC_B200_CAPTURE");
+	if (!path) { fprintf(stderr, "Sorry, no device found (set ACARSDEC_B200_CAPTURE to a CS16 capture)\n"); exit(2); }   /* sdrplay.c:173-176 */
+	int r = cs16_setup(path, argv, optind, 160, ACB_CS16_SDRPLAY, 0, "WARNING: Invalid frequency %d\n");
+	if (r >= 0 || r == -1) return r;
+	fprintf(stderr, "SDRplay capture selects freq %d\n", -r);
+	return 0;
+}
+
+/* sdrplay.c:238 runSdrplaySample never returns in the reference (while(1) sleep); here it returns at
+ * the end of the capture with signalExit set */
+int runSdrplaySample(void)
+{
+	int r = cs16_run();
+	cs16_close();
+	return r;
+}
+#endif /* WITH_SDRPLAY */

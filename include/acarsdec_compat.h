@@ -77,6 +77,13 @@ extern int gain, ppm, rtlMult;
 #ifdef WITH_AIR
 extern int gain;
 #endif
+#ifdef WITH_SOAPY
+extern int rateMult, freq, ppm;
+extern double gain;
+#endif
+#ifdef WITH_SDRPLAY
+extern int gain, ppm;
+#endif
 
 /* callback OUT of the library: every repaired block, from one consumer thread (acars.c:209) */
 extern void outputmsg(const msgblk_t *);
@@ -114,6 +121,21 @@ int runRtlClose(void);
  * IF = rate/4 (AIRSPY_SAMPLE_FLOAT32_REAL); rate from ACARSDEC_B200_AIRRATE (default 2500000). */
 int initAirspy(char **argv, int optind);
 int runAirspySample(void);
+#endif
+
+#ifdef WITH_SOAPY
+/* soapy.c:69 / 178 / 263 / 297 (acarsdec.h:172-175).  argv[optind] (the device string after -d)
+ * names a raw interleaved CS16 capture at rateMult*12500 Hz. */
+int initSoapy(char **argv, int optind);
+int soapySetAntenna(const char *antenna);
+int runSoapySample(void);
+int runSoapyClose(void);
+#endif
+
+#ifdef WITH_SDRPLAY
+/* sdrplay.c:95 / 238.  The capture (interleaved CS16 at 2 MS/s) is named by ACARSDEC_B200_CAPTURE. */
+int initSdrplay(char **argv, int optind);
+int runSdrplaySample(void);
 #endif
 
 #ifdef __cplusplus

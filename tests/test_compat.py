@@ -69,10 +69,15 @@ def test_compat_library_exports_reference_symbols(tmp_path):
     common = {"initMsk", "demodMSK", "initAcars", "decodeAcars", "deinitAcars"}
     rtl = {"initRtl", "runRtlSample", "runRtlCancel", "runRtlClose"}
     air = {"initAirspy", "runAirspySample"}
-    assert declared == common | rtl | air
+    soapy = {"initSoapy", "soapySetAntenna", "runSoapySample", "runSoapyClose"}
+    sdrplay = {"initSdrplay", "runSdrplaySample"}
+    assert declared == common | rtl | air | soapy | sdrplay
     assert common | rtl <= defined
     out = subprocess.run(["nm", "-D", "--defined-only", str(PKG / "libacarsdec_compat_air.so")], capture_output=True, text=True, check=True).stdout
     assert common | air <= set(re.findall(r" T (\w+)", out))
+    for lib, want in (("libacarsdec_compat_soapy.so", soapy), ("libacarsdec_compat_sdrplay.so", sdrplay)):
+        out = subprocess.run(["nm", "-D", "--defined-only", str(PKG / lib)], capture_output=True, text=True, check=True).stdout
+        assert common | want <= set(re.findall(r" T (\w+)", out))
     # and it links into a host that supplies acarsdec.c's globals
     assert _host(tmp_path).exists()
 
@@ -223,3 +228,61 @@ def test_unmodified_acarsdec_main_airspy_front_end(tmp_path):
     assert sorted(blocks(a)) == sorted(blocks(b))
     for ch in "1234":
         assert [x for x in blocks(a) if x.startswith(ch)] == [x for x in blocks(b) if x.startswith(ch)]
+
+
+def _cs16_capture(tmp_path, seed):
+    """2 MS/s interleaved CS16 capture with 3 messages on each of 4 channels."""
+    orc = refs.OracleLib()
+    K, fm = 160, (131.525, 131.725, 131.825, 131.450)
+    fd, _, fc = orc.plan(K, fm)
+    plan = synth.StreamPlan(K=K, freqs_hz=tuple(fd), fc_hz=fc, seed=seed, noise_sigma=1.0)
+    rng = np.random.default_rng(seed)
+    for ch in range(4):
+        t = 0.01 + 0.04 * ch
+        for _ in range(3):
+            fr = synth.frame_bytes(synth.random_text(rng, int(rng.integers(10, 60))))
+            plan.bursts.append(synth.Burst(chan=ch, t0=t, frame=fr, amp=float(rng.uniform(10, 25)), phase=float(rng.uniform(0, 6))))
+            t += len(fr) * 8 / 2400 + 0.05
+    cap = tmp_path / "cap.cs16"
+    synth.render_cs16(plan, 0, int(1.2 * K * 12500)).tofile(cap)
+    return cap, [str(f) for f in fm]
+
+
+def _same_messages_per_channel(a, b, nch=4):
+    def blocks(s):
+        return [blk for blk in s.split("\n[#") if blk.strip()]
+    assert sorted(blocks(a)) == sorted(blocks(b))
+    for ch in "1234"[:nch]:
+        assert [x for x in blocks(a) if x.startswith(ch)] == [x for x in blocks(b) if x.startswith(ch)]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not (REFBIN / "acarsdec_b200_soapy").exists() or not (REFBIN / "acarsdec_ref_soapy").exists(),
+                    reason="oracle/_ref SoapySDR program builds absent")
+def test_unmodified_acarsdec_main_soapy_front_end(tmp_path):
+    """-DWITH_SOAPY hosts: unmodified acarsdec.c + the shim's initSoapy/runSoapySample/runSoapyClose vs
+    unmodified acarsdec.c + soapy.c over a file-replay SoapySDR stub, same CS16 capture."""
+    cap, freqs = _cs16_capture(tmp_path, 23)
+    ref = subprocess.run([str(REFBIN / "acarsdec_ref_soapy"), "-o", "2", "-d", str(cap), *freqs], capture_output=True, text=True, timeout=120)
+    mine = subprocess.run([str(REFBIN / "acarsdec_b200_soapy"), "-o", "2", "-d", str(cap), *freqs], capture_output=True, text=True, timeout=120)
+    assert mine.returncode == 0, mine.stderr
+    a, b = _strip_time(ref.stdout), _strip_time(mine.stdout)
+    assert a.count("<time>") >= 10
+    _same_messages_per_channel(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not (REFBIN / "acarsdec_b200_sdrplay").exists() or not (REFBIN / "acarsdec_ref_sdrplay").exists(),
+                    reason="oracle/_ref SDRplay program builds absent")
+def test_unmodified_acarsdec_main_sdrplay_front_end(tmp_path):
+    """-DWITH_SDRPLAY hosts: the shim's initSdrplay/runSdrplaySample vs sdrplay.c fed planar packets by a
+    file-replay mirsdrapi stub, same CS16 capture."""
+    cap, freqs = _cs16_capture(tmp_path, 29)
+    ref = subprocess.run([str(REFBIN / "acarsdec_ref_sdrplay"), "-o", "2", "-s", *freqs],
+                         env=dict(os.environ, ACARSDEC_STUB_SDRPLAY=str(cap)), capture_output=True, text=True, timeout=120)
+    mine = subprocess.run([str(REFBIN / "acarsdec_b200_sdrplay"), "-o", "2", "-s", *freqs],
+                          env=dict(os.environ, ACARSDEC_B200_CAPTURE=str(cap)), capture_output=True, text=True, timeout=120)
+    assert mine.returncode == 0, mine.stderr
+    a, b = _strip_time(ref.stdout), _strip_time(mine.stdout)
+    assert a.count("<time>") >= 10
+    _same_messages_per_channel(a, b)
