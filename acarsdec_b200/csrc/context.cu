@@ -70,6 +70,10 @@ struct acb_ctx {
 	bool buf_used[2];
 	int next_buf;
 	float *d_wf4;                /* [stream][grp][K][8] float4 (c, d, -d, c) */
+	bool fast;                   /* ACB_FLAG_FAST_CHANNELIZER and a shape k_channelize_dft takes */
+	float *d_tw;                 /* fast form: [stream][grp][8 ch][K/4] (Tr, Ti) twiddles */
+	unsigned *d_twmeta;          /* fast form: [stream][grp] residues k_c mod 4, 2 bits per channel slot */
+	std::vector<unsigned char> fast_ok;   /* per stream: planned on the 12.5 kHz raster (0 after acb_set_wf: caller's own table) */
 	float *d_dm[2];              /* [stream][nsamp][nch], alternating per submit */
 	cudaEvent_t ev_k1_done[2], ev_dm_free[2], ev_ring_read[2];
 	bool ring_read_pending[2];
@@ -228,6 +232,12 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 	const size_t wf_floats = (size_t)cfg->nstreams * c->ngrp * c->taps_pad * CH_GROUP * (c->in_kind == IN_KIND_F32REAL ? 2 : 4);
 	CU(cudaMalloc(&c->d_wf4, wf_floats * sizeof(float)));
 	CU(cudaMemset(c->d_wf4, 0, wf_floats * sizeof(float)));
+	c->fast = (cfg->flags & ACB_FLAG_FAST_CHANNELIZER) && c->in_kind == IN_KIND_U8IQ && c->taps == cfg->K && channelize_dft_supports(cfg->K);
+	c->fast_ok.assign(cfg->nstreams, 0);
+	if (c->fast) {
+		CU(cudaMalloc(&c->d_tw, (size_t)cfg->nstreams * c->ngrp * CH_GROUP * (cfg->K / 4) * 2 * sizeof(float)));
+		CU(cudaMalloc(&c->d_twmeta, (size_t)cfg->nstreams * c->ngrp * sizeof(unsigned)));
+	}
 	c->dm_floats = (size_t)cfg->nstreams * cfg->max_blocks * OUTBLK * cfg->nch;
 	for (int i = 0; i < 2; i++) {
 		CU(cudaMalloc(&c->d_dm[i], c->dm_floats * sizeof(float)));
@@ -289,6 +299,7 @@ extern "C" void acb_destroy(acb_ctx_t *c)
 		for (auto &t : c->inflight) { cudaEventDestroy(t.ev.a); cudaEventDestroy(t.ev.b); cudaEventDestroy(t.ev.b2); cudaEventDestroy(t.ev.c); }
 		for (auto &e : c->ev_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); cudaEventDestroy(e.b2); cudaEventDestroy(e.c); }
 		cudaFree(c->d_wf4); cudaFree(c->d_state);
+		cudaFree(c->d_tw); cudaFree(c->d_twmeta);
 		for (int i = 0; i < 2; i++) { cudaFree(c->d_dm[i]); cudaEventDestroy(c->ev_k1_done[i]); cudaEventDestroy(c->ev_dm_free[i]); cudaEventDestroy(c->ev_ring_read[i]); }
 		for (int i = 0; i < 2; i++) { cudaFree(c->d_ring[i]); cudaFree(c->d_ctl[i]); cudaFreeHost(c->h_ctl[i]); }
 		cudaFreeHost(c->h_ring);
@@ -325,6 +336,7 @@ extern "C" int acb_set_wf(acb_ctx_t *c, int stream, const float *wf, int nch)
 	}
 	if (int r = sync_streams(c)) return r;
 	CU(cudaMemcpy(c->d_wf4 + (size_t)stream * t.size(), t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+	c->fast_ok[stream] = 0;                     /* a caller's table has no known structure: exact kernel */
 	return ACB_OK;
 }
 
@@ -340,7 +352,36 @@ extern "C" int acb_set_plan(acb_ctx_t *c, int stream, const unsigned *freqs_hz, 
 	for (int ch = 0; ch < nch; ch++)
 		acb_build_wf(acb_stored_fr(freqs_hz[ch]), fc, c->cfg.K, &wf[(size_t)ch * c->cfg.K * 2]);
 	if (fc_out) *fc_out = fc;
-	return acb_set_wf(c, stream, wf.data(), nch);
+	if (int r = acb_set_wf(c, stream, wf.data(), nch)) return r;
+	if (!c->fast) return ACB_OK;
+	/* Fast form: wf[ind] = g*exp(-j*2*pi*k*ind/K) needs the mixer offset to be a whole number k of
+	 * 12.5 kHz steps — judged on what the reference actually mixes with: the float images of the
+	 * stored Fr and of Fc (rtl.c:255, 283).  T_c[n2] = g*exp(-j*2*pi*k_c*n2/K), g = 1/K/127.5. */
+	const int K = c->cfg.K, N2 = K / 4;
+	std::vector<float> tw((size_t)c->ngrp * CH_GROUP * N2 * 2, 0.0f);
+	std::vector<unsigned> meta(c->ngrp, 0u);
+	bool ok = true;
+	for (int ch = 0; ch < nch && ok; ch++) {
+		const float d = (float)acb_stored_fr(freqs_hz[ch]) - (float)fc;
+		const float kf = d / (float)ACB_INTRATE;
+		const int k = (int)kf;
+		if ((float)k != kf || (k & 1) || k == 0 || k <= -K / 2 || k >= K / 2) { ok = false; break; }
+		const unsigned r = (unsigned)(((k % 4) + 4) % 4);      /* 0 or 2: float images of Fr, Fc are multiples of 8 Hz */
+		const int g = ch / CH_GROUP, cc = ch % CH_GROUP;
+		meta[g] |= r << (2 * cc);
+		for (int n2 = 0; n2 < N2; n2++) {
+			const double ph = -2.0 * M_PI * (double)(((long long)k * n2) % K) / (double)K;
+			float *o = &tw[(((size_t)g * CH_GROUP + cc) * N2 + n2) * 2];
+			o[0] = (float)(cos(ph) / K / 127.5);
+			o[1] = (float)(sin(ph) / K / 127.5);
+		}
+	}
+	if (ok) {
+		CU(cudaMemcpy(c->d_tw + (size_t)stream * tw.size(), tw.data(), tw.size() * sizeof(float), cudaMemcpyHostToDevice));
+		CU(cudaMemcpy(c->d_twmeta + (size_t)stream * meta.size(), meta.data(), meta.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+		c->fast_ok[stream] = 1;
+	}
+	return ACB_OK;
 }
 
 static EvTriple get_events(acb_ctx *c)
@@ -461,7 +502,13 @@ static int run_kernels(acb_ctx *c, const uint8_t *d_iq, size_t stride, int nblk,
 		/* whole 1024-row blocks through the pipeline kernel, the remaining rows (submits of 4-byte
 		 * samples may carry any count) and unaligned K through the generic one */
 		const int fast = c->use_generic ? 0 : nsamp / OUTBLK;
-		if (fast) {
+		bool dft = c->fast;                         /* every stream planned on the raster? */
+		for (int s = 0; dft && s < c->cfg.nstreams; s++) dft = c->fast_ok[s] != 0;
+		if (fast && dft) {
+			r = launch_channelize_dft(d_iq, stride, c->d_tw, c->d_twmeta, dmbuf, c->cfg.K, c->cfg.nch, c->cfg.nstreams, fast, (size_t)nsamp, c->s_comp);
+			c->stats.kernel_launches++;
+			c->stats.fast_chan_launches++;
+		} else if (fast) {
 			r = launch_channelize(c->in_kind, d_iq, stride, c->d_wf4, dmbuf, c->cfg.K, c->taps_pad, c->cfg.nch, c->cfg.nstreams, fast, (size_t)nsamp, c->s_comp);
 			c->stats.kernel_launches++;
 		}

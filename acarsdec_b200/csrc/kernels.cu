@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "acb_internal.h"
 #include "frame_sm.h"
@@ -290,6 +291,288 @@ int launch_channelize(int mode, const void *in, size_t stream_stride_bytes, cons
 	case IN_CS16IQ: return launch_channelize_t<IN_CS16IQ>(in, stream_stride_bytes, wf, dm, K, taps, nch, nstreams, nblk, nsamp, stream);
 	default: return launch_channelize_t<IN_U8IQ>(in, stream_stride_bytes, wf, dm, K, taps, nch, nstreams, nblk, nsamp, stream);
 	}
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K1, fast form (ACB_FLAG_FAST_CHANNELIZER).  The reference's mixer table is a sampled complex
+ * exponential: when (Fr - Fc) is a whole number k of 12.5 kHz steps — the planner's normal outcome,
+ * frequencies are rounded to that raster (rtl.c:245-247) — wf[ind] = g*exp(-j*2*pi*k*ind/K) and the
+ * boxcar sum D = sum_ind x[ind]*wf[ind] is bin k of a K-point DFT of the row.  Split ind = (K/4)*n1 + n2:
+ *
+ *     D_c = sum_{n2 < K/4} T_c[n2] * Y_{k_c mod 4}[n2],   Y_r[n2] = sum_{n1 < 4} x[(K/4)*n1 + n2] * (-j)^(r*n1)
+ *
+ * (k is always even: the float images of Fr and Fc that the reference mixes with are multiples of 8 Hz,
+ * so only Y_0 = x0+x1+x2+x3 and Y_2 = x0-x1+x2-x3 occur.)
+ *
+ * Y_r is a 4-point DFT across the four quarters of the row: additions only, EXACT in float (integer
+ * samples), and shared by every channel of the stream; each channel then needs K/4 complex MACs instead
+ * of K.  The -127.37 offset of rtl.c:338-339 drops out (a channel is never at bin 0: chooseFc keeps it
+ * 25 kHz from the centre).  FP32 work per input sample falls from 8*C to 2.5 + C lane-ops (C = 8: 64 ->
+ * 10.5), which moves the kernel from the FP32 roof towards the HBM roof.
+ *
+ * This is NOT the reference's operation order: the envelope differs from the reference's in the last
+ * bits.  Measured against the reference (tests/test_gpu_fast.py): |delta dm| <= 1e-5 * rms(dm) per channel
+ * — most of it is the reference's own table rounding (float phase*ind), the fast form is closer to the
+ * exact DFT than the reference is — and decoded messages identical on every fixture.  The default
+ * (exact) kernel above stays bit-identical; this one is what the north star's tolerance (messages
+ * bit-exact, float intermediates within 1e-5) buys.
+ *
+ * Shape: one CTA = one 1024-row block of one stream for 8 channels, 16 tiles of 64 rows dealt round-robin
+ * to its warps; lane l owns rows l and l+32 of a tile, and every FP32 instruction is packed across those
+ * two rows (FADD2/FFMA2: half the issue slots; the twiddle rides FFMA2's scalar-broadcast operand).
+ * Whole rows are fetched by bulk copies (cp.async.bulk of one or two rows, completion on the warp's
+ * mbarrier) issued by one lane: every 32-byte sector fetched is used, no per-unit addressing.
+ * Warps do not synchronise with each other after the twiddles are in shared memory; with one private
+ * buffer per warp, the copy of a warp's next tile hides under the other warps' arithmetic.
+ * ---------------------------------------------------------------------------------------- */
+
+constexpr int DFT_ROWS = 64;                     /* rows per tile: 2 per lane */
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
+{
+	float2 d;
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<unsigned long long &>(d))
+	    : "l"(reinterpret_cast<unsigned long long &>(a)), "l"(reinterpret_cast<unsigned long long &>(b)),
+	      "l"(reinterpret_cast<unsigned long long &>(c)));
+	return d;
+}
+__device__ __forceinline__ float2 fsub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+
+/* byte `k` of word wa / wb as 32768 + u, packed (row A, row B): the byte lands in bits 8..15 of the
+ * mantissa of 2^15, where the unit weight is */
+template <int KB> __device__ __forceinline__ float2 dft_cvt(unsigned wa, unsigned wb)
+{
+	constexpr unsigned sel = 0x7404u | (KB << 4);
+	return make_float2(__uint_as_float(__byte_perm(wa, 0x47000000u, sel)), __uint_as_float(__byte_perm(wb, 0x47000000u, sel)));
+}
+
+struct DftAcc { float2 a, b, p, q; };            /* re = a - b, im = p + q; each packed (row A, row B) */
+
+/* acc += y * t for the lane's two rows; t = (Tr, Ti) is warp-uniform.  Passing the same scalar as both
+ * halves of the multiplier makes ptxas use FFMA2's broadcast operand form (R.F32): no pair to build.
+ * Four independent accumulators keep the dependent FFMA2 chains short. */
+__device__ __forceinline__ void dft_mac(DftAcc &acc, float2 yr, float2 yi, float2 t)
+{
+	const float2 tr = make_float2(t.x, t.x), ti = make_float2(t.y, t.y);
+	acc.a = ffma2(yr, tr, acc.a);
+	acc.b = ffma2(yi, ti, acc.b);
+	acc.p = ffma2(yr, ti, acc.p);
+	acc.q = ffma2(yi, tr, acc.q);
+}
+
+/* mbarrier + bulk-copy (TMA 1-D) plumbing */
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+	asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+	             ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+/* Shared-memory plan of one CTA: WARPS warps, each with STAGES private tile buffers of 64 rows. */
+template <int UNITS, int WARPS, int STAGES> struct DftPlan {
+	static constexpr int ROWBYTES = UNITS * 16;
+	/* rows per bulk copy, each copy followed by 16 bytes of padding.  The eight lanes of an LDS.128
+	 * phase read eight consecutive rows at the same offset: they hit eight different 16-byte bank groups
+	 * when the row stride is an odd number of units (UNITS odd after padding every row), or — UNITS = 20,
+	 * stride = 4 mod 8 — when every second row is shifted by one more unit (pad after every two rows). */
+	static constexpr int RPC = (UNITS % 8 == 4) ? 2 : 1;
+	static constexpr int GROUP = RPC * ROWBYTES + 16;
+	static constexpr int TILE_BYTES = DFT_ROWS / RPC * GROUP;
+	static __device__ __forceinline__ int row_off(int r) { return (r / RPC) * GROUP + (r % RPC) * ROWBYTES; }
+	static constexpr int N2 = UNITS * 2;                                     /* K/4 */
+	static constexpr int TW_BYTES = N2 * CH_GROUP * 8;
+	static constexpr int BAR_OFF = WARPS * STAGES * TILE_BYTES + TW_BYTES;
+	static constexpr int SMEM = BAR_OFF + WARPS * STAGES * 8;
+};
+
+template <int UNITS, int WARPS, int STAGES, int MINB>
+__global__ void __launch_bounds__(32 * WARPS, MINB)
+k_channelize_dft(const uint8_t *__restrict__ in, size_t stream_stride, const float2 *__restrict__ tw,
+                 const unsigned *__restrict__ meta, float *__restrict__ dm, int nch, int ngrp, size_t nsamp)
+{
+	using P = DftPlan<UNITS, WARPS, STAGES>;
+	constexpr int CU = UNITS / 4;                 /* 16-byte units per quarter row */
+	constexpr int N2 = P::N2;
+	constexpr int NTILE = OUTBLK / DFT_ROWS;
+	extern __shared__ __align__(128) unsigned char smem[];
+	const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int blk = blockIdx.x, s = blockIdx.y, g = blockIdx.z;
+	unsigned char *mytiles = smem + (size_t)w * STAGES * P::TILE_BYTES;
+	const float4 *stw = reinterpret_cast<const float4 *>(smem + (size_t)WARPS * STAGES * P::TILE_BYTES);   /* [ch][n2] (Tr, Ti) */
+	unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + P::BAR_OFF) + w * STAGES;
+	const uint8_t *src_blk = in + (size_t)s * stream_stride + (size_t)blk * OUTBLK * P::ROWBYTES;
+	const unsigned m = meta[(size_t)s * ngrp + g];    /* residue k_c mod 4 (0 or 2) of channel slot c in bits 2c, 2c+1 */
+
+	if (l == 0)
+		for (int i = 0; i < STAGES; i++) mbar_init(bars + i, 1);
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	{
+		const uint4 *tsrc = reinterpret_cast<const uint4 *>(tw + ((size_t)s * ngrp + g) * N2 * CH_GROUP);
+		uint4 *tdst = reinterpret_cast<uint4 *>(smem + (size_t)WARPS * STAGES * P::TILE_BYTES);
+		for (int q = threadIdx.x; q < P::TW_BYTES / 16; q += 32 * WARPS) cp_async16(tdst + q, tsrc + q);
+		cp_async_commit();
+		cp_async_wait_all();
+	}
+	__syncthreads();
+
+	/* this warp's tiles: w, w + WARPS, ...; tile n of the warp uses stage n % STAGES */
+	const int ntile = (NTILE - w + WARPS - 1) / WARPS;
+	auto issue = [&](int n) {
+		const int tile = w + n * WARPS;
+		unsigned char *st = mytiles + (size_t)(n % STAGES) * P::TILE_BYTES;
+		unsigned long long *bar = bars + n % STAGES;
+		if (l == 0) {
+			mbar_expect_tx(bar, DFT_ROWS * P::ROWBYTES);
+			const uint8_t *src = src_blk + (size_t)tile * DFT_ROWS * P::ROWBYTES;
+#pragma unroll 4
+			for (int i = 0; i < DFT_ROWS / P::RPC; i++)
+				bulk_g2s(st + (size_t)i * P::GROUP, src + (size_t)i * P::RPC * P::ROWBYTES, P::RPC * P::ROWBYTES, bar);
+		}
+	};
+	for (int n = 0; n < STAGES && n < ntile; n++) issue(n);
+	const int nc = min(CH_GROUP, nch - g * CH_GROUP);
+
+	for (int n = 0; n < ntile; n++) {
+		const int tile = w + n * WARPS;
+		mbar_wait(bars + n % STAGES, (unsigned)((n / STAGES) & 1));
+		const unsigned char *st = mytiles + (size_t)(n % STAGES) * P::TILE_BYTES;
+		const uint4 *rowA = reinterpret_cast<const uint4 *>(st + P::row_off(l));
+		const uint4 *rowB = reinterpret_cast<const uint4 *>(st + P::row_off(l + 32));
+		DftAcc acc[CH_GROUP];
+#pragma unroll
+		for (int c = 0; c < CH_GROUP; c++) acc[c].a = acc[c].b = acc[c].p = acc[c].q = make_float2(0.f, 0.f);
+
+		/* unit j covers samples 8j..8j+7 of each quarter: one LDS.128 per quarter and row (their latency
+		 * is left to the other warps of the SM to cover) */
+#pragma unroll 1
+		for (int j = 0; j < CU; j++) {
+			uint4 qa[4], qb[4];
+#pragma unroll
+			for (int n1 = 0; n1 < 4; n1++) { qa[n1] = rowA[n1 * CU + j]; qb[n1] = rowB[n1 * CU + j]; }
+#pragma unroll
+			for (int eh = 0; eh < 2; eh++) {      /* four samples of each quarter at a time */
+				float2 y0r[4], y0i[4], y2r[4], y2i[4];
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					float2 xi[4], xq[4];
+#pragma unroll
+					for (int n1 = 0; n1 < 4; n1++) {
+						const unsigned wa = eh ? (k < 2 ? qa[n1].z : qa[n1].w) : (k < 2 ? qa[n1].x : qa[n1].y);
+						const unsigned wb = eh ? (k < 2 ? qb[n1].z : qb[n1].w) : (k < 2 ? qb[n1].x : qb[n1].y);
+						if (k & 1) { xi[n1] = dft_cvt<2>(wa, wb); xq[n1] = dft_cvt<3>(wa, wb); }
+						else       { xi[n1] = dft_cvt<0>(wa, wb); xq[n1] = dft_cvt<1>(wa, wb); }
+					}
+					/* sums carry the 2 x 32768 planted by dft_cvt (exact: < 2^24); differences do not.  Y_0
+					 * also sheds the converter's mid-scale 4 x 127.5 here: any constant is invisible to a
+					 * channel (its twiddles sum to zero) but a large one costs accumulate precision */
+					const float2 sI02 = __fadd2_rn(xi[0], xi[2]), sI13 = __fadd2_rn(xi[1], xi[3]);
+					const float2 sQ02 = __fadd2_rn(xq[0], xq[2]), sQ13 = __fadd2_rn(xq[1], xq[3]);
+					const float2 bias = make_float2(-131582.0f, -131582.0f);
+					y0r[k] = __fadd2_rn(__fadd2_rn(sI02, sI13), bias);
+					y0i[k] = __fadd2_rn(__fadd2_rn(sQ02, sQ13), bias);
+					y2r[k] = fsub2(sI02, sI13);
+					y2i[k] = fsub2(sQ02, sQ13);
+				}
+				/* channel c's four twiddles: two LDS.128, fetched one channel ahead of their use so the
+				 * load latency hides under the previous channel's FFMA2s (the residue dispatch below is a
+				 * uniform branch the scheduler does not move loads across) */
+				const float4 *tj = stw + (j * 2 + eh) * 2;
+				float4 t0 = tj[0], t1 = tj[1];
+#pragma unroll
+				for (int c = 0; c < CH_GROUP; c++) {
+					const float4 u0 = t0, u1 = t1;
+					if (c + 1 < CH_GROUP) { t0 = tj[(c + 1) * (N2 / 2)]; t1 = tj[(c + 1) * (N2 / 2) + 1]; }
+					const float2 tt[4] = { make_float2(u0.x, u0.y), make_float2(u0.z, u0.w), make_float2(u1.x, u1.y), make_float2(u1.z, u1.w) };
+					if (((m >> (2 * c)) & 3u) == 0) {             /* warp-uniform: k_c mod 4 is 0 or 2 */
+#pragma unroll
+						for (int k = 0; k < 4; k++) dft_mac(acc[c], y0r[k], y0i[k], tt[k]);
+					} else {
+#pragma unroll
+						for (int k = 0; k < 4; k++) dft_mac(acc[c], y2r[k], y2i[k], tt[k]);
+					}
+				}
+			}
+		}
+		/* every lane has its rows in registers: the stage can take the warp's tile n + STAGES */
+		__syncwarp();
+		if (n + STAGES < ntile) issue(n + STAGES);
+		/* |D| out (rtl.c:353) for the lane's two rows */
+#pragma unroll
+		for (int half = 0; half < 2; half++) {
+			float e[CH_GROUP];
+#pragma unroll
+			for (int c = 0; c < CH_GROUP; c++) {
+				const float re = half ? __fadd_rn(acc[c].a.y, -acc[c].b.y) : __fadd_rn(acc[c].a.x, -acc[c].b.x);
+				const float im = half ? __fadd_rn(acc[c].p.y, acc[c].q.y) : __fadd_rn(acc[c].p.x, acc[c].q.x);
+				e[c] = __fsqrt_rn(__fmaf_rn(re, re, __fmul_rn(im, im)));      /* |D|: half an ulp, this form's tolerance is 1e-5 */
+			}
+			const size_t mrow = (size_t)blk * OUTBLK + (size_t)tile * DFT_ROWS + l + half * 32;
+			float *o = dm + ((size_t)s * nsamp + mrow) * nch + g * CH_GROUP;
+			if (nc == CH_GROUP && (nch & 3) == 0) {
+				reinterpret_cast<float4 *>(o)[0] = make_float4(e[0], e[1], e[2], e[3]);
+				reinterpret_cast<float4 *>(o)[1] = make_float4(e[4], e[5], e[6], e[7]);
+			} else {
+#pragma unroll
+				for (int c = 0; c < CH_GROUP; c++)
+					if (c < nc) o[c] = e[c];
+			}
+		}
+	}
+}
+
+template <int UNITS, int WARPS, int STAGES, int MINB = 1>
+static int launch_dft_t(const uint8_t *in, size_t stream_stride, const float2 *tw, const unsigned *meta, float *dm,
+                        int nch, int nstreams, int nblk, size_t nsamp, cudaStream_t stream)
+{
+	const int ngrp = (nch + CH_GROUP - 1) / CH_GROUP;
+	constexpr int smem = DftPlan<UNITS, WARPS, STAGES>::SMEM;
+	auto kern = k_channelize_dft<UNITS, WARPS, STAGES, MINB>;
+	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	if (e != cudaSuccess) return (int)e;
+	e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+	if (e != cudaSuccess) return (int)e;
+	dim3 grid(nblk, nstreams, ngrp);
+	kern<<<grid, 32 * WARPS, smem, stream>>>(in, stream_stride, tw, meta, dm, nch, ngrp, nsamp);
+	return (int)cudaGetLastError();
+}
+
+bool channelize_dft_supports(int K) { return K == 160 || K == 192; }
+
+/* u8 IQ, K in {160, 192} (the reference's two rates), taps == K, every channel on the 12.5 kHz raster
+ * around Fc (context.cu checks and builds tw/meta) */
+int launch_channelize_dft(const void *in, size_t stream_stride, const float *tw, const unsigned *meta, float *dm,
+                          int K, int nch, int nstreams, int nblk, size_t nsamp, cudaStream_t stream)
+{
+	if (nblk == 0) return 0;
+	const uint8_t *i8 = reinterpret_cast<const uint8_t *>(in);
+	const float2 *t4 = reinterpret_cast<const float2 *>(tw);
+	static int variant = -1;                      /* ACB_DFT_VARIANT=warps*10+stages overrides (tuning aid) */
+	if (variant < 0) { const char *e = getenv("ACB_DFT_VARIANT"); variant = e ? atoi(e) : 0; }
+	if (K == 160) {
+		switch (variant) {
+		case 12: return launch_dft_t<20, 1, 2>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
+		case 22: return launch_dft_t<20, 2, 2>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
+		case 21: return launch_dft_t<20, 2, 1, 4>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
+		case 41: return launch_dft_t<20, 4, 1>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
+		case 31: return launch_dft_t<20, 3, 1, 3>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
+		default: return launch_dft_t<20, 2, 1, 5>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
+		}
+	}
+	if (K == 192) return launch_dft_t<24, 2, 1, 4>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
+	return (int)cudaErrorInvalidValue;
 }
 
 /* Rows the pipeline kernel does not take (K that breaks 16-byte row alignment; the < 1024 rows

@@ -57,6 +57,13 @@ typedef struct {
 #define ACB_FLAG_NO_INPUT_STAGING 1   /* caller only uses acb_submit_device / acb_submit_dm_* */
 #define ACB_FLAG_CS16_INPUT 4         /* SoapySDR / SDRplay front-ends (soapy.c, sdrplay.c): int16 I,Q samples;
                                          use acb_set_plan_cs16 / acb_submit_cs16_host (or _planar_host) */
+#define ACB_FLAG_FAST_CHANNELIZER 8    /* u8 IQ contexts planned with acb_set_plan, K = 160 or 192: run the channelizer
+                                         as a shared 4-point DFT across the row quarters + K/4 MACs per channel
+                                         (5x less FP32 work) when every stream's channels sit on the 12.5 kHz raster
+                                         around Fc; otherwise the exact kernel runs.  NOT the reference's operation
+                                         order: the envelope agrees with the reference to |delta| <= 1e-5 * rms per channel
+                                         (the reference's own table rounding dominates the difference), decoded
+                                         messages are the same; without this flag the envelope is bit-identical */
 #define ACB_FLAG_REAL_INPUT 2         /* Airspy front-end (air.c): float32 REAL samples at IF = rate/4,
                                          rate = K*12500; use acb_set_plan_air / acb_submit_real_host */
 
@@ -197,6 +204,7 @@ typedef struct {
 	double   chan_ms;           /* accumulated device time of the channelizer kernel (CUDA events) */
 	double   demod_ms;          /* accumulated device time of the demod kernel */
 	uint64_t chan_launches, demod_launches;
+	uint64_t fast_chan_launches; /* channelizer launches that took the ACB_FLAG_FAST_CHANNELIZER form */
 } acb_stats_t;
 int acb_get_stats(acb_ctx_t *ctx, acb_stats_t *out, int reset);
 

@@ -27,4 +27,23 @@ xw, exp = load_testwav()
 with api.Context(160, 1, 4, 4, flags=1) as ctx:
     ctx.submit_dm(xw[None, :4096]); ctx.submit_dm(xw[None, 4096:8000]); ctx.sync()
     n3 = len(ctx.drain())
-print("sanitize run ok", n1, n3)
+# fast channelizer (bulk copies + mbarrier), K=160 and K=192, partial channel group
+for Kf, fmf in ((160, fm), (192, (131.525, 131.725, 131.825))):
+    fdf, _, fcf = api.plan(Kf, fmf)
+    pf = synth.make_plan(Kf, fmf, fcf, seconds=0.24, seed=6, text_len=(5, 20))
+    iqf = synth.render_blocks(pf, 0, 2).reshape(1, -1)
+    with api.Context(Kf, 2, len(fmf), 2, flags=8) as ctx:
+        for s in range(2): ctx.set_plan(s, fdf)
+        ctx.submit_host(np.concatenate([iqf, iqf]), 2); ctx.submit_host(np.concatenate([iqf, iqf]), 2); ctx.sync()
+        assert ctx.stats().fast_chan_launches == 2
+        n4 = len(ctx.drain())
+# CS16 front-end with a ragged length, and the batched device FEC
+iqc = synth.render_cs16(plan, 0, 1024 * K + 333)[None]
+with api.Context(K, 1, 8, 2, flags=4) as ctx:
+    ctx.set_plan_cs16(0, fd, 0); ctx.submit_cs16(iqc); ctx.submit_cs16(iqc[:, :4000]); ctx.sync()
+    m = api.Msg(); fr = synth.frame_bytes(b"SANITIZER", prekey=0)[5:-1]
+    m.len = len(fr) - 2; m.txt[:m.len] = fr[:-2]; m.crc[:] = fr[-2:]
+    m.txt[3] ^= 0x04
+    out = ctx.block_fec_batch([m] * 70)
+    assert all(o is not None and o.err == 1 for o in out)
+print("sanitize run ok", n1, n3, n4)
