@@ -76,6 +76,7 @@ ABI = [
     ("acb_air_choose_fc", C.c_uint, [C.c_uint, C.c_uint]),
     ("acb_air_build_wf", None, [C.c_int, C.c_int, C.c_uint, C.c_void_p]),
     ("acb_cs16_build_wf", None, [C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_void_p]),
+    ("acb_fast_plan", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p, C.c_void_p]),
     ("acb_build_h", None, [C.c_void_p]),
     ("acb_create", C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
     ("acb_destroy", None, [C.c_void_p]),
@@ -160,6 +161,18 @@ def build_wf(K: int, freqs_mhz) -> np.ndarray:
     for i, f in enumerate(fr):
         lib.acb_build_wf(f, fc, K, out[i].ctypes.data)
     return out
+
+
+def fast_plan(K: int, freqs_hz, fc: int):
+    """Planning step of the fast channelizer: (k per channel, twiddles (nch, K/4) complex64), or None when
+    some channel is off the 12.5 kHz raster around Fc (the exact kernel runs then)."""
+    lib = load()
+    f = np.asarray(freqs_hz, dtype=np.uint32)
+    k = np.zeros(len(f), dtype=np.int32)
+    tw = np.zeros((len(f), K // 4, 2), dtype=np.float32)
+    if lib.acb_fast_plan(f.ctypes.data, len(f), K, fc, k.ctypes.data, tw.ctypes.data) != 1:
+        return None
+    return k, tw[..., 0] + 1j * tw[..., 1]
 
 
 def air_plan(rate: int, freqs_mhz):

@@ -354,27 +354,17 @@ extern "C" int acb_set_plan(acb_ctx_t *c, int stream, const unsigned *freqs_hz, 
 	if (fc_out) *fc_out = fc;
 	if (int r = acb_set_wf(c, stream, wf.data(), nch)) return r;
 	if (!c->fast) return ACB_OK;
-	/* Fast form: wf[ind] = g*exp(-j*2*pi*k*ind/K) needs the mixer offset to be a whole number k of
-	 * 12.5 kHz steps — judged on what the reference actually mixes with: the float images of the
-	 * stored Fr and of Fc (rtl.c:255, 283).  T_c[n2] = g*exp(-j*2*pi*k_c*n2/K), g = 1/K/127.5. */
+	/* Fast form: per-channel bin numbers and twiddles, when every channel sits on the raster */
 	const int K = c->cfg.K, N2 = K / 4;
+	std::vector<int> kbin(nch);
+	std::vector<float> tw1((size_t)nch * N2 * 2);
+	const bool ok = acb_fast_plan(freqs_hz, nch, K, fc, kbin.data(), tw1.data()) == 1;
 	std::vector<float> tw((size_t)c->ngrp * CH_GROUP * N2 * 2, 0.0f);
 	std::vector<unsigned> meta(c->ngrp, 0u);
-	bool ok = true;
 	for (int ch = 0; ch < nch && ok; ch++) {
-		const float d = (float)acb_stored_fr(freqs_hz[ch]) - (float)fc;
-		const float kf = d / (float)ACB_INTRATE;
-		const int k = (int)kf;
-		if ((float)k != kf || (k & 1) || k == 0 || k <= -K / 2 || k >= K / 2) { ok = false; break; }
-		const unsigned r = (unsigned)(((k % 4) + 4) % 4);      /* 0 or 2: float images of Fr, Fc are multiples of 8 Hz */
 		const int g = ch / CH_GROUP, cc = ch % CH_GROUP;
-		meta[g] |= r << (2 * cc);
-		for (int n2 = 0; n2 < N2; n2++) {
-			const double ph = -2.0 * M_PI * (double)(((long long)k * n2) % K) / (double)K;
-			float *o = &tw[(((size_t)g * CH_GROUP + cc) * N2 + n2) * 2];
-			o[0] = (float)(cos(ph) / K / 127.5);
-			o[1] = (float)(sin(ph) / K / 127.5);
-		}
+		meta[g] |= (unsigned)(((kbin[ch] % 4) + 4) % 4) << (2 * cc);      /* 0 or 2 */
+		memcpy(&tw[((size_t)g * CH_GROUP + cc) * N2 * 2], &tw1[(size_t)ch * N2 * 2], (size_t)N2 * 2 * sizeof(float));
 	}
 	if (ok) {
 		CU(cudaMemcpy(c->d_tw + (size_t)stream * tw.size(), tw.data(), tw.size() * sizeof(float), cudaMemcpyHostToDevice));

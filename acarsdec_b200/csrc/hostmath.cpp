@@ -128,6 +128,31 @@ extern "C" void acb_cs16_build_wf(int variant, unsigned freq_hz, unsigned fc_hz,
 	}
 }
 
+extern "C" int acb_fast_plan(const unsigned *freqs_hz, int nch, int K, unsigned fc_hz, int *k_out, float *tw)
+{
+	/* The reference's table wf[ind] = cexpf(-j*AMFreq*ind)/K/127.5 (rtl.c:283-286) is a sampled complex
+	 * exponential; when the offset it mixes with — the float image of the stored Fr minus the float
+	 * image of Fc (rtl.c:255, 283) — is a whole number k of 12.5 kHz steps, D is bin k of a K-point DFT of
+	 * the row and k_channelize_dft applies.  Both float images are multiples of 8 Hz, so k is even.
+	 * T_c[n2] = exp(-j*2*pi*k*n2/K)/K/127.5 for n2 < K/4, evaluated in double. */
+	if (!freqs_hz || nch <= 0 || K <= 0 || (K & 3)) return 0;
+	const int N2 = K / 4;
+	for (int ch = 0; ch < nch; ch++) {
+		const float d = (float)acb_stored_fr(freqs_hz[ch]) - (float)fc_hz;
+		const float kf = d / (float)ACB_INTRATE;
+		const int k = (int)kf;
+		if ((float)k != kf || (k & 1) || k == 0 || k <= -K / 2 || k >= K / 2) return 0;
+		if (k_out) k_out[ch] = k;
+		if (!tw) continue;
+		for (int n2 = 0; n2 < N2; n2++) {
+			const double ph = -2.0 * M_PI * (double)(((long long)k * n2) % K) / (double)K;
+			tw[((size_t)ch * N2 + n2) * 2] = (float)(cos(ph) / K / 127.5);
+			tw[((size_t)ch * N2 + n2) * 2 + 1] = (float)(sin(ph) / K / 127.5);
+		}
+	}
+	return 1;
+}
+
 extern "C" void acb_build_h(float *h)
 {
 	/* msk.c:44-48: cos(2*pi*600/INTRATE/12 * (i - 66)) evaluated by cosf on the float-rounded

@@ -407,7 +407,7 @@ k_channelize_dft(const uint8_t *__restrict__ in, size_t stream_stride, const flo
 	constexpr int CU = UNITS / 4;                 /* 16-byte units per quarter row */
 	constexpr int N2 = P::N2;
 	constexpr int NTILE = OUTBLK / DFT_ROWS;
-	extern __shared__ __align__(128) unsigned char smem[];
+	extern __shared__ __align__(16) unsigned char smem[];
 	const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
 	const int blk = blockIdx.x, s = blockIdx.y, g = blockIdx.z;
 	unsigned char *mytiles = smem + (size_t)w * STAGES * P::TILE_BYTES;

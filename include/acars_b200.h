@@ -116,6 +116,11 @@ void acb_air_build_wf(int fr_hz, int fc_hz, unsigned rate, float *wf);
 #define ACB_CS16_SOAPY 0
 #define ACB_CS16_SDRPLAY 1
 void acb_cs16_build_wf(int variant, unsigned freq_hz, unsigned fc_hz, int K, float *wf);
+/* Planning step of ACB_FLAG_FAST_CHANNELIZER: returns 1 when every channel's mixer offset (float image
+ * of the stored Fr minus float image of Fc, as rtl.c:283 computes it) is a whole, even number k of
+ * 12.5 kHz steps with 0 < |k| < K/2; then k_out[ch] = k and tw[(ch*(K/4) + n2)*2 + {0,1}] =
+ * exp(-j*2*pi*k*n2/K)/K/127.5.  k_out and tw may be NULL.  Returns 0 otherwise (the exact kernel runs). */
+int acb_fast_plan(const unsigned *freqs_hz, int nch, int K, unsigned fc_hz, int *k_out, float *tw);
 /* msk.c:44-48 — 133-tap oversampled half-cosine matched filter */
 void acb_build_h(float *h);
 

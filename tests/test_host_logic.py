@@ -163,3 +163,44 @@ def test_no_cpu_fallback(native):
 def test_air_planning_matches_oracle(native, oracle, rate, freqs):
     assert api.air_plan(rate, freqs) == oracle.air_plan(rate, freqs)
     assert bits_equal(api.build_wf_air(rate, freqs), oracle.air_wf(rate, freqs))
+
+
+@pytest.mark.parametrize("K", [160, 192])
+def test_fast_plan_factorises_the_reference_table(native, oracle, K):
+    """ACB_FLAG_FAST_CHANNELIZER's planning step, on the CPU: the reference's mixer table (rtl.c:283-286,
+    through the pinned restatement) must be the fast form's factorisation (-j)^(r*n1) * T[n2] up to the
+    table's own float phase rounding — this is the whole mathematical content of k_channelize_dft."""
+    fm = synth.DEFAULT_FREQS_MHZ
+    fd, fr, fc = api.plan(K, fm)
+    res = api.fast_plan(K, fd, fc)
+    assert res is not None
+    k, tw = res
+    assert [int(x) for x in k] == [round((float(np.float32(f)) - float(np.float32(fc))) / 12500) for f in fr]
+    assert all(x % 2 == 0 and x != 0 for x in k)
+    wf = oracle.wf(K, fm)
+    N2 = K // 4
+    for c in range(len(fm)):
+        ref = wf[c, 0::2].astype(np.float64) + 1j * wf[c, 1::2]
+        r = int(k[c]) % 4
+        fact = np.concatenate([(-1j) ** (r * n1) * tw[c].astype(np.complex128) for n1 in range(4)])
+        # the reference's phases are float(AMFreq*ind): up to ~1.5e-5 rad of rounding at ind ~ K
+        assert np.abs(fact - ref).max() <= 3e-5 * np.abs(ref).max()
+        # and the twiddles themselves are the double-precision values rounded once
+        want = np.exp(-2j * np.pi * ((int(k[c]) * np.arange(N2)) % K) / K) / K / 127.5
+        assert np.abs(tw[c] - want).max() <= 1e-7 * np.abs(want).max()
+
+
+def test_fast_plan_rejects_off_raster_channels(native):
+    K = 160
+    fd, _, fc = api.plan(K, (131.525, 131.725, 131.825))
+    assert api.fast_plan(K, fd, fc) is not None
+    # 131.4875 MHz is on the 12.5 kHz raster but its float image (what rtl.c:255 stores) is 4 Hz off
+    fd2, _, fc2 = api.plan(K, (131.4875, 131.725))
+    assert api.fast_plan(K, fd2, fc2) is None
+    # a centre frequency off the raster (fc - 1 would not do: rtl.c:283 mixes with (float)Fc, and the float
+    # image of fc - 1 is fc)
+    assert api.fast_plan(K, fd, fc - 100) is None
+    assert api.fast_plan(K, fd, fc - 1) is not None
+    # a channel at the centre (bin 0) or beyond the band edge
+    assert api.fast_plan(K, [fc], fc) is None
+    assert api.fast_plan(K, [fc - 80 * 12500], fc) is None
