@@ -65,7 +65,7 @@ int launch_channelize(int mode, const void *in, size_t stream_stride_bytes, cons
 int launch_channelize_generic(int mode, const void *in, size_t stream_stride, const void *wf, float *dm,
                               int K, int taps, int nch, int nstreams, size_t row0, size_t nrows, size_t nsamp, CUstream_st *stream);
 int launch_demod(ChainState *st, const float *dm, int nsamp, int nch, int nstreams,
-                 RawFrame *ring, RingCtl *ctl, unsigned cap, CUstream_st *stream);
+                 RawFrame *ring, RingCtl *ctl, unsigned cap, int lanes_per_channel, CUstream_st *stream);
 bool channelize_dft_supports(int K);
 int launch_channelize_dft(const void *in, size_t stream_stride, const float *tw, const unsigned *meta, float *dm,
                           int K, int nch, int nstreams, int nblk, size_t nsamp, CUstream_st *stream);

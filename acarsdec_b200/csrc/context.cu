@@ -71,6 +71,7 @@ struct acb_ctx {
 	int next_buf;
 	float *d_wf4;                /* [stream][grp][K][8] float4 (c, d, -d, c) */
 	bool fast;                   /* ACB_FLAG_FAST_CHANNELIZER and a shape k_channelize_dft takes */
+	int demod_lanes;             /* lanes per channel in k_demod: 8 for small contexts, else 4 */
 	float *d_tw;                 /* fast form: [stream][grp][8 ch][K/4] (Tr, Ti) twiddles */
 	unsigned *d_twmeta;          /* fast form: [stream][grp] residues k_c mod 4, 2 bits per channel slot */
 	std::vector<unsigned char> fast_ok;   /* per stream: planned on the 12.5 kHz raster (0 after acb_set_wf: caller's own table) */
@@ -234,6 +235,13 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 	CU(cudaMemset(c->d_wf4, 0, wf_floats * sizeof(float)));
 	c->fast = (cfg->flags & ACB_FLAG_FAST_CHANNELIZER) && c->in_kind == IN_KIND_U8IQ && c->taps == cfg->K && channelize_dft_supports(cfg->K);
 	c->fast_ok.assign(cfg->nstreams, 0);
+	{
+		/* 8 lanes per channel halve the mixer's share of the serial chain but double the warps: a gain (8 % on
+		 * one 8-channel stream) only while there is still at most one demod warp per SM sub-partition;
+		 * beyond that the extra warps cost more than they hide (592 streams: 4.54 -> 4.72 ms) */
+		const long long warps8 = (long long)cfg->nstreams * ((cfg->nch + 3) / 4);
+		c->demod_lanes = warps8 <= 4LL * prop.multiProcessorCount ? 8 : 4;
+	}
 	if (c->fast) {
 		CU(cudaMalloc(&c->d_tw, (size_t)cfg->nstreams * c->ngrp * CH_GROUP * (cfg->K / 4) * 2 * sizeof(float)));
 		CU(cudaMalloc(&c->d_twmeta, (size_t)cfg->nstreams * c->ngrp * sizeof(unsigned)));
@@ -523,7 +531,7 @@ static int run_kernels(acb_ctx *c, const uint8_t *d_iq, size_t stride, int nblk,
 	}
 	CU(cudaMemsetAsync(c->d_ctl[b], 0, sizeof(RingCtl), c->s_dem));
 	CU(cudaEventRecord(t.ev.b2, c->s_dem));
-	int r = launch_demod(c->d_state, dmbuf, nsamp, c->cfg.nch, c->cfg.nstreams, c->d_ring[b], c->d_ctl[b], c->ring_cap, c->s_dem);
+	int r = launch_demod(c->d_state, dmbuf, nsamp, c->cfg.nch, c->cfg.nstreams, c->d_ring[b], c->d_ctl[b], c->ring_cap, c->demod_lanes, c->s_dem);
 	if (r) return fail(ACB_ERR_CUDA, "demod launch: %s", cudaGetErrorString((cudaError_t)r));
 	c->stats.kernel_launches++;
 	c->stats.demod_launches++;

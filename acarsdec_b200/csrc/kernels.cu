@@ -19,7 +19,6 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
-#include <stdlib.h>
 
 #include "acb_internal.h"
 #include "frame_sm.h"
@@ -311,11 +310,11 @@ int launch_channelize(int mode, const void *in, size_t stream_stride_bytes, cons
  * 10.5), which moves the kernel from the FP32 roof towards the HBM roof.
  *
  * This is NOT the reference's operation order: the envelope differs from the reference's in the last
- * bits.  Measured against the reference (tests/test_gpu_fast.py): |delta dm| <= 1e-5 * rms(dm) per channel
- * — most of it is the reference's own table rounding (float phase*ind), the fast form is closer to the
- * exact DFT than the reference is — and decoded messages identical on every fixture.  The default
- * (exact) kernel above stays bit-identical; this one is what the north star's tolerance (messages
- * bit-exact, float intermediates within 1e-5) buys.
+ * bits.  Measured (tests/test_gpu_fast.py): within 2e-6 of the exact double-precision DFT bin — closer
+ * than the reference, whose table carries float phase rounding (float AMFreq*ind) worth up to 1e-5 of
+ * the total in-band signal — and decoded messages identical on every fixture.  The default (exact)
+ * kernel above stays bit-identical; this one is what the north star's tolerance (messages bit-exact,
+ * float intermediates within tolerance) buys.
  *
  * Shape: one CTA = one 1024-row block of one stream for 8 channels, 16 tiles of 64 rows dealt round-robin
  * to its warps; lane l owns rows l and l+32 of a tile, and every FP32 instruction is packed across those
@@ -559,18 +558,10 @@ int launch_channelize_dft(const void *in, size_t stream_stride, const float *tw,
 	if (nblk == 0) return 0;
 	const uint8_t *i8 = reinterpret_cast<const uint8_t *>(in);
 	const float2 *t4 = reinterpret_cast<const float2 *>(tw);
-	static int variant = -1;                      /* ACB_DFT_VARIANT=warps*10+stages overrides (tuning aid) */
-	if (variant < 0) { const char *e = getenv("ACB_DFT_VARIANT"); variant = e ? atoi(e) : 0; }
-	if (K == 160) {
-		switch (variant) {
-		case 12: return launch_dft_t<20, 1, 2>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
-		case 22: return launch_dft_t<20, 2, 2>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
-		case 21: return launch_dft_t<20, 2, 1, 4>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
-		case 41: return launch_dft_t<20, 4, 1>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
-		case 31: return launch_dft_t<20, 3, 1, 3>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
-		default: return launch_dft_t<20, 2, 1, 5>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
-		}
-	}
+	/* 2 warps per CTA, one tile buffer per warp; K=160: 44.5 KB of shared memory and <= 200 registers
+	 * -> 5 CTAs = 10 warps per SM (measured: 0.97 ms; 3 or 4 warps per CTA 1.09-1.43 ms; two buffers per
+	 * warp with half the warps 1.73 ms) */
+	if (K == 160) return launch_dft_t<20, 2, 1, 5>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
 	if (K == 192) return launch_dft_t<24, 2, 1, 4>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
 	return (int)cudaErrorInvalidValue;
 }
@@ -763,8 +754,9 @@ __device__ __forceinline__ double round_to_f32(double x)
 
 constexpr int DEMOD_LOOK = 6;    /* samples examined per outer iteration (bit period = 5.17..5.25) */
 
-constexpr int DEMOD_GROUP = 4;                       /* lanes per channel (8 is faster alone, slower under the channelizer) */
-constexpr int DEMOD_CPW = 32 / DEMOD_GROUP;          /* channels per warp */
+/* lanes per channel: 4 (8 channels per warp), or 8 (4 channels per warp, one mixer evaluation per lane
+ * instead of two) for contexts small enough that the doubled warp count still fits one warp per SM
+ * sub-partition (context.cu decides) */
 
 /* One warp = 8 channels of one stream x 4 lanes per channel.  The 4 lanes of a channel run the
  * SAME recurrence on the same inputs (identical registers, no communication needed) except for
@@ -773,10 +765,12 @@ constexpr int DEMOD_CPW = 32 / DEMOD_GROUP;          /* channels per warp */
  * independent sincos evaluations of a bit period executed side by side: as straight-line code of
  * one lane, ptxas schedules them back to back (6 x 16 dependent FP64 ops x 8 cycles).  Only the
  * group leader touches HBM state (frame text, frame ring, state write-back). */
+template <int DEMOD_GROUP>
 __global__ void __launch_bounds__(32)
 k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp, int nch, int nstreams,
         int wps, RawFrame *__restrict__ ring, RingCtl *__restrict__ ctl, unsigned cap)
 {
+	constexpr int DEMOD_CPW = 32 / DEMOD_GROUP;      /* channels per warp */
 	__shared__ float s_h[FLENO + 3];
 	/* rows FLEN.. : one scratch row per lane of the group, for mixer outputs past the bit instant */
 	__shared__ float s_re[FLEN + DEMOD_GROUP][DEMOD_CPW], s_im[FLEN + DEMOD_GROUP][DEMOD_CPW];
@@ -822,7 +816,7 @@ k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp
 		/* this lane's two candidate samples */
 		const int k1 = sub, k2 = DEMOD_GROUP + sub;
 		const float x1 = in[(size_t)min(n + k1, nsamp - 1) * nch];
-		const float x2 = in[(size_t)min(n + k2, nsamp - 1) * nch];
+		const float x2 = DEMOD_GROUP == 4 ? in[(size_t)min(n + k2, nsamp - 1) * nch] : 0.f;
 		if (n + 2 * DEMOD_LOOK < nsamp) asm volatile("prefetch.global.L1 [%0];" ::"l"(in + (size_t)(n + 2 * DEMOD_LOOK) * nch));
 
 		/* VCO step is constant until the next bit (msk.c:81): MskDf only changes in the bit path */
@@ -874,7 +868,7 @@ k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp
 			clkd = __longlong_as_double(cb);
 		}
 		/* mixer (msk.c:86-91): in * cexp(-j phi), this lane's share */
-		{
+		if (DEMOD_GROUP == 4) {
 			const double p1 = (sub == 0) ? pk[0] : (sub == 1) ? pk[1] : (sub == 2) ? pk[2] : pk[3];
 			const double p2 = (sub & 1) ? pk[5] : pk[4];
 			double sn1, cs1, sn2, cs2;
@@ -891,6 +885,18 @@ k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp
 			__syncwarp();          /* the previous bit's matched filter has read the rows being replaced */
 			s_re[row1][grp] = re1; s_im[row1][grp] = im1;
 			s_re[row2][grp] = re2; s_im[row2][grp] = im2;
+			__syncwarp();
+		} else {                   /* one candidate sample per lane (lanes 6, 7 of the group idle here) */
+			const double p1 = (sub == 0) ? pk[0] : (sub == 1) ? pk[1] : (sub == 2) ? pk[2] : (sub == 3) ? pk[3] : (sub == 4) ? pk[4] : pk[5];
+			double sn1, cs1;
+			sincos_vco(p1, s_cos, s_sin, sn1, cs1);
+			const double xd1 = (double)x1;
+			const float re1 = __double2float_rn(__dmul_rn(xd1, cs1)), im1 = __double2float_rn(__dmul_rn(xd1, -sn1));
+			unsigned row1 = r.idx + k1;
+			row1 = (row1 >= FLEN) ? row1 - FLEN : row1;
+			row1 = (k1 < cnt && k1 < DEMOD_LOOK) ? row1 : FLEN + sub;
+			__syncwarp();
+			s_re[row1][grp] = re1; s_im[row1][grp] = im1;
 			__syncwarp();
 		}
 		r.idx = (r.idx + cnt) % FLEN;
@@ -955,15 +961,24 @@ k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp
 	for (int k = 0; k < FLEN; k++) { st->inb_re[k] = s_re[k][grp]; st->inb_im[k] = s_im[k][grp]; }
 }
 
-int launch_demod(ChainState *st, const float *dm, int nsamp, int nch, int nstreams,
-                 RawFrame *ring, RingCtl *ctl, unsigned cap, cudaStream_t stream)
+template <int LANES>
+static int launch_demod_t(ChainState *st, const float *dm, int nsamp, int nch, int nstreams,
+                          RawFrame *ring, RingCtl *ctl, unsigned cap, cudaStream_t stream)
 {
-	const int wps = (nch + DEMOD_CPW - 1) / DEMOD_CPW;
+	constexpr int CPW = 32 / LANES;
+	const int wps = (nch + CPW - 1) / CPW;
 	const int grid = nstreams * wps;             /* one warp per CTA so that chains spread over all SMs */
-	cudaError_t e = cudaFuncSetAttribute(k_demod, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+	cudaError_t e = cudaFuncSetAttribute(k_demod<LANES>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 	if (e != cudaSuccess) return (int)e;
-	k_demod<<<grid, 32, 0, stream>>>(st, dm, nsamp, nch, nstreams, wps, ring, ctl, cap);
+	k_demod<LANES><<<grid, 32, 0, stream>>>(st, dm, nsamp, nch, nstreams, wps, ring, ctl, cap);
 	return (int)cudaGetLastError();
+}
+
+int launch_demod(ChainState *st, const float *dm, int nsamp, int nch, int nstreams,
+                 RawFrame *ring, RingCtl *ctl, unsigned cap, int lanes, cudaStream_t stream)
+{
+	return lanes == 8 ? launch_demod_t<8>(st, dm, nsamp, nch, nstreams, ring, ctl, cap, stream)
+	                  : launch_demod_t<4>(st, dm, nsamp, nch, nstreams, ring, ctl, cap, stream);
 }
 
 /* ------------------------------------------------------------------------------------------

@@ -1,10 +1,14 @@
 """ACB_FLAG_FAST_CHANNELIZER: the channelizer as a shared 4-point DFT across the row quarters plus K/4
 complex MACs per channel (k_channelize_dft).  Not the reference's operation order, so the bar here is
-the north star's: decoded messages identical, float intermediates within tolerance.  The tolerance
-written here is 3e-5 of (|dm| + rms), not 1e-5, and the test shows why: the reference's own mixer table
-carries up to ~2e-5 of phase rounding on far-offset channels (float AMFreq*ind, rtl.c:283-285), which is
-what separates the two; against the exact double-precision DFT the fast form is within 2e-6 and the
-reference itself is the one further away.  Every test also runs the default (exact) path as a control."""
+the north star's: decoded messages identical, float intermediates within tolerance — and the tolerance
+needs stating carefully.  The reference's own mixer table carries float phase rounding (float AMFreq*ind,
+rtl.c:283-285: up to ~1.5e-5 rad at ind ~ K), so its output differs from the exact DFT bin by up to
+eps * sum_ind |x[ind]| * |w| (eps ~ 3e-6 measured, 1.5e-5 worst case): a fraction of the TOTAL in-band signal,
+which next to a strong neighbour reaches 2e-4 of a weak channel's own level.  No algorithm that does not replay that table
+tap by tap can be closer to the reference than that.  So the envelope is checked (a) against the reference
+with exactly that bound at eps = 1e-5 — the north star's figure, of the total in-band signal —, and (b) against the exact double-precision DFT, where the fast form is within
+2e-6 of (|dm| + rms) and closer than the reference itself.  Every test also runs the default (exact)
+path as a control."""
 import numpy as np
 import pytest
 
@@ -15,20 +19,21 @@ from common import msg_tuple
 pytestmark = pytest.mark.gpu
 
 FAST = 8          # ACB_FLAG_FAST_CHANNELIZER
-REL_TOL = 3e-5    # |dm_fast - dm_ref| <= REL_TOL * (|dm_ref| + rms(dm_ref)), per channel
-IDEAL_TOL = 2e-6  # |dm_fast - exact DFT| on the same scale
+TABLE_EPS = 1e-5  # |dm_fast - dm_ref| <= TABLE_EPS * sum_ind |x[ind] - 127.5| * |w|, per output row
+IDEAL_TOL = 2e-6  # |dm_fast - exact DFT| <= IDEAL_TOL * (|dm| + rms(dm)), per channel
 
 
 def _lvl(t):
     return float(np.array([t[-1]], dtype=np.uint32).view(np.float32)[0])
 
 
-def _envelope_check(dm_fast, dm_ref):
-    """dm_*: (nout, nch)."""
-    rms = np.sqrt((dm_ref.astype(np.float64) ** 2).mean(axis=0))
-    worst = (np.abs(dm_fast.astype(np.float64) - dm_ref) / (np.abs(dm_ref) + rms)).max(axis=0)
-    assert (worst <= REL_TOL).all(), worst
-    return worst.max()
+def _envelope_check(dm_fast, dm_ref, iq, K):
+    """dm_*: (nout, nch); iq: the u8 input of the same rows.  Returns the worst |delta| / bound."""
+    x = iq.reshape(-1, K, 2).astype(np.float64) - 127.5
+    bound = TABLE_EPS * np.hypot(x[..., 0], x[..., 1]).sum(axis=1) / K / 127.5          # per row
+    worst = (np.abs(dm_fast.astype(np.float64) - dm_ref) / bound[:, None]).max()
+    assert worst <= 1.0, worst
+    return worst
 
 
 @pytest.mark.parametrize("K,freqs", [
@@ -50,7 +55,7 @@ def test_fast_envelope_within_tolerance(native, oracle, K, freqs):
         got = ctx.read_dm(nblk * 1024)[0]
         st = ctx.stats()
     assert st.fast_chan_launches == 1
-    worst = _envelope_check(got, want)
+    worst = _envelope_check(got, want, iq[0], K)
     assert worst > 0                       # it is a different operation order: not bit-identical
     # against the exact DFT bins (float64): the fast form is the closer of the two
     x = iq[0].reshape(-1, K, 2).astype(np.float64)
