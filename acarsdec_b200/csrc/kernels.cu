@@ -8,9 +8,14 @@
  *                     and 4 rounded sums in tap order, no FMA contraction — reproduced exactly
  *                     (packed FMUL2/FADD2 where ptxas keeps them unfused) so dm is bit-identical
  *                     to the strict-IEEE build of the reference.
- *  K2  k_demod      : demodMSK + putbit + decodeAcars for one channel per lane
+ *      k_channelize_dft   : opt-in fast form of the u8 path (ACB_FLAG_FAST_CHANNELIZER): the same bins as a
+ *                     shared 4-point DFT across the row quarters + K/4 MACs per channel; HBM-bound
+ *                     (bulk copies, packed FFMA2); messages identical, envelope within tolerance.
+ *  K2  k_demod<LANES>     : demodMSK + putbit + decodeAcars, 4 or 8 lanes per channel
  *                     (reference: msk.c:67-137, acars.c:246-375), state carried in HBM between
  *                     launches; serial recurrence per channel, parallel across channels/streams.
+ *  K3  k_block_fec        : blk_thread's parity/CRC/syndrome repair, one thread per finished frame
+ *                     (reference: acars.c:39-215).
  *
  * Numerics contract: all order/rounding-sensitive arithmetic uses the
  * explicit round-to-nearest intrinsics, which the compiler never contracts; the TU is also
