@@ -315,9 +315,10 @@ int launch_channelize(int mode, const void *in, size_t stream_stride_bytes, cons
  * 10.5), which moves the kernel from the FP32 roof towards the HBM roof.
  *
  * This is NOT the reference's operation order: the envelope differs from the reference's in the last
- * bits.  Measured (tests/test_gpu_fast.py): within 2e-6 of the exact double-precision DFT bin — closer
- * than the reference, whose table carries float phase rounding (float AMFreq*ind) worth up to 1e-5 of
- * the total in-band signal — and decoded messages identical on every fixture.  The default (exact)
+ * bits.  Measured (tests/test_gpu_fast.py, tests/test_fast_oracle.py), relative to the total in-band
+ * signal: 3e-7 from the exact double-precision DFT bin — the reference, whose table carries float phase
+ * rounding (float AMFreq*ind), sits at 1.8e-6 — bit-identical to its CPU restatement
+ * (oracle: orc_channelize_dft), and decoded messages identical on every fixture.  The default (exact)
  * kernel above stays bit-identical; this one is what the north star's tolerance (messages bit-exact,
  * float intermediates within tolerance) buys.
  *

@@ -61,8 +61,8 @@ typedef struct {
                                          as a shared 4-point DFT across the row quarters + K/4 MACs per channel
                                          (5x less FP32 work) when every stream's channels sit on the 12.5 kHz raster
                                          around Fc; otherwise the exact kernel runs.  NOT the reference's operation
-                                         order: the envelope is within 2e-6 of the exact DFT bin and within the reference's own
-                                         table rounding (1e-5 of the total in-band signal) of the reference; decoded
+                                         order: relative to the total in-band signal the envelope is within 1e-6 of the exact DFT
+                                         bin and within the reference's own table rounding (1e-5) of the reference; decoded
                                          messages are the same; without this flag the envelope is bit-identical */
 #define ACB_FLAG_REAL_INPUT 2         /* Airspy front-end (air.c): float32 REAL samples at IF = rate/4,
                                          rate = K*12500; use acb_set_plan_air / acb_submit_real_host */

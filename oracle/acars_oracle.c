@@ -147,6 +147,60 @@ void orc_channelize_fir(const uint8_t *iq, int nout, int K, int taps, int nch, c
 	}
 }
 
+/* The product's opt-in FAST channelizer (ACB_FLAG_FAST_CHANNELIZER, k_channelize_dft) — not in the
+ * reference: this restatement is its definition, operation for operation, so the GPU kernel can be held
+ * to it bit for bit while the CPU tests hold IT to the reference (envelope within the reference's own
+ * table rounding, decoded messages identical; tests/test_fast_oracle.py).
+ *
+ * rtl.c:283-286 builds wf[ind] = cexpf(-j*AMFreq*ind)/K/127.5, a sampled complex exponential.  When the
+ * offset the reference mixes with — float image of the stored Fr minus float image of Fc — is a whole,
+ * even number k of 12.5 kHz steps, D = sum_ind x[ind]*wf[ind] is bin k of a K-point DFT of the row:
+ *   D = sum_{n2<K/4} T[n2] * Y_r[n2],  T[n2] = exp(-j*2*pi*k*n2/K)/K/127.5,  r = k mod 4 (0 or 2),
+ *   Y_0 = x0+x1+x2+x3 - 4*127.5,  Y_2 = x0-x1+x2-x3,  x_q = x[(K/4)*q + n2]   (exact in float). */
+int orc_fast_plan(const unsigned *freqs_hz, int nch, int K, unsigned fc, int *kbin, float *tw)
+{
+	const int N2 = K / 4;
+	for (int ch = 0; ch < nch; ch++) {
+		const float d = (float)orc_stored_fr(freqs_hz[ch]) - (float)fc;
+		const float kf = d / (float)ORC_INTRATE;
+		const int k = (int)kf;
+		if ((float)k != kf || (k & 1) || k == 0 || k <= -K / 2 || k >= K / 2) return 0;
+		kbin[ch] = k;
+		for (int n2 = 0; n2 < N2; n2++) {
+			const double ph = -2.0 * M_PI * (double)(((long long)k * n2) % K) / (double)K;
+			tw[((size_t)ch * N2 + n2) * 2] = (float)(cos(ph) / K / 127.5);
+			tw[((size_t)ch * N2 + n2) * 2 + 1] = (float)(sin(ph) / K / 127.5);
+		}
+	}
+	return 1;
+}
+
+void orc_channelize_dft(const uint8_t *iq, int nout, int K, int nch, const int *kbin, const float *tw, float *dm)
+{
+	const int N2 = K / 4;
+	for (int m = 0; m < nout; m++) {
+		const uint8_t *p = iq + (size_t)m * K * 2;
+		for (int ch = 0; ch < nch; ch++) {
+			const int r = ((kbin[ch] % 4) + 4) % 4;
+			const float *t = tw + (size_t)ch * N2 * 2;
+			float a = 0, b = 0, pp = 0, q = 0;          /* re = a - b, im = pp + q: four FMA chains in n2 order */
+			for (int n2 = 0; n2 < N2; n2++) {
+				const int i0 = p[2 * n2], i1 = p[2 * (N2 + n2)], i2 = p[2 * (2 * N2 + n2)], i3 = p[2 * (3 * N2 + n2)];
+				const int q0 = p[2 * n2 + 1], q1 = p[2 * (N2 + n2) + 1], q2 = p[2 * (2 * N2 + n2) + 1], q3 = p[2 * (3 * N2 + n2) + 1];
+				const float yr = r == 0 ? (float)(i0 + i1 + i2 + i3 - 510) : (float)(i0 - i1 + i2 - i3);
+				const float yi = r == 0 ? (float)(q0 + q1 + q2 + q3 - 510) : (float)(q0 - q1 + q2 - q3);
+				const float tr = t[2 * n2], ti = t[2 * n2 + 1];
+				a = fmaf(yr, tr, a);
+				b = fmaf(yi, ti, b);
+				pp = fmaf(yr, ti, pp);
+				q = fmaf(yi, tr, q);
+			}
+			const float re = a - b, im = pp + q;
+			dm[(size_t)ch * nout + m] = sqrtf(fmaf(re, re, im * im));
+		}
+	}
+}
+
 /* ------------------------------------------------------------------ Airspy front-end (air.c) */
 
 /* air.c:42-64 with filter == 0 (every rate but 5 MS/s): centre of the span on the 12.5 kHz raster */

@@ -351,6 +351,8 @@ class OracleLib:
         L.orc_air_build_wf.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_void_p]
         L.orc_channelize_real.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_channelize_fir.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_fast_plan.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p, C.c_void_p]
+        L.orc_channelize_dft.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_cs16_build_osc.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_void_p]
         L.orc_channelize_cs16.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_chan_init.argtypes = [C.POINTER(OrcChan), C.c_int]
@@ -424,6 +426,24 @@ class OracleLib:
         wf = np.ascontiguousarray(wf, dtype=np.float32)
         assert wf.shape[1] == 2 * taps
         self.lib.orc_channelize_fir(iq.ctypes.data, nout, K, taps, wf.shape[0], wf.ctypes.data, dm.ctypes.data)
+        return dm
+
+    def fast_plan(self, K: int, freqs_hz, fc: int):
+        """(k per channel, twiddles (nch, K/4, 2) float32) of the fast channelizer's restatement, or None."""
+        f = np.asarray(freqs_hz, dtype=np.uint32)
+        k = np.zeros(len(f), dtype=np.int32)
+        tw = np.zeros((len(f), K // 4, 2), dtype=np.float32)
+        if self.lib.orc_fast_plan(f.ctypes.data, len(f), K, int(fc), k.ctypes.data, tw.ctypes.data) != 1:
+            return None
+        return k, tw
+
+    def channelize_dft(self, iq: np.ndarray, K: int, k: np.ndarray, tw: np.ndarray) -> np.ndarray:
+        iq = np.ascontiguousarray(iq, dtype=np.uint8).reshape(-1)
+        nout = iq.size // (2 * K)
+        dm = np.empty((len(k), nout), dtype=np.float32)
+        k = np.ascontiguousarray(k, dtype=np.int32)
+        tw = np.ascontiguousarray(tw, dtype=np.float32)
+        self.lib.orc_channelize_dft(iq.ctypes.data, nout, K, len(k), k.ctypes.data, tw.ctypes.data, dm.ctypes.data)
         return dm
 
     def cs16_osc(self, variant: int, K: int, freqs_hz, fc: int) -> np.ndarray:

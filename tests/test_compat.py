@@ -140,13 +140,14 @@ def test_demodMSK_shim_on_testwav(tmp_path):
 
 
 def _strip_time(s: str) -> str:
+    s = re.sub(r'"timestamp":[0-9.e+]+', '"timestamp":<time>', s)          # JSON wire format (output.c:244-245)
     return re.sub(r"\d\d/\d\d/\d{4} \d\d:\d\d:\d\d\.\d{3}", "<time>", s)
 
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not (REFBIN / "acarsdec_b200").exists() or not (REFBIN / "acarsdec_ref").exists(),
                     reason="oracle/_ref program builds absent")
-@pytest.mark.parametrize("K,outtype", [(160, "2"), (192, "1")])
+@pytest.mark.parametrize("K,outtype", [(160, "2"), (192, "1"), (160, "4")])      # full text, one line, JSON
 def test_unmodified_acarsdec_main_links_against_shim(tmp_path, K, outtype):
     """The drop-in claim: the reference's own acarsdec.c/output.c/label.c (unmodified, compiled in
     place) linked against libacarsdec_compat + libacars_b200 prints the same decoded messages as the

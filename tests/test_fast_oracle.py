@@ -1,0 +1,94 @@
+"""The fast channelizer (ACB_FLAG_FAST_CHANNELIZER) on the CPU: oracle/acars_oracle.c restates the kernel
+operation for operation (orc_channelize_dft).  Here that restatement is held to the reference: envelope
+within the reference's own table rounding, closer to the exact DFT than the reference is, and — over many
+seeded captures, corrupted frames included — the same decoded messages.  tests/test_gpu_fast.py then holds
+the GPU kernel to the restatement bit for bit."""
+import numpy as np
+import pytest
+
+import refs
+from acarsdec_b200 import api, synth
+from common import msg_tuple
+
+TABLE_EPS = 1e-5   # |dm_fast - dm_ref| <= TABLE_EPS * sum_ind |x[ind] - 127.5| * |w| per output row
+IDEAL_EPS = 1e-6   # |dm_fast - exact DFT| <= IDEAL_EPS * the same sum (measured 3e-7; the reference: 1.8e-6)
+
+
+def _decode(orc, dm):
+    """demod + frame sync + FEC of every channel of dm (nch, nout) through the pinned restatement."""
+    out = []
+    for c in range(dm.shape[0]):
+        ch, sink = orc.new_chan(c), refs.Sink()
+        orc.demod(ch, dm[c], sink)
+        for m in sink.msgs():
+            f = orc.fec(m)
+            if f is not None:
+                out.append(msg_tuple(f)[:-1] + (float(m.lvl),))
+    return out
+
+
+def test_plan_restatement_matches_library(native, oracle):
+    for K in (160, 192):
+        fd, _, fc = api.plan(K, synth.DEFAULT_FREQS_MHZ)
+        k1, tw1 = oracle.fast_plan(K, fd, fc)
+        k2, tw2 = api.fast_plan(K, fd, fc)
+        assert (k1 == k2).all()
+        # value equality (the complex view api.fast_plan returns does not keep the sign of a zero)
+        assert np.array_equal(tw1[..., 0], tw2.real) and np.array_equal(tw1[..., 1], tw2.imag)
+    fd, _, fc = api.plan(160, (131.4875, 131.725))
+    assert oracle.fast_plan(160, fd, fc) is None
+
+
+@pytest.mark.parametrize("K", [160, 192])
+def test_envelope_vs_reference_and_exact_dft(oracle, K):
+    fm = synth.DEFAULT_FREQS_MHZ
+    fd, fr, fc = oracle.plan(K, fm)
+    k, tw = oracle.fast_plan(K, fd, fc)
+    wf = oracle.wf(K, fm)
+    worst_ref = worst_ideal = worst_ref_ideal = 0.0
+    for seed in range(6):
+        plan = synth.make_plan(K, fm, fc, seconds=0.3, seed=900 + seed, text_len=(5, 60), msgs_per_chan_per_sec=4.0)
+        iq = synth.render_blocks(plan, 0, 3).reshape(-1)
+        ref = oracle.channelize(iq, K, wf).astype(np.float64)
+        fast = oracle.channelize_dft(iq, K, k, tw).astype(np.float64)
+        x = iq.reshape(-1, K, 2).astype(np.float64)
+        bound = TABLE_EPS * np.hypot(x[..., 0] - 127.5, x[..., 1] - 127.5).sum(axis=1) / K / 127.5
+        worst_ref = max(worst_ref, (np.abs(fast - ref) / bound[None, :]).max())
+        xc = x[..., 0] + 1j * x[..., 1]
+        ideal = np.stack([np.abs(xc @ (np.exp(-2j * np.pi * int(kk) * np.arange(K) / K) / K / 127.5)) for kk in k])
+        total = bound[None, :] / TABLE_EPS
+        worst_ideal = max(worst_ideal, (np.abs(fast - ideal) / total).max())
+        worst_ref_ideal = max(worst_ref_ideal, (np.abs(ref - ideal) / total).max())
+    assert worst_ref <= 1.0, worst_ref
+    assert worst_ideal <= IDEAL_EPS and worst_ideal < worst_ref_ideal, (worst_ideal, worst_ref_ideal)
+
+
+@pytest.mark.parametrize("K,nseeds", [(160, 24), (192, 8)])
+def test_messages_identical_over_many_captures(oracle, K, nseeds):
+    """Same frames — channel, length, error count, text, BCS, in the same order — from the reference's
+    envelope and from the fast form's, over seeded captures with clean and corrupted frames, weak and
+    strong bursts; lvl (dB) within 0.001."""
+    fm = synth.DEFAULT_FREQS_MHZ
+    fd, _, fc = oracle.plan(K, fm)
+    k, tw = oracle.fast_plan(K, fd, fc)
+    wf = oracle.wf(K, fm)
+    flips = [[], [(3, 0x04)], [(5, 0x01), (9, 0x80)], [(7, 0x21)], [(-2, 0x10)], [(2, 1), (4, 2), (6, 4), (8, 8)],
+             [(1, 0x40), (-3, 0x02)], [(20, 0xFF)], [(0, 0x08), (10, 0x08), (11, 0x08)]]
+    total = repaired = 0
+    for seed in range(nseeds):
+        secs = 0.9
+        plan = synth.make_plan(K, fm, fc, seconds=secs, seed=5000 + seed, text_len=(5, 90), msgs_per_chan_per_sec=5.0)
+        rng = np.random.default_rng(seed)
+        for i, b in enumerate(plan.bursts):
+            b.amp = float(rng.uniform(3.0, 30.0))                    # down to marginal SNR
+            if seed % 2:
+                b.frame = synth.corrupt_frame(b.frame, flips[(i + seed) % len(flips)])
+        iq = synth.render_blocks(plan, 0, synth.blocks_for_seconds(K, secs)).reshape(-1)
+        a = _decode(oracle, oracle.channelize(iq, K, wf))
+        b = _decode(oracle, oracle.channelize_dft(iq, K, k, tw))
+        assert [t[:-1] for t in a] == [t[:-1] for t in b], seed
+        for x, y in zip(a, b):
+            assert abs(x[-1] - y[-1]) <= 1e-3                          # lvl, in dB
+        total += len(a)
+        repaired += sum(t[2] > 0 for t in a)
+    assert total >= 8 * nseeds and repaired > 0

@@ -6,8 +6,10 @@ rtl.c:283-285: up to ~1.5e-5 rad at ind ~ K), so its output differs from the exa
 eps * sum_ind |x[ind]| * |w| (eps ~ 3e-6 measured, 1.5e-5 worst case): a fraction of the TOTAL in-band signal,
 which next to a strong neighbour reaches 2e-4 of a weak channel's own level.  No algorithm that does not replay that table
 tap by tap can be closer to the reference than that.  So the envelope is checked (a) against the reference
-with exactly that bound at eps = 1e-5 — the north star's figure, of the total in-band signal —, and (b) against the exact double-precision DFT, where the fast form is within
-2e-6 of (|dm| + rms) and closer than the reference itself.  Every test also runs the default (exact)
+with exactly that bound at eps = 1e-5 — the north star's figure, of the total in-band signal —, (b) against
+the exact double-precision DFT, where the fast form is within 1e-6 of the same sum and closer than the
+reference itself, and (c) bit for bit against its own CPU restatement (oracle: orc_channelize_dft), which
+tests/test_fast_oracle.py holds to the reference over many more captures.  Every test also runs the default (exact)
 path as a control."""
 import numpy as np
 import pytest
@@ -20,7 +22,7 @@ pytestmark = pytest.mark.gpu
 
 FAST = 8          # ACB_FLAG_FAST_CHANNELIZER
 TABLE_EPS = 1e-5  # |dm_fast - dm_ref| <= TABLE_EPS * sum_ind |x[ind] - 127.5| * |w|, per output row
-IDEAL_TOL = 2e-6  # |dm_fast - exact DFT| <= IDEAL_TOL * (|dm| + rms(dm)), per channel
+IDEAL_EPS = 1e-6  # |dm_fast - exact DFT| <= IDEAL_EPS * the same sum (measured 3e-7; the reference itself: 1.8e-6)
 
 
 def _lvl(t):
@@ -63,10 +65,13 @@ def test_fast_envelope_within_tolerance(native, oracle, K, freqs):
     _, fr, _ = oracle.plan(K, freqs)
     ideal = np.stack([np.abs(xc @ (np.exp(-2j * np.pi * round((float(np.float32(f)) - float(np.float32(fc))) / 12500) * np.arange(K) / K) / K / 127.5))
                       for f in fr], axis=1)
-    scale = np.abs(ideal) + np.sqrt((ideal ** 2).mean(axis=0))
-    err_fast = (np.abs(got - ideal) / scale).max()
-    err_ref = (np.abs(want - ideal) / scale).max()
-    assert err_fast <= IDEAL_TOL and err_fast < err_ref, (err_fast, err_ref)
+    total = np.hypot(x[..., 0] - 127.5, x[..., 1] - 127.5).sum(axis=1)[:, None] / K / 127.5
+    err_fast = (np.abs(got - ideal) / total).max()
+    err_ref = (np.abs(want - ideal) / total).max()
+    assert err_fast <= IDEAL_EPS and err_fast < err_ref, (err_fast, err_ref)
+    # (c) the kernel against its CPU restatement, operation for operation: bit-identical
+    kbin, tw = oracle.fast_plan(K, fd, fc)
+    assert np.array_equal(got.view(np.uint32), oracle.channelize_dft(iq[0], K, kbin, tw).T.view(np.uint32))
     with api.Context(K, 1, len(freqs), nblk) as ctx:                          # control: default path is exact
         ctx.set_plan(0, fd)
         ctx.submit_host(iq, nblk)
@@ -78,7 +83,7 @@ def test_fast_envelope_within_tolerance(native, oracle, K, freqs):
 @pytest.mark.parametrize("K,seed,nstreams", [(160, 3, 2), (192, 4, 1), (160, 41, 6)])
 def test_fast_messages_identical(native, oracle, K, seed, nstreams):
     """Whole path with injected messages: same frames (channel, length, errors, text, CRC) in the same
-    order as the reference restatement; lvl within 1e-5 relative."""
+    order as the reference restatement; lvl (dB) within 0.001."""
     fm = synth.DEFAULT_FREQS_MHZ
     fd, _, fc = api.plan(K, fm)
     secs = 1.0
@@ -105,7 +110,7 @@ def test_fast_messages_identical(native, oracle, K, seed, nstreams):
         assert [t[:-1] for t in mine] == [t[:-1] for t in want], s        # all fields but lvl: identical
         for a, b in zip(mine, want):
             la, lb = _lvl(a), _lvl(b)
-            assert abs(la - lb) <= 1e-5 * max(abs(lb), 1.0), (la, lb)
+            assert abs(la - lb) <= 1e-3, (la, lb)                     # lvl, in dB
         total += len(want)
     assert total >= 6 * nstreams
 

@@ -1,5 +1,6 @@
 set -x
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; tail -4 gpurun_out/pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 python bench.py --impl reference --steps 3 --warmup 1 | tail -1 > gpurun_out/bench_ref_n1.json
 python bench.py --steps 20 --warmup 3 | tail -1 > gpurun_out/bench_n1.json
