@@ -68,7 +68,7 @@ int launch_demod(ChainState *st, const float *dm, int nsamp, int nch, int nstrea
                  RawFrame *ring, RingCtl *ctl, unsigned cap, int lanes_per_channel, CUstream_st *stream);
 bool channelize_dft_supports(int K);
 int launch_channelize_dft(const void *in, size_t stream_stride, const float *tw, const unsigned *meta, float *dm,
-                          int K, int nch, int nstreams, int nblk, size_t nsamp, CUstream_st *stream);
+                          int K, int nch, int nstreams, int nblk, size_t nsamp, bool fold8, CUstream_st *stream);
 int launch_block_fec(RawFrame *ring, const RingCtl *ctl, unsigned cap, CUstream_st *stream);
 int upload_matched_filter(const float *h);
 int upload_sincos_table(const double *cos_hi_lo, const double *sin_hi_lo);

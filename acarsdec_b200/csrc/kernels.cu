@@ -403,7 +403,7 @@ template <int UNITS, int WARPS, int STAGES> struct DftPlan {
 	static constexpr int SMEM = BAR_OFF + WARPS * STAGES * 8;
 };
 
-template <int UNITS, int WARPS, int STAGES, int MINB>
+template <int UNITS, int WARPS, int STAGES, int MINB, bool FOLD8>
 __global__ void __launch_bounds__(32 * WARPS, MINB)
 k_channelize_dft(const uint8_t *__restrict__ in, size_t stream_stride, const float2 *__restrict__ tw,
                  const unsigned *__restrict__ meta, float *__restrict__ dm, int nch, int ngrp, size_t nsamp)
@@ -460,53 +460,124 @@ k_channelize_dft(const uint8_t *__restrict__ in, size_t stream_stride, const flo
 #pragma unroll
 		for (int c = 0; c < CH_GROUP; c++) acc[c].a = acc[c].b = acc[c].p = acc[c].q = make_float2(0.f, 0.f);
 
-		/* unit j covers samples 8j..8j+7 of each quarter: one LDS.128 per quarter and row (their latency
-		 * is left to the other warps of the SM to cover) */
+		if constexpr (!FOLD8) {
+			/* unit j covers samples 8j..8j+7 of each quarter: one LDS.128 per quarter and row (their latency
+			 * is left to the other warps of the SM to cover) */
+	#pragma unroll 1
+			for (int j = 0; j < CU; j++) {
+				uint4 qa[4], qb[4];
+	#pragma unroll
+				for (int n1 = 0; n1 < 4; n1++) { qa[n1] = rowA[n1 * CU + j]; qb[n1] = rowB[n1 * CU + j]; }
+	#pragma unroll
+				for (int eh = 0; eh < 2; eh++) {      /* four samples of each quarter at a time */
+					float2 y0r[4], y0i[4], y2r[4], y2i[4];
+	#pragma unroll
+					for (int k = 0; k < 4; k++) {
+						float2 xi[4], xq[4];
+	#pragma unroll
+						for (int n1 = 0; n1 < 4; n1++) {
+							const unsigned wa = eh ? (k < 2 ? qa[n1].z : qa[n1].w) : (k < 2 ? qa[n1].x : qa[n1].y);
+							const unsigned wb = eh ? (k < 2 ? qb[n1].z : qb[n1].w) : (k < 2 ? qb[n1].x : qb[n1].y);
+							if (k & 1) { xi[n1] = dft_cvt<2>(wa, wb); xq[n1] = dft_cvt<3>(wa, wb); }
+							else       { xi[n1] = dft_cvt<0>(wa, wb); xq[n1] = dft_cvt<1>(wa, wb); }
+						}
+						/* sums carry the 2 x 32768 planted by dft_cvt (exact: < 2^24); differences do not.  Y_0
+						 * also sheds the converter's mid-scale 4 x 127.5 here: any constant is invisible to a
+						 * channel (its twiddles sum to zero) but a large one costs accumulate precision */
+						const float2 sI02 = __fadd2_rn(xi[0], xi[2]), sI13 = __fadd2_rn(xi[1], xi[3]);
+						const float2 sQ02 = __fadd2_rn(xq[0], xq[2]), sQ13 = __fadd2_rn(xq[1], xq[3]);
+						const float2 bias = make_float2(-131582.0f, -131582.0f);
+						y0r[k] = __fadd2_rn(__fadd2_rn(sI02, sI13), bias);
+						y0i[k] = __fadd2_rn(__fadd2_rn(sQ02, sQ13), bias);
+						y2r[k] = fsub2(sI02, sI13);
+						y2i[k] = fsub2(sQ02, sQ13);
+					}
+					/* channel c's four twiddles: two LDS.128, fetched one channel ahead of their use so the
+					 * load latency hides under the previous channel's FFMA2s (the residue dispatch below is a
+					 * uniform branch the scheduler does not move loads across) */
+					const float4 *tj = stw + (j * 2 + eh) * 2;
+					float4 t0 = tj[0], t1 = tj[1];
+	#pragma unroll
+					for (int c = 0; c < CH_GROUP; c++) {
+						const float4 u0 = t0, u1 = t1;
+						if (c + 1 < CH_GROUP) { t0 = tj[(c + 1) * (N2 / 2)]; t1 = tj[(c + 1) * (N2 / 2) + 1]; }
+						const float2 tt[4] = { make_float2(u0.x, u0.y), make_float2(u0.z, u0.w), make_float2(u1.x, u1.y), make_float2(u1.z, u1.w) };
+						if (((m >> (2 * c)) & 3u) == 0) {             /* warp-uniform: k_c mod 4 is 0 or 2 */
+	#pragma unroll
+							for (int k = 0; k < 4; k++) dft_mac(acc[c], y0r[k], y0i[k], tt[k]);
+						} else {
+	#pragma unroll
+							for (int k = 0; k < 4; k++) dft_mac(acc[c], y2r[k], y2i[k], tt[k]);
+						}
+					}
+				}
+			}
+		} else {
+			/* Bins are even (k = 2k'), so the row folds in half first: z[n] = x[n] + x[n + K/2] and D is bin
+			 * k' of the K/2-point DFT of z; the same four-way split of THAT gives
+			 *   D = sum_{n2 < K/8} T[n2] * Y'_{k' mod 4}[n2],   Y'_r[n2] = sum_{n1<4} z[(K/8)*n1 + n2] * (-j)^(r*n1)
+			 * with the same twiddles T[n2] = exp(-j*2*pi*k*n2/K)/K/127.5 and all four residues in play:
+			 * 26 packed additions per n2 (exact) and K/8 complex MACs per channel.  Group g4 covers samples
+			 * 4*g4..4*g4+3 of each eighth of the row: one LDS.64 per eighth and row. */
+			const unsigned char *ra = st + P::row_off(l), *rb = st + P::row_off(l + 32);
 #pragma unroll 1
-		for (int j = 0; j < CU; j++) {
-			uint4 qa[4], qb[4];
+			for (int g4 = 0; g4 < CU; g4++) {
+				uint2 ea[8], eb[8];
 #pragma unroll
-			for (int n1 = 0; n1 < 4; n1++) { qa[n1] = rowA[n1 * CU + j]; qb[n1] = rowB[n1 * CU + j]; }
-#pragma unroll
-			for (int eh = 0; eh < 2; eh++) {      /* four samples of each quarter at a time */
-				float2 y0r[4], y0i[4], y2r[4], y2i[4];
+				for (int e = 0; e < 8; e++) {
+					ea[e] = *reinterpret_cast<const uint2 *>(ra + e * (UNITS * 2) + g4 * 8);
+					eb[e] = *reinterpret_cast<const uint2 *>(rb + e * (UNITS * 2) + g4 * 8);
+				}
+				float2 yr[4][4], yi[4][4];            /* [residue][sample of the group] */
 #pragma unroll
 				for (int k = 0; k < 4; k++) {
-					float2 xi[4], xq[4];
+					float2 zi[4], zq[4];
 #pragma unroll
 					for (int n1 = 0; n1 < 4; n1++) {
-						const unsigned wa = eh ? (k < 2 ? qa[n1].z : qa[n1].w) : (k < 2 ? qa[n1].x : qa[n1].y);
-						const unsigned wb = eh ? (k < 2 ? qb[n1].z : qb[n1].w) : (k < 2 ? qb[n1].x : qb[n1].y);
-						if (k & 1) { xi[n1] = dft_cvt<2>(wa, wb); xq[n1] = dft_cvt<3>(wa, wb); }
-						else       { xi[n1] = dft_cvt<0>(wa, wb); xq[n1] = dft_cvt<1>(wa, wb); }
+						const unsigned wa0 = k < 2 ? ea[n1].x : ea[n1].y, wb0 = k < 2 ? eb[n1].x : eb[n1].y;
+						const unsigned wa1 = k < 2 ? ea[n1 + 4].x : ea[n1 + 4].y, wb1 = k < 2 ? eb[n1 + 4].x : eb[n1 + 4].y;
+						if (k & 1) {
+							zi[n1] = __fadd2_rn(dft_cvt<2>(wa0, wb0), dft_cvt<2>(wa1, wb1));
+							zq[n1] = __fadd2_rn(dft_cvt<3>(wa0, wb0), dft_cvt<3>(wa1, wb1));
+						} else {
+							zi[n1] = __fadd2_rn(dft_cvt<0>(wa0, wb0), dft_cvt<0>(wa1, wb1));
+							zq[n1] = __fadd2_rn(dft_cvt<1>(wa0, wb0), dft_cvt<1>(wa1, wb1));
+						}
 					}
-					/* sums carry the 2 x 32768 planted by dft_cvt (exact: < 2^24); differences do not.  Y_0
-					 * also sheds the converter's mid-scale 4 x 127.5 here: any constant is invisible to a
-					 * channel (its twiddles sum to zero) but a large one costs accumulate precision */
-					const float2 sI02 = __fadd2_rn(xi[0], xi[2]), sI13 = __fadd2_rn(xi[1], xi[3]);
-					const float2 sQ02 = __fadd2_rn(xq[0], xq[2]), sQ13 = __fadd2_rn(xq[1], xq[3]);
-					const float2 bias = make_float2(-131582.0f, -131582.0f);
-					y0r[k] = __fadd2_rn(__fadd2_rn(sI02, sI13), bias);
-					y0i[k] = __fadd2_rn(__fadd2_rn(sQ02, sQ13), bias);
-					y2r[k] = fsub2(sI02, sI13);
-					y2i[k] = fsub2(sQ02, sQ13);
+					/* every z carries 2 x 32768 from dft_cvt: sums of four carry 262144 (exact, < 2^24) and Y'_0
+					 * also sheds the converter's mid-scale 8 x 127.5; differences carry nothing */
+					const float2 sI02 = __fadd2_rn(zi[0], zi[2]), sI13 = __fadd2_rn(zi[1], zi[3]);
+					const float2 sQ02 = __fadd2_rn(zq[0], zq[2]), sQ13 = __fadd2_rn(zq[1], zq[3]);
+					const float2 dI02 = fsub2(zi[0], zi[2]), dI13 = fsub2(zi[1], zi[3]);
+					const float2 dQ02 = fsub2(zq[0], zq[2]), dQ13 = fsub2(zq[1], zq[3]);
+					const float2 bias = make_float2(-263164.0f, -263164.0f);
+					yr[0][k] = __fadd2_rn(__fadd2_rn(sI02, sI13), bias);
+					yi[0][k] = __fadd2_rn(__fadd2_rn(sQ02, sQ13), bias);
+					yr[2][k] = fsub2(sI02, sI13);
+					yi[2][k] = fsub2(sQ02, sQ13);
+					yr[1][k] = __fadd2_rn(dI02, dQ13); yi[1][k] = fsub2(dQ02, dI13);      /* (z0-z2) - j(z1-z3) */
+					yr[3][k] = fsub2(dI02, dQ13);      yi[3][k] = __fadd2_rn(dQ02, dI13); /* (z0-z2) + j(z1-z3) */
 				}
-				/* channel c's four twiddles: two LDS.128, fetched one channel ahead of their use so the
-				 * load latency hides under the previous channel's FFMA2s (the residue dispatch below is a
-				 * uniform branch the scheduler does not move loads across) */
-				const float4 *tj = stw + (j * 2 + eh) * 2;
+				const float4 *tj = stw + g4 * 2;
 				float4 t0 = tj[0], t1 = tj[1];
 #pragma unroll
 				for (int c = 0; c < CH_GROUP; c++) {
 					const float4 u0 = t0, u1 = t1;
 					if (c + 1 < CH_GROUP) { t0 = tj[(c + 1) * (N2 / 2)]; t1 = tj[(c + 1) * (N2 / 2) + 1]; }
 					const float2 tt[4] = { make_float2(u0.x, u0.y), make_float2(u0.z, u0.w), make_float2(u1.x, u1.y), make_float2(u1.z, u1.w) };
-					if (((m >> (2 * c)) & 3u) == 0) {             /* warp-uniform: k_c mod 4 is 0 or 2 */
+					const unsigned r8 = (m >> (16 + 2 * c)) & 3u;     /* warp-uniform: (k_c / 2) mod 4 */
+					if (r8 == 0) {
 #pragma unroll
-						for (int k = 0; k < 4; k++) dft_mac(acc[c], y0r[k], y0i[k], tt[k]);
+						for (int k = 0; k < 4; k++) dft_mac(acc[c], yr[0][k], yi[0][k], tt[k]);
+					} else if (r8 == 1) {
+#pragma unroll
+						for (int k = 0; k < 4; k++) dft_mac(acc[c], yr[1][k], yi[1][k], tt[k]);
+					} else if (r8 == 2) {
+#pragma unroll
+						for (int k = 0; k < 4; k++) dft_mac(acc[c], yr[2][k], yi[2][k], tt[k]);
 					} else {
 #pragma unroll
-						for (int k = 0; k < 4; k++) dft_mac(acc[c], y2r[k], y2i[k], tt[k]);
+						for (int k = 0; k < 4; k++) dft_mac(acc[c], yr[3][k], yi[3][k], tt[k]);
 					}
 				}
 			}
@@ -538,13 +609,13 @@ k_channelize_dft(const uint8_t *__restrict__ in, size_t stream_stride, const flo
 	}
 }
 
-template <int UNITS, int WARPS, int STAGES, int MINB = 1>
+template <int UNITS, int WARPS, int STAGES, int MINB, bool FOLD8>
 static int launch_dft_t(const uint8_t *in, size_t stream_stride, const float2 *tw, const unsigned *meta, float *dm,
                         int nch, int nstreams, int nblk, size_t nsamp, cudaStream_t stream)
 {
 	const int ngrp = (nch + CH_GROUP - 1) / CH_GROUP;
 	constexpr int smem = DftPlan<UNITS, WARPS, STAGES>::SMEM;
-	auto kern = k_channelize_dft<UNITS, WARPS, STAGES, MINB>;
+	auto kern = k_channelize_dft<UNITS, WARPS, STAGES, MINB, FOLD8>;
 	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	if (e != cudaSuccess) return (int)e;
 	e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -559,7 +630,7 @@ bool channelize_dft_supports(int K) { return K == 160 || K == 192; }
 /* u8 IQ, K in {160, 192} (the reference's two rates), taps == K, every channel on the 12.5 kHz raster
  * around Fc (context.cu checks and builds tw/meta) */
 int launch_channelize_dft(const void *in, size_t stream_stride, const float *tw, const unsigned *meta, float *dm,
-                          int K, int nch, int nstreams, int nblk, size_t nsamp, cudaStream_t stream)
+                          int K, int nch, int nstreams, int nblk, size_t nsamp, bool fold8, cudaStream_t stream)
 {
 	if (nblk == 0) return 0;
 	const uint8_t *i8 = reinterpret_cast<const uint8_t *>(in);
@@ -567,8 +638,10 @@ int launch_channelize_dft(const void *in, size_t stream_stride, const float *tw,
 	/* 2 warps per CTA, one tile buffer per warp; K=160: 44.5 KB of shared memory and <= 200 registers
 	 * -> 5 CTAs = 10 warps per SM (measured: 0.97 ms; 3 or 4 warps per CTA 1.09-1.43 ms; two buffers per
 	 * warp with half the warps 1.73 ms) */
-	if (K == 160) return launch_dft_t<20, 2, 1, 5>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
-	if (K == 192) return launch_dft_t<24, 2, 1, 4>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
+	if (K == 160) return fold8 ? launch_dft_t<20, 2, 1, 5, true>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream)
+	                           : launch_dft_t<20, 2, 1, 5, false>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
+	if (K == 192) return fold8 ? launch_dft_t<24, 2, 1, 4, true>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream)
+	                           : launch_dft_t<24, 2, 1, 4, false>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
 	return (int)cudaErrorInvalidValue;
 }
 

@@ -201,6 +201,44 @@ void orc_channelize_dft(const uint8_t *iq, int nout, int K, int nch, const int *
 	}
 }
 
+/* Folded variant of the same (k is even, k = 2k'): z[n] = x[n] + x[n+K/2], then the four-way split of the
+ * K/2-point DFT of z: D = sum_{n2<K/8} T[n2] * Y'_r[n2], r = k' mod 4, same twiddles T[n2], n2 < K/8,
+ *   Y'_0 = z0+z1+z2+z3 - 8*127.5, Y'_2 = z0-z1+z2-z3, Y'_1 = (z0-z2) - j(z1-z3), Y'_3 = (z0-z2) + j(z1-z3),
+ *   z_q = z[(K/8)*q + n2].  `tw` is the table of orc_fast_plan (K/4 entries per channel, first K/8 used). */
+void orc_channelize_dft8(const uint8_t *iq, int nout, int K, int nch, const int *kbin, const float *tw, float *dm)
+{
+	const int N2 = K / 4, N8 = K / 8;
+	for (int m = 0; m < nout; m++) {
+		const uint8_t *p = iq + (size_t)m * K * 2;
+		for (int ch = 0; ch < nch; ch++) {
+			const int r = (((kbin[ch] / 2) % 4) + 4) % 4;
+			const float *t = tw + (size_t)ch * N2 * 2;
+			float a = 0, b = 0, pp = 0, q = 0;
+			for (int n2 = 0; n2 < N8; n2++) {
+				int zi[4], zq[4];
+				for (int n1 = 0; n1 < 4; n1++) {
+					zi[n1] = p[2 * (N8 * n1 + n2)] + p[2 * (N8 * (n1 + 4) + n2)];
+					zq[n1] = p[2 * (N8 * n1 + n2) + 1] + p[2 * (N8 * (n1 + 4) + n2) + 1];
+				}
+				int yr, yi;
+				switch (r) {
+				case 0: yr = zi[0] + zi[1] + zi[2] + zi[3] - 1020; yi = zq[0] + zq[1] + zq[2] + zq[3] - 1020; break;
+				case 2: yr = zi[0] - zi[1] + zi[2] - zi[3]; yi = zq[0] - zq[1] + zq[2] - zq[3]; break;
+				case 1: yr = (zi[0] - zi[2]) + (zq[1] - zq[3]); yi = (zq[0] - zq[2]) - (zi[1] - zi[3]); break;
+				default: yr = (zi[0] - zi[2]) - (zq[1] - zq[3]); yi = (zq[0] - zq[2]) + (zi[1] - zi[3]); break;
+				}
+				const float fr = (float)yr, fi = (float)yi, tr = t[2 * n2], ti = t[2 * n2 + 1];
+				a = fmaf(fr, tr, a);
+				b = fmaf(fi, ti, b);
+				pp = fmaf(fr, ti, pp);
+				q = fmaf(fi, tr, q);
+			}
+			const float re = a - b, im = pp + q;
+			dm[(size_t)ch * nout + m] = sqrtf(fmaf(re, re, im * im));
+		}
+	}
+}
+
 /* ------------------------------------------------------------------ Airspy front-end (air.c) */
 
 /* air.c:42-64 with filter == 0 (every rate but 5 MS/s): centre of the span on the 12.5 kHz raster */

@@ -71,6 +71,7 @@ void orc_channelize_fir(const uint8_t *iq, int nout, int K, int taps, int nch,
 /* the product's opt-in fast channelizer (no reference implementation: this is its definition; see the .c) */
 int  orc_fast_plan(const unsigned *freqs_hz, int nch, int K, unsigned fc, int *kbin /*nch*/, float *tw /*nch x K/4 x 2*/);
 void orc_channelize_dft(const uint8_t *iq, int nout, int K, int nch, const int *kbin, const float *tw, float *dm /*nch x nout*/);
+void orc_channelize_dft8(const uint8_t *iq, int nout, int K, int nch, const int *kbin, const float *tw, float *dm);   /* folded variant */
 
 /* Airspy front-end (air.c): float32 real samples at IF = rate/4 */
 unsigned orc_air_choose_fc(unsigned minf, unsigned maxf);                 /* air.c:42-64, no-filter branch */

@@ -353,6 +353,7 @@ class OracleLib:
         L.orc_channelize_fir.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_fast_plan.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p, C.c_void_p]
         L.orc_channelize_dft.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_channelize_dft8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_cs16_build_osc.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_void_p]
         L.orc_channelize_cs16.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_chan_init.argtypes = [C.POINTER(OrcChan), C.c_int]
@@ -437,13 +438,14 @@ class OracleLib:
             return None
         return k, tw
 
-    def channelize_dft(self, iq: np.ndarray, K: int, k: np.ndarray, tw: np.ndarray) -> np.ndarray:
+    def channelize_dft(self, iq: np.ndarray, K: int, k: np.ndarray, tw: np.ndarray, fold8: bool = False) -> np.ndarray:
         iq = np.ascontiguousarray(iq, dtype=np.uint8).reshape(-1)
         nout = iq.size // (2 * K)
         dm = np.empty((len(k), nout), dtype=np.float32)
         k = np.ascontiguousarray(k, dtype=np.int32)
         tw = np.ascontiguousarray(tw, dtype=np.float32)
-        self.lib.orc_channelize_dft(iq.ctypes.data, nout, K, len(k), k.ctypes.data, tw.ctypes.data, dm.ctypes.data)
+        fn = self.lib.orc_channelize_dft8 if fold8 else self.lib.orc_channelize_dft
+        fn(iq.ctypes.data, nout, K, len(k), k.ctypes.data, tw.ctypes.data, dm.ctypes.data)
         return dm
 
     def cs16_osc(self, variant: int, K: int, freqs_hz, fc: int) -> np.ndarray:

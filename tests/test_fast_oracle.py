@@ -39,8 +39,9 @@ def test_plan_restatement_matches_library(native, oracle):
     assert oracle.fast_plan(160, fd, fc) is None
 
 
+@pytest.mark.parametrize("fold8", [False, True])
 @pytest.mark.parametrize("K", [160, 192])
-def test_envelope_vs_reference_and_exact_dft(oracle, K):
+def test_envelope_vs_reference_and_exact_dft(oracle, K, fold8):
     fm = synth.DEFAULT_FREQS_MHZ
     fd, fr, fc = oracle.plan(K, fm)
     k, tw = oracle.fast_plan(K, fd, fc)
@@ -50,7 +51,7 @@ def test_envelope_vs_reference_and_exact_dft(oracle, K):
         plan = synth.make_plan(K, fm, fc, seconds=0.3, seed=900 + seed, text_len=(5, 60), msgs_per_chan_per_sec=4.0)
         iq = synth.render_blocks(plan, 0, 3).reshape(-1)
         ref = oracle.channelize(iq, K, wf).astype(np.float64)
-        fast = oracle.channelize_dft(iq, K, k, tw).astype(np.float64)
+        fast = oracle.channelize_dft(iq, K, k, tw, fold8).astype(np.float64)
         x = iq.reshape(-1, K, 2).astype(np.float64)
         bound = TABLE_EPS * np.hypot(x[..., 0] - 127.5, x[..., 1] - 127.5).sum(axis=1) / K / 127.5
         worst_ref = max(worst_ref, (np.abs(fast - ref) / bound[None, :]).max())
@@ -63,8 +64,8 @@ def test_envelope_vs_reference_and_exact_dft(oracle, K):
     assert worst_ideal <= IDEAL_EPS and worst_ideal < worst_ref_ideal, (worst_ideal, worst_ref_ideal)
 
 
-@pytest.mark.parametrize("K,nseeds", [(160, 24), (192, 8)])
-def test_messages_identical_over_many_captures(oracle, K, nseeds):
+@pytest.mark.parametrize("K,nseeds,fold8", [(160, 24, False), (192, 8, False), (160, 12, True), (192, 6, True)])
+def test_messages_identical_over_many_captures(oracle, K, nseeds, fold8):
     """Same frames — channel, length, error count, text, BCS, in the same order — from the reference's
     envelope and from the fast form's, over seeded captures with clean and corrupted frames, weak and
     strong bursts; lvl (dB) within 0.001."""
@@ -85,7 +86,7 @@ def test_messages_identical_over_many_captures(oracle, K, nseeds):
                 b.frame = synth.corrupt_frame(b.frame, flips[(i + seed) % len(flips)])
         iq = synth.render_blocks(plan, 0, synth.blocks_for_seconds(K, secs)).reshape(-1)
         a = _decode(oracle, oracle.channelize(iq, K, wf))
-        b = _decode(oracle, oracle.channelize_dft(iq, K, k, tw))
+        b = _decode(oracle, oracle.channelize_dft(iq, K, k, tw, fold8))
         assert [t[:-1] for t in a] == [t[:-1] for t in b], seed
         for x, y in zip(a, b):
             assert abs(x[-1] - y[-1]) <= 1e-3                          # lvl, in dB

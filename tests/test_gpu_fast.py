@@ -38,13 +38,15 @@ def _envelope_check(dm_fast, dm_ref, iq, K):
     return worst
 
 
+@pytest.mark.parametrize("fold8", [False, True])      # the 4-way split and the folded 8-way one (ACB_FAST_FOLD8)
 @pytest.mark.parametrize("K,freqs", [
     (160, synth.DEFAULT_FREQS_MHZ),
     (192, synth.DEFAULT_FREQS_MHZ),
     (160, (131.525, 131.725, 131.825)),             # partial channel group
     (192, (129.125, 130.025, 130.425, 130.45)),
 ])
-def test_fast_envelope_within_tolerance(native, oracle, K, freqs):
+def test_fast_envelope_within_tolerance(native, oracle, monkeypatch, K, freqs, fold8):
+    monkeypatch.setenv("ACB_FAST_FOLD8", "1" if fold8 else "0")
     fd, _, fc = api.plan(K, freqs)
     nblk = 3
     plan = synth.make_plan(K, freqs, fc, seconds=nblk * 1024 / 12500, seed=K + len(freqs))
@@ -71,7 +73,7 @@ def test_fast_envelope_within_tolerance(native, oracle, K, freqs):
     assert err_fast <= IDEAL_EPS and err_fast < err_ref, (err_fast, err_ref)
     # (c) the kernel against its CPU restatement, operation for operation: bit-identical
     kbin, tw = oracle.fast_plan(K, fd, fc)
-    assert np.array_equal(got.view(np.uint32), oracle.channelize_dft(iq[0], K, kbin, tw).T.view(np.uint32))
+    assert np.array_equal(got.view(np.uint32), oracle.channelize_dft(iq[0], K, kbin, tw, fold8).T.view(np.uint32))
     with api.Context(K, 1, len(freqs), nblk) as ctx:                          # control: default path is exact
         ctx.set_plan(0, fd)
         ctx.submit_host(iq, nblk)
@@ -80,8 +82,9 @@ def test_fast_envelope_within_tolerance(native, oracle, K, freqs):
         assert ctx.stats().fast_chan_launches == 0
 
 
-@pytest.mark.parametrize("K,seed,nstreams", [(160, 3, 2), (192, 4, 1), (160, 41, 6)])
-def test_fast_messages_identical(native, oracle, K, seed, nstreams):
+@pytest.mark.parametrize("K,seed,nstreams,fold8", [(160, 3, 2, False), (192, 4, 1, False), (160, 41, 6, False), (160, 7, 3, True), (192, 8, 2, True)])
+def test_fast_messages_identical(native, oracle, monkeypatch, K, seed, nstreams, fold8):
+    monkeypatch.setenv("ACB_FAST_FOLD8", "1" if fold8 else "0")
     """Whole path with injected messages: same frames (channel, length, errors, text, CRC) in the same
     order as the reference restatement; lvl (dB) within 0.001."""
     fm = synth.DEFAULT_FREQS_MHZ
