@@ -178,6 +178,7 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 	if (cfg->K < 1 || cfg->K > ACB_MAXK) return fail(ACB_ERR_ARG, "K=%d out of range 1..%d", cfg->K, ACB_MAXK);
 	if (cfg->nstreams < 1 || cfg->nch < 1 || cfg->max_blocks < 1) return fail(ACB_ERR_ARG, "nstreams/nch/max_blocks must be >= 1");
 	if (cfg->taps < 0 || cfg->taps > cfg->K) return fail(ACB_ERR_ARG, "taps=%d must be 0 (= K) or 1..K=%d", cfg->taps, cfg->K);
+	if ((cfg->flags & ACB_FLAG_REAL_INPUT) && (cfg->flags & ACB_FLAG_CS16_INPUT)) return fail(ACB_ERR_ARG, "REAL_INPUT and CS16_INPUT are exclusive");
 	int ndev = 0;
 	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
 		return fail(ACB_ERR_CUDA, "no CUDA device: libacars_b200 has no CPU fallback");
@@ -192,7 +193,6 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 	c->cfg = *cfg;
 	c->ngrp = (cfg->nch + CH_GROUP - 1) / CH_GROUP;
 	c->blk_bytes = (size_t)OUTBLK * cfg->K * 2;
-	if ((cfg->flags & ACB_FLAG_REAL_INPUT) && (cfg->flags & ACB_FLAG_CS16_INPUT)) return fail(ACB_ERR_ARG, "REAL_INPUT and CS16_INPUT are exclusive");
 	c->in_kind = (cfg->flags & ACB_FLAG_REAL_INPUT) ? IN_KIND_F32REAL : (cfg->flags & ACB_FLAG_CS16_INPUT) ? IN_KIND_CS16IQ : IN_KIND_U8IQ;
 	c->real_input = c->in_kind != IN_KIND_U8IQ;
 	c->use_generic = c->real_input ? (cfg->K % 4) != 0 : (cfg->K % 8) != 0;
@@ -779,16 +779,16 @@ extern "C" int acb_block_fec_batch(acb_ctx_t *c, acb_msg_t *msgs, int n, int *ke
 	RingCtl *dc = nullptr, hc;
 	memset(&hc, 0, sizeof(hc));
 	hc.count = (unsigned)n;
-	CU(cudaMalloc(&d, (size_t)n * sizeof(RawFrame)));
-	CU(cudaMalloc(&dc, sizeof(RingCtl)));
-	CU(cudaMemcpy(d, raw.data(), (size_t)n * sizeof(RawFrame), cudaMemcpyHostToDevice));
-	CU(cudaMemcpy(dc, &hc, sizeof(hc), cudaMemcpyHostToDevice));
-	int r = launch_block_fec(d, dc, (unsigned)n, c->s_d2h);
-	if (r) return fail(ACB_ERR_CUDA, "block FEC launch: %s", cudaGetErrorString((cudaError_t)r));
-	CU(cudaMemcpyAsync(raw.data(), d, (size_t)n * sizeof(RawFrame), cudaMemcpyDeviceToHost, c->s_d2h));
-	CU(cudaStreamSynchronize(c->s_d2h));
+	cudaError_t e = cudaMalloc(&d, (size_t)n * sizeof(RawFrame));
+	if (e == cudaSuccess) e = cudaMalloc(&dc, sizeof(RingCtl));
+	if (e == cudaSuccess) e = cudaMemcpy(d, raw.data(), (size_t)n * sizeof(RawFrame), cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = cudaMemcpy(dc, &hc, sizeof(hc), cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = (cudaError_t)launch_block_fec(d, dc, (unsigned)n, c->s_d2h);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(raw.data(), d, (size_t)n * sizeof(RawFrame), cudaMemcpyDeviceToHost, c->s_d2h);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_d2h);
 	cudaFree(d);
 	cudaFree(dc);
+	if (e != cudaSuccess) return fail(ACB_ERR_CUDA, "block FEC batch: %s", cudaGetErrorString(e));
 	int kept = 0;
 	for (int i = 0; i < n; i++) {
 		keep[i] = raw[i].pad0 == 1;
