@@ -116,6 +116,16 @@ static int ctx_use(acb_ctx *c)
 	return ACB_OK;
 }
 
+/* Host -> device upload that is complete when it returns.  A plain cudaMemcpy from pageable memory may
+ * return once the data is staged, before the DMA has landed, and the context's streams are non-blocking
+ * (not ordered behind the legacy stream): a kernel launched right after could read the old contents. */
+static int upload(acb_ctx *c, void *dst, const void *src, size_t bytes)
+{
+	CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->s_copy));
+	CU(cudaStreamSynchronize(c->s_copy));
+	return ACB_OK;
+}
+
 extern "C" void *acb_host_alloc(size_t bytes)
 {
 	void *p = nullptr;
@@ -143,8 +153,7 @@ extern "C" int acb_copy_to_device(acb_ctx_t *c, void *dst, const void *src, size
 {
 	if (!c) return fail(ACB_ERR_ARG, "null context");
 	if (int r = ctx_use(c)) return r;
-	CU(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
-	return ACB_OK;
+	return upload(c, dst, src, bytes);
 }
 
 static int sync_streams(acb_ctx *c)
@@ -163,7 +172,7 @@ static int reset_states(acb_ctx *c)
 		s.nbits = 8;
 		s.state = 0;             /* WSYN */
 	}
-	CU(cudaMemcpy(c->d_state, init.data(), n * sizeof(ChainState), cudaMemcpyHostToDevice));
+	if (int r = upload(c, c->d_state, init.data(), n * sizeof(ChainState))) return r;
 	for (int i = 0; i < 2; i++) CU(cudaMemset(c->d_ctl[i], 0, sizeof(RingCtl)));
 	c->pos = 0;
 	c->carry = 0;
@@ -346,7 +355,7 @@ extern "C" int acb_set_wf(acb_ctx_t *c, int stream, const float *wf, int nch)
 		}
 	}
 	if (int r = sync_streams(c)) return r;
-	CU(cudaMemcpy(c->d_wf4 + (size_t)stream * t.size(), t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+	if (int r = upload(c, c->d_wf4 + (size_t)stream * t.size(), t.data(), t.size() * sizeof(float))) return r;
 	c->fast_ok[stream] = 0;                     /* a caller's table has no known structure: exact kernel */
 	return ACB_OK;
 }
@@ -379,8 +388,8 @@ extern "C" int acb_set_plan(acb_ctx_t *c, int stream, const unsigned *freqs_hz, 
 		memcpy(&tw[((size_t)g * CH_GROUP + cc) * N2 * 2], &tw1[(size_t)ch * N2 * 2], (size_t)N2 * 2 * sizeof(float));
 	}
 	if (ok) {
-		CU(cudaMemcpy(c->d_tw + (size_t)stream * tw.size(), tw.data(), tw.size() * sizeof(float), cudaMemcpyHostToDevice));
-		CU(cudaMemcpy(c->d_twmeta + (size_t)stream * meta.size(), meta.data(), meta.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+		if (int r = upload(c, c->d_tw + (size_t)stream * tw.size(), tw.data(), tw.size() * sizeof(float))) return r;
+		if (int r = upload(c, c->d_twmeta + (size_t)stream * meta.size(), meta.data(), meta.size() * sizeof(unsigned))) return r;
 		c->fast_ok[stream] = 1;
 	}
 	return ACB_OK;
@@ -781,8 +790,8 @@ extern "C" int acb_block_fec_batch(acb_ctx_t *c, acb_msg_t *msgs, int n, int *ke
 	hc.count = (unsigned)n;
 	cudaError_t e = cudaMalloc(&d, (size_t)n * sizeof(RawFrame));
 	if (e == cudaSuccess) e = cudaMalloc(&dc, sizeof(RingCtl));
-	if (e == cudaSuccess) e = cudaMemcpy(d, raw.data(), (size_t)n * sizeof(RawFrame), cudaMemcpyHostToDevice);
-	if (e == cudaSuccess) e = cudaMemcpy(dc, &hc, sizeof(hc), cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(d, raw.data(), (size_t)n * sizeof(RawFrame), cudaMemcpyHostToDevice, c->s_d2h);   /* same stream as the kernel */
+	if (e == cudaSuccess) e = cudaMemcpyAsync(dc, &hc, sizeof(hc), cudaMemcpyHostToDevice, c->s_d2h);
 	if (e == cudaSuccess) e = (cudaError_t)launch_block_fec(d, dc, (unsigned)n, c->s_d2h);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(raw.data(), d, (size_t)n * sizeof(RawFrame), cudaMemcpyDeviceToHost, c->s_d2h);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_d2h);
@@ -866,7 +875,7 @@ extern "C" int acb_set_state(acb_ctx_t *c, int stream, int chn, const acb_chan_s
 	ChainState s;
 	from_api(in, s);
 	if (int r = sync_streams(c)) return r;
-	CU(cudaMemcpy(c->d_state + (size_t)stream * c->cfg.nch + chn, &s, sizeof(s), cudaMemcpyHostToDevice));
+	if (int r = upload(c, c->d_state + (size_t)stream * c->cfg.nch + chn, &s, sizeof(s))) return r;
 	return ACB_OK;
 }
 

@@ -887,6 +887,17 @@ k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp
 	const float *in = dm + (size_t)s * nsamp * nch + ch;
 	const unsigned long long pos0 = r.pos;
 	double clkd = (double)r.clk;             /* MskClk: a float value carried in a double register */
+	/* which of the six candidate phases this lane mixes: 4 lanes -> samples sub and 4 + sub (the latter
+	 * only for sub < 2; lanes 2, 3 get phase 4 or 5 for their discarded second evaluation, as before);
+	 * 8 lanes -> sample sub (lanes 6, 7 idle on phase 5) */
+	long long pick[DEMOD_LOOK];
+#pragma unroll
+	for (int k = 0; k < DEMOD_LOOK; k++) {
+		bool mine;
+		if (DEMOD_GROUP == 4) mine = k < 4 ? (sub == k) : ((sub & 1) == (k - 4));
+		else mine = k < DEMOD_LOOK - 1 ? (sub == k) : (sub >= k);
+		pick[k] = mine ? -1LL : 0LL;
+	}
 	int n = 0;
 	/* channels of a warp consume 5 or 6 samples per iteration each, so they finish a few
 	 * iterations apart: finished groups idle through empty iterations (m = 0) */
@@ -948,8 +959,11 @@ k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp
 		}
 		/* mixer (msk.c:86-91): in * cexp(-j phi), this lane's share */
 		if (DEMOD_GROUP == 4) {
-			const double p1 = (sub == 0) ? pk[0] : (sub == 1) ? pk[1] : (sub == 2) ? pk[2] : pk[3];
-			const double p2 = (sub & 1) ? pk[5] : pk[4];
+			/* lane-dependent picks as mask selects: written as a ?: chain on `sub` the compiler branches,
+			 * and the lanes of a group then run the arms one after the other */
+			const double p1 = __longlong_as_double((__double_as_longlong(pk[0]) & pick[0]) | (__double_as_longlong(pk[1]) & pick[1]) |
+			                                       (__double_as_longlong(pk[2]) & pick[2]) | (__double_as_longlong(pk[3]) & pick[3]));
+			const double p2 = __longlong_as_double((__double_as_longlong(pk[4]) & pick[4]) | (__double_as_longlong(pk[5]) & pick[5]));
 			double sn1, cs1, sn2, cs2;
 			sincos_vco(p1, s_cos, s_sin, sn1, cs1);
 			sincos_vco(p2, s_cos, s_sin, sn2, cs2);
@@ -966,7 +980,9 @@ k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp
 			s_re[row2][grp] = re2; s_im[row2][grp] = im2;
 			__syncwarp();
 		} else {                   /* one candidate sample per lane (lanes 6, 7 of the group idle here) */
-			const double p1 = (sub == 0) ? pk[0] : (sub == 1) ? pk[1] : (sub == 2) ? pk[2] : (sub == 3) ? pk[3] : (sub == 4) ? pk[4] : pk[5];
+			const double p1 = __longlong_as_double((__double_as_longlong(pk[0]) & pick[0]) | (__double_as_longlong(pk[1]) & pick[1]) |
+			                                       (__double_as_longlong(pk[2]) & pick[2]) | (__double_as_longlong(pk[3]) & pick[3]) |
+			                                       (__double_as_longlong(pk[4]) & pick[4]) | (__double_as_longlong(pk[5]) & pick[5]));
 			double sn1, cs1;
 			sincos_vco(p1, s_cos, s_sin, sn1, cs1);
 			const double xd1 = (double)x1;

@@ -1,6 +1,6 @@
 """CPU study behind the fast channelizer's "same messages" claim: over many seeded captures (marginal to
 strong bursts, clean and corrupted frames) decode the reference's envelope and the fast form's
-restatement (oracle/acars_oracle.c: orc_channelize_dft) with the pinned demodulator and compare the
+restatements (oracle/acars_oracle.c: orc_channelize_dft8, the default, and orc_channelize_dft) with the pinned demodulator and compare the
 messages.  Writes profiles/<tag>_fast_message_identity.json.
   python tools/fast_vs_exact_study.py [ncaptures] [tag]"""
 import json, sys
@@ -30,7 +30,7 @@ def decode(dm):
     return out
 
 
-res = {"captures": 0, "injected_frames": 0, "raw_frames_exact": 0, "delivered_exact": 0, "repaired": 0, "dropped_by_fec": 0,
+res = {"captures_with_any_difference_plain_split": 0, "captures": 0, "injected_frames": 0, "raw_frames_exact": 0, "delivered_exact": 0, "repaired": 0, "dropped_by_fec": 0,
        "captures_with_any_difference": 0, "frames_differing": 0, "max_abs_lvl_diff_db": 0.0, "by_K": {}}
 for i in range(N):
     K = 192 if i % 4 == 3 else 160
@@ -47,7 +47,10 @@ for i in range(N):
             b.frame = synth.corrupt_frame(b.frame, flips[(i + j) % len(flips)])
     iq = synth.render_blocks(plan, 0, synth.blocks_for_seconds(K, secs)).reshape(-1)
     a = decode(orc.channelize(iq, K, orc.wf(K, fm)))
-    b = decode(orc.channelize_dft(iq, K, k, tw))
+    b = decode(orc.channelize_dft(iq, K, k, tw, fold8=True))        # the default (folded) form
+    b4 = decode(orc.channelize_dft(iq, K, k, tw, fold8=False))      # the plain 4-way split
+    if [x[:2] for x in a] != [x[:2] for x in b4]:
+        res["captures_with_any_difference_plain_split"] = res.get("captures_with_any_difference_plain_split", 0) + 1
     res["captures"] += 1
     res["injected_frames"] += len(plan.bursts)
     res["raw_frames_exact"] += len(a)
