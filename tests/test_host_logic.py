@@ -204,3 +204,27 @@ def test_fast_plan_rejects_off_raster_channels(native):
     # a channel at the centre (bin 0) or beyond the band edge
     assert api.fast_plan(K, [fc], fc) is None
     assert api.fast_plan(K, [fc - 80 * 12500], fc) is None
+
+
+def test_fast_plan_coverage_of_real_channel_sets(native):
+    """Which real-world plans take the fast channelizer: all sets of 25 kHz-raster channels below 2^27 Hz
+    (the 129-132 MHz ACARS channels); in the 136 MHz band (float ulp 16 Hz) the float image of the channel
+    or of Fc is 8 Hz off, the reference then mixes off-raster and the plan is refused (exact kernel)."""
+    import random
+    low = [129.125, 129.35, 129.525, 130.025, 130.425, 130.45, 130.825, 130.85, 131.125, 131.25, 131.45, 131.475,
+           131.525, 131.55, 131.725, 131.825, 131.85, 131.95]
+    rnd = random.Random(3)
+    for K in (160, 192):
+        span = (K * 12500 - 4 * 12500) / 1e6
+        for n in (1, 2, 3, 5, 8):
+            for _ in range(40):
+                base = rnd.choice(low)
+                cand = [f for f in low if abs(f - base) <= span / 2]
+                sel = rnd.sample(cand, min(n, len(cand)))
+                fd, _, fc = api.plan(K, sel)
+                assert fc != 0 and api.fast_plan(K, fd, fc) is not None, sel
+    # 136.975 MHz = 136975000 Hz is not a multiple of 16: its float image is 136975008
+    fd, fr, fc = api.plan(160, (136.975,))
+    assert float(np.float32(fr[0])) != fd[0] and api.fast_plan(160, fd, fc) is None
+    fd, fr, fc = api.plan(160, (136.8,))              # 136800000 is a multiple of 16, its Fc = 136825000 is not
+    assert float(np.float32(fr[0])) == fd[0] and float(np.float32(fc)) != fc and api.fast_plan(160, fd, fc) is None
