@@ -57,10 +57,31 @@ def _run(cmd, log: Path) -> None:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """Build what is stale.  Several processes may call this at once (one rank per GPU under torchrun): an
+    exclusive file lock serialises them, each link goes to a temporary name and is renamed into place, and
+    whoever gets the lock second finds everything up to date."""
+    import fcntl
     (PKG / "build").mkdir(exist_ok=True)
+    with open(PKG / "build" / ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _link(cmd, target: Path, log: Path) -> None:
+    """Run a link command whose output is `target`, via a temporary file so a reader never sees a
+    half-written library."""
+    tmp = target.with_name(target.name + f".tmp{os.getpid()}")
+    _run([tmp if c is target else c for c in cmd], log)
+    os.replace(tmp, target)
+
+
+def _build_locked(force: bool, verbose: bool) -> Path:
     if force or _stale(LIB, LIB_SRC + HEADERS + [Path(__file__)]):
         cmd = [nvcc(), *ARCH, *NVCC_FLAGS, "-shared", "-o", LIB, *LIB_SRC, "-I", ROOT / "include"]
-        _run(cmd, PKG / "build" / "libacars_b200.log")
+        _link(cmd, LIB, PKG / "build" / "libacars_b200.log")
         if verbose:
             print((PKG / "build" / "libacars_b200.log").read_text())
     if all(p.exists() for p in COMPAT_SRC) and (
@@ -71,7 +92,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             cmd = [os.environ.get("CC", "gcc"), "-O2", "-std=gnu11", "-fPIC", "-shared", "-Wall", "-D" + macro,
                    "-ffp-contract=off", "-o", target, *COMPAT_SRC, "-I", ROOT / "include", "-L", PKG, "-lacars_b200",
                    "-Wl,-rpath,$ORIGIN", "-lpthread", "-lm"]
-            _run(cmd, PKG / "build" / (target.stem + ".log"))
+            _link(cmd, target, PKG / "build" / (target.stem + ".log"))
     return LIB
 
 
