@@ -64,7 +64,7 @@ class Stats(C.Structure):
     _fields_ = [("submits", C.c_uint64), ("kernel_launches", C.c_uint64), ("blocks", C.c_uint64),
                 ("raw_frames", C.c_uint64), ("fec_dropped", C.c_uint64), ("chan_ms", C.c_double),
                 ("demod_ms", C.c_double), ("chan_launches", C.c_uint64), ("demod_launches", C.c_uint64),
-                ("fast_chan_launches", C.c_uint64)]
+                ("fast_chan_launches", C.c_uint64), ("frames_lost", C.c_uint64)]
 
 
 # every symbol include/acars_b200.h declares: (name, restype, argtypes)

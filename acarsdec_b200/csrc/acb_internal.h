@@ -47,7 +47,8 @@ struct RawFrame {
 
 struct RingCtl {
 	unsigned count;                   /* frames appended (may exceed capacity: overflow) */
-	unsigned pad[3];
+	unsigned short_frames;            /* frames of fewer than 13 bytes, dropped before taking a slot (acars.c:124-129) */
+	unsigned pad[2];
 };
 
 /* channelizer tile geometry */
@@ -66,12 +67,13 @@ int launch_channelize_generic(int mode, const void *in, size_t stream_stride, co
                               int K, int taps, int nch, int nstreams, size_t row0, size_t nrows, size_t nsamp, CUstream_st *stream);
 int launch_demod(ChainState *st, const float *dm, int nsamp, int nch, int nstreams,
                  RawFrame *ring, RingCtl *ctl, unsigned cap, int lanes_per_channel, CUstream_st *stream);
+int demod_pick_lanes(long long nchains, int sm_count);
 bool channelize_dft_supports(int K);
 int launch_channelize_dft(const void *in, size_t stream_stride, const float *tw, const unsigned *meta, float *dm,
                           int K, int nch, int nstreams, int nblk, size_t nsamp, bool fold8, CUstream_st *stream);
 int launch_block_fec(RawFrame *ring, const RingCtl *ctl, unsigned cap, CUstream_st *stream);
-int upload_matched_filter(const float *h);
-int upload_sincos_table(const double *cos_hi_lo, const double *sin_hi_lo);
+int upload_matched_filter(const float *h, CUstream_st *stream);
+int upload_sincos_table(const double *cos_hi_lo, const double *sin_hi_lo, CUstream_st *stream);
 size_t channelize_smem_bytes(int mode);
 } // namespace acb
 

@@ -30,6 +30,8 @@
 
 using namespace acb;
 
+extern "C" void acb_build_sincos_table(double *cos_hi_lo, double *sin_hi_lo);
+
 static thread_local char g_err[512] = "";
 
 static int fail(int code, const char *fmt, ...)
@@ -172,8 +174,11 @@ static int reset_states(acb_ctx *c)
 		s.nbits = 8;
 		s.state = 0;             /* WSYN */
 	}
+	/* everything stream-ordered on s_copy and complete on return: the context's streams are non-blocking,
+	 * so nothing on the legacy stream (plain cudaMemset/cudaMemcpy) is ordered against them */
 	if (int r = upload(c, c->d_state, init.data(), n * sizeof(ChainState))) return r;
-	for (int i = 0; i < 2; i++) CU(cudaMemset(c->d_ctl[i], 0, sizeof(RingCtl)));
+	for (int i = 0; i < 2; i++) CU(cudaMemsetAsync(c->d_ctl[i], 0, sizeof(RingCtl), c->s_copy));
+	CU(cudaStreamSynchronize(c->s_copy));
 	c->pos = 0;
 	c->carry = 0;
 	c->outq.clear();
@@ -242,7 +247,8 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 	}
 	const size_t wf_floats = (size_t)cfg->nstreams * c->ngrp * c->taps_pad * CH_GROUP * (c->in_kind == IN_KIND_F32REAL ? 2 : 4);
 	CU(cudaMalloc(&c->d_wf4, wf_floats * sizeof(float)));
-	CU(cudaMemset(c->d_wf4, 0, wf_floats * sizeof(float)));
+	CU(cudaMemsetAsync(c->d_wf4, 0, wf_floats * sizeof(float), c->s_copy));
+	CU(cudaStreamSynchronize(c->s_copy));
 	c->fast = (cfg->flags & ACB_FLAG_FAST_CHANNELIZER) && c->in_kind == IN_KIND_U8IQ && c->taps == cfg->K && channelize_dft_supports(cfg->K);
 	c->fast_ok.assign(cfg->nstreams, 0);
 	c->fold8 = true;             /* 0.89 ms vs 0.95 ms for the plain 4-way split at 592 streams x 16 blocks */
@@ -251,8 +257,13 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 		/* 8 lanes per channel halve the mixer's share of the serial chain but double the warps: a gain (8 % on
 		 * one 8-channel stream) only while there is still at most one demod warp per SM sub-partition;
 		 * beyond that the extra warps cost more than they hide (592 streams: 4.54 -> 4.72 ms) */
-		const long long warps8 = (long long)cfg->nstreams * ((cfg->nch + 3) / 4);
-		c->demod_lanes = warps8 <= 4LL * prop.multiProcessorCount ? 8 : 4;
+		c->demod_lanes = demod_pick_lanes((long long)cfg->nstreams * cfg->nch, prop.multiProcessorCount);
+		/* comparison switch (tests force every width; tools/ab_demod.py sweeps it): 1, 2, 4, 8 lanes per channel,
+		 * +16 = F2F bit-clock rounding, -4 / -8 = the round-1 kernel (launch_demod) */
+		if (const char *e = getenv("ACB_DEMOD_LANES")) {
+			const int v = atoi(e), l = v & 15;
+			if (v == -4 || v == -8 || (v > 0 && v < 32 && (l == 1 || l == 2 || l == 4 || l == 8))) c->demod_lanes = v;
+		}
 	}
 	if (c->fast) {
 		CU(cudaMalloc(&c->d_tw, (size_t)cfg->nstreams * c->ngrp * CH_GROUP * (cfg->K / 4) * 2 * sizeof(float)));
@@ -270,8 +281,10 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 	c->last_dm = 0;
 	const size_t nchain = (size_t)cfg->nstreams * cfg->nch;
 	CU(cudaMalloc(&c->d_state, nchain * sizeof(ChainState)));
-	/* a frame needs >= 20 bytes on air = 833 envelope samples, so < 2 per chain per block:
-	 * one submit can never overflow its ring */
+	/* Frames of fewer than 13 text bytes never take a slot (emit_frame drops them like blk_thread does,
+	 * acars.c:124-129).  The shortest frame that does is SYN SYN SOH + 13 + BCS(2) + the byte the END
+	 * state swallows = 19 bytes = 152 bits = 791 envelope samples (frame_sm.h), so a chain finishes
+	 * < 1.3 per 1024-sample block: 2 per block (+4 for the ends of the submit) cannot be overrun */
 	size_t cap = nchain * (2 * (size_t)cfg->max_blocks + 4);
 	if (cap > (1u << 22)) cap = 1u << 22;
 	c->ring_cap = (unsigned)cap;
@@ -284,22 +297,11 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 
 	float h[FLENO];
 	acb_build_h(h);
-	CU((cudaError_t)upload_matched_filter(h));
+	CU((cudaError_t)upload_matched_filter(h, c->s_copy));
 	{
-		/* cos/sin(k*pi/32) as double-double for the demod kernel's VCO sincos; long double (64-bit
-		 * mantissa) is ample for the non-zero entries, the multiples of pi/2 are set exactly */
 		double tc[128], ts[128];
-		const long double pi = 3.14159265358979323846264338327950288L;
-		for (int k = 0; k < 64; k++) {
-			const long double c = cosl(k * pi / 32), s = sinl(k * pi / 32);
-			tc[2 * k] = (double)c; tc[2 * k + 1] = (double)(c - (long double)tc[2 * k]);
-			ts[2 * k] = (double)s; ts[2 * k + 1] = (double)(s - (long double)ts[2 * k]);
-			if (k % 16 == 0) {
-				static const double qc[4] = { 1, 0, -1, 0 }, qs[4] = { 0, 1, 0, -1 };
-				tc[2 * k] = qc[k / 16]; tc[2 * k + 1] = 0; ts[2 * k] = qs[k / 16]; ts[2 * k + 1] = 0;
-			}
-		}
-		CU((cudaError_t)upload_sincos_table(tc, ts));
+		acb_build_sincos_table(tc, ts);             /* hostmath.cpp */
+		CU((cudaError_t)upload_sincos_table(tc, ts, c->s_copy));
 	}
 	if (int r = reset_states(c)) return r;
 	return ACB_OK;
@@ -334,6 +336,10 @@ extern "C" int acb_reset(acb_ctx_t *c)
 	if (!c) return fail(ACB_ERR_ARG, "null context");
 	if (int r = ctx_use(c)) return r;
 	CU(cudaDeviceSynchronize());
+	/* submits still in flight are abandoned with their frames: recycle their events, forget pending reads */
+	for (auto &t : c->inflight) c->ev_free.push_back(t.ev);
+	c->inflight.clear();
+	for (int i = 0; i < 2; i++) c->ring_read_pending[i] = false;
 	return reset_states(c);
 }
 
@@ -435,7 +441,16 @@ static int harvest_begin(acb_ctx *c, Harvest &h)
 	if (cudaEventElapsedTime(&ms, h.t.ev.b2, h.t.ev.c) == cudaSuccess) c->stats.demod_ms += ms;
 	c->ev_free.push_back(h.t.ev);
 	h.count = c->h_ctl[h.t.ring]->count;
-	if (h.count > c->ring_cap) { c->overflowed = true; h.count = c->ring_cap; }
+	{
+		const unsigned shortf = c->h_ctl[h.t.ring]->short_frames;     /* dropped on the device like acars.c:124-129 */
+		c->stats.raw_frames += shortf;
+		c->stats.fec_dropped += shortf;
+	}
+	if (h.count > c->ring_cap) {                   /* reported once by the collecting call; decoding goes on */
+		c->overflowed = true;
+		c->stats.frames_lost += h.count - c->ring_cap;
+		h.count = c->ring_cap;
+	}
 	if (h.count)
 		CU(cudaMemcpyAsync(c->h_ring, c->d_ring[h.t.ring], (size_t)h.count * sizeof(RawFrame), cudaMemcpyDeviceToHost, c->s_d2h));
 	CU(cudaEventRecord(c->ev_ring_read[h.t.ring], c->s_d2h));
@@ -727,7 +742,10 @@ extern "C" int acb_collect(acb_ctx_t *c)
 	if (!c) return fail(ACB_ERR_ARG, "null context");
 	if (int r = ctx_use(c)) return r;
 	if (int r = collect_oldest(c)) return r;
-	if (c->overflowed) return fail(ACB_ERR_OVERFLOW, "device frame ring overflowed (%u slots)", c->ring_cap);
+	if (c->overflowed) {
+		c->overflowed = false;
+		return fail(ACB_ERR_OVERFLOW, "device frame ring overflowed (%u slots): %llu frames lost so far", c->ring_cap, (unsigned long long)c->stats.frames_lost);
+	}
 	return (int)c->outq.size();
 }
 
@@ -739,7 +757,10 @@ extern "C" int acb_sync(acb_ctx_t *c)
 		if (int r = collect_oldest(c)) return r;
 	CU(cudaStreamSynchronize(c->s_comp));
 	CU(cudaStreamSynchronize(c->s_dem));
-	if (c->overflowed) return fail(ACB_ERR_OVERFLOW, "device frame ring overflowed (%u slots)", c->ring_cap);
+	if (c->overflowed) {
+		c->overflowed = false;
+		return fail(ACB_ERR_OVERFLOW, "device frame ring overflowed (%u slots): %llu frames lost so far", c->ring_cap, (unsigned long long)c->stats.frames_lost);
+	}
 	return (int)c->outq.size();
 }
 
@@ -824,7 +845,8 @@ extern "C" int acb_read_dm(acb_ctx_t *c, float *out, size_t nfloats)
 	if (nfloats > have) return fail(ACB_ERR_ARG, "asked for %zu floats, last submit produced %zu", nfloats, have);
 	CU(cudaStreamSynchronize(c->s_comp));
 	CU(cudaStreamSynchronize(c->s_dem));
-	CU(cudaMemcpy(out, c->d_dm[c->last_dm], nfloats * sizeof(float), cudaMemcpyDeviceToHost));
+	CU(cudaMemcpyAsync(out, c->d_dm[c->last_dm], nfloats * sizeof(float), cudaMemcpyDeviceToHost, c->s_copy));
+	CU(cudaStreamSynchronize(c->s_copy));
 	return ACB_OK;
 }
 
@@ -861,7 +883,8 @@ extern "C" int acb_get_state(acb_ctx_t *c, int stream, int chn, acb_chan_state_t
 	if (int r = ctx_use(c)) return r;
 	ChainState s;
 	if (int r = sync_streams(c)) return r;
-	CU(cudaMemcpy(&s, c->d_state + (size_t)stream * c->cfg.nch + chn, sizeof(s), cudaMemcpyDeviceToHost));
+	CU(cudaMemcpyAsync(&s, c->d_state + (size_t)stream * c->cfg.nch + chn, sizeof(s), cudaMemcpyDeviceToHost, c->s_copy));
+	CU(cudaStreamSynchronize(c->s_copy));
 	to_api(s, out);
 	return ACB_OK;
 }

@@ -26,6 +26,24 @@
 #include "../../include/acars_b200.h"
 #include "frame_sm.h"
 
+/* cos/sin(k*pi/32), k < 64, as double-double (hi, lo) pairs for the demod kernel's VCO sincos
+ * (demod_core.h sincos_vco); long double (64-bit mantissa) is ample for the non-zero entries, the
+ * multiples of pi/2 are set exactly.  Internal (not in the public header): context.cu uploads it, the CPU
+ * tests' host emulation of the demod loop reads it. */
+extern "C" void acb_build_sincos_table(double *tc, double *ts)
+{
+	const long double pi = 3.14159265358979323846264338327950288L;
+	for (int k = 0; k < 64; k++) {
+		const long double c = cosl(k * pi / 32), s = sinl(k * pi / 32);
+		tc[2 * k] = (double)c; tc[2 * k + 1] = (double)(c - (long double)tc[2 * k]);
+		ts[2 * k] = (double)s; ts[2 * k + 1] = (double)(s - (long double)ts[2 * k]);
+		if (k % 16 == 0) {
+			static const double qc[4] = { 1, 0, -1, 0 }, qs[4] = { 0, 1, 0, -1 };
+			tc[2 * k] = qc[k / 16]; tc[2 * k + 1] = 0; ts[2 * k] = qs[k / 16]; ts[2 * k + 1] = 0;
+		}
+	}
+}
+
 /* ------------------------------------------------------------------ front-end planning */
 
 extern "C" int acb_round_freq(double mhz)

@@ -27,15 +27,15 @@
 
 #include "acb_internal.h"
 #include "frame_sm.h"
+#include "demod_core.h"
 
 namespace acb {
 
 __constant__ float c_h[FLENO];     /* matched filter, built on the host with glibc cosf (msk.c:44-48) */
 
-int upload_matched_filter(const float *h)
-{
-	return (int)cudaMemcpyToSymbol(c_h, h, sizeof(float) * FLENO);
-}
+/* stream-ordered uploads: the caller synchronises `stream` before it launches anything (the context's
+ * streams are non-blocking, i.e. not ordered behind the legacy stream a plain cudaMemcpyToSymbol uses) */
+int upload_matched_filter(const float *h, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K1: channelizer
@@ -716,17 +716,6 @@ int launch_channelize_generic(int mode, const void *in, size_t stream_stride, co
  * of the library one (~45 + slow path), (d) prefetch the 6 envelope samples.
  * ---------------------------------------------------------------------------------------- */
 
-struct DemodRegs {
-	double phi, df, lvlsum;
-	float clk;
-	int bitcount;
-	unsigned S, idx;
-	int nbits, state;
-	unsigned outbits;
-	int blk_len, blk_err;
-	unsigned long long pos, soh_pos;
-};
-
 /* acars.c:350-366: queue the finished block.  lvl = 10*log10(lvlsum/bitcount) is left to the host
  * (glibc log10) so the float matches the reference bit for bit.  Out of line and by value: it
  * runs once per frame, and keeping it away from the loop keeps the loop's state in registers. */
@@ -734,8 +723,12 @@ static __device__ __noinline__ void emit_frame(const ChainState *st, RawFrame *r
                                                int stream, int chn, int len, int err, double lvlsum, int bitcount,
                                                unsigned long long pos, unsigned long long soh_pos)
 {
+	/* blk_thread drops blocks shorter than 13 bytes unseen (acars.c:124-129): they never take a slot, so a
+	 * ring sized for the shortest deliverable frame (19 bytes on air = 792 samples) cannot be overrun by a
+	 * transmitter sending degenerate frames; the host adds the count to raw_frames / fec_dropped */
+	if (len < 13) { atomicAdd(&ctl->short_frames, 1u); return; }
 	const unsigned slot = atomicAdd(&ctl->count, 1u);
-	if (slot >= cap) return;                       /* overflow is reported by the host */
+	if (slot >= cap) return;                       /* overflow: counted by the host (frames_lost), decoding goes on */
 	RawFrame *f = ring + slot;
 	f->stream = stream; f->chn = chn;
 	f->len = len; f->err = err;
@@ -770,21 +763,25 @@ struct DevFrameAcc {
 	/* only the leader's value is ever stored (crc_put); the shadows' reads are don't-cares */
 	__device__ __forceinline__ unsigned char txt_get(int i) { return leader ? st->txt[i] : (unsigned char)0; }
 	__device__ __forceinline__ void crc_put(int i, unsigned char c) { if (leader) st->crc[i] = c; }
-	__device__ __forceinline__ bool frame_begin() { r.soh_pos = r.pos; return true; }   /* acars.c:283-292 */
+	bool v2;                 /* demod_core.h's loop: the bit's sample position is pos0 + fire_n (r.pos is only set at the end) */
+	__device__ __forceinline__ unsigned long long bit_pos() const { return v2 ? r.pos0 + (unsigned long long)(long long)r.fire_n : r.pos; }
+	__device__ __forceinline__ bool frame_begin() { r.soh_pos = bit_pos(); return true; }   /* acars.c:283-292 */
 	__device__ __forceinline__ void frame_emit()
 	{
-		if (leader) emit_frame(st, ring, ctl, cap, stream, chn, r.blk_len, r.blk_err, r.lvlsum, r.bitcount, r.pos, r.soh_pos);
+		if (leader) emit_frame(st, ring, ctl, cap, stream, chn, r.blk_len, r.blk_err, r.lvlsum, r.bitcount, bit_pos(), r.soh_pos);
 	}
 };
 
 /* cos/sin of k*pi/32 as double-double (hi, lo), built on the host in long double */
 __device__ double2 g_sc_cos[64], g_sc_sin[64];
 
-int upload_sincos_table(const double *cos_hi_lo, const double *sin_hi_lo)
+int upload_sincos_table(const double *cos_hi_lo, const double *sin_hi_lo, cudaStream_t stream)
 {
-	cudaError_t e = cudaMemcpyToSymbol(g_sc_cos, cos_hi_lo, sizeof(double) * 128);
+	cudaError_t e = cudaMemcpyToSymbolAsync(g_sc_cos, cos_hi_lo, sizeof(double) * 128, 0, cudaMemcpyHostToDevice, stream);
 	if (e != cudaSuccess) return (int)e;
-	return (int)cudaMemcpyToSymbol(g_sc_sin, sin_hi_lo, sizeof(double) * 128);
+	e = cudaMemcpyToSymbolAsync(g_sc_sin, sin_hi_lo, sizeof(double) * 128, 0, cudaMemcpyHostToDevice, stream);
+	if (e != cudaSuccess) return (int)e;
+	return (int)cudaStreamSynchronize(stream);      /* the sources are the caller's stack arrays */
 }
 
 /* cos(p), sin(p) for p in [0, 2*pi] — the VCO phase after msk.c:82-83.  p = k*pi/32 + r with
@@ -794,7 +791,6 @@ int upload_sincos_table(const double *cos_hi_lo, const double *sin_hi_lo)
  * references: 1.7 ulp (typ. < 0.6), i.e. the class of CUDA's own sincos; see DESIGN.md for why
  * ~1 ulp here is invisible after the (float) rounding of in*cexp(-j p) (msk.c:90). */
 constexpr double SC_MAGIC = 6755399441055744.0;     /* 1.5 * 2^52 */
-
 __device__ __forceinline__ void sincos_vco(double p, const double2 *tcos, const double2 *tsin, double &sn, double &cs)
 {
 	const double t = fma(p, 0x1.45f306dc9c883p+3, SC_MAGIC);               /* p * 32/pi, rounded to integer */
@@ -816,22 +812,6 @@ __device__ __forceinline__ void sincos_vco(double p, const double2 *tcos, const 
 	cs = C.x + fma(-S.x, sr, fma(C.x, cm, C.y));
 	sn = S.x + fma(C.x, sr, fma(S.x, cm, S.y));
 }
-
-/* Round a double to float precision, result kept as a double: bit-identical to
- * (double)(float)x (round to nearest even) for zero and for every x whose float image is a normal
- * number.  MskClk lives in [-0.5, 5.3]; differences of such values are zero or >= 2^-52 in
- * magnitude, so the float-denormal range (< 2^-126) cannot occur.  Integer ops on the bit pattern
- * instead of two F2F conversions: the bit clock (msk.c:95) is a serial chain of these, six per
- * bit, and it must stay branch-free to be scheduled among the sincos evaluations. */
-__device__ __forceinline__ double round_to_f32(double x)
-{
-	unsigned long long u = (unsigned long long)__double_as_longlong(x);
-	u += 0x0FFFFFFFull + ((u >> 29) & 1ull);
-	u &= ~0x1FFFFFFFull;
-	return __longlong_as_double((long long)u);
-}
-
-constexpr int DEMOD_LOOK = 6;    /* samples examined per outer iteration (bit period = 5.17..5.25) */
 
 /* lanes per channel: 4 (8 channels per warp), or 8 (4 channels per warp, one mixer evaluation per lane
  * instead of two) for contexts small enough that the doubled warp count still fits one warp per SM
@@ -875,7 +855,7 @@ k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp
 	for (int k = sub; k < FLEN; k += DEMOD_GROUP) { s_re[k][grp] = st->inb_re[k]; s_im[k][grp] = st->inb_im[k]; }
 	__syncwarp();
 
-	DevFrameAcc acc{ r, st, ring, ctl, cap, s, ch, leader };
+	DevFrameAcc acc{ r, st, ring, ctl, cap, s, ch, leader, false };
 
 	const double TWO_PI = 2.0 * M_PI;
 	const double S0 = 1800.0 / 12500 * 2.0 * M_PI;             /* msk.c:81 */
@@ -929,7 +909,7 @@ k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp
 			for (int k = 0; k < DEMOD_LOOK; k++) {
 				p = __dadd_rn(p, sv);
 				p = (p >= TWO_PI) ? __dadd_rn(p, -TWO_PI) : p;
-				c = round_to_f32(__dadd_rn(c, sv));
+				c = round_to_f32<false>(__dadd_rn(c, sv));
 				pk[k] = p;
 				ck[k] = c;
 			}
@@ -999,7 +979,7 @@ k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp
 		r.pos = pos0 + (unsigned long long)(n + cnt - 1);       /* the sample that fired the bit */
 
 		if (fired) {
-			clkd = round_to_f32(__dadd_rn(clkd, -THR));
+			clkd = round_to_f32<false>(__dadd_rn(clkd, -THR));
 
 			/* matched filter (msk.c:103-107): 11 taps out of the x12 oversampled half cosine.
 			 * Phase index o = (int)(12*(MskClk/s + 0.5)): with inv_s good to 1e-15 the product gives
@@ -1056,24 +1036,134 @@ k_demod(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp
 	for (int k = 0; k < FLEN; k++) { st->inb_re[k] = s_re[k][grp]; st->inb_im[k] = s_im[k][grp]; }
 }
 
-template <int LANES>
+/* K2, current form: the loop lives in demod_core.h (shared with the CPU tests' single-lane emulation).
+ * One warp per CTA so chains spread over all SMs; L lanes per channel, 32/L channels per warp; state in
+ * registers across the whole launch, ring and tables in shared memory, state written back at the end
+ * (channel_t's role between demodMSK calls, msk.c:71-72, 134-135). */
+struct WarpEnv {
+	static __device__ __forceinline__ bool any(bool x) { return __any_sync(0xffffffffu, x) != 0; }
+	static __device__ __forceinline__ bool all(bool x) { return __all_sync(0xffffffffu, x) != 0; }
+	static __device__ __forceinline__ void sync() { __syncwarp(); }
+};
+
+__device__ DcF4 g_h2[MFLTOVER + 1][3];           /* matched filter, transposed: g_h2[o] = h[o + 12 j] (msk.c:104-107) */
+
+int upload_matched_filter(const float *h, cudaStream_t stream)
+{
+	float t[MFLTOVER + 1][12];
+	for (int o = 0; o <= MFLTOVER; o++)
+		for (int j = 0; j < 12; j++) t[o][j] = j < FLEN ? h[o + MFLTOVER * j] : 0.f;
+	cudaError_t e = cudaMemcpyToSymbolAsync(c_h, h, sizeof(float) * FLENO, 0, cudaMemcpyHostToDevice, stream);
+	if (e != cudaSuccess) return (int)e;
+	e = cudaMemcpyToSymbolAsync(g_h2, t, sizeof(t), 0, cudaMemcpyHostToDevice, stream);
+	if (e != cudaSuccess) return (int)e;
+	return (int)cudaStreamSynchronize(stream);
+}
+
+template <int L, bool F2F>
+__global__ void __launch_bounds__(32)
+k_demod2(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp, int nch, int nstreams,
+         int wps, RawFrame *__restrict__ ring, RingCtl *__restrict__ ctl, unsigned cap)
+{
+	constexpr int CPW = 32 / L;                  /* channels per warp */
+	__shared__ DemodShared<CPW> sm;
+	const int lane = threadIdx.x;
+	for (int i = lane; i < 64; i += 32) {
+		sm.tcos[i].x = g_sc_cos[i].x; sm.tcos[i].y = g_sc_cos[i].y;
+		sm.tsin[i].x = g_sc_sin[i].x; sm.tsin[i].y = g_sc_sin[i].y;
+	}
+	for (int i = lane; i < (MFLTOVER + 1) * 3; i += 32) (&sm.h2[0][0])[i] = (&g_h2[0][0])[i];
+
+	const int grp = lane / L, sub = lane % L;
+	const int warp = blockIdx.x;
+	const int s = warp / wps;
+	const int ch_raw = (warp - s * wps) * CPW + grp;
+	const bool valid = ch_raw < nch;                 /* surplus groups shadow the last channel, silently */
+	const int ch = valid ? ch_raw : nch - 1;
+	const bool leader = valid && sub == 0;
+
+	ChainState *st = states + (size_t)s * nch + ch;
+	DemodRegs r;
+	r.phi = st->phi; r.df = st->df; r.lvlsum = st->lvlsum; r.clk = st->clk; r.bitcount = st->bitcount;
+	r.S = st->S; r.idx = st->idx; r.nbits = st->nbits; r.state = st->state; r.outbits = st->outbits;
+	r.blk_len = st->blk_len; r.blk_err = st->blk_err; r.pos = st->pos; r.soh_pos = st->soh_pos;
+	for (int k = sub; k < FLEN; k += L) {
+		DcF2 v;
+		v.x = st->inb_re[k]; v.y = st->inb_im[k];
+		sm.ring[k][grp] = v;
+		sm.ring[k + FLEN][grp] = v;
+	}
+	__syncwarp();
+
+	DevFrameAcc acc{ r, st, ring, ctl, cap, s, ch, leader, true };
+	demod_run<L, F2F, WarpEnv>(r, sm, dm + (size_t)s * nsamp * nch + ch, nch, nsamp, sub, grp, acc);
+
+	if (!leader) return;
+	st->phi = r.phi; st->df = r.df; st->lvlsum = r.lvlsum; st->clk = r.clk; st->bitcount = r.bitcount;
+	st->S = r.S; st->idx = r.idx; st->nbits = r.nbits; st->state = r.state; st->outbits = r.outbits;
+	st->blk_len = r.blk_len; st->blk_err = r.blk_err; st->pos = r.pos; st->soh_pos = r.soh_pos;
+#pragma unroll
+	for (int k = 0; k < FLEN; k++) { st->inb_re[k] = sm.ring[k][grp].x; st->inb_im[k] = sm.ring[k][grp].y; }
+}
+
+template <int LANES, bool F2F>
 static int launch_demod_t(ChainState *st, const float *dm, int nsamp, int nch, int nstreams,
                           RawFrame *ring, RingCtl *ctl, unsigned cap, cudaStream_t stream)
 {
 	constexpr int CPW = 32 / LANES;
 	const int wps = (nch + CPW - 1) / CPW;
 	const int grid = nstreams * wps;             /* one warp per CTA so that chains spread over all SMs */
-	cudaError_t e = cudaFuncSetAttribute(k_demod<LANES>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+	cudaError_t e = cudaFuncSetAttribute(k_demod2<LANES, F2F>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 	if (e != cudaSuccess) return (int)e;
-	k_demod<LANES><<<grid, 32, 0, stream>>>(st, dm, nsamp, nch, nstreams, wps, ring, ctl, cap);
+	k_demod2<LANES, F2F><<<grid, 32, 0, stream>>>(st, dm, nsamp, nch, nstreams, wps, ring, ctl, cap);
 	return (int)cudaGetLastError();
 }
 
+template <int LANES>
+static int launch_demod_v1(ChainState *st, const float *dm, int nsamp, int nch, int nstreams,
+                           RawFrame *ring, RingCtl *ctl, unsigned cap, cudaStream_t stream)
+{
+	constexpr int CPW = 32 / LANES;
+	const int wps = (nch + CPW - 1) / CPW;
+	cudaError_t e = cudaFuncSetAttribute(k_demod<LANES>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+	if (e != cudaSuccess) return (int)e;
+	k_demod<LANES><<<nstreams * wps, 32, 0, stream>>>(st, dm, nsamp, nch, nstreams, wps, ring, ctl, cap);
+	return (int)cudaGetLastError();
+}
+
+/* Lanes per channel.  Every lane of a channel's group repeats the serial part of a bit period and the group
+ * only splits the six mixer evaluations, so fewer lanes = fewer instructions per channel; more lanes = a
+ * shorter chain per bit.  The kernel is latency bound until there are several warps per scheduler, so: the
+ * most lanes that still leave about one warp per SM sub-partition, the fewest once the chains alone fill
+ * the machine. */
+int demod_pick_lanes(long long nchains, int sm_count)
+{
+	const long long slots = 4LL * sm_count;      /* one warp per scheduler */
+	if (nchains * 8 <= 32 * slots * 2) return 8;
+	if (nchains * 4 <= 32 * slots * 2) return 4;
+	if (nchains * 2 <= 32 * slots * 2) return 2;
+	return 1;
+}
+
+/* lanes: 1, 2, 4 or 8 lanes per channel; + 16 = bit clock rounded with the F2F conversion pair instead of
+ * integer ops (round_to_f32); negative (-4, -8) = the round-1 kernel, kept for A/B runs */
 int launch_demod(ChainState *st, const float *dm, int nsamp, int nch, int nstreams,
                  RawFrame *ring, RingCtl *ctl, unsigned cap, int lanes, cudaStream_t stream)
 {
-	return lanes == 8 ? launch_demod_t<8>(st, dm, nsamp, nch, nstreams, ring, ctl, cap, stream)
-	                  : launch_demod_t<4>(st, dm, nsamp, nch, nstreams, ring, ctl, cap, stream);
+#define ACB_DEMOD_ARGS st, dm, nsamp, nch, nstreams, ring, ctl, cap, stream
+	switch (lanes) {
+	case -8: return launch_demod_v1<8>(ACB_DEMOD_ARGS);
+	case -4: return launch_demod_v1<4>(ACB_DEMOD_ARGS);
+	case 8: return launch_demod_t<8, false>(ACB_DEMOD_ARGS);
+	case 2: return launch_demod_t<2, false>(ACB_DEMOD_ARGS);
+	case 1: return launch_demod_t<1, false>(ACB_DEMOD_ARGS);
+	case 24: return launch_demod_t<8, true>(ACB_DEMOD_ARGS);
+	case 20: return launch_demod_t<4, true>(ACB_DEMOD_ARGS);
+	case 18: return launch_demod_t<2, true>(ACB_DEMOD_ARGS);
+	case 17: return launch_demod_t<1, true>(ACB_DEMOD_ARGS);
+	default: return launch_demod_t<4, false>(ACB_DEMOD_ARGS);
+	}
+#undef ACB_DEMOD_ARGS
 }
 
 /* ------------------------------------------------------------------------------------------

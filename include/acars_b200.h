@@ -210,6 +210,7 @@ typedef struct {
 	double   demod_ms;          /* accumulated device time of the demod kernel */
 	uint64_t chan_launches, demod_launches;
 	uint64_t fast_chan_launches; /* channelizer launches that took the ACB_FLAG_FAST_CHANNELIZER form */
+	uint64_t frames_lost;       /* frames that found the device ring full (ACB_ERR_OVERFLOW was returned once per submit) */
 } acb_stats_t;
 int acb_get_stats(acb_ctx_t *ctx, acb_stats_t *out, int reset);
 

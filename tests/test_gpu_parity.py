@@ -254,6 +254,40 @@ def test_full_path_synthetic_vs_oracle(native, oracle, K, seed, nstreams):
     assert keys == sorted(keys)
 
 
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8, 17, 18, 20, 24, -4, -8])
+def test_demod_every_lane_width(native, oracle, lanes, monkeypatch):
+    """k_demod2 with 1, 2, 4 and 8 lanes per channel (the context picks by chain count; ACB_DEMOD_LANES forces),
+    both bit-clock rounding forms (+16), and the round-1 kernel (negative): same frames, same bit-identical
+    state as the oracle; 11 channels so that the last warp carries surplus (shadow) groups at every width."""
+    monkeypatch.setenv("ACB_DEMOD_LANES", str(lanes))
+    K, fm = 160, tuple(130.000 + 0.025 * i for i in range(11))
+    fd, _, fc = api.plan(K, fm)
+    secs = 0.5
+    nblk = synth.blocks_for_seconds(K, secs)
+    plans = [synth.make_plan(K, fm, fc, seconds=secs, seed=40 + s) for s in range(2)]
+    iq = np.stack([synth.render_blocks(p, 0, nblk).reshape(-1) for p in plans])
+    wf = oracle.wf(K, fm)
+    with api.Context(K, 2, len(fm), nblk) as ctx:
+        for s in range(2):
+            ctx.set_plan(s, fd)
+        bb = 2048 * K
+        ctx.submit_host(np.ascontiguousarray(iq[:, :2 * bb]), 2)            # launches end mid-bit: general path
+        ctx.submit_host(np.ascontiguousarray(iq[:, 2 * bb:]), nblk - 2)
+        ctx.sync()
+        got = ctx.drain()
+        states = [[ctx.get_state(s, c).vec() for c in range(len(fm))] for s in range(2)]
+    total = 0
+    for s in range(2):
+        o = refs.OracleStream(oracle, K, wf)
+        o.blocks(iq[s])
+        want = [msg_tuple(m) for m in o.msgs()]
+        assert [msg_tuple(m) for m in got if m.stream == s] == want, s
+        total += len(want)
+        for c in range(len(fm)):
+            assert states[s][c] == o.chan(c).vec(), (s, c)
+    assert total >= 4
+
+
 def test_corrupted_frames_fec_on_gpu_path(native, oracle):
     K, fm = 160, (131.525, 131.725, 131.825)
     fd, _, fc = api.plan(K, fm)
