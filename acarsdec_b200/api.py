@@ -92,6 +92,7 @@ ABI = [
     ("acb_submit_real_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     ("acb_submit_cs16_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
     ("acb_submit_cs16_planar_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    ("acb_set_emission_groups", C.c_int, [C.c_void_p, C.c_int, C.c_uint64]),
     ("acb_submit_dm_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     ("acb_sync", C.c_int, [C.c_void_p]),
     ("acb_collect", C.c_int, [C.c_void_p]),
@@ -315,6 +316,10 @@ class Context:
         """xi, xq: int16 (nstreams, nsamples) separate I and Q planes (the SDRplay callback's layout)."""
         assert xi.dtype == np.int16 and xq.dtype == np.int16 and xi.shape == xq.shape and xi.flags.c_contiguous and xq.flags.c_contiguous
         return _check(self.lib, self.lib.acb_submit_cs16_planar_host(self.h, xi.ctypes.data, xq.ctypes.data, xi.shape[1], xi.shape[1]))
+
+    def set_emission_groups(self, unit: int, period: int = 0) -> None:
+        """unit: 0 per submit, 1 every `period` envelope samples, 2 per transfer of `period` input samples."""
+        _check(self.lib, self.lib.acb_set_emission_groups(self.h, unit, period))
 
     def submit_dm(self, dm: np.ndarray) -> None:
         """dm: float32 (nstreams, nsamp, nch)."""

@@ -73,6 +73,41 @@ static void q_push(msgblk_t *b)
 	pthread_mutex_unlock(&q_mtx);
 }
 
+/* Wall-clock time of an envelope sample.  The reference stamps a block with gettimeofday() when its loop reaches
+ * the SOH byte (acars.c:290), i.e. when the transfer holding that sample is processed.  The shim processes
+ * batches of transfers, so it stamps every batch when its input has been read and places a sample inside its
+ * batch at the stream's own rate (12.5 kS/s per channel): the last sample of a batch arrived at the stamp. */
+#define NSTAMP 8
+static struct { uint64_t end_pos; struct timeval tv; } stamps[NSTAMP];
+static unsigned nstamps;
+
+static void stamp_reset(void) { nstamps = 0; }
+
+static void stamp_batch(uint64_t end_pos)
+{
+	gettimeofday(&stamps[nstamps % NSTAMP].tv, NULL);
+	stamps[nstamps % NSTAMP].end_pos = end_pos;
+	nstamps++;
+}
+
+static struct timeval stamp_time(uint64_t pos)
+{
+	struct timeval tv;
+	if (nstamps == 0) { gettimeofday(&tv, NULL); return tv; }
+	unsigned first = nstamps > NSTAMP ? nstamps - NSTAMP : 0, pick = nstamps - 1;
+	for (unsigned i = first; i < nstamps; i++)
+		if (stamps[i % NSTAMP].end_pos > pos) { pick = i; break; }
+	const uint64_t end = stamps[pick % NSTAMP].end_pos;
+	tv = stamps[pick % NSTAMP].tv;
+	if (end > pos + 1) {
+		const uint64_t us = (end - 1 - pos) * 1000000ull / INTRATE;
+		const long long t = (long long)tv.tv_sec * 1000000ll + tv.tv_usec - (long long)us;
+		tv.tv_sec = (time_t)(t / 1000000ll);
+		tv.tv_usec = (suseconds_t)(t % 1000000ll);
+	}
+	return tv;
+}
+
 /* a repaired block from the library -> msgblk_t on the consumer queue */
 static void deliver(const acb_msg_t *m, int chn, const struct timeval *tv)
 {
@@ -87,6 +122,18 @@ static void deliver(const acb_msg_t *m, int chn, const struct timeval *tv)
 	b->crc[0] = m->crc[0];
 	b->crc[1] = m->crc[1];
 	q_push(b);
+}
+
+/* everything the library has queued -> the consumer, stamped with the time of its SOH sample */
+static void deliver_ready(acb_ctx_t *ctx) __attribute__((unused));
+static void deliver_ready(acb_ctx_t *ctx)
+{
+	acb_msg_t out[16];
+	for (int n; (n = acb_drain(ctx, out, 16)) > 0;)
+		for (int i = 0; i < n; i++) {
+			const struct timeval tv = stamp_time(out[i].soh_pos);      /* acars.c:290 */
+			deliver(&out[i], out[i].chn, &tv);
+		}
 }
 
 /* ---------------------------------------------------------------- initAcars / deinitAcars */
@@ -357,13 +404,6 @@ int initRtl(char **argv, int optind)
 	return 0;
 }
 
-static void rtl_deliver_ready(const struct timeval *tv)
-{
-	acb_msg_t out[16];
-	for (int n; (n = acb_drain(rtl_ctx, out, 16)) > 0;)
-		for (int i = 0; i < n; i++) deliver(&out[i], out[i].chn, tv);
-}
-
 int runRtlSample(void)
 {
 	if (!rtl_ctx || !rtl_src) return 1;
@@ -379,34 +419,31 @@ int runRtlSample(void)
 		acb_set_state(rtl_ctx, 0, (int)n, &st);
 	}
 	int which = 0, rc = ACB_OK, inflight = 0;
-	struct timeval tv_prev;
-	gettimeofday(&tv_prev, NULL);
+	uint64_t pos = 0;
+	stamp_reset();
 	while (!signalExit && !rtl_cancel) {
 		if (inflight == 2) {
 			/* buf[which] was the source of the submit two back: it must have been consumed */
 			rc = acb_collect(rtl_ctx);
 			if (rc < 0) break;
 			inflight--;
-			rtl_deliver_ready(&tv_prev);
+			deliver_ready(rtl_ctx);
 		}
 		size_t got = fread(buf[which], 1, rtl_inbufsize * rtl_batch, rtl_src);
 		int nblk = (int)(got / rtl_inbufsize);
 		if (got % rtl_inbufsize) fprintf(stderr, "warning: partial read\n");     /* rtl.c:322-326 */
 		if (nblk == 0) break;
-		struct timeval tv;
-		gettimeofday(&tv, NULL);
+		pos += (uint64_t)nblk * RTLOUTBUFSZ;
+		stamp_batch(pos);
 		rc = acb_submit_host(rtl_ctx, buf[which], rtl_inbufsize * nblk, nblk);
 		if (rc != ACB_OK) break;
 		which ^= 1;
 		inflight++;
-		tv_prev = tv;
 		if (nblk < rtl_batch) break;
 	}
 	if (rc >= 0) rc = acb_sync(rtl_ctx);
 	if (rc < 0) fprintf(stderr, "acarsdec_b200: %s\n", acb_last_error());
-	struct timeval tv;
-	gettimeofday(&tv, NULL);
-	rtl_deliver_ready(&tv);
+	deliver_ready(rtl_ctx);
 	for (unsigned n = 0; n < nbch; n++)
 		if (acb_get_state(rtl_ctx, 0, (int)n, &st) == ACB_OK) state_unpack(&st, &channel[n]);
 	for (int i = 0; i < 2; i++) acb_host_free(buf[i]);
@@ -504,35 +541,46 @@ int initAirspy(char **argv, int optind)
 	return 0;
 }
 
-/* air.c:344 runAirspySample — batches of 8 transfers per submit; any length is fine, the library
- * carries what does not fill an output row (the reference carries ch->D / ind) */
+/* air.c:344 runAirspySample — batches of 8 transfers per submit, two pinned buffers so that reading batch i+1
+ * overlaps the device work of batch i; any length is fine, the library carries what does not fill an output
+ * row (the reference carries ch->D / ind).  Frames are queued in the reference's order: per 65536-sample
+ * transfer, channel by channel (air.c:336). */
 int runAirspySample(void)
 {
 	if (!air_ctx || !air_src) return -1;
 	const size_t cap = (size_t)AIR_TRANSFER * 8;
-	float *buf = acb_host_alloc(cap * sizeof(float));
-	if (!buf) { fprintf(stderr, "acarsdec_b200: %s\n", acb_last_error()); return -1; }
+	float *buf[2] = { acb_host_alloc(cap * sizeof(float)), acb_host_alloc(cap * sizeof(float)) };
+	if (!buf[0] || !buf[1]) { fprintf(stderr, "acarsdec_b200: %s\n", acb_last_error()); return -1; }
 	acb_chan_state_t st;
-	acb_msg_t out[16];
 	for (unsigned n = 0; n < nbch; n++) { state_pack(&channel[n], &st); acb_set_state(air_ctx, 0, (int)n, &st); }
-	int rc = ACB_OK;
+	acb_set_emission_groups(air_ctx, ACB_GROUP_INPUT, AIR_TRANSFER);
+	int rc = ACB_OK, which = 0, inflight = 0;
+	uint64_t pos = 0;
+	stamp_reset();
 	while (!signalExit && !air_cancel) {
-		size_t got = fread(buf, sizeof(float), cap, air_src);
+		if (inflight == 2) {                 /* buf[which] fed the submit two back: it has been consumed */
+			rc = acb_collect(air_ctx);
+			if (rc < 0) break;
+			inflight--;
+			deliver_ready(air_ctx);
+		}
+		size_t got = fread(buf[which], sizeof(float), cap, air_src);
 		if (got == 0) break;
-		struct timeval tv;
-		gettimeofday(&tv, NULL);
-		rc = acb_submit_real_host(air_ctx, buf, got, got);
+		rc = acb_submit_real_host(air_ctx, buf[which], got, got);
 		if (rc < 0) break;
-		rc = acb_sync(air_ctx);          /* the one pinned buffer is refilled next */
-		if (rc < 0) break;
-		for (int n; (n = acb_drain(air_ctx, out, 16)) > 0;)
-			for (int i = 0; i < n; i++) deliver(&out[i], out[i].chn, &tv);
+		if (rc > 0) { pos += (uint64_t)rc; inflight++; which ^= 1; }
+		else if ((rc = acb_sync(air_ctx)) < 0) break;             /* fewer samples than one output row: copy done before reuse */
+		else inflight = 0;
+		stamp_batch(pos);
 		if (got < cap) break;
 	}
+	if (rc >= 0) rc = acb_sync(air_ctx);
 	if (rc < 0) fprintf(stderr, "acarsdec_b200: %s\n", acb_last_error());
+	deliver_ready(air_ctx);
 	for (unsigned n = 0; n < nbch; n++)
 		if (acb_get_state(air_ctx, 0, (int)n, &st) == ACB_OK) state_unpack(&st, &channel[n]);
-	acb_host_free(buf);
+	acb_host_free(buf[0]);
+	acb_host_free(buf[1]);
 	acb_destroy(air_ctx);
 	air_ctx = NULL;
 	return rc < 0 ? -1 : 0;
@@ -603,33 +651,44 @@ static int cs16_setup(const char *path, char **argv, int optind, int mult, int v
 	return (int)-(long)Fc;                                   /* <= -1: success, the centre frequency negated */
 }
 
-static int cs16_run(void)
+static int cs16_run(int group_outputs)
 {
 	if (!cs_ctx || !cs_src) return -1;
 	const size_t cap = (size_t)RTLOUTBUFSZ * cs_mult * CS_BATCH;          /* complex samples per submit */
-	int16_t *buf = acb_host_alloc(cap * 2 * sizeof(int16_t));
-	if (!buf) { fprintf(stderr, "acarsdec_b200: %s\n", acb_last_error()); return -1; }
+	int16_t *buf[2] = { acb_host_alloc(cap * 2 * sizeof(int16_t)), acb_host_alloc(cap * 2 * sizeof(int16_t)) };
+	if (!buf[0] || !buf[1]) { fprintf(stderr, "acarsdec_b200: %s\n", acb_last_error()); return -1; }
 	acb_chan_state_t st;
-	acb_msg_t out[16];
 	for (unsigned n = 0; n < nbch; n++) { state_pack(&channel[n], &st); acb_set_state(cs_ctx, 0, (int)n, &st); }
-	int rc = ACB_OK;
+	/* the reference runs demodMSK channel by channel whenever dm_buffer is full (soapy.c:247: 1024 outputs,
+	 * sdrplay.c:229: 512): frames are queued in that order */
+	acb_set_emission_groups(cs_ctx, ACB_GROUP_OUTPUTS, (uint64_t)group_outputs);
+	int rc = ACB_OK, which = 0, inflight = 0;
+	uint64_t pos = 0;
+	stamp_reset();
 	while (!signalExit) {
-		size_t got = fread(buf, 2 * sizeof(int16_t), cap, cs_src);
+		if (inflight == 2) {                 /* buf[which] fed the submit two back: it has been consumed */
+			rc = acb_collect(cs_ctx);
+			if (rc < 0) break;
+			inflight--;
+			deliver_ready(cs_ctx);
+		}
+		size_t got = fread(buf[which], 2 * sizeof(int16_t), cap, cs_src);
 		if (got == 0) break;
-		struct timeval tv;
-		gettimeofday(&tv, NULL);
-		rc = acb_submit_cs16_host(cs_ctx, buf, got, got);      /* any count: the remainder is carried */
+		rc = acb_submit_cs16_host(cs_ctx, buf[which], got, got);      /* any count: the remainder is carried */
 		if (rc < 0) break;
-		rc = acb_sync(cs_ctx);
-		if (rc < 0) break;
-		for (int n; (n = acb_drain(cs_ctx, out, 16)) > 0;)
-			for (int i = 0; i < n; i++) deliver(&out[i], out[i].chn, &tv);
+		if (rc > 0) { pos += (uint64_t)rc; inflight++; which ^= 1; }
+		else if ((rc = acb_sync(cs_ctx)) < 0) break;
+		else inflight = 0;
+		stamp_batch(pos);
 		if (got < cap) break;
 	}
+	if (rc >= 0) rc = acb_sync(cs_ctx);
 	if (rc < 0) fprintf(stderr, "acarsdec_b200: %s\n", acb_last_error());
+	deliver_ready(cs_ctx);
 	for (unsigned n = 0; n < nbch; n++)
 		if (acb_get_state(cs_ctx, 0, (int)n, &st) == ACB_OK) state_unpack(&st, &channel[n]);
-	acb_host_free(buf);
+	acb_host_free(buf[0]);
+	acb_host_free(buf[1]);
 	signalExit = 1;
 	return rc < 0 ? -1 : 0;
 }
@@ -673,7 +732,7 @@ int soapySetAntenna(const char *antenna)
 	return 0;                                                /* nothing to switch on a capture */
 }
 
-int runSoapySample(void) { return cs16_run() < 0 ? 1 : 0; }   /* soapy.c:263 */
+int runSoapySample(void) { return cs16_run(RTLOUTBUFSZ) < 0 ? 1 : 0; }   /* soapy.c:263; SOAPYOUTBUFSZ = 1024 */
 
 int runSoapyClose(void) { cs16_close(); return 0; }           /* soapy.c:297 */
 #endif /* WITH_SOAPY */
@@ -695,7 +754,7 @@ int initSdrplay(char **argv, int optind)
  * the end of the capture with signalExit set */
 int runSdrplaySample(void)
 {
-	int r = cs16_run();
+	int r = cs16_run(512);                                  /* sdrplay.c:229 */
 	cs16_close();
 	return r;
 }

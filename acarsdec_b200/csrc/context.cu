@@ -110,6 +110,12 @@ struct acb_ctx {
 	size_t real_cap;             /* floats per stream in d_real */
 	size_t carry;                /* samples of every stream not yet consumed (< K) */
 	int real_buf;
+	cudaEvent_t ev_real_copied, ev_real_free[2];   /* H2D of a streaming submit landed | d_real[b] may be overwritten */
+	bool real_used[2];
+	int16_t *d_planar;           /* CS16 planar input: both planes of one submit, interleaved on the device */
+	size_t planar_cap;           /* int16 elements per plane and stream */
+	int group_unit;              /* ACB_GROUP_*: how the streaming front-ends' frames are grouped for emission */
+	unsigned long long group_period;
 };
 
 static int ctx_use(acb_ctx *c)
@@ -217,8 +223,14 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 		if (c->taps_pad > cfg->K) c->taps_pad = cfg->K;      /* K itself is a multiple of per_unit here */
 	}
 	c->d_real[0] = c->d_real[1] = nullptr;
+	c->d_planar = nullptr;
+	c->planar_cap = 0;
+	c->ev_real_copied = nullptr;
+	c->ev_real_free[0] = c->ev_real_free[1] = nullptr;
 	c->carry = 0;
 	c->real_buf = 0;
+	c->group_unit = ACB_GROUP_SUBMIT;
+	c->group_period = 0;
 	c->next_buf = 0;
 	c->last_nsamp = 0;
 	c->nsubmit = 0;
@@ -241,10 +253,13 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 			/* room for the carried remainder (< K) plus one submit, rounded so streams stay 16-B aligned */
 			c->real_cap = (((size_t)cfg->max_blocks * OUTBLK + 1) * cfg->K + 3) & ~(size_t)3;
 			CU(cudaMalloc(&c->d_real[i], (size_t)cfg->nstreams * c->real_cap * sizeof(float)));
+			CU(cudaEventCreateWithFlags(&c->ev_real_free[i], cudaEventDisableTiming));
+			c->real_used[i] = false;
 		}
 		CU(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
 		CU(cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
 	}
+	if (c->real_input) CU(cudaEventCreateWithFlags(&c->ev_real_copied, cudaEventDisableTiming));
 	const size_t wf_floats = (size_t)cfg->nstreams * c->ngrp * c->taps_pad * CH_GROUP * (c->in_kind == IN_KIND_F32REAL ? 2 : 4);
 	CU(cudaMalloc(&c->d_wf4, wf_floats * sizeof(float)));
 	CU(cudaMemsetAsync(c->d_wf4, 0, wf_floats * sizeof(float), c->s_copy));
@@ -315,11 +330,14 @@ extern "C" void acb_destroy(acb_ctx_t *c)
 		for (int i = 0; i < 2; i++) {
 			if (c->d_iq[i]) cudaFree(c->d_iq[i]);
 			if (c->d_real[i]) cudaFree(c->d_real[i]);
+			if (c->ev_real_free[i]) cudaEventDestroy(c->ev_real_free[i]);
 			cudaEventDestroy(c->ev_copied[i]);
 			cudaEventDestroy(c->ev_consumed[i]);
 		}
 		for (auto &t : c->inflight) { cudaEventDestroy(t.ev.a); cudaEventDestroy(t.ev.b); cudaEventDestroy(t.ev.b2); cudaEventDestroy(t.ev.c); }
 		for (auto &e : c->ev_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); cudaEventDestroy(e.b2); cudaEventDestroy(e.c); }
+		if (c->ev_real_copied) cudaEventDestroy(c->ev_real_copied);
+		cudaFree(c->d_planar);
 		cudaFree(c->d_wf4); cudaFree(c->d_state);
 		cudaFree(c->d_tw); cudaFree(c->d_twmeta);
 		for (int i = 0; i < 2; i++) { cudaFree(c->d_dm[i]); cudaEventDestroy(c->ev_k1_done[i]); cudaEventDestroy(c->ev_dm_free[i]); cudaEventDestroy(c->ev_ring_read[i]); }
@@ -632,6 +650,37 @@ extern "C" int acb_submit_host(acb_ctx_t *c, const uint8_t *iq, size_t stride, i
 	return ACB_OK;
 }
 
+extern "C" int acb_set_emission_groups(acb_ctx_t *c, int unit, uint64_t period)
+{
+	if (!c) return fail(ACB_ERR_ARG, "null context");
+	if (unit != ACB_GROUP_SUBMIT && unit != ACB_GROUP_OUTPUTS && unit != ACB_GROUP_INPUT) return fail(ACB_ERR_ARG, "unknown group unit");
+	if (unit != ACB_GROUP_SUBMIT && period == 0) return fail(ACB_ERR_ARG, "period must be > 0");
+	c->group_unit = unit;
+	c->group_period = period;
+	return ACB_OK;
+}
+
+/* Emission groups of one streaming submit covering envelope samples [pos, pos + nout): the reference hands a
+ * channel's new samples to demodMSK per transfer (air.c:336: output m completes with input sample (m+1)K - 1, so
+ * transfer g of T samples starts at output floor(g*T/K)) or per full dm_buffer (soapy.c:247 every 1024 outputs,
+ * sdrplay.c:229 every 512), channel by channel: frames leave in (group, channel, time) order. */
+static std::vector<unsigned long long> stream_groups(const acb_ctx *c, size_t nout)
+{
+	std::vector<unsigned long long> g{ c->pos };
+	const unsigned long long lo = c->pos, hi = c->pos + nout, K = (unsigned long long)c->cfg.K;
+	if (c->group_unit == ACB_GROUP_OUTPUTS) {
+		for (unsigned long long b = (lo / c->group_period + 1) * c->group_period; b < hi; b += c->group_period) g.push_back(b);
+	} else if (c->group_unit == ACB_GROUP_INPUT) {
+		const unsigned long long T = c->group_period;
+		for (unsigned long long t = (lo * K) / T + 1;; t++) {        /* transfers that start after output `lo` began */
+			const unsigned long long b = t * T / K;                  /* first output completed inside transfer t */
+			if (b >= hi) break;
+			if (b > g.back()) g.push_back(b);
+		}
+	}
+	return g;
+}
+
 /* 4-byte samples (float32 real or int16 I,Q) of arbitrary count: appended behind the carried
  * remainder in d_real[b]; `x2` != NULL means planar int16 input (x = I plane, x2 = Q plane), which
  * two strided copies interleave on the way to the device */
@@ -644,30 +693,46 @@ static int submit4(acb_ctx *c, const void *x, const void *x2, size_t stride_samp
 		return fail(ACB_ERR_ARG, "nsamples=%zu exceeds max_blocks*1024*K", nsamples);
 	if (c->cfg.nstreams > 1 && stride_samples < nsamples) return fail(ACB_ERR_ARG, "stream stride smaller than one stream's input");
 	const int b = c->real_buf;
-	/* d_real[b] was last read by the channelizer two submits ago (its carry has been copied on);
-	 * everything below is stream-ordered on the channelizer stream, the copies included */
+	/* The copy runs on the copy stream, so the H2D of submit i+1 overlaps the channelizer of submit i.
+	 * d_real[b] was last read by the channelizer two submits ago and by the copy that moved its tail on. */
 	float *buf = c->d_real[b];
+	if (c->real_used[b]) CU(cudaStreamWaitEvent(c->s_copy, c->ev_real_free[b], 0));
 	if (!x2) {
 		CU(cudaMemcpy2DAsync(buf + c->carry, c->real_cap * sizeof(float), x, stride_samples * sizeof(float),
-		                     nsamples * sizeof(float), c->cfg.nstreams, cudaMemcpyHostToDevice, c->s_comp));
+		                     nsamples * sizeof(float), c->cfg.nstreams, cudaMemcpyHostToDevice, c->s_copy));
 	} else {
-		for (int s = 0; s < c->cfg.nstreams; s++) {
-			char *dst = (char *)(buf + (size_t)s * c->real_cap + c->carry);
-			CU(cudaMemcpy2DAsync(dst, 4, (const char *)x + (size_t)s * stride_samples * 2, 2, 2, nsamples, cudaMemcpyHostToDevice, c->s_comp));
-			CU(cudaMemcpy2DAsync(dst + 2, 4, (const char *)x2 + (size_t)s * stride_samples * 2, 2, 2, nsamples, cudaMemcpyHostToDevice, c->s_comp));
+		/* planar int16 (the SDRplay callback's xi / xq): both planes go over as they are (two dense copies),
+		 * a small kernel interleaves them behind the carried remainder */
+		if (nsamples > c->planar_cap) {
+			CU(cudaStreamSynchronize(c->s_copy));
+			cudaFree(c->d_planar);
+			c->d_planar = nullptr;
+			c->planar_cap = std::max(nsamples, (size_t)c->cfg.max_blocks * OUTBLK * K);
+			CU(cudaMalloc(&c->d_planar, 2 * (size_t)c->cfg.nstreams * c->planar_cap * sizeof(int16_t)));
 		}
+		int16_t *pi = c->d_planar, *pq = c->d_planar + (size_t)c->cfg.nstreams * c->planar_cap;
+		CU(cudaMemcpy2DAsync(pi, c->planar_cap * 2, x, stride_samples * 2, nsamples * 2, c->cfg.nstreams, cudaMemcpyHostToDevice, c->s_copy));
+		CU(cudaMemcpy2DAsync(pq, c->planar_cap * 2, x2, stride_samples * 2, nsamples * 2, c->cfg.nstreams, cudaMemcpyHostToDevice, c->s_copy));
+		int r = launch_interleave_cs16(pi, pq, c->planar_cap, reinterpret_cast<uint32_t *>(buf + c->carry), c->real_cap, nsamples, c->cfg.nstreams, c->s_copy);
+		if (r) return fail(ACB_ERR_CUDA, "interleave launch: %s", cudaGetErrorString((cudaError_t)r));
+		c->stats.kernel_launches++;
 	}
+	CU(cudaEventRecord(c->ev_real_copied, c->s_copy));
+	CU(cudaStreamWaitEvent(c->s_comp, c->ev_real_copied, 0));
 	const size_t rem = total - nout * K;
 	if (nout) {
-		if (int r = run_kernels(c, (const uint8_t *)buf, c->real_cap * sizeof(float), 0, (int)nout, nullptr,
-		                        std::vector<unsigned long long>{ c->pos }))
+		if (int r = run_kernels(c, (const uint8_t *)buf, c->real_cap * sizeof(float), 0, (int)nout, nullptr, stream_groups(c, nout)))
 			return r;
 		c->pos += nout;
 		/* the unconsumed tail (air.c:329-334 / soapy.c:238-252 keep a partial sum instead: same
 		 * arithmetic order) moves to the front of the other buffer */
-		if (rem)
+		if (rem) {
+			if (c->real_used[b ^ 1]) CU(cudaStreamWaitEvent(c->s_comp, c->ev_real_free[b ^ 1], 0));
 			CU(cudaMemcpy2DAsync(c->d_real[b ^ 1], c->real_cap * sizeof(float), buf + nout * K, c->real_cap * sizeof(float),
 			                     rem * sizeof(float), c->cfg.nstreams, cudaMemcpyDeviceToDevice, c->s_comp));
+		}
+		CU(cudaEventRecord(c->ev_real_free[b], c->s_comp));
+		c->real_used[b] = true;
 		c->real_buf = b ^ 1;
 	}
 	c->carry = rem;          /* nout == 0: the samples simply stay behind the previous carry */

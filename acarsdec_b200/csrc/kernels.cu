@@ -25,6 +25,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 #include "acb_internal.h"
 #include "frame_sm.h"
 #include "demod_core.h"
@@ -643,6 +645,29 @@ int launch_channelize_dft(const void *in, size_t stream_stride, const float *tw,
 	if (K == 192) return fold8 ? launch_dft_t<24, 2, 1, 4, true>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream)
 	                           : launch_dft_t<24, 2, 1, 4, false>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
 	return (int)cudaErrorInvalidValue;
+}
+
+/* SDRplay's stream callback delivers I and Q as separate int16 arrays (sdrplay.c:196-205): out[s][i] = (xi[s][i], xq[s][i])
+ * as the interleaved CS16 sample the channelizer reads.  Pure data movement, 8 bytes per sample. */
+__global__ void __launch_bounds__(256)
+k_interleave_cs16(const int16_t *__restrict__ xi, const int16_t *__restrict__ xq, size_t plane_stride,
+                  uint32_t *__restrict__ out, size_t out_stride, size_t nsamples)
+{
+	const int s = blockIdx.y;
+	const uint16_t *pi = reinterpret_cast<const uint16_t *>(xi) + (size_t)s * plane_stride;
+	const uint16_t *pq = reinterpret_cast<const uint16_t *>(xq) + (size_t)s * plane_stride;
+	uint32_t *o = out + (size_t)s * out_stride;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nsamples; i += (size_t)gridDim.x * blockDim.x)
+		o[i] = (uint32_t)pi[i] | ((uint32_t)pq[i] << 16);
+}
+
+int launch_interleave_cs16(const int16_t *xi, const int16_t *xq, size_t plane_stride, uint32_t *out, size_t out_stride,
+                           size_t nsamples, int nstreams, cudaStream_t stream)
+{
+	if (nsamples == 0) return 0;
+	const unsigned gx = (unsigned)std::min<size_t>((nsamples + 255) / 256, 1184);
+	k_interleave_cs16<<<dim3(gx, nstreams), 256, 0, stream>>>(xi, xq, plane_stride, out, out_stride, nsamples);
+	return (int)cudaGetLastError();
 }
 
 /* Rows the pipeline kernel does not take (K that breaks 16-byte row alignment; the < 1024 rows

@@ -163,6 +163,16 @@ int acb_submit_real_host(acb_ctx_t *ctx, const float *x, size_t stream_stride_sa
  * carried (the reference carries ch->D and the tap index).  Returns envelope samples produced. */
 int acb_submit_cs16_host(acb_ctx_t *ctx, const int16_t *iq, size_t stream_stride_samples, size_t nsamples);
 int acb_submit_cs16_planar_host(acb_ctx_t *ctx, const int16_t *xi, const int16_t *xq, size_t stream_stride_samples, size_t nsamples);
+/* Emission order of the streaming front-ends.  The reference runs demodMSK channel by channel on
+ * whatever a transfer (air.c:336) or a full dm_buffer (soapy.c:247: 1024 outputs; sdrplay.c:229: 512) delivered, so
+ * its messages leave in (group, channel, time) order.  A submit may carry many such groups; tell the context how
+ * they are cut and acb_sync / acb_collect queue the frames exactly in the reference's order:
+ *   ACB_GROUP_SUBMIT   one group per submit call (default);
+ *   ACB_GROUP_OUTPUTS  a group every `period` envelope samples, counted from the start of the stream;
+ *   ACB_GROUP_INPUT    a group per transfer of `period` input samples, counted from the start of the stream.
+ * (u8 IQ contexts always group per 1024-sample block, rtl.c:357-360.) */
+enum { ACB_GROUP_SUBMIT = 0, ACB_GROUP_OUTPUTS = 1, ACB_GROUP_INPUT = 2 };
+int acb_set_emission_groups(acb_ctx_t *ctx, int unit, uint64_t period);
 /* Replaces demodMSK's input side (msk.c:67; soundfile.c:71-77): 12.5 kS/s envelope samples,
  * dm[(s*nsamp + n)*nch + c], fed straight to the demodulator (no channelizer). */
 int acb_submit_dm_host(acb_ctx_t *ctx, const float *dm, int nsamp);

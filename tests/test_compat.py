@@ -222,13 +222,9 @@ def test_unmodified_acarsdec_main_airspy_front_end(tmp_path):
     assert mine.returncode == 0, mine.stderr
     a, b = _strip_time(ref.stdout), _strip_time(mine.stdout)
     assert a.count("<time>") >= 10
-    # the reference emits per 65536-sample transfer, the shim per 8 transfers: same messages, and the
-    # same order within each channel
-    def blocks(s):
-        return [blk for blk in s.split("\n[#") if blk.strip()]
-    assert sorted(blocks(a)) == sorted(blocks(b))
-    for ch in "1234":
-        assert [x for x in blocks(a) if x.startswith(ch)] == [x for x in blocks(b) if x.startswith(ch)]
+    # the shim submits 8 transfers at a time and queues the frames per transfer, channel by channel, like
+    # air.c:336 does: byte-identical output, order included
+    assert a == b
 
 
 def _cs16_capture(tmp_path, seed):
@@ -270,6 +266,7 @@ def test_unmodified_acarsdec_main_soapy_front_end(tmp_path):
     a, b = _strip_time(ref.stdout), _strip_time(mine.stdout)
     assert a.count("<time>") >= 10
     _same_messages_per_channel(a, b)
+    assert a == b            # emission order too: per full dm_buffer, channel by channel (soapy.c:247, sdrplay.c:229)
 
 
 @pytest.mark.gpu
@@ -287,3 +284,4 @@ def test_unmodified_acarsdec_main_sdrplay_front_end(tmp_path):
     a, b = _strip_time(ref.stdout), _strip_time(mine.stdout)
     assert a.count("<time>") >= 10
     _same_messages_per_channel(a, b)
+    assert a == b            # emission order too: per full dm_buffer, channel by channel (soapy.c:247, sdrplay.c:229)
