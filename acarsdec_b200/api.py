@@ -85,6 +85,7 @@ ABI = [
     ("acb_set_plan", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_uint)]),
     ("acb_set_plan_air", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_uint)]),
     ("acb_set_plan_cs16", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.POINTER(C.c_uint)]),
+    ("acb_set_plan_at", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_uint]),
     ("acb_set_wf", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     ("acb_reset", C.c_int, [C.c_void_p]),
     ("acb_submit_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
@@ -96,6 +97,20 @@ ABI = [
     ("acb_submit_dm_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     ("acb_sync", C.c_int, [C.c_void_p]),
     ("acb_collect", C.c_int, [C.c_void_p]),
+    ("acb_wait_event", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("acb_multi_create", C.c_int, [C.POINTER(Config), C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    ("acb_multi_destroy", None, [C.c_void_p]),
+    ("acb_multi_parts", C.c_int, [C.c_void_p]),
+    ("acb_multi_part", C.c_void_p, [C.c_void_p, C.c_int]),
+    ("acb_multi_set_plan", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_uint)]),
+    ("acb_multi_set_wf", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    ("acb_multi_reset", C.c_int, [C.c_void_p]),
+    ("acb_multi_submit_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
+    ("acb_multi_collect", C.c_int, [C.c_void_p]),
+    ("acb_multi_sync", C.c_int, [C.c_void_p]),
+    ("acb_multi_drain", C.c_int, [C.c_void_p, C.POINTER(Msg), C.c_int]),
+    ("acb_multi_get_state", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(ChanState)]),
+    ("acb_multi_set_state", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(ChanState)]),
     ("acb_mark", C.c_int, [C.c_void_p, C.c_int]),
     ("acb_elapsed_ms", C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     ("acb_drain", C.c_int, [C.c_void_p, C.POINTER(Msg), C.c_int]),
@@ -413,3 +428,83 @@ class Context:
     def copy_to_device(self, dst: int, src: np.ndarray) -> None:
         src = np.ascontiguousarray(src)
         _check(self.lib, self.lib.acb_copy_to_device(self.h, dst, src.ctypes.data, src.nbytes))
+
+    def set_plan_at(self, stream: int, freqs_hz, fc_hz: int) -> None:
+        f = np.asarray(freqs_hz, dtype=np.uint32)
+        _check(self.lib, self.lib.acb_set_plan_at(self.h, stream, f.ctypes.data, len(f), int(fc_hz)))
+
+    def wait_event(self, cuda_event: int) -> None:
+        """Order the next submit_device behind a cudaEvent_t of another stream (torch.cuda.Event.cuda_event)."""
+        _check(self.lib, self.lib.acb_wait_event(self.h, cuda_event))
+
+
+class MultiContext:
+    """acb_multi_t: one process, several GPUs; streams (mode 0) or channels (mode 1) split among them."""
+
+    def __init__(self, K: int, nstreams: int, nch: int, max_blocks: int, devices, mode: int = 0, flags: int = 0, taps: int = 0):
+        self.lib = load()
+        self.K, self.nstreams, self.nch = K, nstreams, nch
+        cfg = Config(0, K, nstreams, nch, max_blocks, flags, taps)
+        dev = np.asarray(list(devices), dtype=np.int32)
+        h = C.c_void_p()
+        rc = self.lib.acb_multi_create(C.byref(cfg), dev.ctypes.data, len(dev), mode, C.byref(h))
+        if rc < 0:
+            msg = self.lib.acb_last_error().decode()
+            if h:
+                self.lib.acb_multi_destroy(h)
+            raise AcbError(f"acb_multi_create failed ({rc}): {msg}")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.acb_multi_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def parts(self) -> int:
+        return self.lib.acb_multi_parts(self.h)
+
+    def set_plan(self, stream: int, freqs_hz) -> int:
+        f = np.asarray(freqs_hz, dtype=np.uint32)
+        fc = C.c_uint()
+        _check(self.lib, self.lib.acb_multi_set_plan(self.h, stream, f.ctypes.data, len(f), C.byref(fc)))
+        return fc.value
+
+    def set_wf(self, stream: int, wf: np.ndarray) -> None:
+        wf = np.ascontiguousarray(wf, dtype=np.float32)
+        _check(self.lib, self.lib.acb_multi_set_wf(self.h, stream, wf.ctypes.data, wf.shape[0]))
+
+    def submit_host(self, iq: np.ndarray, nblk: int) -> None:
+        assert iq.dtype == np.uint8 and iq.flags.c_contiguous
+        stride = iq.strides[0] if iq.ndim == 2 else nblk * OUTBLK * self.K * 2
+        _check(self.lib, self.lib.acb_multi_submit_host(self.h, iq.ctypes.data, stride, nblk))
+
+    def sync(self) -> int:
+        return _check(self.lib, self.lib.acb_multi_sync(self.h))
+
+    def collect(self) -> int:
+        return _check(self.lib, self.lib.acb_multi_collect(self.h))
+
+    def drain(self):
+        out = []
+        buf = (Msg * 256)()
+        while True:
+            n = self.lib.acb_multi_drain(self.h, buf, 256)
+            for i in range(n):
+                m = Msg()
+                C.memmove(C.byref(m), C.byref(buf[i]), C.sizeof(Msg))
+                out.append(m)
+            if n < 256:
+                return out
+
+    def get_state(self, stream: int, chn: int) -> ChanState:
+        s = ChanState()
+        _check(self.lib, self.lib.acb_multi_get_state(self.h, stream, chn, C.byref(s)))
+        return s

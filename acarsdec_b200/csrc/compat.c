@@ -323,8 +323,36 @@ void demodMSK(channel_t *ch, int len)
 
 #ifdef WITH_RTL
 
-static acb_ctx_t *rtl_ctx;
+/* One stream, nbch channels — on one GPU, or with ACARSDEC_B200_DEVICES=0,1,... the channels split over
+ * several (acb_multi_*, channel-split mode): the unmodified C host reaches a whole node this way. */
+static acb_multi_t *rtl_ctx;
 static FILE *rtl_src;
+
+static int parse_devices(int *dev, int max)
+{
+	const char *e = getenv("ACARSDEC_B200_DEVICES");
+	int n = 0;
+	if (e && *e) {
+		char *dup = strdup(e), *save = NULL;
+		for (char *t = strtok_r(dup, ",", &save); t && n < max; t = strtok_r(NULL, ",", &save)) dev[n++] = atoi(t);
+		free(dup);
+	}
+	if (n == 0) {
+		e = getenv("ACARSDEC_B200_DEVICE");
+		dev[n++] = e ? atoi(e) : 0;
+	}
+	return n;
+}
+
+static void rtl_deliver_ready(void)
+{
+	acb_msg_t out[16];
+	for (int n; (n = acb_multi_drain(rtl_ctx, out, 16)) > 0;)
+		for (int i = 0; i < n; i++) {
+			const struct timeval tv = stamp_time(out[i].soh_pos);      /* acars.c:290 */
+			deliver(&out[i], out[i].chn, &tv);
+		}
+}
 static int rtl_batch = 16;              /* blocks per submit; ACARSDEC_B200_BLOCKS */
 static volatile int rtl_cancel;
 static size_t rtl_inbufsize;
@@ -372,10 +400,11 @@ int initRtl(char **argv, int optind)
 	const char *e = getenv("ACARSDEC_B200_BLOCKS");
 	if (e && atoi(e) > 0) rtl_batch = atoi(e);
 	acb_config_t cfg = { 0, rtlMult, 1, (int)nbch, rtl_batch, 0, 0 };
-	if ((e = getenv("ACARSDEC_B200_DEVICE"))) cfg.device = atoi(e);
-	if (acb_create(&cfg, &rtl_ctx) != ACB_OK) {
+	int devs[MAXNBCHANNELS];
+	const int ndev = parse_devices(devs, MAXNBCHANNELS);
+	if (acb_multi_create(&cfg, devs, ndev, ACB_MULTI_SPLIT_CHANNELS, &rtl_ctx) != ACB_OK) {
 		fprintf(stderr, "acarsdec_b200: %s\n", acb_last_error());
-		if (rtl_ctx) acb_destroy(rtl_ctx);
+		if (rtl_ctx) acb_multi_destroy(rtl_ctx);
 		rtl_ctx = NULL;
 		return 1;
 	}
@@ -393,7 +422,7 @@ int initRtl(char **argv, int optind)
 		for (int i = 0; i < rtlMult; i++)
 			ch->wf[i] = wf[((size_t)n * rtlMult + i) * 2] + wf[((size_t)n * rtlMult + i) * 2 + 1] * I;
 	}
-	int rc = acb_set_wf(rtl_ctx, 0, wf, (int)nbch);
+	int rc = acb_multi_set_wf(rtl_ctx, 0, wf, (int)nbch);
 	free(wf);
 	if (rc != ACB_OK) {
 		fprintf(stderr, "acarsdec_b200: %s\n", acb_last_error());
@@ -416,7 +445,7 @@ int runRtlSample(void)
 	acb_chan_state_t st;
 	for (unsigned n = 0; n < nbch; n++) {
 		state_pack(&channel[n], &st);
-		acb_set_state(rtl_ctx, 0, (int)n, &st);
+		acb_multi_set_state(rtl_ctx, 0, (int)n, &st);
 	}
 	int which = 0, rc = ACB_OK, inflight = 0;
 	uint64_t pos = 0;
@@ -424,10 +453,10 @@ int runRtlSample(void)
 	while (!signalExit && !rtl_cancel) {
 		if (inflight == 2) {
 			/* buf[which] was the source of the submit two back: it must have been consumed */
-			rc = acb_collect(rtl_ctx);
+			rc = acb_multi_collect(rtl_ctx);
 			if (rc < 0) break;
 			inflight--;
-			deliver_ready(rtl_ctx);
+			rtl_deliver_ready();
 		}
 		size_t got = fread(buf[which], 1, rtl_inbufsize * rtl_batch, rtl_src);
 		int nblk = (int)(got / rtl_inbufsize);
@@ -435,17 +464,17 @@ int runRtlSample(void)
 		if (nblk == 0) break;
 		pos += (uint64_t)nblk * RTLOUTBUFSZ;
 		stamp_batch(pos);
-		rc = acb_submit_host(rtl_ctx, buf[which], rtl_inbufsize * nblk, nblk);
+		rc = acb_multi_submit_host(rtl_ctx, buf[which], rtl_inbufsize * nblk, nblk);
 		if (rc != ACB_OK) break;
 		which ^= 1;
 		inflight++;
 		if (nblk < rtl_batch) break;
 	}
-	if (rc >= 0) rc = acb_sync(rtl_ctx);
+	if (rc >= 0) rc = acb_multi_sync(rtl_ctx);
 	if (rc < 0) fprintf(stderr, "acarsdec_b200: %s\n", acb_last_error());
-	deliver_ready(rtl_ctx);
+	rtl_deliver_ready();
 	for (unsigned n = 0; n < nbch; n++)
-		if (acb_get_state(rtl_ctx, 0, (int)n, &st) == ACB_OK) state_unpack(&st, &channel[n]);
+		if (acb_multi_get_state(rtl_ctx, 0, (int)n, &st) == ACB_OK) state_unpack(&st, &channel[n]);
 	for (int i = 0; i < 2; i++) acb_host_free(buf[i]);
 	signalExit = 1;                                     /* rtl.c:366: the reader thread ended */
 	return rc < 0 ? 1 : 0;
@@ -459,7 +488,7 @@ int runRtlCancel(void)
 
 int runRtlClose(void)
 {
-	if (rtl_ctx) { acb_destroy(rtl_ctx); rtl_ctx = NULL; }
+	if (rtl_ctx) { acb_multi_destroy(rtl_ctx); rtl_ctx = NULL; }
 	if (rtl_src && rtl_src != stdin) fclose(rtl_src);
 	rtl_src = NULL;
 	return 0;

@@ -387,15 +387,22 @@ extern "C" int acb_set_wf(acb_ctx_t *c, int stream, const float *wf, int nch)
 extern "C" int acb_set_plan(acb_ctx_t *c, int stream, const unsigned *freqs_hz, int nch, unsigned *fc_out)
 {
 	if (!c || !freqs_hz) return fail(ACB_ERR_ARG, "null argument");
+	const unsigned fc = acb_choose_fc(freqs_hz, nch, c->cfg.K);
+	if (fc == 0) return fail(ACB_ERR_PLAN, "Frequencies too far apart");    /* rtl.c:149-152 */
+	if (fc_out) *fc_out = fc;
+	return acb_set_plan_at(c, stream, freqs_hz, nch, fc);
+}
+
+extern "C" int acb_set_plan_at(acb_ctx_t *c, int stream, const unsigned *freqs_hz, int nch, unsigned fc)
+{
+	if (!c || !freqs_hz) return fail(ACB_ERR_ARG, "null argument");
 	if (nch != c->cfg.nch) return fail(ACB_ERR_ARG, "nch mismatch");
 	if (c->real_input) return fail(ACB_ERR_ARG, "not a u8-IQ context: use acb_set_plan_air / acb_set_plan_cs16");
 	if (c->taps != c->cfg.K) return fail(ACB_ERR_ARG, "taps != K: the reference planner builds K-tap tables; supply yours with acb_set_wf");
-	const unsigned fc = acb_choose_fc(freqs_hz, nch, c->cfg.K);
-	if (fc == 0) return fail(ACB_ERR_PLAN, "Frequencies too far apart");    /* rtl.c:149-152 */
+	if (fc == 0) return fail(ACB_ERR_PLAN, "centre frequency 0");
 	std::vector<float> wf((size_t)nch * c->cfg.K * 2);
 	for (int ch = 0; ch < nch; ch++)
 		acb_build_wf(acb_stored_fr(freqs_hz[ch]), fc, c->cfg.K, &wf[(size_t)ch * c->cfg.K * 2]);
-	if (fc_out) *fc_out = fc;
 	if (int r = acb_set_wf(c, stream, wf.data(), nch)) return r;
 	if (!c->fast) return ACB_OK;
 	/* Fast form: per-channel bin numbers and twiddles, when every channel sits on the raster */
@@ -799,6 +806,14 @@ extern "C" int acb_submit_dm_host(acb_ctx_t *c, const float *dm, int nsamp)
 	 * until the submit is collected. */
 	if (int r = run_kernels(c, nullptr, 0, 0, nsamp, dm, std::vector<unsigned long long>{ c->pos })) return r;
 	c->pos += (unsigned long long)nsamp;
+	return ACB_OK;
+}
+
+extern "C" int acb_wait_event(acb_ctx_t *c, void *cuda_event)
+{
+	if (!c || !cuda_event) return fail(ACB_ERR_ARG, "null argument");
+	if (int r = ctx_use(c)) return r;
+	CU(cudaStreamWaitEvent(c->s_comp, (cudaEvent_t)cuda_event, 0));
 	return ACB_OK;
 }
 

@@ -134,6 +134,9 @@ const char *acb_version(void);
 /* Replaces the channel part of initRtl (rtl.c:243-287) for one stream: freqs in CLI order,
  * chooses Fc, builds and uploads the tables.  fc_out may be NULL. */
 int acb_set_plan(acb_ctx_t *ctx, int stream, const unsigned *freqs_hz, int nch, unsigned *fc_out);
+/* Same with the centre frequency given (a host that tuned already; a context that serves only SOME of the
+ * channels chooseFc planned for — acb_multi_* in channel-split mode, the wide-stream case of SURVEY.md §8e). */
+int acb_set_plan_at(acb_ctx_t *ctx, int stream, const unsigned *freqs_hz, int nch, unsigned fc_hz);
 /* The channel part of initAirspy (air.c:165-285) for a real-input context. */
 int acb_set_plan_air(acb_ctx_t *ctx, int stream, const unsigned *freqs_hz, int nch, unsigned *fc_out);
 /* The channel part of initSoapy (soapy.c:112-163) / initSdrplay (sdrplay.c:95-138) for a CS16
@@ -176,6 +179,9 @@ int acb_set_emission_groups(acb_ctx_t *ctx, int unit, uint64_t period);
 /* Replaces demodMSK's input side (msk.c:67; soundfile.c:71-77): 12.5 kS/s envelope samples,
  * dm[(s*nsamp + n)*nch + c], fed straight to the demodulator (no channelizer). */
 int acb_submit_dm_host(acb_ctx_t *ctx, const float *dm, int nsamp);
+/* Order the next acb_submit_device behind work of ANOTHER CUDA stream: `cuda_event` is a cudaEvent_t recorded there
+ * (e.g. behind the NCCL broadcast that fills the input buffer; torch.cuda.Event.cuda_event).  No host sync. */
+int acb_wait_event(acb_ctx_t *ctx, void *cuda_event);
 /* Wait for the OLDEST submit still in flight only (at most two are), run the block FEC on its
  * frames and queue the survivors; later submits keep running.  This is what lets the H2D copy
  * of step i+1 overlap the kernels of step i.  Returns the number of messages waiting. */
@@ -223,6 +229,32 @@ typedef struct {
 	uint64_t frames_lost;       /* frames that found the device ring full (ACB_ERR_OVERFLOW was returned once per submit) */
 } acb_stats_t;
 int acb_get_stats(acb_ctx_t *ctx, acb_stats_t *out, int reset);
+
+/* ---- one process, several GPUs (the C host's way to a whole node) ----
+ *
+ * acb_multi_* fronts one context per device.  Two ways to cut the work, neither with any device-to-device
+ * traffic (channels and streams share nothing):
+ *   ACB_MULTI_SPLIT_STREAMS   device d serves a contiguous range of the streams (BASELINE config 4);
+ *   ACB_MULTI_SPLIT_CHANNELS  every device sees every stream and serves a contiguous range of its channels
+ *                             (one wide stream, configs 3/5); each device fetches the block over its own PCIe link.
+ * Stream / channel indices in the API and in the messages are global; messages are merged into the reference's
+ * emission order (block, stream, channel, time; rtl.c:357-360).  cfg->device is ignored, `devices` names the
+ * CUDA ordinals (repeats allowed: two contexts on one GPU). */
+typedef struct acb_multi acb_multi_t;
+enum { ACB_MULTI_SPLIT_STREAMS = 0, ACB_MULTI_SPLIT_CHANNELS = 1 };
+int  acb_multi_create(const acb_config_t *cfg, const int *devices, int ndev, int mode, acb_multi_t **out);
+void acb_multi_destroy(acb_multi_t *m);
+int  acb_multi_parts(acb_multi_t *m);                        /* number of per-device contexts */
+acb_ctx_t *acb_multi_part(acb_multi_t *m, int i);            /* the i-th one (stats, inspection) */
+int  acb_multi_set_plan(acb_multi_t *m, int stream, const unsigned *freqs_hz, int nch, unsigned *fc_out);
+int  acb_multi_set_wf(acb_multi_t *m, int stream, const float *wf, int nch);
+int  acb_multi_reset(acb_multi_t *m);
+int  acb_multi_submit_host(acb_multi_t *m, const uint8_t *iq, size_t stream_stride, int nblk);
+int  acb_multi_collect(acb_multi_t *m);
+int  acb_multi_sync(acb_multi_t *m);
+int  acb_multi_drain(acb_multi_t *m, acb_msg_t *out, int max);
+int  acb_multi_get_state(acb_multi_t *m, int stream, int chn, acb_chan_state_t *out);
+int  acb_multi_set_state(acb_multi_t *m, int stream, int chn, const acb_chan_state_t *in);
 
 /* Block FEC on one frame in place on the HOST (acars.c:123-207): 1 = deliver, 0 = drop.  The
  * processing path runs the same repair on the device (k_block_fec, one thread per frame, right
