@@ -189,6 +189,19 @@ def make_plan(K: int = 160, freqs_mhz=DEFAULT_FREQS_MHZ, fc_hz: int | None = Non
     return plan
 
 
+def fir_tables(K: int, taps: int, offsets_hz, rate: int) -> np.ndarray:
+    """Generalised-FIR mixer tables for BASELINE configs 3/5 (taps < K; the reference has no such mode, SURVEY.md
+    note 1): Hamming-windowed w[t] = hamming(t) * exp(-j 2 pi f t / rate) / sum / 127.5, (nch, 2*taps) float32."""
+    t = np.arange(taps)
+    win = 0.54 - 0.46 * np.cos(2 * np.pi * t / max(taps - 1, 1))
+    out = np.empty((len(offsets_hz), 2 * taps), dtype=np.float32)
+    for i, f in enumerate(offsets_hz):
+        w = win * np.exp(-2j * np.pi * f * t / rate) / win.sum() / 127.5
+        out[i, 0::2] = w.real
+        out[i, 1::2] = w.imag
+    return out
+
+
 def blocks_for_seconds(K: int, seconds: float) -> int:
     return int(np.ceil(seconds * INTRATE / OUTBLK))
 

@@ -4,18 +4,27 @@
   python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
   python bench.py --impl reference [...]                         # the reference's own CPU path
 
-One "step" is one pass of the hot path over one batch: S independent 2 MS/s uint8 IQ streams
-(configs[1] shape: K=160, 8 ACARS channels per stream) x B blocks of 1024*K complex samples per
-stream.  Per-GPU work is fixed (weak scaling): N GPUs serve N*S streams, sharded by stream index
-with no collective on the data path.
+Headline workload: BASELINE configs[1] (synthetic 2 MS/s uint8 IQ, K=160, 8 ACARS channels per stream) x S
+independent streams per GPU.  One "step" = one pass of the hot path over B blocks of 1024*K complex samples of
+every stream.  S is the stream count at which a B200 saturates: the demodulator is a serial recurrence per
+channel (msk.c:67-137), so one stream alone is latency bound; the bench sweeps S in {592, 1184, 2368, 4736}
+(4..32 streams per SM) on the device and quotes `value` at the best one, naming it in config.workload.
+Per-GPU work is fixed as N grows (weak scaling): N GPUs serve N*S streams, sharded by stream index with no
+collective on the data path.
 
 Printed JSON (rank 0, one line):
-  value      device-resident throughput: inputs already in HBM, CUDA events on the library's
-             compute stream around exactly K steps, max over ranks
-  e2e        same metric through the C ABI with HOST buffers: pinned H2D copy of every step's
-             input and D2H read-back of the decoded frames inside the timed region
-  roofline   channelizer kernel: algorithmic bytes / CUDA-event duration vs measured HBM peak
-  cpu_baseline  the unmodified reference (oracle/_ref, -Ofast) on all host threads, bounded sample
+  value        device-resident throughput: inputs already in HBM, CUDA events on the library's streams around
+               exactly K steps, max over ranks
+  e2e          same metric through the C ABI with HOST buffers: pinned H2D copy of every step's input and D2H
+               read-back of the decoded frames inside the timed region
+  roofline     channelizer kernel (the dominant kernel) of --channelizer: algorithmic bytes / CUDA-event duration
+               vs measured HBM peak, in the pipeline (demod running underneath) and isolated
+  alt_channelizer  the other channelizer form at the same S, same treatment (its own roofline object)
+  checked      every frame of the timed steps (and the passes before them) of the distinct pool streams against the
+               CPU port of the reference (oracle/), which the tests pin to the unmodified reference
+  cpu_baseline the unmodified reference (oracle/_ref, -Ofast) on all host threads, bounded sample
+  configs      the literal BASELINE configs 2..5 (one stream x 8 ch; K=192 x 64 ch x 165 taps; 128 streams total,
+               strong-scaled; 20 MS/s x 256 ch tap sweep) with the wide-stream broadcast inside the timed region at N>1
 """
 from __future__ import annotations
 
@@ -36,7 +45,14 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 METRIC = "IQ Msamples/s through channelize+demodMSK (msgs bit-exact)"
 UNIT = "Msamples/s"
-FREQS = None  # filled from synth.DEFAULT_FREQS_MHZ
+SWEEP = (592, 1184, 2368, 4736)          # 4, 8, 16, 32 streams per SM
+FRAME_BYTES = 304                        # RawFrame record read back per decoded frame
+
+
+def blocks_for(S: int, want: int) -> int:
+    """Blocks per step: `want` (16 = 1.31 s of signal) while a step's input stays <= 6.2 GB, so that the
+    e2e leg's pinned host buffer and the two device staging buffers stay modest at large S."""
+    return max(1, min(want, 18944 // S))
 
 
 def parse_args():
@@ -45,17 +61,19 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--streams", type=int, default=592, help="IQ streams per GPU")
-    ap.add_argument("--blocks", type=int, default=16, help="1024-sample output blocks per stream per step")
+    ap.add_argument("--streams", type=int, default=0, help="IQ streams per GPU; 0 = sweep %s and take the best" % (SWEEP,))
+    ap.add_argument("--blocks", type=int, default=16, help="1024-sample output blocks per stream per step (capped so a step's input stays <= 6.2 GB)")
     ap.add_argument("--K", type=int, default=160, help="rtlMult (160 = 2.0 MS/s)")
     ap.add_argument("--channelizer", default="exact", choices=["exact", "fast"],
                     help="exact: the reference's rounding sequence, envelope bit-identical; fast: ACB_FLAG_FAST_CHANNELIZER "
-                         "(shared 4-point DFT + K/4 MACs per channel; envelope within 1e-5 of rms, messages identical)")
+                         "(shared DFT factorisation; messages identical, envelope within its stated tolerance)")
     ap.add_argument("--pool", type=int, default=4, help="distinct synthetic streams generated (tiled over S)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--config", default="all", help="BASELINE configs to add to the line: all | none | comma list of 2,3,4,5")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-alt", action="store_true", help="skip the secondary measurement of the other channelizer form")
+    ap.add_argument("--no-alt", action="store_true", help="skip the measurement of the other channelizer form")
+    ap.add_argument("--no-check", action="store_true", help="skip the oracle check of the timed frames")
     ap.add_argument("--cpu-worker", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--variant", default="", help=argparse.SUPPRESS)
     ap.add_argument("--worker-blocks", type=int, default=256, help=argparse.SUPPRESS)
@@ -146,37 +164,6 @@ def run_cpu_reference(K: int, steps: int, warmup: int, blocks_per_step: int, npr
             "ms_per_step": slowest / steps * 1e3, "single_thread_value": None}
 
 
-def cpu_port_check(K: int, streams, gpu_msgs, exact: bool = True):
-    """cpu_baseline leg, correctness half: the C port of the reference (oracle/acars_oracle.c, pinned
-    against the unmodified reference by the tests) decodes `streams`; the frames the GPU produced for
-    the same streams must be identical (chn, len, err, text, BCS, lvl bits) and in the same order."""
-    import refs
-    from common import msg_tuple
-    from acarsdec_b200 import synth
-    refs.ensure_built()
-    orc = refs.OracleLib()
-    wf = orc.wf(K, synth.DEFAULT_FREQS_MHZ)
-    frames, ok = 0, True
-    for i, iq in enumerate(streams):
-        o = refs.OracleStream(orc, K, wf)
-        o.blocks(iq)
-        want = [msg_tuple(m) for m in o.msgs()]
-        mine = [msg_tuple(m) for m in gpu_msgs if m.stream == i]
-        if exact:
-            ok = ok and mine == want
-        else:
-            # fast channelizer: every message field identical; lvl (a float, dB) within 0.05 (weakest frames; < 0.001 typical)
-            ok = ok and [t[:-1] for t in mine] == [t[:-1] for t in want]
-            la = np.array([t[-1] for t in mine], dtype=np.uint32).view(np.float32)
-            lb = np.array([t[-1] for t in want], dtype=np.uint32).view(np.float32)
-            ok = ok and la.shape == lb.shape and bool(np.all(np.abs(la - lb) <= 0.05))
-        frames += len(want)
-    out = {"streams_vs_cpu_port": len(streams), "frames": frames, "bit_exact": ok}
-    if not exact:
-        out["note"] = "messages (chn, len, err, text, BCS) identical; lvl within 0.05 dB (fast channelizer)"
-    return out
-
-
 def run_cpu_port(K, steps, warmup, blocks_per_step, nproc=None):
     """Fallback when oracle/_ref is absent: the C restatement on all threads."""
     import refs
@@ -193,6 +180,64 @@ def run_cpu_port(K, steps, warmup, blocks_per_step, nproc=None):
     return {"value": samples / secs / 1e6, "unit": UNIT, "cores": nproc, "kind": "port",
             "sample": f"{nproc} threads x 1 stream x 8 ch, {steps * blocks_per_step} blocks each, oracle/acars_oracle.c -O2",
             "ms_per_step": secs / steps * 1e3}
+
+
+# ----------------------------------------------------------------------------- the checker (oracle/)
+
+def oracle_frames(K: int, streams, reps: int):
+    """The CPU port of the reference (oracle/acars_oracle.c, pinned against the unmodified reference by the
+    tests) over each stream's blocks fed `reps` times in a row (state carried, like the bench's repeated
+    submits of the same device buffer).  One thread per stream (ctypes releases the GIL)."""
+    import refs
+    from common import msg_tuple
+    from acarsdec_b200 import synth
+    refs.ensure_built()
+    orc = refs.OracleLib()
+    wf = orc.wf(K, synth.DEFAULT_FREQS_MHZ)
+    out = [None] * len(streams)
+
+    def work(i):
+        o = refs.OracleStream(orc, K, wf)
+        for _ in range(reps):
+            o.blocks(streams[i])
+        out[i] = [msg_tuple(m) for m in o.msgs()]
+        o.close()
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(streams))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    return out
+
+
+def check_frames(K: int, pool, reps: int, recs, exact: bool, nstreams: int):
+    """recs: numpy records (api.MSG_DTYPE) of EVERYTHING the context decoded since reset, in emission order.
+    Streams s and s + len(pool) carry the same bytes: the first len(pool) streams must equal the CPU port frame
+    for frame (text, BCS, err, lvl bits; order), and every replica must have decoded the same number of frames."""
+    want = oracle_frames(K, pool, reps)
+    ok, frames = True, 0
+    for i in range(len(pool)):
+        mine = [rec_tuple(m) for m in recs[recs["stream"] == i]]
+        if exact:
+            ok = ok and mine == want[i]
+        else:
+            ok = ok and [t[:-1] for t in mine] == [t[:-1] for t in want[i]]
+            la = np.array([t[-1] for t in mine], dtype=np.uint32).view(np.float32)
+            lb = np.array([t[-1] for t in want[i]], dtype=np.uint32).view(np.float32)
+            ok = ok and la.shape == lb.shape and bool(np.all(np.abs(la - lb) <= 0.05))
+        frames += len(want[i])
+    per_stream = np.bincount(recs["stream"], minlength=nstreams)
+    replicas_ok = all(len(set(per_stream[i::len(pool)].tolist())) == 1 for i in range(len(pool)))
+    out = {"streams_vs_cpu_port": len(pool), "passes_checked": reps, "frames": frames, "bit_exact": bool(ok),
+           "replicas_identical_counts": bool(replicas_ok), "frames_all_streams": int(per_stream.sum())}
+    if not exact:
+        out["note"] = "messages (chn, len, err, text, BCS) identical; lvl within 0.05 dB (fast channelizer)"
+    return out
+
+
+def rec_tuple(m):
+    return (int(m["chn"]), int(m["len"]), int(m["err"]), bytes(m["txt"][:int(m["len"])]), bytes(m["crc"]), int(np.float32(m["lvl"]).view(np.uint32)))
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -238,7 +283,7 @@ class ClockSampler:
                 "power_w_max": max(float(r[3]) for r in rows), "samples": len(rows)}
 
 
-# ----------------------------------------------------------------------------- GPU arm
+# ----------------------------------------------------------------------------- GPU arm helpers
 
 def measured_peak():
     p = ROOT / "MEASURED_PEAKS.json"
@@ -250,6 +295,58 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def traffic_per_launch(channelizer: str, S: int, B: int, K: int):
+    """dram__bytes_read + dram__bytes_write of the channelizer kernel from the committed ncu capture
+    (profiles/k1_traffic.json, written by tools/summarize_ncu.py).  The kernel's grid is one CTA per (block, stream,
+    channel group) and every CTA reads its own rows once, so a capture at S0 x B0 scales by S*B/(S0*B0); the
+    entry says which shape was captured."""
+    tp = ROOT / "profiles" / "k1_traffic.json"
+    try:
+        tj = json.load(open(tp)).get(channelizer)
+        if tj and tj.get("K") == K:
+            return tj["dram_bytes_per_launch"] * (S * B) / (tj["streams"] * tj["blocks"]), f"ncu capture at {tj['streams']} x {tj['blocks']}, scaled by stream-blocks"
+    except Exception:
+        pass
+    return None, None
+
+
+class DeviceInput:
+    """The pool tiled over S streams, resident in HBM (streams s and s + len(pool) carry the same bytes)."""
+
+    def __init__(self, ctx, pool, S: int, stride: int):
+        self.ctx, self.ptr = ctx, ctx.device_alloc(S * stride)
+        for s in range(S):
+            ctx.copy_to_device(self.ptr + s * stride, pool[s % len(pool)][:stride])
+
+    def free(self):
+        self.ctx.device_free(self.ptr)
+
+
+def roofline_obj(channelizer: str, fast_ran: bool, k1_ms: float, k1_iso_ms, S: int, B: int, K: int, nch: int, sm_mhz: float):
+    peak, peak_src = measured_peak()
+    blk_bytes = 2048 * K
+    alg = S * B * (blk_bytes + 1024 * nch * 4)            # u8 IQ read once + dm written once (K1 and K2 are separate kernels)
+    achieved = alg / (k1_ms * 1e-3) / 1e9
+    traffic, tsrc = traffic_per_launch(channelizer, S, B, K)
+    cmacs = S * B * 1024 * K * nch
+    # FP32 lane-ops per complex MAC-equivalent: exact = 8 rounded ops; fast (folded) = (3.25 + C/2) per input sample over C channels
+    ops_per_cmac = (3.25 + nch / 2) / nch if fast_ran else 8.0
+    fp32_peak_cmac = 148 * 128 * sm_mhz * 1e6 / ops_per_cmac
+    o = {"kernel": "k_channelize_dft" if fast_ran else "k_channelize", "channelizer": channelizer, "bound": "hbm",
+         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": tsrc,
+         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "launch_ms": k1_ms,
+         "timing": "CUDA events around the kernel on its own stream, averaged over the timed steps, demod of the previous step running underneath",
+         "fp32_issue_frac": (cmacs / (k1_ms * 1e-3)) / fp32_peak_cmac,
+         "note": ("fast form: K-point DFT bins via an exact fold + 4-point split shared by the channels, K/8 MACs per channel"
+                  if fast_ran else
+                  "FP32-issue bound: the reference's rounding sequence costs 8 rounded FP32 ops per complex "
+                  "MAC per channel (4*C flop/B, C=8); ceiling 17.7 % of HBM peak, see DESIGN.md")}
+    if k1_iso_ms:
+        o["isolated"] = {"launch_ms": k1_iso_ms, "achieved": alg / (k1_iso_ms * 1e-3) / 1e9, "frac": alg / (k1_iso_ms * 1e-3) / 1e9 / peak,
+                         "timing": "same kernel, nothing else on the GPU (sync between steps)"}
+    return o
+
+
 def main():
     args = parse_args()
     if args.cpu_worker:
@@ -259,9 +356,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    K, S, B = args.K, args.streams, args.blocks
+    K = args.K
     nch = 8
-    samples_per_step_rank = S * B * 1024 * K
 
     if args.impl == "reference":
         if rank != 0:
@@ -281,7 +377,7 @@ def main():
         return
 
     from acarsdec_b200 import sharding
-    dist, rank, world, local = sharding.init_process_group()      # NCCL rendezvous only: no data-path collective
+    dist, rank, world, local = sharding.init_process_group()      # NCCL: rendezvous, timing reductions, the wide-stream broadcast
     dev = f"cuda:{local}" if dist is not None else None
 
     def barrier():
@@ -305,206 +401,204 @@ def main():
     build.build()
 
     fd, _, fc = api.plan(K, synth.DEFAULT_FREQS_MHZ)
-    pool = make_pool(K, B, args.pool, fc, seed0=1000 + 17 * rank)
     blk_bytes = 2048 * K
+    pool = make_pool(K, min(args.blocks, 16), args.pool, fc, seed0=1000 + 17 * rank)
+    do_check = (not args.no_check) and rank == 0
+    fastflag = {"exact": 0, "fast": 8}                    # ACB_FLAG_FAST_CHANNELIZER
+
+    # ---- stream-count sweep (device-resident, short): where does this GPU saturate?
+    sweep = None
+    if args.streams > 0:
+        S = args.streams
+    else:
+        sweep = []
+        for Ssw in SWEEP:
+            Bsw = blocks_for(Ssw, args.blocks)
+            st_b = Bsw * blk_bytes
+            with api.Context(K, Ssw, nch, Bsw, device=local, flags=1 | fastflag[args.channelizer]) as c:
+                for s in range(Ssw):
+                    c.set_plan(s, fd)
+                din = DeviceInput(c, pool, Ssw, st_b)
+                for _ in range(2):
+                    c.submit_device(din.ptr, Bsw, st_b)
+                c.sync(); c.drain_records()
+                barrier()
+                c.mark(0)
+                for _ in range(4):
+                    c.submit_device(din.ptr, Bsw, st_b)
+                    c.drain_records()
+                c.mark(1)
+                c.sync(); c.drain_records()
+                ms = max_over_ranks(c.elapsed_ms()) / 4
+                din.free()
+            sweep.append({"streams_per_gpu": Ssw, "blocks_per_step": Bsw, "ms_per_step": ms,
+                          "value": Ssw * Bsw * 1024 * K * world / ms / 1e3})
+        S = max(sweep, key=lambda r: r["value"])["streams_per_gpu"]
+    B = blocks_for(S, args.blocks)
     stride = B * blk_bytes
-    fastflag = 8 if args.channelizer == "fast" else 0          # ACB_FLAG_FAST_CHANNELIZER
-    ctx = api.Context(K, S, nch, B, device=local, flags=fastflag)
-    for s in range(S):
-        ctx.set_plan(s, fd)
-    pinned = api.PinnedBuffer(S * stride)
-    host = pinned.array.reshape(S, stride)
-    for s in range(S):
-        host[s] = pool[s % args.pool]
+    pool_b = [p[:stride] for p in pool]
+    samples_per_step_rank = S * B * 1024 * K
 
-    # ---- first pass from reset state; as part of the cpu_baseline leg (rank 0, N=1) the CPU port of
-    # the reference decodes the same pool streams and the GPU frames must match it frame for frame
-    ctx.submit_host(host, B)
-    ctx.sync()
-    got = ctx.drain()
-    checked = None
-    if cpu is not None:
-        checked = cpu_port_check(K, pool[:min(args.pool, S)], got, exact=args.channelizer == "exact")
-        if not checked["bit_exact"]:
-            raise SystemExit("bench: GPU frames differ from the CPU reference port on the bench workload")
-
-    # ---- device-resident throughput
-    d_in = ctx.device_alloc(S * stride)
-    ctx.copy_to_device(d_in, host)
-    for _ in range(args.warmup):
-        ctx.submit_device(d_in, B, stride)
-    ctx.sync()
-    ctx.drain_records()
-    ctx.stats(reset=True)
-    clk = ClockSampler(local)
-    clk.start()
-    time.sleep(0.3)
-    barrier()
-    t0 = time.perf_counter()
-    ctx.mark(0)
-    frames_dev = 0
-    for _ in range(args.steps):
-        ctx.submit_device(d_in, B, stride)
-        frames_dev += len(ctx.drain_records())
-    ctx.mark(1)
-    ctx.sync()
-    frames_dev += len(ctx.drain_records())
-    t1 = time.perf_counter()
-    ev_ms = ctx.elapsed_ms()
-    barrier()
-    st = ctx.stats(reset=True)
-    ev_ms_max = max_over_ranks(ev_ms)
-    wall_ms_max = max_over_ranks((t1 - t0) * 1e3)
-    total_samples = sum_over_ranks(float(samples_per_step_rank * args.steps))
-    value = total_samples / (ev_ms_max * 1e-3) / 1e6
-    clocks = clk.summary(t0, t1)
-    ctx.device_free(d_in)
-
-    # ---- end to end through the C ABI with host buffers (pinned H2D + frame read-back per step)
-    e2e = None
-    if not args.no_e2e:
-        for _ in range(max(1, min(args.warmup, 2))):
+    def measure(channelizer: str, steps: int, warmup: int, with_e2e: bool, clk=None):
+        """One context at (S, B): first pass through the host API from reset state, `warmup` + `steps` device-resident
+        submits (timed with the library's CUDA events), an isolated-kernel pass, optionally the host-buffer leg."""
+        out = {}
+        recs = []
+        flags = fastflag[channelizer] | (0 if with_e2e else 1)
+        ctx = api.Context(K, S, nch, B, device=local, flags=flags)
+        for s in range(S):
+            ctx.set_plan(s, fd)
+        din = DeviceInput(ctx, pool_b, S, stride)
+        pinned = host = None
+        if with_e2e:
+            pinned = api.PinnedBuffer(S * stride)
+            host = pinned.array.reshape(S, stride)
+            for s in range(S):
+                host[s] = pool_b[s % len(pool_b)]
+        # first pass from reset state (through the host path when this context has one)
+        if with_e2e:
             ctx.submit_host(host, B)
+        else:
+            ctx.submit_device(din.ptr, B, stride)
+        for _ in range(warmup):
+            ctx.submit_device(din.ptr, B, stride)
+            recs.append(ctx.drain_records())
         ctx.sync()
-        ctx.drain_records()
+        recs.append(ctx.drain_records())
         ctx.stats(reset=True)
+        if clk is not None:
+            clk.start()
+            time.sleep(0.3)
         barrier()
-        e0 = time.perf_counter()
-        frames_e2e = 0
-        for _ in range(args.steps):
-            ctx.submit_host(host, B)          # queues H2D + kernels; collects the submit two back
-            frames_e2e += len(ctx.drain_records())    # decoded frames of completed steps, on the host
+        t0 = time.perf_counter()
+        ctx.mark(0)
+        for _ in range(steps):
+            ctx.submit_device(din.ptr, B, stride)
+            recs.append(ctx.drain_records())
+        ctx.mark(1)
         ctx.sync()
-        frames_e2e += len(ctx.drain_records())
-        e1 = time.perf_counter()
+        recs.append(ctx.drain_records())
+        t1 = time.perf_counter()
+        ev_ms = ctx.elapsed_ms()
         barrier()
-        st2 = ctx.stats(reset=True)
-        e_ms = max_over_ranks((e1 - e0) * 1e3)
-        e2e = {"value": total_samples / (e_ms * 1e-3) / 1e6, "unit": UNIT,
-               "h2d_bytes_per_step": S * stride * world,
-               "d2h_bytes_per_step": int((st2.raw_frames * 304 + 16 * st2.submits) / max(1, args.steps)) * world,
-               "ms_per_step": e_ms / args.steps, "frames_per_step": frames_e2e / args.steps,
-               "timing": "host wall clock between full device syncs, max over ranks"}
-    clk.stop()
-    ctx.close()
+        st = ctx.stats(reset=True)
+        out["ev_ms"] = max_over_ranks(ev_ms)
+        out["wall_ms"] = max_over_ranks((t1 - t0) * 1e3)
+        out["t0"], out["t1"] = t0, t1
+        out["st"] = st
+        out["recs"] = np.concatenate(recs) if recs else np.empty(0, dtype=api.MSG_DTYPE)
+        out["passes"] = 1 + warmup + steps
+        out["frames_timed"] = int(sum(len(r) for r in recs[-(steps + 1):]))
+        # isolated kernels: sync between steps, so nothing overlaps
+        for _ in range(3):
+            ctx.submit_device(din.ptr, B, stride)
+            ctx.sync()
+        ctx.drain_records()
+        iso = ctx.stats(reset=True)
+        out["k1_iso_ms"] = iso.chan_ms / max(1, iso.chan_launches)
+        out["k2_iso_ms"] = iso.demod_ms / max(1, iso.demod_launches)
+        if with_e2e:
+            for _ in range(2):
+                ctx.submit_host(host, B)
+            ctx.sync()
+            ctx.drain_records()
+            ctx.stats(reset=True)
+            barrier()
+            e0 = time.perf_counter()
+            frames_e2e = 0
+            for _ in range(steps):
+                ctx.submit_host(host, B)          # queues H2D + kernels; collects the submit two back
+                frames_e2e += len(ctx.drain_records())    # decoded frames of completed steps, on the host
+            ctx.sync()
+            frames_e2e += len(ctx.drain_records())
+            e1 = time.perf_counter()
+            barrier()
+            st2 = ctx.stats(reset=True)
+            e_ms = max_over_ranks((e1 - e0) * 1e3)
+            tot = sum_over_ranks(float(samples_per_step_rank * steps))
+            out["e2e"] = {"value": tot / (e_ms * 1e-3) / 1e6, "unit": UNIT,
+                          "h2d_bytes_per_step": S * stride * world,
+                          "d2h_bytes_per_step": int((st2.raw_frames * FRAME_BYTES + 16 * st2.submits) / max(1, steps)) * world,
+                          "ms_per_step": e_ms / steps, "frames_per_step": frames_e2e / steps,
+                          "timing": "host wall clock between full device syncs, max over ranks"}
+            pinned.close()
+        din.free()
+        ctx.close()
+        return out
 
-    # ---- the other channelizer form on the same workload, device-resident, for the record: the line's
-    # `value`/`roofline` belong to --channelizer; this object shows what the alternative does
+    clk = ClockSampler(local)
+    main_m = measure(args.channelizer, args.steps, args.warmup, not args.no_e2e, clk)
+    clocks = clk.summary(main_m["t0"], main_m["t1"])
+    clk.stop()
+    total_samples = sum_over_ranks(float(samples_per_step_rank * args.steps))
+    value = total_samples / (main_m["ev_ms"] * 1e-3) / 1e6
+    st = main_m["st"]
+    checked = {"skipped": "rank != 0 or --no-check"}
+    if do_check:
+        checked = check_frames(K, pool_b, main_m["passes"], main_m["recs"], args.channelizer == "exact", S)
+        if not (checked["bit_exact"] and checked["replicas_identical_counts"]):
+            raise SystemExit("bench: GPU frames of the timed region differ from the CPU reference port")
+    checked["frames_per_step_device"] = main_m["frames_timed"] / args.steps
+
+    # ---- the other channelizer form at the same S, same treatment (its own roofline object)
     other = None
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
     if not args.no_alt:
         alt = "fast" if args.channelizer == "exact" else "exact"
-        nst = max(3, min(args.steps, 8))
-        with api.Context(K, S, nch, B, device=local, flags=1 | (8 if alt == "fast" else 0)) as c2:
-            for s in range(S):
-                c2.set_plan(s, fd)
-            d2 = c2.device_alloc(S * stride)
-            c2.copy_to_device(d2, host)
-            c2.submit_device(d2, B, stride)
-            c2.sync()
-            got2 = c2.drain()
-            chk2 = None
-            if cpu is not None:
-                chk2 = cpu_port_check(K, pool[:min(args.pool, S)], got2, exact=alt == "exact")
-                if not chk2["bit_exact"]:
-                    # reported, not fatal: the line's own numbers belong to --channelizer, checked above
-                    print(f"bench: GPU frames ({alt} channelizer) differ from the CPU reference port", file=sys.stderr)
-            for _ in range(2):
-                c2.submit_device(d2, B, stride)
-            c2.sync(); c2.drain_records(); c2.stats(reset=True)
-            barrier()
-            c2.mark(0)
-            for _ in range(nst):
-                c2.submit_device(d2, B, stride)
-                c2.drain_records()
-            c2.mark(1)
-            c2.sync(); c2.drain_records()
-            ms2 = max_over_ranks(c2.elapsed_ms())
-            st3 = c2.stats()
-            c2.device_free(d2)
-        k1b = st3.chan_ms / max(1, st3.chan_launches)
-        other = {"channelizer": alt, "value": sum_over_ranks(float(samples_per_step_rank * nst)) / (ms2 * 1e-3) / 1e6, "unit": UNIT,
-                 "steps": nst, "ms_per_step": ms2 / nst, "k_channelize_ms": k1b, "k_demod_and_fec_ms": st3.demod_ms / max(1, st3.demod_launches),
-                 "roofline_frac": S * B * (blk_bytes + 1024 * nch * 4) / (k1b * 1e-3) / 1e9 / measured_peak()[0],
-                 "fast_launches": int(st3.fast_chan_launches), "checked": chk2}
-    pinned.close()
+        nst = max(3, min(args.steps, 10))
+        am = measure(alt, nst, 2, False)
+        k1b = am["st"].chan_ms / max(1, am["st"].chan_launches)
+        chk2 = {"skipped": "rank != 0 or --no-check"}
+        if do_check:
+            chk2 = check_frames(K, pool_b, am["passes"], am["recs"], alt == "exact", S)
+            if not chk2["bit_exact"]:
+                # reported, not fatal: the line's own numbers belong to --channelizer, checked above
+                print(f"bench: GPU frames ({alt} channelizer) differ from the CPU reference port", file=sys.stderr)
+        other = {"channelizer": alt, "value": sum_over_ranks(float(samples_per_step_rank * nst)) / (am["ev_ms"] * 1e-3) / 1e6, "unit": UNIT,
+                 "steps": nst, "ms_per_step": am["ev_ms"] / nst, "k_channelize_ms": k1b,
+                 "k_demod_and_fec_ms": am["st"].demod_ms / max(1, am["st"].demod_launches),
+                 "fast_launches": int(am["st"].fast_chan_launches), "checked": chk2,
+                 "roofline": roofline_obj(alt, am["st"].fast_chan_launches > 0, k1b, am["k1_iso_ms"], S, B, K, nch, sm_mhz)}
 
-    # ---- the literal configs[1] shape for reference: ONE 2 MS/s stream, 8 channels (latency bound by
-    # the serial demodulator: this is what a single receiver's backlog is decoded at)
-    single = None
-    if rank == 0:
-        with api.Context(K, 1, nch, B, device=local, flags=1 | fastflag) as c1:
-            c1.set_plan(0, fd)
-            d1 = c1.device_alloc(stride)
-            c1.copy_to_device(d1, pool[0])
-            for _ in range(2):
-                c1.submit_device(d1, B, stride)
-            c1.sync()
-            c1.drain_records()
-            c1.mark(0)
-            nst = max(3, min(args.steps, 10))
-            for _ in range(nst):
-                c1.submit_device(d1, B, stride)
-            c1.mark(1)
-            c1.sync()
-            ms1 = c1.elapsed_ms() / nst
-            c1.device_free(d1)
-        single = {"value": B * 1024 * K / ms1 / 1e3, "unit": UNIT, "ms_per_step": ms1, "streams": 1, "channels": nch}
+    # ---- the literal BASELINE configs
+    configs = None
+    if args.config != "none":
+        import bench_configs
+        want = {"2", "3", "4", "5"} if args.config == "all" else set(args.config.split(","))
+        configs = bench_configs.run(want, dist, rank, world, local, dev, fastflag[args.channelizer], do_check)
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    peak, peak_src = measured_peak()
     k1_ms = st.chan_ms / max(1, st.chan_launches)
     k2_ms = st.demod_ms / max(1, st.demod_launches)
-    alg_bytes = S * B * (blk_bytes + 1024 * nch * 4)          # u8 IQ read once + dm written once (not fused)
-    achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
-    traffic = None
-    tp = ROOT / "profiles" / "k1_traffic.json"
-    if tp.exists():
-        try:
-            tj = json.load(open(tp))
-            tj = tj.get(args.channelizer, tj if args.channelizer == "exact" else {})
-            if tj.get("streams") == S and tj.get("blocks") == B and tj.get("K") == K:
-                traffic = tj["dram_bytes_per_launch"]
-        except Exception:
-            pass
-    sm_mhz = clocks.get("sm_mhz") or 1965.0
-    cmacs = S * B * 1024 * K * nch
     fast_ran = st.fast_chan_launches > 0
-    # FP32 lane-ops per complex MAC-equivalent: exact = 8 rounded ops; fast = (2.5 + C) per input sample over C channels
-    ops_per_cmac = (2.5 + nch) / nch if fast_ran else 8.0
-    fp32_peak_cmac = 148 * 128 * sm_mhz * 1e6 / ops_per_cmac
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": main_m["ev_ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": f"synthetic ({args.pool} distinct seeded streams per rank, tiled over {S})",
-        "config": {"workload": f"configs[1] x {S} streams per GPU: synthetic 2 MS/s uint8 IQ (K={K}), 8 ACARS channels "
-                               f"per stream, {B} blocks of 1024*K samples per stream per step",
-                   "K": K, "streams_per_gpu": S, "channels_per_stream": nch, "blocks_per_step": B,
+        "config": {"workload": f"configs[1] x {S} streams per GPU (the saturating stream count of the sweep): synthetic 2 MS/s uint8 IQ "
+                               f"(K={K}), 8 ACARS channels per stream, {B} blocks of 1024*K samples per stream per step",
+                   "K": K, "streams_per_gpu": S, "channels_per_stream": nch, "blocks_per_step": B, "channelizer": args.channelizer,
                    "channels_total": S * nch * world, "input_bytes_per_step_per_gpu": S * stride,
                    "l2": "inputs larger than L2 (no flush needed)" if S * stride > 200e6 else "input smaller than L2",
-                   "sharding": "streams by index, no data-path collective", "timing": "CUDA events on the library's compute stream, max over ranks"},
+                   "sharding": "streams by index, no data-path collective", "timing": "CUDA events on the library's streams, max over ranks"},
+        "streams_sweep": sweep,
         "clocks": clocks,
-        "e2e": e2e,
+        "e2e": main_m.get("e2e"),
         "gpu_launches": int(st.kernel_launches),
-        "wall_ms_per_step": wall_ms_max / args.steps,
-        "kernels": {"k_channelize_ms": k1_ms, "k_demod_and_fec_ms": k2_ms, "launches_per_step": st.kernel_launches / args.steps},
-        "single_stream": single,
+        "wall_ms_per_step": main_m["wall_ms"] / args.steps,
+        "kernels": {"k_channelize_ms": k1_ms, "k_demod_and_fec_ms": k2_ms, "k_channelize_isolated_ms": main_m["k1_iso_ms"],
+                    "k_demod_and_fec_isolated_ms": main_m["k2_iso_ms"], "launches_per_step": st.kernel_launches / args.steps},
         "alt_channelizer": other,
-        "real_time_receivers": {"device_resident": value / (K * 12500 / 1e6), "e2e": (e2e["value"] / (K * 12500 / 1e6)) if e2e else None,
+        "configs": configs,
+        "real_time_receivers": {"device_resident": value / (K * 12500 / 1e6),
+                                "e2e": (main_m["e2e"]["value"] / (K * 12500 / 1e6)) if main_m.get("e2e") else None,
                                 "note": "2 MS/s receivers this rate serves in real time"},
-        "roofline": {"kernel": "k_channelize_dft" if fast_ran else "k_channelize", "channelizer": args.channelizer, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_bytes,
-                     "fp32_issue_frac": (cmacs / (k1_ms * 1e-3)) / fp32_peak_cmac,
-                     "note": ("fast form: shared 4-point DFT + K/4 MACs per channel, (2.5 + C)/2 FP32 lane-ops per input byte"
-                              if fast_ran else
-                              "FP32-issue bound: the reference's rounding sequence costs 8 rounded FP32 ops per complex "
-                              "MAC per channel (4*C flop/B, C=8), see DESIGN.md")},
-        "checked": dict(checked or {"skipped": "cpu_baseline leg disabled (N>1 or --no-cpu-baseline)"},
-                        frames_per_step_device=frames_dev / args.steps),
+        "roofline": roofline_obj(args.channelizer, fast_ran, k1_ms, main_m["k1_iso_ms"], S, B, K, nch, sm_mhz),
+        "checked": checked,
     }
     if cpu is not None:
         line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}

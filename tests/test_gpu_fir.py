@@ -13,16 +13,7 @@ from common import bits_equal
 pytestmark = pytest.mark.gpu
 
 
-def fir_tables(K, taps, offsets_hz, rate):
-    """Hamming-windowed mixer tables: w[t] = hamming(t) * exp(-j 2 pi f t / rate) / sum / 127.5."""
-    t = np.arange(taps)
-    win = 0.54 - 0.46 * np.cos(2 * np.pi * t / max(taps - 1, 1))
-    out = np.empty((len(offsets_hz), 2 * taps), dtype=np.float32)
-    for i, f in enumerate(offsets_hz):
-        w = win * np.exp(-2j * np.pi * f * t / rate) / win.sum() / 127.5
-        out[i, 0::2] = w.real
-        out[i, 1::2] = w.imag
-    return out
+fir_tables = synth.fir_tables
 
 
 def test_fir_equals_reference_arithmetic_at_taps_eq_k(native, oracle):
