@@ -118,6 +118,7 @@ struct DcConsts {
 	0.5, 6.0, 12.0, 1e-8 /* msk.c:111 */, 1e-4, 0.01 }
 #if defined(__CUDACC__)
 static __constant__ DcConsts c_dcc = DC_CONSTS_INIT;
+static __device__ DcConsts g_dcc = DC_CONSTS_INIT;      /* the same in global memory: see demod_run */
 #endif
 static const DcConsts h_dcc = DC_CONSTS_INIT;
 #if defined(__CUDA_ARCH__)
@@ -132,22 +133,22 @@ static const DcConsts h_dcc = DC_CONSTS_INIT;
  * cos r - 1; angle addition against the double-double table.  Max error measured against 80-bit
  * references: 1.7 ulp (typ. < 0.6), i.e. the class of CUDA's own sincos; see DESIGN.md for why
  * ~1 ulp here is invisible after the (float) rounding of in*cexp(-j p) (msk.c:90). */
-ACB_HD void sincos_vco(double p, const DcD2 *tcos, const DcD2 *tsin, double &sn, double &cs)
+ACB_HD void sincos_vco(const DcConsts &DCK_, double p, const DcD2 *tcos, const DcD2 *tsin, double &sn, double &cs)
 {
-	const double t = fma(p, DCK.k32_pi, DCK.sc_magic);       /* p * 32/pi, rounded to integer */
+	const double t = fma(p, DCK_.k32_pi, DCK_.sc_magic);       /* p * 32/pi, rounded to integer */
 	const int k = DC_LOINT(t) & 63;
-	const double kd = t - DCK.sc_magic;
-	double r = fma(-kd, DCK.pi32_a, p);
-	r = fma(-kd, DCK.pi32_b, r);
-	r = fma(-kd, DCK.pi32_c, r);
+	const double kd = t - DCK_.sc_magic;
+	double r = fma(-kd, DCK_.pi32_a, p);
+	r = fma(-kd, DCK_.pi32_b, r);
+	r = fma(-kd, DCK_.pi32_c, r);
 	const double r2 = r * r;
-	double sp = fma(r2, DCK.s9, DCK.s7);
-	sp = fma(sp, r2, DCK.s5);
-	sp = fma(sp, r2, DCK.s3);
+	double sp = fma(r2, DCK_.s9, DCK_.s7);
+	sp = fma(sp, r2, DCK_.s5);
+	sp = fma(sp, r2, DCK_.s3);
 	const double sr = fma(r * r2, sp, r);                    /* sin r */
-	double cp = fma(r2, DCK.c8, DCK.c6);
-	cp = fma(cp, r2, DCK.c4);
-	cp = fma(cp, r2, DCK.c2);
+	double cp = fma(r2, DCK_.c8, DCK_.c6);
+	cp = fma(cp, r2, DCK_.c4);
+	cp = fma(cp, r2, DCK_.c2);
 	const double cm = r2 * cp;                               /* cos r - 1 */
 	const DcD2 C = tcos[k], S = tsin[k];
 	cs = C.x + fma(-S.x, sr, fma(C.x, cm, C.y));
@@ -171,17 +172,17 @@ template <bool F2F> ACB_HD double round_to_f32(double x)
 }
 
 /* one step of the VCO phase (msk.c:82-83) */
-ACB_HD double phase_step(double p, double sv)
+ACB_HD double phase_step(const DcConsts &DCK_, double p, double sv)
 {
 	p = DC_DADD(p, sv);
-	return (p >= DCK.two_pi) ? DC_DADD(p, -DCK.two_pi) : p;
+	return (p >= DCK_.two_pi) ? DC_DADD(p, -DCK_.two_pi) : p;
 }
 
 /* in * cexp(-j p) rounded to float complex (msk.c:86-91) */
-ACB_HD DcF2 mix_sample(float x, double p, const DcD2 *tcos, const DcD2 *tsin)
+ACB_HD DcF2 mix_sample(const DcConsts &DCK_, float x, double p, const DcD2 *tcos, const DcD2 *tsin)
 {
 	double sn, cs;
-	sincos_vco(p, tcos, tsin, sn, cs);
+	sincos_vco(DCK_, p, tcos, tsin, sn, cs);
 	const double xd = (double)x;
 	DcF2 o;
 	o.x = DC_D2F(DC_DMUL(xd, cs));
@@ -194,14 +195,14 @@ ACB_HD DcF2 mix_sample(float x, double p, const DcD2 *tcos, const DcD2 *tsin)
  * the PLL is in charge: 1e-7 relative) gives the value to ~1e-6; only when that lands within 1e-4 of an
  * integer (where the truncation could differ), or MskDf is outside the PLL's range, is the reference's exact
  * division sequence replayed. */
-template <bool F2F> ACB_HD int bit_clock_fire(double &clkd, double sv, double df)
+template <bool F2F> ACB_HD int bit_clock_fire(const DcConsts &DCK_, double &clkd, double sv, double df)
 {
-	clkd = round_to_f32<F2F>(DC_DADD(clkd, -DCK.thr));
-	const double xs = DC_DMUL(df, DCK.inv_s0);
-	const double inv_s = fma(DCK.inv_s0, fma(xs, xs, -xs), DCK.inv_s0);
-	double u = fma(DC_DMUL(clkd, inv_s), DCK.twelve, DCK.six);
-	if (!(fabs(u - rint(u)) >= DCK.guard_u) || !(fabs(df) <= DCK.guard_df))
-		u = DC_DMUL(DCK.twelve, DC_DADD(DC_DDIV(clkd, sv), DCK.half));
+	clkd = round_to_f32<F2F>(DC_DADD(clkd, -DCK_.thr));
+	const double xs = DC_DMUL(df, DCK_.inv_s0);
+	const double inv_s = fma(DCK_.inv_s0, fma(xs, xs, -xs), DCK_.inv_s0);
+	double u = fma(DC_DMUL(clkd, inv_s), DCK_.twelve, DCK_.six);
+	if (!(fabs(u - rint(u)) >= DCK_.guard_u) || !(fabs(df) <= DCK_.guard_df))
+		u = DC_DMUL(DCK_.twelve, DC_DADD(DC_DDIV(clkd, sv), DCK_.half));
 	const int o = DC_D2I_RZ(u);
 	return o < 0 ? 0 : (o > MFLTOVER ? MFLTOVER : o);
 }
@@ -216,18 +217,42 @@ ACB_HD void demod_run(DemodRegs &r, DemodShared<CPW> &sm, const float *in, int n
                       FrameAcc &acc)
 {
 	constexpr int ROUNDS = (DEMOD_LOOK + L - 1) / L;         /* mixer evaluations per lane and bit */
+	/* the loop's double constants, held in registers for the whole launch (left to itself the compiler re-reads
+	 * them from the constant bank into uniform registers every iteration: 26 instructions of ~440) */
+#if defined(__CUDA_ARCH__)
+	/* read through a volatile global pointer: a value the compiler cannot re-create at its uses */
+	DcConsts DCK_;
+	{
+		const volatile double *src = reinterpret_cast<const volatile double *>(&g_dcc);
+		double *dst = reinterpret_cast<double *>(&DCK_);
+#pragma unroll
+		for (int i = 0; i < (int)(sizeof(DcConsts) / sizeof(double)); i++) dst[i] = src[i];
+	}
+#else
+	const DcConsts DCK_ = DCK;
+#endif
 	r.pos0 = r.pos;
 	double clkd = (double)r.clk;             /* MskClk: a float value carried in a double register */
 	int n = 0;
-	const float *px = in + (size_t)sub * nch;                /* this lane's first sample of the iteration */
-	const size_t round_stride = (size_t)L * nch;
+	/* This lane's envelope samples of the coming iteration (sample n + sub + i*L of round i), loaded one iteration
+	 * ahead: an iteration's first sample is only known once the previous bit clock has fired, and a load issued then
+	 * has a whole bit period (~2000 cycles) to come back from L2/HBM instead of stalling the mixer (the loads were
+	 * 23 % of the kernel's cycles as `long scoreboard` stalls when they were issued where they are used).  Indices
+	 * past the launch are clamped: such values are never stored (the general path loads its own). */
+	float xn[ROUNDS];
+	const int last = nsamp - 1;
+#pragma unroll
+	for (int i = 0; i < ROUNDS; i++) {
+		const int k = sub + i * L;
+		xn[i] = nsamp > 0 ? in[(size_t)(k < last ? k : last) * nch] : 0.f;
+	}
 	/* channels of a warp consume 5 or 6 samples per iteration each, so they finish a few
 	 * iterations apart: finished groups idle through the general path (m <= 0) */
 	while (Env::any(n < nsamp)) {
 		const int m = nsamp - n;
 		/* VCO step is constant until the next bit (msk.c:81): MskDf only changes in the bit path */
-		const double sv = DC_DADD(DCK.s0, r.df);
-		const double fire_at = fma(sv, -DCK.half, DCK.thr);    /* 3*pi/2 - s/2: the halving is exact */
+		const double sv = DC_DADD(DCK_.s0, r.df);
+		const double fire_at = fma(sv, -DCK_.half, DCK_.thr);    /* 3*pi/2 - s/2: the halving is exact */
 
 		/* the two cheap serial chains: phase (msk.c:82-83) and bit clock (msk.c:95-96), each rounded
 		 * step by step exactly like the reference's loop */
@@ -236,7 +261,7 @@ ACB_HD void demod_run(DemodRegs &r, DemodShared<CPW> &sm, const float *in, int n
 			double p = r.phi, c = clkd;
 #pragma unroll
 			for (int k = 0; k < DEMOD_LOOK; k++) {
-				p = phase_step(p, sv);
+				p = phase_step(DCK_, p, sv);
 				c = round_to_f32<F2F>(DC_DADD(c, sv));
 				pk[k] = p;
 				ck[k] = c;
@@ -254,9 +279,7 @@ ACB_HD void demod_run(DemodRegs &r, DemodShared<CPW> &sm, const float *in, int n
 #pragma unroll
 			for (int j = 1; j < L; j++)
 				if (k0 + j < DEMOD_LOOK && sub == j) ps = pk[k0 + j];
-			const bool have = inside && (k0 + L <= DEMOD_LOOK || k0 + sub < DEMOD_LOOK);
-			const float x = have ? px[(size_t)i * round_stride] : 0.f;
-			mv[i] = mix_sample(x, ps, sm.tcos, sm.tsin);
+			mv[i] = mix_sample(DCK_, xn[i], ps, sm.tcos, sm.tsin);
 		}
 		int cnt = 0;                 /* samples consumed this iteration */
 		bool fired = false;
@@ -270,7 +293,12 @@ ACB_HD void demod_run(DemodRegs &r, DemodShared<CPW> &sm, const float *in, int n
 			fired = true;
 			r.phi = five ? pk[4] : pk[5];
 			clkd = five ? ck[4] : ck[5];
-			o = bit_clock_fire<F2F>(clkd, sv, r.df);
+#pragma unroll
+			for (int i = 0; i < ROUNDS; i++) {                     /* next iteration's samples: in flight during the bit part */
+				const int k = n + cnt + sub + i * L;
+				xn[i] = in[(size_t)(k < last ? k : last) * nch];
+			}
+			o = bit_clock_fire<F2F>(DCK_, clkd, sv, r.df);
 			Env::sync();             /* the previous bit's matched filter has read the rows being replaced */
 #pragma unroll
 			for (int i = 0; i < ROUNDS; i++) {
@@ -292,8 +320,8 @@ ACB_HD void demod_run(DemodRegs &r, DemodShared<CPW> &sm, const float *in, int n
 			const int mm = m < DEMOD_LOOK ? m : DEMOD_LOOK;
 			double p = r.phi, c = clkd;
 			for (int k = 0; k < mm; k++) {
-				p = phase_step(p, sv);
-				const DcF2 v = mix_sample(in[(size_t)(n + k) * nch], p, sm.tcos, sm.tsin);
+				p = phase_step(DCK_, p, sv);
+				const DcF2 v = mix_sample(DCK_, in[(size_t)(n + k) * nch], p, sm.tcos, sm.tsin);
 				if (sub == 0) {
 					sm.ring[r.idx][grp] = v;
 					sm.ring[r.idx + FLEN][grp] = v;
@@ -305,7 +333,12 @@ ACB_HD void demod_run(DemodRegs &r, DemodShared<CPW> &sm, const float *in, int n
 			}
 			r.phi = p;
 			clkd = c;
-			if (fired) o = bit_clock_fire<F2F>(clkd, sv, r.df);
+			if (fired) o = bit_clock_fire<F2F>(DCK_, clkd, sv, r.df);
+#pragma unroll
+			for (int i = 0; i < ROUNDS; i++) {
+				const int k = n + cnt + sub + i * L;
+				xn[i] = last >= 0 ? in[(size_t)(k < last ? k : last) * nch] : 0.f;
+			}
 			Env::sync();
 		}
 		r.fire_n = n + cnt - 1;                                /* the sample that fired the bit */
@@ -326,7 +359,7 @@ ACB_HD void demod_run(DemodRegs &r, DemodShared<CPW> &sm, const float *in, int n
 			/* normalise (msk.c:110-113): cabsf is (float)sqrt((double)x*x + (double)y*y) in glibc */
 			const double dvr = (double)vr, dvi = (double)vi;
 			const float lvl = DC_D2F(DC_DSQRT(DC_DADD(DC_DMUL(dvr, dvr), DC_DMUL(dvi, dvi))));
-			const double d = DC_DADD((double)lvl, DCK.eps_d);
+			const double d = DC_DADD((double)lvl, DCK_.eps_d);
 			r.lvlsum = DC_DADD(r.lvlsum, (double)DC_FMUL(DC_FMUL(lvl, lvl), 0.25f));
 			r.bitcount++;
 
@@ -353,10 +386,9 @@ ACB_HD void demod_run(DemodRegs &r, DemodShared<CPW> &sm, const float *in, int n
 			r.S++;
 
 			/* PLL filter (msk.c:130) — after putbit, so a frame resync's MskDf=0 is filtered too */
-			r.df = DC_DADD(DC_DMUL(DCK.pllc, r.df), DC_DMUL(DCK.pllk, dphi));
+			r.df = DC_DADD(DC_DMUL(DCK_.pllc, r.df), DC_DMUL(DCK_.pllk, dphi));
 		}
 		n += cnt;
-		px += (size_t)cnt * nch;
 	}
 	r.pos = r.pos0 + (unsigned long long)nsamp;
 	r.clk = (float)clkd;

@@ -1100,12 +1100,15 @@ k_demod2(ChainState *__restrict__ states, const float *__restrict__ dm, int nsam
 	for (int i = lane; i < (MFLTOVER + 1) * 3; i += 32) (&sm.h2[0][0])[i] = (&g_h2[0][0])[i];
 
 	const int grp = lane / L, sub = lane % L;
-	const int warp = blockIdx.x;
-	const int s = warp / wps;
-	const int ch_raw = (warp - s * wps) * CPW + grp;
-	const bool valid = ch_raw < nch;                 /* surplus groups shadow the last channel, silently */
-	const int ch = valid ? ch_raw : nch - 1;
+	/* chains (stream, channel) are numbered stream-major and dealt CPW to a warp, across stream boundaries: a
+	 * warp of 32 single-lane chains serves four 8-channel streams */
+	const long long nchain = (long long)nstreams * nch;
+	const long long g_raw = (long long)blockIdx.x * CPW + grp;
+	const bool valid = g_raw < nchain;               /* surplus groups of the last warp shadow the last chain, silently */
+	const long long g = valid ? g_raw : nchain - 1;
+	const int s = (int)(g / nch), ch = (int)(g - (long long)s * nch);
 	const bool leader = valid && sub == 0;
+	(void)wps;
 
 	ChainState *st = states + (size_t)s * nch + ch;
 	DemodRegs r;
@@ -1137,7 +1140,8 @@ static int launch_demod_t(ChainState *st, const float *dm, int nsamp, int nch, i
 {
 	constexpr int CPW = 32 / LANES;
 	const int wps = (nch + CPW - 1) / CPW;
-	const int grid = nstreams * wps;             /* one warp per CTA so that chains spread over all SMs */
+	const long long nchain = (long long)nstreams * nch;
+	const int grid = (int)((nchain + CPW - 1) / CPW);    /* one warp per CTA so that chains spread over all SMs */
 	cudaError_t e = cudaFuncSetAttribute(k_demod2<LANES, F2F>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 	if (e != cudaSuccess) return (int)e;
 	k_demod2<LANES, F2F><<<grid, 32, 0, stream>>>(st, dm, nsamp, nch, nstreams, wps, ring, ctl, cap);

@@ -78,3 +78,43 @@ def test_fir_config3_frames(native, oracle):
         for c in (0, 9, 40, 63):
             assert ctx.get_state(0, c).vec() == chans[c].vec(), c
     assert sorted(got) == sorted(want) and len(want) >= 10
+
+
+@pytest.mark.parametrize("taps", [65, 513])
+def test_fir_config5_full_width(native, oracle, taps):
+    """BASELINE config 5 at its full width: K=1600 (20 MS/s), 256 channels on a 25 kHz raster, shortest and longest
+    tap count of the sweep: envelope bit-exact for all 256 channels (32 channel groups in grid.z), and frames +
+    demodulator state vs the oracle (channelize_fir -> orc_demod -> FEC) on injected messages."""
+    K, nch, nblk = 1600, 256, 3
+    fm = tuple(126.000 + 0.025 * i for i in range(nch))
+    fd, _, fc = api.plan(K, fm)
+    rate = K * 12500
+    wf = fir_tables(K, taps, [f - fc for f in fd], rate)
+    plan = synth.StreamPlan(K=K, freqs_hz=tuple(fd), fc_hz=fc, seed=5, noise_sigma=1.5)
+    rng = np.random.default_rng(5)
+    carriers = (0, 7, 8, 100, 255)                                   # first / last channel, both sides of a group boundary
+    for i, ch in enumerate(carriers):
+        fr = synth.frame_bytes(synth.random_text(rng, 6 + 2 * i))
+        plan.bursts.append(synth.Burst(chan=ch, t0=0.008 + 0.01 * i, frame=fr, amp=9.0, phase=0.5 * i))
+    iq = synth.render_blocks(plan, 0, nblk).reshape(1, -1)
+    dm = oracle.channelize_fir(iq[0], K, taps, wf)                   # (256, nblk*1024)
+    with api.Context(K, 1, nch, nblk, taps=taps) as ctx:
+        ctx.set_wf(0, wf)
+        ctx.submit_host(iq, nblk)
+        ctx.sync()
+        got = [m.as_tuple() for m in ctx.drain()]
+        env = ctx.read_dm(nblk * 1024)
+        states = {c: ctx.get_state(0, c).vec() for c in carriers + (1, 254)}
+    assert bits_equal(env[0], dm.T.copy())
+    sink = refs.Sink()
+    want = []
+    for c in carriers + (1, 254):
+        ch = oracle.new_chan(c)
+        oracle.demod(ch, dm[c], sink)
+        assert states[c] == ch.vec(), c
+    for m in sink.msgs():
+        f = oracle.fec(m)
+        if f is not None:
+            want.append((f.chn, f.len, f.err, bytes(f.txt[:f.len]), bytes(f.crc)))
+    assert sorted(g for g in got if g[0] in carriers + (1, 254)) == sorted(want) and len(want) == len(carriers)
+    assert all(g[0] in carriers for g in got)                        # nothing decoded where nothing was sent
