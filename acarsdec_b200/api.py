@@ -72,6 +72,7 @@ ABI = [
     ("acb_round_freq", C.c_int, [C.c_double]),
     ("acb_stored_fr", C.c_int, [C.c_uint]),
     ("acb_choose_fc", C.c_uint, [C.c_void_p, C.c_int, C.c_int]),
+    ("acb_plan_bands", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     ("acb_build_wf", None, [C.c_int, C.c_uint, C.c_int, C.c_void_p]),
     ("acb_air_choose_fc", C.c_uint, [C.c_uint, C.c_uint]),
     ("acb_air_build_wf", None, [C.c_int, C.c_int, C.c_uint, C.c_void_p]),
@@ -168,6 +169,18 @@ def plan(K: int, freqs_mhz):
     fd = np.array([lib.acb_round_freq(float(f)) for f in freqs_mhz], dtype=np.uint32)
     fc = lib.acb_choose_fc(fd.ctypes.data, len(fd), K)
     return [int(f) for f in fd], [lib.acb_stored_fr(int(f)) for f in fd], int(fc)
+
+
+def plan_bands(K: int, freqs_hz, max_groups: int = 64):
+    """Fewest receiver bands covering `freqs_hz` (any span): (band index per channel, centre per band)."""
+    lib = load()
+    f = np.asarray(freqs_hz, dtype=np.uint32)
+    grp = np.zeros(len(f), dtype=np.int32)
+    fc = np.zeros(max_groups, dtype=np.uint32)
+    n = lib.acb_plan_bands(f.ctypes.data, len(f), K, grp.ctypes.data, fc.ctypes.data, max_groups)
+    if n < 0:
+        raise AcbError(f"acb_plan_bands failed ({n})")
+    return grp, fc[:n]
 
 
 def build_wf(K: int, freqs_mhz) -> np.ndarray:

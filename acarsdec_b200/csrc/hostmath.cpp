@@ -81,6 +81,49 @@ extern "C" unsigned acb_choose_fc(const unsigned *freqs_hz, int n, int K)
 	return (unsigned)fc;      /* like the reference, an exhausted scan returns its last candidate */
 }
 
+/* Band planner for channel sets one tuner cannot cover.  chooseFc (rtl.c:149-152) gives up when the span
+ * exceeds rate - 4*INTRATE; the scan script of the reference (scan.sh:1-16) then walks the band with one
+ * dongle, eight channels and five minutes at a time.  Here the whole set is cut into the FEWEST receiver bands
+ * (greedy over the sorted frequencies: extend the current band while its span still fits — optimal for
+ * interval covering), each with the centre chooseFc picks for its members.  group_of[i] is the band of
+ * freqs_hz[i] (CLI order kept inside a band), fc_out[g] its centre.  Returns the number of bands, or
+ * ACB_ERR_PLAN when more than max_groups are needed / ACB_ERR_ARG. */
+extern "C" int acb_plan_bands(const unsigned *freqs_hz, int n, int K, int *group_of, unsigned *fc_out, int max_groups)
+{
+	if (!freqs_hz || !group_of || !fc_out || n < 1 || K < 1 || max_groups < 1) return ACB_ERR_ARG;
+	std::vector<int> order(n);
+	for (int i = 0; i < n; i++) order[i] = i;
+	std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return freqs_hz[a] < freqs_hz[b]; });
+	const long long span = (long long)ACB_INTRATE * K - 4LL * ACB_INTRATE;
+	int ng = 0;
+	size_t i = 0;
+	while (i < order.size()) {
+		if (ng == max_groups) return ACB_ERR_PLAN;
+		size_t j = i;
+		std::vector<unsigned> members;
+		unsigned fc = 0;
+		/* longest run that fits AND that chooseFc can centre (the mirror rule can refuse a set that fits) */
+		for (size_t e = i; e < order.size() && (long long)freqs_hz[order[e]] - (long long)freqs_hz[order[i]] <= span; e++) {
+			members.push_back(freqs_hz[order[e]]);
+			const unsigned c = acb_choose_fc(members.data(), (int)members.size(), K);
+			/* an exhausted scan returns its last candidate (rtl.c:154-167 does): only a centre that really keeps
+			 * every member off DC, inside the band and off its neighbour's mirror image counts */
+			bool ok = c != 0;
+			const long long rate = (long long)ACB_INTRATE * K, guard = 2 * ACB_INTRATE;
+			for (size_t m = 0; ok && m < members.size(); m++) {
+				const long long d = llabs((long long)c - (long long)members[m]);
+				ok = d <= rate / 2 - guard && d >= guard && !(m > 0 && (long long)c - (long long)members[m - 1] == (long long)members[m] - (long long)c);
+			}
+			if (ok) { fc = c; j = e + 1; }
+		}
+		if (fc == 0) return ACB_ERR_PLAN;             /* not even the first channel alone: K too small for the guard bands */
+		for (size_t e = i; e < j; e++) group_of[order[e]] = ng;
+		fc_out[ng++] = fc;
+		i = j;
+	}
+	return ng;
+}
+
 extern "C" void acb_build_wf(int fr_stored, unsigned fc_hz, int K, float *wf)
 {
 	/* rtl.c:283-286.  Types matter: the offset is a float difference divided by a float rate,

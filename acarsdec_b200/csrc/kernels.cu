@@ -1167,11 +1167,13 @@ static int launch_demod_v1(ChainState *st, const float *dm, int nsamp, int nch, 
  * the machine. */
 int demod_pick_lanes(long long nchains, int sm_count)
 {
+	/* measured on B200 (profiles/r2_ab_demod.jsonl, 8 channels per stream): 592 streams: 8 or 4 lanes (2.9 ms per 16
+	 * blocks), 1 lane 4.0 ms; 2368 streams: 1 lane 4.1 ms, 4 lanes 4.5 ms, 8 lanes 7.7 ms; 4736 x 8 blocks: 1 lane 2.4 ms,
+	 * 4 lanes 4.4 ms: the fewest lanes that still put a warp on every scheduler */
 	const long long slots = 4LL * sm_count;      /* one warp per scheduler */
-	if (nchains * 8 <= 32 * slots * 2) return 8;
-	if (nchains * 4 <= 32 * slots * 2) return 4;
-	if (nchains * 2 <= 32 * slots * 2) return 2;
-	return 1;
+	for (int lanes = 1; lanes < 8; lanes *= 2)
+		if (nchains * lanes >= 32 * slots) return lanes;
+	return 8;
 }
 
 /* lanes: 1, 2, 4 or 8 lanes per channel; + 16 = bit clock rounded with the F2F conversion pair instead of

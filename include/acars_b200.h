@@ -105,6 +105,10 @@ int acb_round_freq(double mhz);
 int acb_stored_fr(unsigned freq_hz);
 /* rtl.c:131-168 chooseFc — 0 when the span does not fit */
 unsigned acb_choose_fc(const unsigned *freqs_hz, int n, int K);
+/* Channel sets wider than one tuner span (rtl.c:149-152 gives up; scan.sh:1-16 walks the band sequentially): the
+ * fewest receiver bands that cover them, each with its chooseFc centre.  group_of[i] = band of freqs_hz[i],
+ * fc_out[g] = centre of band g; returns the number of bands (<= max_groups) or a negative error. */
+int acb_plan_bands(const unsigned *freqs_hz, int n, int K, int *group_of, unsigned *fc_out, int max_groups);
 /* rtl.c:283-286 — wf[ind] = cexpf(-j*AMFreq*ind)/K/127.5 as 2K floats (re,im interleaved) */
 void acb_build_wf(int fr_stored, unsigned fc_hz, int K, float *wf);
 /* air.c:42-64 (filter == 0) — Airspy tuner centre for the span [min,max] */

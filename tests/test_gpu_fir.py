@@ -106,15 +106,16 @@ def test_fir_config5_full_width(native, oracle, taps):
         env = ctx.read_dm(nblk * 1024)
         states = {c: ctx.get_state(0, c).vec() for c in carriers + (1, 254)}
     assert bits_equal(env[0], dm.T.copy())
+    # 65 taps at 20 MS/s pass ~300 kHz: a burst is decoded on its neighbours 25 kHz away too — every channel counts
     sink = refs.Sink()
     want = []
-    for c in carriers + (1, 254):
+    for c in range(nch):
         ch = oracle.new_chan(c)
         oracle.demod(ch, dm[c], sink)
-        assert states[c] == ch.vec(), c
+        if c in states:
+            assert states[c] == ch.vec(), c
     for m in sink.msgs():
         f = oracle.fec(m)
         if f is not None:
             want.append((f.chn, f.len, f.err, bytes(f.txt[:f.len]), bytes(f.crc)))
-    assert sorted(g for g in got if g[0] in carriers + (1, 254)) == sorted(want) and len(want) == len(carriers)
-    assert all(g[0] in carriers for g in got)                        # nothing decoded where nothing was sent
+    assert sorted(got) == sorted(want) and {w[0] for w in want} >= set(carriers)

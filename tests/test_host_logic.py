@@ -228,3 +228,45 @@ def test_fast_plan_coverage_of_real_channel_sets(native):
     assert float(np.float32(fr[0])) != fd[0] and api.fast_plan(160, fd, fc) is None
     fd, fr, fc = api.plan(160, (136.8,))              # 136800000 is a multiple of 16, its Fc = 136825000 is not
     assert float(np.float32(fr[0])) == fd[0] and float(np.float32(fc)) != fc and api.fast_plan(160, fd, fc) is None
+
+
+def test_band_planner_covers_wide_sets(native, oracle):
+    """acb_plan_bands: what chooseFc refuses (span > rate - 4*INTRATE, rtl.c:149-152) is cut into the fewest bands,
+    each centred by chooseFc itself — the whole 130-137 MHz raster scan.sh walks in 280 five-minute steps fits
+    eight 2 MS/s receivers at once (on a dense 25 kHz raster chooseFc's "nobody within 25 kHz of DC" rule pushes the
+    centre outside the band, so one receiver takes 39 channels = 950 kHz, not the full 1.95 MHz)."""
+    K = 160
+    span = 12500 * K - 4 * 12500
+    scan = [130_000_000 + 25_000 * i for i in range(280)]                 # scan.sh:3-14: 130.000 .. 136.975
+    rng = np.random.default_rng(0)
+    for freqs in (scan, list(rng.permutation(scan)), [131_525_000, 131_725_000], [118_000_000, 137_000_000, 127_500_000],
+                  [129_125_000, 131_550_000, 136_900_000, 136_925_000, 131_125_000]):
+        grp, fc = api.plan_bands(K, freqs)
+        f = np.asarray(freqs)
+        for g in range(len(fc)):
+            mine = f[grp == g]
+            assert mine.max() - mine.min() <= span
+            assert int(fc[g]) == native.acb_choose_fc(np.sort(mine).astype(np.uint32).ctypes.data, len(mine), K) != 0
+            if len(mine) <= 64:                                                       # the restatement's table size
+                assert int(fc[g]) == oracle.lib.orc_choose_fc(np.sort(mine).astype(np.uint32).ctypes.data, len(mine), K)
+            d = np.abs(mine.astype(np.int64) - int(fc[g]))
+            assert np.all(d >= 2 * 12500) and np.all(d <= 12500 * K // 2 - 2 * 12500)   # nobody on DC, everybody in band
+        # fewest bands: the first member of every band could not have joined the previous one
+        srt = np.sort(f)
+        lo = [f[grp == g].min() for g in range(len(fc))]
+        hi = [f[grp == g].max() for g in range(len(fc))]
+        for g in range(1, len(fc)):
+            nxt = srt[srt > hi[g - 1]].min()
+            assert nxt == lo[g]
+            if nxt - lo[g - 1] <= span:              # it fitted by span: then chooseFc must have had no valid centre for it
+                m = np.sort(np.append(f[grp == g - 1], nxt)).astype(np.uint32)
+                c = native.acb_choose_fc(m.ctypes.data, len(m), K)
+                dd = np.abs(m.astype(np.int64) - int(c))
+                mirror = any(int(c) - int(m[i - 1]) == int(m[i]) - int(c) for i in range(1, len(m)))
+                assert c == 0 or dd.min() < 2 * 12500 or dd.max() > 12500 * K // 2 - 2 * 12500 or mirror
+    grp, fc = api.plan_bands(K, scan)
+    assert len(fc) == 8 and [int((grp == g).sum()) for g in range(8)] == [39] * 7 + [7]
+    grp1, fc1 = api.plan_bands(K, [131_525_000, 131_725_000, 131_825_000])
+    assert len(fc1) == 1 and int(fc1[0]) == api.plan(K, (131.525, 131.725, 131.825))[2]      # one band = chooseFc
+    with pytest.raises(api.AcbError):
+        api.plan_bands(K, scan, max_groups=7)
