@@ -274,10 +274,10 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 		 * beyond that the extra warps cost more than they hide (592 streams: 4.54 -> 4.72 ms) */
 		c->demod_lanes = demod_pick_lanes((long long)cfg->nstreams * cfg->nch, prop.multiProcessorCount);
 		/* comparison switch (tests force every width; tools/ab_demod.py sweeps it): 1, 2, 4, 8 lanes per channel,
-		 * +16 = F2F bit-clock rounding, -4 / -8 = the round-1 kernel (launch_demod) */
+		 * +16 = F2F bit-clock rounding, +32 = constants not pinned, -4 / -8 = the round-1 kernel (launch_demod) */
 		if (const char *e = getenv("ACB_DEMOD_LANES")) {
 			const int v = atoi(e), l = v & 15;
-			if (v == -4 || v == -8 || (v > 0 && v < 32 && (l == 1 || l == 2 || l == 4 || l == 8))) c->demod_lanes = v;
+			if (v == -4 || v == -8 || (v > 0 && v < 64 && (l == 1 || l == 2 || l == 4 || l == 8))) c->demod_lanes = v;
 		}
 	}
 	if (c->fast) {
@@ -538,6 +538,12 @@ static int run_kernels(acb_ctx *c, const uint8_t *d_iq, size_t stride, int nblk,
 	old.active = false;
 	if (c->inflight.size() == 2)
 		if (int r = harvest_begin(c, old)) return r;
+	/* whatever happens below (a failed launch returns early), the frames of the submit just harvested are
+	 * queued: harvest_finish runs from this guard unless the normal path at the end already did it */
+	struct FinishGuard {
+		acb_ctx *c; Harvest *h;
+		~FinishGuard() { if (h->active) harvest_finish(c, *h); }
+	} finish_guard{ c, &old };
 	Ticket t;
 	t.ring = (int)(c->nsubmit & 1);
 	t.group_starts = std::move(groups);

@@ -212,7 +212,7 @@ template <bool F2F> ACB_HD int bit_clock_fire(const DcConsts &DCK_, double &clkd
  * registers and only differ in which mixer evaluations they contribute.  Env supplies the warp
  * collectives (identity on the host).  FrameAcc is frame_sm.h's accessor over `r`; it reads r.pos0 +
  * r.fire_n when it needs a sample position. */
-template <int L, bool F2F, class Env, class FrameAcc, int CPW>
+template <int L, bool F2F, bool PIN, class Env, class FrameAcc, int CPW>
 ACB_HD void demod_run(DemodRegs &r, DemodShared<CPW> &sm, const float *in, int nch, int nsamp, int sub, int grp,
                       FrameAcc &acc)
 {
@@ -220,9 +220,12 @@ ACB_HD void demod_run(DemodRegs &r, DemodShared<CPW> &sm, const float *in, int n
 	/* the loop's double constants, held in registers for the whole launch (left to itself the compiler re-reads
 	 * them from the constant bank into uniform registers every iteration: 26 instructions of ~440) */
 #if defined(__CUDA_ARCH__)
-	/* read through a volatile global pointer: a value the compiler cannot re-create at its uses */
+	/* PIN: read through a volatile global pointer — a value the compiler cannot re-create at its uses; costs ~50
+	 * registers per thread, which matters when the kernel shares the SMs with the channelizer (contexts with
+	 * many chains run the unpinned form) */
 	DcConsts DCK_;
-	{
+	if (!PIN) DCK_ = DCK;
+	else {
 		const volatile double *src = reinterpret_cast<const volatile double *>(&g_dcc);
 		double *dst = reinterpret_cast<double *>(&DCK_);
 #pragma unroll
@@ -246,9 +249,19 @@ ACB_HD void demod_run(DemodRegs &r, DemodShared<CPW> &sm, const float *in, int n
 		const int k = sub + i * L;
 		xn[i] = nsamp > 0 ? in[(size_t)(k < last ? k : last) * nch] : 0.f;
 	}
-	/* channels of a warp consume 5 or 6 samples per iteration each, so they finish a few
-	 * iterations apart: finished groups idle through the general path (m <= 0) */
-	while (Env::any(n < nsamp)) {
+	/* Channels of a warp consume 5 or 6 samples per iteration each, so they finish a few iterations apart: finished
+	 * groups idle through the general path (m <= 0).  The "does anybody still have samples" vote (a warp
+	 * reconvergence point, 7 % of the kernel's cycles when taken every iteration) is only needed near the end: as long
+	 * as the lane furthest ahead has 6*q samples left, q more iterations cannot exhaust anybody. */
+	int budget = 0;                          /* iterations that need no vote */
+	bool hunting = r.state == F_WSYN;        /* acars.c:254: the bit-sliding SYN search, tested once per bit */
+	for (;;) {
+		if (budget == 0) {
+			if (!Env::any(n < nsamp)) break;
+			budget = (nsamp - Env::max(n)) / DEMOD_LOOK;
+			if (budget < 1) budget = 1;
+		}
+		budget--;
 		const int m = nsamp - n;
 		/* VCO step is constant until the next bit (msk.c:81): MskDf only changes in the bit path */
 		const double sv = DC_DADD(DCK_.s0, r.df);
@@ -382,7 +395,31 @@ ACB_HD void demod_run(DemodRegs &r, DemodShared<CPW> &sm, const float *in, int n
 			/* putbit (msk.c:53-63) */
 			r.outbits >>= 1;
 			if (bit) r.outbits |= 0x80u;
-			if (--r.nbits <= 0) frame_byte(acc, (unsigned char)r.outbits);
+			if (--r.nbits <= 0) {
+				if (hunting) {
+					/* decodeAcars' WSYN state (acars.c:254-268), the state a channel is in whenever nobody transmits: kept
+					 * out of frame_byte's state dispatch, which compiles to an indirect branch */
+					const unsigned ob = r.outbits & 0xffu;
+					if (ob == C_SYN || ob == C_NSYN) {
+						if (ob == C_NSYN) r.S ^= 2u;           /* inverted polarity */
+						r.state = F_SYN2;
+						r.nbits = 8;
+						hunting = false;
+					} else {
+						r.nbits = 1;
+					}
+				} else {
+					frame_byte(acc, (unsigned char)r.outbits);
+					hunting = r.state == F_WSYN;
+				}
+#if defined(__CUDA_ARCH__)
+				{
+					int h = hunting;                     /* an opaque copy: the compiler must not fold the test back into the dispatch */
+					asm volatile("" : "+r"(h));
+					hunting = h != 0;
+				}
+#endif
+			}
 			r.S++;
 
 			/* PLL filter (msk.c:130) — after putbit, so a frame resync's MskDf=0 is filtered too */

@@ -1069,6 +1069,7 @@ struct WarpEnv {
 	static __device__ __forceinline__ bool any(bool x) { return __any_sync(0xffffffffu, x) != 0; }
 	static __device__ __forceinline__ bool all(bool x) { return __all_sync(0xffffffffu, x) != 0; }
 	static __device__ __forceinline__ void sync() { __syncwarp(); }
+	static __device__ __forceinline__ int max(int x) { return __reduce_max_sync(0xffffffffu, x); }
 };
 
 __device__ DcF4 g_h2[MFLTOVER + 1][3];           /* matched filter, transposed: g_h2[o] = h[o + 12 j] (msk.c:104-107) */
@@ -1085,7 +1086,7 @@ int upload_matched_filter(const float *h, cudaStream_t stream)
 	return (int)cudaStreamSynchronize(stream);
 }
 
-template <int L, bool F2F>
+template <int L, bool F2F, bool PIN>
 __global__ void __launch_bounds__(32)
 k_demod2(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp, int nch, int nstreams,
          int wps, RawFrame *__restrict__ ring, RingCtl *__restrict__ ctl, unsigned cap)
@@ -1124,7 +1125,7 @@ k_demod2(ChainState *__restrict__ states, const float *__restrict__ dm, int nsam
 	__syncwarp();
 
 	DevFrameAcc acc{ r, st, ring, ctl, cap, s, ch, leader, true };
-	demod_run<L, F2F, WarpEnv>(r, sm, dm + (size_t)s * nsamp * nch + ch, nch, nsamp, sub, grp, acc);
+	demod_run<L, F2F, PIN, WarpEnv>(r, sm, dm + (size_t)s * nsamp * nch + ch, nch, nsamp, sub, grp, acc);
 
 	if (!leader) return;
 	st->phi = r.phi; st->df = r.df; st->lvlsum = r.lvlsum; st->clk = r.clk; st->bitcount = r.bitcount;
@@ -1134,7 +1135,7 @@ k_demod2(ChainState *__restrict__ states, const float *__restrict__ dm, int nsam
 	for (int k = 0; k < FLEN; k++) { st->inb_re[k] = sm.ring[k][grp].x; st->inb_im[k] = sm.ring[k][grp].y; }
 }
 
-template <int LANES, bool F2F>
+template <int LANES, bool F2F, bool PIN>
 static int launch_demod_t(ChainState *st, const float *dm, int nsamp, int nch, int nstreams,
                           RawFrame *ring, RingCtl *ctl, unsigned cap, cudaStream_t stream)
 {
@@ -1142,9 +1143,9 @@ static int launch_demod_t(ChainState *st, const float *dm, int nsamp, int nch, i
 	const int wps = (nch + CPW - 1) / CPW;
 	const long long nchain = (long long)nstreams * nch;
 	const int grid = (int)((nchain + CPW - 1) / CPW);    /* one warp per CTA so that chains spread over all SMs */
-	cudaError_t e = cudaFuncSetAttribute(k_demod2<LANES, F2F>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+	cudaError_t e = cudaFuncSetAttribute(k_demod2<LANES, F2F, PIN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 	if (e != cudaSuccess) return (int)e;
-	k_demod2<LANES, F2F><<<grid, 32, 0, stream>>>(st, dm, nsamp, nch, nstreams, wps, ring, ctl, cap);
+	k_demod2<LANES, F2F, PIN><<<grid, 32, 0, stream>>>(st, dm, nsamp, nch, nstreams, wps, ring, ctl, cap);
 	return (int)cudaGetLastError();
 }
 
@@ -1177,7 +1178,8 @@ int demod_pick_lanes(long long nchains, int sm_count)
 }
 
 /* lanes: 1, 2, 4 or 8 lanes per channel; + 16 = bit clock rounded with the F2F conversion pair instead of
- * integer ops (round_to_f32); negative (-4, -8) = the round-1 kernel, kept for A/B runs */
+ * integer ops (round_to_f32); + 32 = loop constants NOT pinned in registers (72 instead of 124 registers per
+ * thread); negative (-4, -8) = the round-1 kernel, kept for A/B runs */
 int launch_demod(ChainState *st, const float *dm, int nsamp, int nch, int nstreams,
                  RawFrame *ring, RingCtl *ctl, unsigned cap, int lanes, cudaStream_t stream)
 {
@@ -1185,14 +1187,16 @@ int launch_demod(ChainState *st, const float *dm, int nsamp, int nch, int nstrea
 	switch (lanes) {
 	case -8: return launch_demod_v1<8>(ACB_DEMOD_ARGS);
 	case -4: return launch_demod_v1<4>(ACB_DEMOD_ARGS);
-	case 8: return launch_demod_t<8, false>(ACB_DEMOD_ARGS);
-	case 2: return launch_demod_t<2, false>(ACB_DEMOD_ARGS);
-	case 1: return launch_demod_t<1, false>(ACB_DEMOD_ARGS);
-	case 24: return launch_demod_t<8, true>(ACB_DEMOD_ARGS);
-	case 20: return launch_demod_t<4, true>(ACB_DEMOD_ARGS);
-	case 18: return launch_demod_t<2, true>(ACB_DEMOD_ARGS);
-	case 17: return launch_demod_t<1, true>(ACB_DEMOD_ARGS);
-	default: return launch_demod_t<4, false>(ACB_DEMOD_ARGS);
+	case 8: return launch_demod_t<8, false, true>(ACB_DEMOD_ARGS);
+	case 2: return launch_demod_t<2, false, true>(ACB_DEMOD_ARGS);
+	case 1: return launch_demod_t<1, false, true>(ACB_DEMOD_ARGS);
+	case 24: return launch_demod_t<8, true, true>(ACB_DEMOD_ARGS);
+	case 20: return launch_demod_t<4, true, true>(ACB_DEMOD_ARGS);
+	case 40: return launch_demod_t<8, false, false>(ACB_DEMOD_ARGS);
+	case 36: return launch_demod_t<4, false, false>(ACB_DEMOD_ARGS);
+	case 34: return launch_demod_t<2, false, false>(ACB_DEMOD_ARGS);
+	case 33: return launch_demod_t<1, false, false>(ACB_DEMOD_ARGS);
+	default: return launch_demod_t<4, false, true>(ACB_DEMOD_ARGS);
 	}
 #undef ACB_DEMOD_ARGS
 }

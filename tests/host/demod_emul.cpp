@@ -29,6 +29,7 @@ struct HostEnv {
 	static bool any(bool x) { return x; }
 	static bool all(bool x) { return x; }
 	static void sync() {}
+	static int max(int x) { return x; }
 };
 
 struct HostFrameAcc {
@@ -93,8 +94,8 @@ extern "C" int demod_emul(acb_chan_state_t *st, const float *dm, int nsamp, int 
 		sm.ring[k + FLEN][0] = v;
 	}
 	HostFrameAcc acc{ r, st, frames, maxframes, 0 };
-	if (f2f) demod_run<1, true, HostEnv>(r, sm, dm, stride, nsamp, 0, 0, acc);
-	else demod_run<1, false, HostEnv>(r, sm, dm, stride, nsamp, 0, 0, acc);
+	if (f2f) demod_run<1, true, true, HostEnv>(r, sm, dm, stride, nsamp, 0, 0, acc);
+	else demod_run<1, false, true, HostEnv>(r, sm, dm, stride, nsamp, 0, 0, acc);
 	st->MskPhi = r.phi; st->MskDf = r.df; st->MskLvlSum = r.lvlsum; st->MskClk = r.clk; st->MskBitCount = r.bitcount;
 	st->MskS = r.S; st->idx = r.idx; st->nbits = r.nbits; st->Acarsstate = r.state; st->outbits = r.outbits;
 	st->blk_len = r.blk_len; st->blk_err = r.blk_err; st->pos = r.pos; st->soh_pos = r.soh_pos;
