@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -640,6 +641,9 @@ int launch_channelize_dft(const void *in, size_t stream_stride, const float *tw,
 	/* 2 warps per CTA, one tile buffer per warp; K=160: 44.5 KB of shared memory and <= 200 registers
 	 * -> 5 CTAs = 10 warps per SM (measured: 0.97 ms; 3 or 4 warps per CTA 1.09-1.43 ms; two buffers per
 	 * warp with half the warps 1.73 ms) */
+	static const int minb = getenv("ACB_DFT_MINB") ? atoi(getenv("ACB_DFT_MINB")) : 0;     /* experiment switch: register cap */
+	if (K == 160 && fold8 && minb == 8) return launch_dft_t<20, 2, 1, 8, true>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
+	if (K == 160 && fold8 && minb == 6) return launch_dft_t<20, 2, 1, 6, true>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
 	if (K == 160) return fold8 ? launch_dft_t<20, 2, 1, 5, true>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream)
 	                           : launch_dft_t<20, 2, 1, 5, false>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
 	if (K == 192) return fold8 ? launch_dft_t<24, 2, 1, 4, true>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream)
