@@ -250,8 +250,8 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 		c->buf_used[i] = false;
 		if (!(cfg->flags & ACB_FLAG_NO_INPUT_STAGING) && !c->real_input) CU(cudaMalloc(&c->d_iq[i], in_bytes));
 		if (c->real_input) {
-			/* room for the carried remainder (< K) plus one submit, rounded so streams stay 16-B aligned */
-			c->real_cap = (((size_t)cfg->max_blocks * OUTBLK + 1) * cfg->K + 3) & ~(size_t)3;
+			/* room for the carried remainder (< K) plus one submit, rounded so streams stay 32-B aligned */
+			c->real_cap = (((size_t)cfg->max_blocks * OUTBLK + 1) * cfg->K + 7) & ~(size_t)7;     /* streams 32-B aligned: whole sectors per chunk */
 			CU(cudaMalloc(&c->d_real[i], (size_t)cfg->nstreams * c->real_cap * sizeof(float)));
 			CU(cudaEventCreateWithFlags(&c->ev_real_free[i], cudaEventDisableTiming));
 			c->real_used[i] = false;

@@ -300,7 +300,10 @@ ACB_HD void demod_run(DemodRegs &r, DemodShared<CPW> &sm, const float *in, int n
 		/* the bit clock rises by sv > 0 per step, so "not before sample 5, at sample 6 at the latest" is
 		 * two compares */
 		const bool regular = inside & (ck[3] < fire_at) & (ck[5] >= fire_at);
-		if (Env::all(regular)) {
+		/* no vote: the lanes of a group carry identical registers, so the branch is uniform per group, and groups
+		 * share nothing — a group on the general path just makes the warp run both arms once (both arms pass the
+		 * same two warp barriers) */
+		if (regular) {
 			const bool five = ck[4] >= fire_at;
 			cnt = five ? 5 : 6;
 			fired = true;
@@ -312,7 +315,7 @@ ACB_HD void demod_run(DemodRegs &r, DemodShared<CPW> &sm, const float *in, int n
 				xn[i] = in[(size_t)(k < last ? k : last) * nch];
 			}
 			o = bit_clock_fire<F2F>(DCK_, clkd, sv, r.df);
-			Env::sync();             /* the previous bit's matched filter has read the rows being replaced */
+			if (L > 1) Env::sync();  /* the previous bit's matched filter has read the rows being replaced */
 #pragma unroll
 			for (int i = 0; i < ROUNDS; i++) {
 				const int k = i * L + sub;
@@ -323,13 +326,13 @@ ACB_HD void demod_run(DemodRegs &r, DemodShared<CPW> &sm, const float *in, int n
 					sm.ring[row + FLEN][grp] = mv[i];
 				}
 			}
-			Env::sync();
+			if (L > 1) Env::sync();
 			r.idx += (unsigned)cnt;
 			r.idx = r.idx >= (unsigned)FLEN ? r.idx - FLEN : r.idx;
 		} else {
 			/* general path: msk.c:74-96 as written, one sample at a time, every lane for itself (lane 0
 			 * of the group stores) */
-			Env::sync();
+			if (L > 1) Env::sync();
 			const int mm = m < DEMOD_LOOK ? m : DEMOD_LOOK;
 			double p = r.phi, c = clkd;
 			for (int k = 0; k < mm; k++) {
@@ -352,7 +355,7 @@ ACB_HD void demod_run(DemodRegs &r, DemodShared<CPW> &sm, const float *in, int n
 				const int k = n + cnt + sub + i * L;
 				xn[i] = last >= 0 ? in[(size_t)(k < last ? k : last) * nch] : 0.f;
 			}
-			Env::sync();
+			if (L > 1) Env::sync();
 		}
 		r.fire_n = n + cnt - 1;                                /* the sample that fired the bit */
 

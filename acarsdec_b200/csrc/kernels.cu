@@ -100,13 +100,20 @@ constexpr int C2_ROWS = 256;
 enum { IN_U8IQ = 0, IN_F32REAL = 1, IN_CS16IQ = 2 };   /* input sample formats (acb_internal.h: InputKind) */
 
 template <int MODE> struct C2 {
-	static constexpr int UNITS = 5;                              /* 16-byte units of a row per chunk: odd */
+	/* 16-byte units of a row per chunk.  u8 IQ: 5 (80 B; odd, so the strided per-thread LDS.128 row reads are
+	 * conflict free with rows packed back to back).  The 4-byte-per-tap inputs (float32 real, CS16) are load-path
+	 * bound rather than FP32 bound, and an 80-byte piece of a row starts on a 16-byte boundary half the time: 4
+	 * sectors fetched for 2.5 used (ncu round 1: 1.66x L2->SM over-fetch).  They take 6 units = 96 B = three whole
+	 * 32-byte sectors (rows are 32-B aligned for every K the pipeline takes at 4 bytes per tap with K % 8 == 0; other K
+	 * lose nothing against before), stored in shared memory with a row stride of 7 units to stay conflict free. */
+	static constexpr int UNITS = MODE == IN_U8IQ ? 5 : 6;
+	static constexpr int ROW_UNITS = UNITS | 1;                  /* shared-memory row stride in units: odd */
 	static constexpr int STAGES = 2;                             /* cp.async ring depth */
 	static constexpr int TAP_BYTES = MODE == IN_U8IQ ? 2 : 4;    /* input bytes per tap */
 	static constexpr int TAPS_PER_UNIT = 16 / TAP_BYTES;
 	static constexpr int W_BYTES = MODE == IN_F32REAL ? 8 : 16;  /* table bytes per (tap, channel) */
 	static constexpr int CHUNK_TAPS = UNITS * TAPS_PER_UNIT;
-	static constexpr int TILE_BYTES = C2_ROWS * UNITS * 16;
+	static constexpr int TILE_BYTES = C2_ROWS * ROW_UNITS * 16;
 	static constexpr int WF_BYTES = CHUNK_TAPS * CH_GROUP * W_BYTES;
 	static constexpr int STAGE_BYTES = TILE_BYTES + WF_BYTES;
 };
@@ -160,10 +167,10 @@ k_channelize(const uint8_t *__restrict__ in, size_t stream_stride, const uint8_t
 				 * instructions otherwise) */
 				int row = t / uc, j = t - row * uc;
 				const int drow = CH_TILE / uc, dj = CH_TILE - drow * uc;
-				unsigned char *dst = st + ((size_t)row * T::UNITS + j) * 16;
+				unsigned char *dst = st + ((size_t)row * T::ROW_UNITS + j) * 16;
 				const uint8_t *src = tsrc + (size_t)row * rowbytes + (size_t)j * 16;
-				const size_t dstep = ((size_t)drow * T::UNITS + dj) * 16, sstep = (size_t)drow * rowbytes + (size_t)dj * 16;
-				const size_t dwrap = (size_t)(T::UNITS - uc) * 16, swrap = rowbytes - (size_t)uc * 16;
+				const size_t dstep = ((size_t)drow * T::ROW_UNITS + dj) * 16, sstep = (size_t)drow * rowbytes + (size_t)dj * 16;
+				const size_t dwrap = (size_t)(T::ROW_UNITS - uc) * 16, swrap = rowbytes - (size_t)uc * 16;
 				for (int u = t; u < C2_ROWS * uc; u += CH_TILE) {
 					cp_async16(dst, src);
 					dst += dstep; src += sstep; j += dj;
@@ -193,8 +200,8 @@ k_channelize(const uint8_t *__restrict__ in, size_t stream_stride, const uint8_t
 			const int tile = step / nchunk, ck = step - tile * nchunk;
 			const unsigned char *st = smem + (size_t)(step % T::STAGES) * T::STAGE_BYTES;
 			const int uc = min(T::UNITS, U - ck * T::UNITS);
-			const uint4 *rowA = reinterpret_cast<const uint4 *>(st) + (size_t)t * T::UNITS;
-			const uint4 *rowB = reinterpret_cast<const uint4 *>(st) + (size_t)(t + CH_TILE) * T::UNITS;
+			const uint4 *rowA = reinterpret_cast<const uint4 *>(st) + (size_t)t * T::ROW_UNITS;
+			const uint4 *rowB = reinterpret_cast<const uint4 *>(st) + (size_t)(t + CH_TILE) * T::ROW_UNITS;
 			for (int j = 0; j < uc; j++) {
 				const uint4 qa = rowA[j], qb = rowB[j];
 				const unsigned wa[4] = { qa.x, qa.y, qa.z, qa.w }, wb[4] = { qb.x, qb.y, qb.z, qb.w };
@@ -266,7 +273,8 @@ k_channelize(const uint8_t *__restrict__ in, size_t stream_stride, const uint8_t
 size_t channelize_smem_bytes(int mode)
 {
 	return mode == IN_F32REAL ? (size_t)C2<IN_F32REAL>::STAGES * C2<IN_F32REAL>::STAGE_BYTES
-	                          : (size_t)C2<IN_U8IQ>::STAGES * C2<IN_U8IQ>::STAGE_BYTES;    /* cs16 == u8 layout */
+	       : mode == IN_CS16IQ ? (size_t)C2<IN_CS16IQ>::STAGES * C2<IN_CS16IQ>::STAGE_BYTES
+	                           : (size_t)C2<IN_U8IQ>::STAGES * C2<IN_U8IQ>::STAGE_BYTES;
 }
 
 template <int MODE>
@@ -1181,9 +1189,11 @@ int demod_pick_lanes(long long nchains, int sm_count)
 	return 8;
 }
 
-/* lanes: 1, 2, 4 or 8 lanes per channel; + 16 = bit clock rounded with the F2F conversion pair instead of
- * integer ops (round_to_f32); + 32 = loop constants NOT pinned in registers (72 instead of 124 registers per
- * thread); negative (-4, -8) = the round-1 kernel, kept for A/B runs */
+/* lanes: 1, 2, 4 or 8 lanes per channel, each in its measured-best form (profiles/r2_ab_demod_pinning.jsonl): loop
+ * constants pinned in registers for 2, 4, 8 lanes (592 streams, 4 lanes: 2.75 vs 3.08 ms), not pinned for 1 lane (4736
+ * streams: 2.18 vs 2.30 ms alone, and the pipelined step is no slower); + 32 = the other choice; + 16 = bit clock rounded
+ * with the F2F conversion pair instead of integer ops (round_to_f32); negative (-4, -8) = the round-1 kernel, kept for
+ * A/B runs */
 int launch_demod(ChainState *st, const float *dm, int nsamp, int nch, int nstreams,
                  RawFrame *ring, RingCtl *ctl, unsigned cap, int lanes, cudaStream_t stream)
 {
@@ -1193,13 +1203,13 @@ int launch_demod(ChainState *st, const float *dm, int nsamp, int nch, int nstrea
 	case -4: return launch_demod_v1<4>(ACB_DEMOD_ARGS);
 	case 8: return launch_demod_t<8, false, true>(ACB_DEMOD_ARGS);
 	case 2: return launch_demod_t<2, false, true>(ACB_DEMOD_ARGS);
-	case 1: return launch_demod_t<1, false, true>(ACB_DEMOD_ARGS);
+	case 1: return launch_demod_t<1, false, false>(ACB_DEMOD_ARGS);
 	case 24: return launch_demod_t<8, true, true>(ACB_DEMOD_ARGS);
 	case 20: return launch_demod_t<4, true, true>(ACB_DEMOD_ARGS);
 	case 40: return launch_demod_t<8, false, false>(ACB_DEMOD_ARGS);
 	case 36: return launch_demod_t<4, false, false>(ACB_DEMOD_ARGS);
 	case 34: return launch_demod_t<2, false, false>(ACB_DEMOD_ARGS);
-	case 33: return launch_demod_t<1, false, false>(ACB_DEMOD_ARGS);
+	case 33: return launch_demod_t<1, false, true>(ACB_DEMOD_ARGS);
 	default: return launch_demod_t<4, false, true>(ACB_DEMOD_ARGS);
 	}
 #undef ACB_DEMOD_ARGS

@@ -49,10 +49,13 @@ SWEEP = (592, 1184, 2368, 4736)          # 4, 8, 16, 32 streams per SM
 FRAME_BYTES = 304                        # RawFrame record read back per decoded frame
 
 
-def blocks_for(S: int, want: int) -> int:
-    """Blocks per step: `want` (16 = 1.31 s of signal) while a step's input stays <= 6.2 GB, so that the
-    e2e leg's pinned host buffer and the two device staging buffers stay modest at large S."""
-    return max(1, min(want, 18944 // S))
+STEP_CAP = 37888                         # stream-blocks per step: 12.4 GB of input (halved if the host cannot pin that much)
+
+
+def blocks_for(S: int, want: int, cap: int = STEP_CAP) -> int:
+    """Blocks per step: `want` (16 = 1.31 s of signal) while a step's input stays <= 12.4 GB, so that the
+    e2e leg's pinned host buffer and the two device staging buffers stay bounded at large S."""
+    return max(1, min(want, cap // S))
 
 
 def parse_args():
@@ -62,7 +65,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=0, help="IQ streams per GPU; 0 = sweep %s and take the best" % (SWEEP,))
-    ap.add_argument("--blocks", type=int, default=16, help="1024-sample output blocks per stream per step (capped so a step's input stays <= 6.2 GB)")
+    ap.add_argument("--blocks", type=int, default=16, help="1024-sample output blocks per stream per step (capped so a step's input stays <= 12.4 GB)")
     ap.add_argument("--K", type=int, default=160, help="rtlMult (160 = 2.0 MS/s)")
     ap.add_argument("--channelizer", default="exact", choices=["exact", "fast"],
                     help="exact: the reference's rounding sequence, envelope bit-identical; fast: ACB_FLAG_FAST_CHANNELIZER "
@@ -406,6 +409,17 @@ def main():
     do_check = (not args.no_check) and rank == 0
     fastflag = {"exact": 0, "fast": 8}                    # ACB_FLAG_FAST_CHANNELIZER
 
+    # how much input one step may carry: the e2e leg pins a step's worth of host memory; if this host cannot pin
+    # 12.4 GB the whole run uses half of that (all ranks agree through the min over ranks)
+    cap = STEP_CAP
+    if not args.no_e2e:
+        try:
+            probe = api.PinnedBuffer(STEP_CAP * blk_bytes)
+            probe.close()
+        except Exception:
+            cap = STEP_CAP // 2
+    cap = int(-max_over_ranks(-float(cap)))
+
     # ---- stream-count sweep (device-resident, short): where does this GPU saturate?
     sweep = None
     if args.streams > 0:
@@ -413,7 +427,7 @@ def main():
     else:
         sweep = []
         for Ssw in SWEEP:
-            Bsw = blocks_for(Ssw, args.blocks)
+            Bsw = blocks_for(Ssw, args.blocks, cap)
             st_b = Bsw * blk_bytes
             with api.Context(K, Ssw, nch, Bsw, device=local, flags=1 | fastflag[args.channelizer]) as c:
                 for s in range(Ssw):
@@ -434,7 +448,7 @@ def main():
             sweep.append({"streams_per_gpu": Ssw, "blocks_per_step": Bsw, "ms_per_step": ms,
                           "value": Ssw * Bsw * 1024 * K * world / ms / 1e3})
         S = max(sweep, key=lambda r: r["value"])["streams_per_gpu"]
-    B = blocks_for(S, args.blocks)
+    B = blocks_for(S, args.blocks, cap)
     stride = B * blk_bytes
     pool_b = [p[:stride] for p in pool]
     samples_per_step_rank = S * B * 1024 * K

@@ -210,6 +210,11 @@ int   acb_copy_to_device(acb_ctx_t *ctx, void *dst_dev, const void *src_host, si
 
 /* ---- inspection (parity tests, the compat shim, bench instrumentation) ---- */
 
+/* Tolerance of what these return (default, exact channelizer): envelope samples and messages are bit-identical to the
+ * reference's; the demodulator state is bit-identical on every fixture of the test suite, and structurally within 1 ulp of
+ * a float ring entry with probability ~2^-29 per sample (the device's VCO sincos is a 1.7-ulp table evaluation, glibc's is
+ * 0.52 ulp, and the product is rounded to float, msk.c:90) — far inside the stated bar of 1e-5 relative.  With
+ * ACB_FLAG_FAST_CHANNELIZER: messages identical, intermediates as documented in DESIGN.md §2. */
 /* Envelope samples the channelizer produced for the last submit: out[(s*nsamp+n)*nch + c]. */
 int acb_read_dm(acb_ctx_t *ctx, float *out, size_t nfloats);
 int acb_get_state(acb_ctx_t *ctx, int stream, int chn, acb_chan_state_t *out);

@@ -7,10 +7,11 @@ from acarsdec_b200 import api, synth
 
 
 def test_blocks_per_step_rule():
-    assert [bench.blocks_for(s, 16) for s in bench.SWEEP] == [16, 16, 8, 4]
+    assert [bench.blocks_for(s, 16) for s in bench.SWEEP] == [16, 16, 16, 8]
+    assert [bench.blocks_for(s, 16, bench.STEP_CAP // 2) for s in bench.SWEEP] == [16, 16, 8, 4]      # host cannot pin 12.4 GB
     assert bench.blocks_for(592, 8) == 8 and bench.blocks_for(100000, 16) == 1
     for s in bench.SWEEP:
-        assert s * bench.blocks_for(s, 16) * 2048 * 160 <= 6.3e9          # a step's input stays <= 6.2 GB
+        assert s * bench.blocks_for(s, 16) * 2048 * 160 <= 12.5e9         # a step's input stays <= 12.4 GB
 
 
 def test_check_frames_accepts_oracle_and_rejects_a_flipped_bit(oracle):

@@ -93,3 +93,23 @@ def test_messages_identical_over_many_captures(oracle, K, nseeds, fold8):
         total += len(a)
         repaired += sum(t[2] > 0 for t in a)
     assert total >= 8 * nseeds and repaired > 0
+
+
+def test_fast_intermediates_stated_bounds(oracle):
+    """What the fast form does NOT meet, with numbers: the north star's "demod float intermediates within 1e-5 rel" holds
+    for most envelope samples, not all (the difference is bounded by the total in-band signal — the reference's own table
+    rounding — not by the sample), and the demodulator state follows.  The distributions are asserted so that a change of
+    the kernel's arithmetic shows up here; the same figures for longer captures are in profiles/r2_fast_tolerance.json
+    (tools/fast_tolerance.py).  Messages stay identical (asserted inside study())."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    import fast_tolerance
+    r = fast_tolerance.study(oracle, 160, synth.DEFAULT_FREQS_MHZ, 1.5, 91)
+    e = r["envelope_rel_diff"]
+    assert e["fraction_within_1e-5"] >= 0.75 and e["fraction_within_1e-4"] >= 0.96      # measured 0.80 / 0.98
+    assert e["p50"] <= 2e-6 and e["p99"] <= 5e-4
+    assert e["fraction_within_1e-5"] < 1.0                                              # i.e. the 1e-5 clause is NOT met sample by sample
+    assert r["envelope_diff_over_total_inband_signal"]["max"] <= 1e-5                   # the bound that does hold (measured 1.6e-6)
+    assert r["MskDf_abs_diff"]["max"] <= 1e-3 and r["MskDf_abs_diff"]["p50"] <= 1e-7    # PLL range is +-3.8e-3
+    assert r["lvl_dB_abs_diff_max"] <= 0.05 and r["raw_frames_identical"] >= 8

@@ -16,6 +16,11 @@ python bench.py --steps 20 --warmup 5 | tail -1 > gpurun_out/bench_n1.json
 python bench.py --steps 20 --warmup 5 --channelizer fast --config none | tail -1 > gpurun_out/bench_n1_fast.json
 python tools/bench_k1.py fast | tail -1 > gpurun_out/bench_k1_fast.json
 python tools/bench_k1.py exact | tail -1 > gpurun_out/bench_k1_exact.json
+python tools/bench_air.py 2500000 296 8 | tail -1 > gpurun_out/bench_air_c8.json
+python tools/bench_cs16.py 0 | tail -1 > gpurun_out/bench_cs16_soapy.json
+python tools/bench_cs16.py 1 | tail -1 > gpurun_out/bench_cs16_sdrplay.json
+cat gpurun_out/bench_air_c8.json gpurun_out/bench_cs16_soapy.json gpurun_out/bench_cs16_sdrplay.json
+timeout 300 python tools/ab_demod.py 592,4736 8,4,1 fast > gpurun_out/r2_ab6.jsonl 2>/dev/null; cat gpurun_out/r2_ab6.jsonl
 python - <<'PY'
 import json
 d=json.load(open('gpurun_out/bench_n1.json')); a=d['alt_channelizer']
