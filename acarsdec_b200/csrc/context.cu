@@ -23,6 +23,7 @@
 
 #include <algorithm>
 #include <deque>
+#include <memory>
 #include <vector>
 
 #include "../../include/acars_b200.h"
@@ -96,7 +97,12 @@ struct acb_ctx {
 	unsigned long long nsubmit;
 	unsigned long long pos;      /* envelope samples submitted so far (all chains move together) */
 	std::deque<Ticket> inflight; /* oldest first; at most 2 */
-	std::deque<acb_msg_t> outq;
+	/* output queue: one batch per harvested submit, already in emission order; drained by bulk copies (at a
+	 * Tsample/s a step carries tens of thousands of messages: per-message queue operations were the host's
+	 * largest cost) */
+	struct Batch { std::unique_ptr<acb_msg_t[]> v; size_t n, rd; };
+	std::deque<Batch> outq;
+	size_t outq_count;
 	std::vector<EvTriple> ev_free;
 	cudaEvent_t mark[2];
 	bool overflowed;
@@ -188,6 +194,7 @@ static int reset_states(acb_ctx *c)
 	c->pos = 0;
 	c->carry = 0;
 	c->outq.clear();
+	c->outq_count = 0;
 	c->overflowed = false;
 	return ACB_OK;
 }
@@ -234,6 +241,7 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 	c->next_buf = 0;
 	c->last_nsamp = 0;
 	c->nsubmit = 0;
+	c->outq_count = 0;
 	c->overflowed = false;
 	memset(&c->stats, 0, sizeof(c->stats));
 	*out = c;
@@ -489,31 +497,50 @@ static int harvest_finish(acb_ctx *c, Harvest &h)
 	h.active = false;
 	CU(cudaStreamSynchronize(c->s_d2h));
 	const unsigned count = h.count;
-	struct Key { size_t group; int stream, chn; unsigned long long pos; unsigned idx; };
-	std::vector<Key> keys(count);
 	const auto &gs = h.t.group_starts;
+	/* emission order = (group, stream, channel, time).  The four fit one 64-bit key (12 + 20 + 12 + 20 bits: groups of a
+	 * submit, streams, channels, sample offset inside the submit), so the sort is on integers; contexts beyond those
+	 * widths take the comparator */
+	const unsigned long long base = gs.empty() ? 0 : gs.front();
+	const bool packed = gs.size() < 4096 && c->cfg.nstreams < (1 << 20) && c->cfg.nch < 4096 &&
+	                    (unsigned long long)c->cfg.max_blocks * OUTBLK < (1u << 20);
+	std::vector<std::pair<unsigned long long, unsigned>> keys(count);
 	for (unsigned i = 0; i < count; i++) {
 		const RawFrame &f = c->h_ring[i];
-		keys[i] = Key{ (size_t)(std::upper_bound(gs.begin(), gs.end(), f.pos) - gs.begin()), f.stream, f.chn, f.pos, i };
+		const unsigned long long g = (unsigned long long)(std::upper_bound(gs.begin(), gs.end(), f.pos) - gs.begin());
+		keys[i].second = i;
+		keys[i].first = packed ? (g << 52) | ((unsigned long long)f.stream << 32) | ((unsigned long long)f.chn << 20) | ((f.pos - base) & 0xFFFFFull) : g;
 	}
-	std::sort(keys.begin(), keys.end(), [](const Key &a, const Key &b) {
-		if (a.group != b.group) return a.group < b.group;
-		if (a.stream != b.stream) return a.stream < b.stream;
-		if (a.chn != b.chn) return a.chn < b.chn;
-		return a.pos < b.pos;
-	});
-	for (const Key &k : keys) {
-		const RawFrame &f = c->h_ring[k.idx];
-		acb_msg_t m;
-		memset(&m, 0, sizeof(m));
+	if (packed) {
+		std::sort(keys.begin(), keys.end());
+	} else {
+		const RawFrame *ring = c->h_ring;
+		std::sort(keys.begin(), keys.end(), [ring](const std::pair<unsigned long long, unsigned> &a, const std::pair<unsigned long long, unsigned> &b) {
+			if (a.first != b.first) return a.first < b.first;
+			const RawFrame &x = ring[a.second], &y = ring[b.second];
+			if (x.stream != y.stream) return x.stream < y.stream;
+			if (x.chn != y.chn) return x.chn < y.chn;
+			return x.pos < y.pos;
+		});
+	}
+	acb_ctx::Batch b;
+	b.v.reset(new acb_msg_t[count ? count : 1]());      /* zeroed in one go */
+	b.n = 0;
+	b.rd = 0;
+	for (const auto &k : keys) {
+		const RawFrame &f = c->h_ring[k.second];
+		c->stats.raw_frames++;
+		if (f.pad0 != 1) { c->stats.fec_dropped++; continue; }        /* 1 = repaired and parity-stripped on the device (k_block_fec) */
+		acb_msg_t &m = b.v[b.n++];
 		m.stream = f.stream; m.chn = f.chn; m.len = f.len; m.err = f.err;
 		m.lvl = (float)(10 * log10(f.lvlsum / f.bitcount));          /* acars.c:351 */
 		m.block = f.pos / OUTBLK; m.pos = f.pos; m.soh_pos = f.soh_pos;
 		memcpy(m.txt, f.txt, ACB_TXTMAX);
 		m.crc[0] = f.crc[0]; m.crc[1] = f.crc[1];
-		c->stats.raw_frames++;
-		if (f.pad0 == 1) c->outq.push_back(m);          /* repaired and parity-stripped on the device (k_block_fec) */
-		else c->stats.fec_dropped++;
+	}
+	if (b.n) {
+		c->outq_count += b.n;
+		c->outq.push_back(std::move(b));
 	}
 	return ACB_OK;
 }
@@ -832,7 +859,7 @@ extern "C" int acb_collect(acb_ctx_t *c)
 		c->overflowed = false;
 		return fail(ACB_ERR_OVERFLOW, "device frame ring overflowed (%u slots): %llu frames lost so far", c->ring_cap, (unsigned long long)c->stats.frames_lost);
 	}
-	return (int)c->outq.size();
+	return (int)c->outq_count;
 }
 
 extern "C" int acb_sync(acb_ctx_t *c)
@@ -847,7 +874,7 @@ extern "C" int acb_sync(acb_ctx_t *c)
 		c->overflowed = false;
 		return fail(ACB_ERR_OVERFLOW, "device frame ring overflowed (%u slots): %llu frames lost so far", c->ring_cap, (unsigned long long)c->stats.frames_lost);
 	}
-	return (int)c->outq.size();
+	return (int)c->outq_count;
 }
 
 extern "C" int acb_mark(acb_ctx_t *c, int which)
@@ -873,9 +900,14 @@ extern "C" int acb_drain(acb_ctx_t *c, acb_msg_t *out, int max)
 	if (!c || (!out && max > 0)) return fail(ACB_ERR_ARG, "null argument");
 	int n = 0;
 	while (n < max && !c->outq.empty()) {
-		out[n++] = c->outq.front();
-		c->outq.pop_front();
+		acb_ctx::Batch &b = c->outq.front();
+		const size_t take = std::min((size_t)(max - n), b.n - b.rd);
+		memcpy(out + n, b.v.get() + b.rd, take * sizeof(acb_msg_t));
+		n += (int)take;
+		b.rd += take;
+		if (b.rd == b.n) c->outq.pop_front();
 	}
+	c->outq_count -= (size_t)n;
 	return n;
 }
 
@@ -920,7 +952,7 @@ extern "C" int acb_block_fec_batch(acb_ctx_t *c, acb_msg_t *msgs, int n, int *ke
 extern "C" int acb_pending(acb_ctx_t *c)
 {
 	if (!c) return fail(ACB_ERR_ARG, "null context");
-	return (int)c->outq.size();
+	return (int)c->outq_count;
 }
 
 extern "C" int acb_read_dm(acb_ctx_t *c, float *out, size_t nfloats)

@@ -1244,6 +1244,9 @@ k_block_fec(RawFrame *__restrict__ ring, const RingCtl *__restrict__ ctl, unsign
 {
 	__shared__ unsigned short s_crc[256];
 	__shared__ unsigned short s_syn[8 * FEC_SYN_BYTES];
+	/* the grid is sized for the busiest step (one thread per frame up to 75 776 frames, then a stride loop); CTAs
+	 * with no frame leave before building the tables */
+	if (blockIdx.x * blockDim.x >= min(ctl->count, cap)) return;
 	for (int b = threadIdx.x; b < 256; b += blockDim.x) {
 		unsigned r = b;
 		for (int k = 0; k < 8; k++) r = (r & 1u) ? (r >> 1) ^ 0x8408u : r >> 1;
@@ -1335,7 +1338,7 @@ k_block_fec(RawFrame *__restrict__ ring, const RingCtl *__restrict__ ctl, unsign
 
 int launch_block_fec(RawFrame *ring, const RingCtl *ctl, unsigned cap, cudaStream_t stream)
 {
-	k_block_fec<<<64, 128, 0, stream>>>(ring, ctl, cap);
+	k_block_fec<<<592, 128, 0, stream>>>(ring, ctl, cap);
 	return (int)cudaGetLastError();
 }
 

@@ -214,8 +214,9 @@ def oracle_frames(K: int, streams, reps: int):
     return out
 
 
-def check_frames(K: int, pool, reps: int, recs, exact: bool, nstreams: int):
-    """recs: numpy records (api.MSG_DTYPE) of EVERYTHING the context decoded since reset, in emission order.
+def check_frames(K: int, pool, reps: int, recs, exact: bool, nstreams: int, per_stream=None):
+    """recs: numpy records (api.MSG_DTYPE) of everything the context decoded since reset for the first len(pool)
+    streams, in emission order; per_stream: frames decoded per stream, all streams (default: counted from recs).
     Streams s and s + len(pool) carry the same bytes: the first len(pool) streams must equal the CPU port frame
     for frame (text, BCS, err, lvl bits; order), and every replica must have decoded the same number of frames."""
     want = oracle_frames(K, pool, reps)
@@ -230,7 +231,8 @@ def check_frames(K: int, pool, reps: int, recs, exact: bool, nstreams: int):
             lb = np.array([t[-1] for t in want[i]], dtype=np.uint32).view(np.float32)
             ok = ok and la.shape == lb.shape and bool(np.all(np.abs(la - lb) <= 0.05))
         frames += len(want[i])
-    per_stream = np.bincount(recs["stream"], minlength=nstreams)
+    if per_stream is None:
+        per_stream = np.bincount(recs["stream"], minlength=nstreams)
     replicas_ok = all(len(set(per_stream[i::len(pool)].tolist())) == 1 for i in range(len(pool)))
     out = {"streams_vs_cpu_port": len(pool), "passes_checked": reps, "frames": frames, "bit_exact": bool(ok),
            "replicas_identical_counts": bool(replicas_ok), "frames_all_streams": int(per_stream.sum())}
@@ -287,6 +289,30 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- GPU arm helpers
+
+def pin_to_gpu_numa_node(gpu_index: int):
+    """Run this rank on the CPUs of the NUMA node its GPU hangs off (the e2e leg streams 55 GB/s per GPU out of
+    pinned host memory; across the socket link that costs a few percent at N=8).  Best effort: returns the node or None."""
+    try:
+        bus = subprocess.run(["nvidia-smi", f"--id={gpu_index}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bus.startswith("0000"):
+            bus = bus[4:]                     # nvidia-smi prints an 8-digit domain, sysfs a 4-digit one
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
 
 def measured_peak():
     p = ROOT / "MEASURED_PEAKS.json"
@@ -380,6 +406,7 @@ def main():
         return
 
     from acarsdec_b200 import sharding
+    numa = pin_to_gpu_numa_node(local) if world > 1 else None      # before any pinned allocation: first touch lands on the GPU's node
     dist, rank, world, local = sharding.init_process_group()      # NCCL: rendezvous, timing reductions, the wide-stream broadcast
     dev = f"cuda:{local}" if dist is not None else None
 
@@ -457,7 +484,17 @@ def main():
         """One context at (S, B): first pass through the host API from reset state, `warmup` + `steps` device-resident
         submits (timed with the library's CUDA events), an isolated-kernel pass, optionally the host-buffer leg."""
         out = {}
-        recs = []
+        kept, per_stream, nframes = [], np.zeros(S, dtype=np.int64), []
+
+        def take():
+            # what the checker needs: every record of the distinct pool streams, and a per-stream count of the rest
+            # (a step carries tens of thousands of messages at this rate: nothing else is kept)
+            r = ctx.drain_records()
+            if len(r):
+                per_stream[:] += np.bincount(r["stream"], minlength=S)
+                kept.append(r[r["stream"] < len(pool_b)].copy())
+            nframes.append(len(r))
+
         flags = fastflag[channelizer] | (0 if with_e2e else 1)
         ctx = api.Context(K, S, nch, B, device=local, flags=flags)
         for s in range(S):
@@ -476,10 +513,11 @@ def main():
             ctx.submit_device(din.ptr, B, stride)
         for _ in range(warmup):
             ctx.submit_device(din.ptr, B, stride)
-            recs.append(ctx.drain_records())
+            take()
         ctx.sync()
-        recs.append(ctx.drain_records())
+        take()
         ctx.stats(reset=True)
+        n_before = len(nframes)
         if clk is not None:
             clk.start()
             time.sleep(0.3)
@@ -488,10 +526,10 @@ def main():
         ctx.mark(0)
         for _ in range(steps):
             ctx.submit_device(din.ptr, B, stride)
-            recs.append(ctx.drain_records())
+            take()
         ctx.mark(1)
         ctx.sync()
-        recs.append(ctx.drain_records())
+        take()
         t1 = time.perf_counter()
         ev_ms = ctx.elapsed_ms()
         barrier()
@@ -500,9 +538,10 @@ def main():
         out["wall_ms"] = max_over_ranks((t1 - t0) * 1e3)
         out["t0"], out["t1"] = t0, t1
         out["st"] = st
-        out["recs"] = np.concatenate(recs) if recs else np.empty(0, dtype=api.MSG_DTYPE)
+        out["recs"] = np.concatenate(kept) if kept else np.empty(0, dtype=api.MSG_DTYPE)
+        out["per_stream"] = per_stream
         out["passes"] = 1 + warmup + steps
-        out["frames_timed"] = int(sum(len(r) for r in recs[-(steps + 1):]))
+        out["frames_timed"] = int(sum(nframes[n_before:]))
         # isolated kernels: sync between steps, so nothing overlaps
         for _ in range(3):
             ctx.submit_device(din.ptr, B, stride)
@@ -549,7 +588,7 @@ def main():
     st = main_m["st"]
     checked = {"skipped": "rank != 0 or --no-check"}
     if do_check:
-        checked = check_frames(K, pool_b, main_m["passes"], main_m["recs"], args.channelizer == "exact", S)
+        checked = check_frames(K, pool_b, main_m["passes"], main_m["recs"], args.channelizer == "exact", S, main_m["per_stream"])
         if not (checked["bit_exact"] and checked["replicas_identical_counts"]):
             raise SystemExit("bench: GPU frames of the timed region differ from the CPU reference port")
     checked["frames_per_step_device"] = main_m["frames_timed"] / args.steps
@@ -564,7 +603,7 @@ def main():
         k1b = am["st"].chan_ms / max(1, am["st"].chan_launches)
         chk2 = {"skipped": "rank != 0 or --no-check"}
         if do_check:
-            chk2 = check_frames(K, pool_b, am["passes"], am["recs"], alt == "exact", S)
+            chk2 = check_frames(K, pool_b, am["passes"], am["recs"], alt == "exact", S, am["per_stream"])
             if not chk2["bit_exact"]:
                 # reported, not fatal: the line's own numbers belong to --channelizer, checked above
                 print(f"bench: GPU frames ({alt} channelizer) differ from the CPU reference port", file=sys.stderr)
@@ -598,7 +637,8 @@ def main():
                    "K": K, "streams_per_gpu": S, "channels_per_stream": nch, "blocks_per_step": B, "channelizer": args.channelizer,
                    "channels_total": S * nch * world, "input_bytes_per_step_per_gpu": S * stride,
                    "l2": "inputs larger than L2 (no flush needed)" if S * stride > 200e6 else "input smaller than L2",
-                   "sharding": "streams by index, no data-path collective", "timing": "CUDA events on the library's streams, max over ranks"},
+                   "sharding": "streams by index, no data-path collective", "timing": "CUDA events on the library's streams, max over ranks",
+                   "numa_node_of_rank0": numa},
         "streams_sweep": sweep,
         "clocks": clocks,
         "e2e": main_m.get("e2e"),
