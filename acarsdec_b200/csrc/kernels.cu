@@ -100,14 +100,12 @@ constexpr int C2_ROWS = 256;
 enum { IN_U8IQ = 0, IN_F32REAL = 1, IN_CS16IQ = 2 };   /* input sample formats (acb_internal.h: InputKind) */
 
 template <int MODE> struct C2 {
-	/* 16-byte units of a row per chunk.  u8 IQ: 5 (80 B; odd, so the strided per-thread LDS.128 row reads are
-	 * conflict free with rows packed back to back).  The 4-byte-per-tap inputs (float32 real, CS16) are load-path
-	 * bound rather than FP32 bound, and an 80-byte piece of a row starts on a 16-byte boundary half the time: 4
-	 * sectors fetched for 2.5 used (ncu round 1: 1.66x L2->SM over-fetch).  They take 6 units = 96 B = three whole
-	 * 32-byte sectors (rows are 32-B aligned for every K the pipeline takes at 4 bytes per tap with K % 8 == 0; other K
-	 * lose nothing against before), stored in shared memory with a row stride of 7 units to stay conflict free. */
-	static constexpr int UNITS = MODE == IN_U8IQ ? 5 : 6;
-	static constexpr int ROW_UNITS = UNITS | 1;                  /* shared-memory row stride in units: odd */
+	/* 16-byte units of a row per chunk: odd, so the strided per-thread LDS.128 row reads are conflict free with rows
+	 * packed back to back.  (Whole-sector chunks of 6 units with a padded row stride were tried for the 4-byte-per-tap
+	 * inputs: no gain, 42.4 % vs 43 % of HBM peak on the real-input kernel — their limit was elsewhere, see
+	 * k_channelize_real4.) */
+	static constexpr int UNITS = 5;
+	static constexpr int ROW_UNITS = UNITS;                      /* shared-memory row stride in units */
 	static constexpr int STAGES = 2;                             /* cp.async ring depth */
 	static constexpr int TAP_BYTES = MODE == IN_U8IQ ? 2 : 4;    /* input bytes per tap */
 	static constexpr int TAPS_PER_UNIT = 16 / TAP_BYTES;
@@ -270,6 +268,123 @@ k_channelize(const uint8_t *__restrict__ in, size_t stream_stride, const uint8_t
 	}
 }
 
+/* The float32 real-input form of the same pipeline with FOUR output rows per thread (64 threads per 256-row tile).
+ * air.c:317-318 is D += wf[i]*S: half the arithmetic of a complex tap per table entry, so with two rows per thread the
+ * warp-uniform table loads (64 bytes per tap) were a fifth of the instruction stream and the shared-memory pipe, not the
+ * FP32 pipe, set the pace (round 1: 43 % of HBM peak, 58 % of this arithmetic's FP32 ceiling).  Four rows per thread
+ * halve the table traffic per MAC; same arithmetic, same order, bit-identical results. */
+constexpr int R4_THREADS = 64, R4_RPT = C2_ROWS / R4_THREADS;
+
+__global__ void __launch_bounds__(R4_THREADS)
+k_channelize_real4(const uint8_t *__restrict__ in, size_t stream_stride, const uint8_t *__restrict__ wf,
+                   float *__restrict__ dm, int K, int taps, int nch, int ngrp, size_t nsamp)
+{
+	constexpr int UNITS = 5, TAPS_PER_UNIT = 4, W_BYTES = 8, CHUNK_TAPS = UNITS * TAPS_PER_UNIT, STAGES = 2;
+	constexpr int TILE_BYTES = C2_ROWS * UNITS * 16, STAGE_BYTES = TILE_BYTES + CHUNK_TAPS * CH_GROUP * W_BYTES;
+	extern __shared__ __align__(16) unsigned char smem[];
+	const int t = threadIdx.x;
+	const int blk = blockIdx.x, s = blockIdx.y, g = blockIdx.z;
+	const size_t rowbytes = (size_t)K * 4;
+	const int U = taps / TAPS_PER_UNIT;                              /* taps is padded to whole units by the caller */
+	const int nchunk = (U + UNITS - 1) / UNITS;
+	const uint8_t *src_blk = in + (size_t)s * stream_stride + (size_t)blk * OUTBLK * rowbytes;
+	constexpr int NTILE = OUTBLK / C2_ROWS;
+	const int nstep = NTILE * nchunk;
+	const uint8_t *wsrc = wf + ((size_t)s * ngrp + g) * taps * CH_GROUP * W_BYTES;
+
+	auto issue = [&](int step) {
+		const int tile = step / nchunk, ck = step - tile * nchunk;
+		unsigned char *st = smem + (size_t)(step % STAGES) * STAGE_BYTES;
+		const int uc = min(UNITS, U - ck * UNITS);
+		const uint8_t *tsrc = src_blk + (size_t)tile * C2_ROWS * rowbytes + (size_t)ck * UNITS * 16;
+		int row = t / uc, j = t - row * uc;
+		const int drow = R4_THREADS / uc, dj = R4_THREADS - drow * uc;
+		unsigned char *dst = st + ((size_t)row * UNITS + j) * 16;
+		const uint8_t *src = tsrc + (size_t)row * rowbytes + (size_t)j * 16;
+		const size_t dstep = ((size_t)drow * UNITS + dj) * 16, sstep = (size_t)drow * rowbytes + (size_t)dj * 16;
+		const size_t dwrap = (size_t)(UNITS - uc) * 16, swrap = rowbytes - (size_t)uc * 16;
+		for (int u = t; u < C2_ROWS * uc; u += R4_THREADS) {
+			cp_async16(dst, src);
+			dst += dstep; src += sstep; j += dj;
+			if (j >= uc) { j -= uc; dst += dwrap; src += swrap; }
+		}
+		const int wunits = uc * TAPS_PER_UNIT * CH_GROUP * W_BYTES / 16;
+		const uint8_t *ws = wsrc + (size_t)ck * CHUNK_TAPS * CH_GROUP * W_BYTES;
+		for (int u = t; u < wunits; u += R4_THREADS) cp_async16(st + TILE_BYTES + (size_t)u * 16, ws + (size_t)u * 16);
+		cp_async_commit();
+	};
+
+	float2 acc[R4_RPT][CH_GROUP];
+#pragma unroll
+	for (int r = 0; r < R4_RPT; r++)
+#pragma unroll
+		for (int c = 0; c < CH_GROUP; c++) acc[r][c] = make_float2(0.f, 0.f);
+
+	if (0 < nstep) issue(0); else cp_async_commit();
+	for (int step = 0; step < nstep; step++) {
+		if (step + 1 < nstep) issue(step + 1); else cp_async_commit();
+		asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
+		__syncthreads();
+		const int tile = step / nchunk, ck = step - tile * nchunk;
+		const unsigned char *st = smem + (size_t)(step % STAGES) * STAGE_BYTES;
+		const int uc = min(UNITS, U - ck * UNITS);
+		const uint4 *rows = reinterpret_cast<const uint4 *>(st) + (size_t)t * UNITS;
+		for (int j = 0; j < uc; j++) {
+			uint4 q[R4_RPT];
+#pragma unroll
+			for (int r = 0; r < R4_RPT; r++) q[r] = rows[(size_t)r * R4_THREADS * UNITS + j];
+			const float2 *wj = reinterpret_cast<const float2 *>(st + TILE_BYTES) + (size_t)j * 4 * CH_GROUP;
+#pragma unroll
+			for (int e = 0; e < 4; e++) {
+				float sv[R4_RPT];
+#pragma unroll
+				for (int r = 0; r < R4_RPT; r++) sv[r] = __uint_as_float(e == 0 ? q[r].x : e == 1 ? q[r].y : e == 2 ? q[r].z : q[r].w);
+#pragma unroll
+				for (int c = 0; c < CH_GROUP; c++) {
+					const float2 w = wj[e * CH_GROUP + c];
+#pragma unroll
+					for (int r = 0; r < R4_RPT; r++) rmac(acc[r][c], sv[r], w);
+				}
+			}
+		}
+		if (ck == nchunk - 1) {                                  /* rows complete: |D| out, restart */
+			const int nc = min(CH_GROUP, nch - g * CH_GROUP);
+#pragma unroll
+			for (int r = 0; r < R4_RPT; r++) {
+				const size_t m = (size_t)blk * OUTBLK + (size_t)tile * C2_ROWS + t + r * R4_THREADS;
+				float *o = dm + ((size_t)s * nsamp + m) * nch + g * CH_GROUP;
+				if (nc == CH_GROUP && (nch & 3) == 0) {
+					reinterpret_cast<float4 *>(o)[0] = make_float4(envelope(acc[r][0]), envelope(acc[r][1]), envelope(acc[r][2]), envelope(acc[r][3]));
+					reinterpret_cast<float4 *>(o)[1] = make_float4(envelope(acc[r][4]), envelope(acc[r][5]), envelope(acc[r][6]), envelope(acc[r][7]));
+				} else {
+#pragma unroll
+					for (int c = 0; c < CH_GROUP; c++)
+						if (c < nc) o[c] = envelope(acc[r][c]);
+				}
+#pragma unroll
+				for (int c = 0; c < CH_GROUP; c++) acc[r][c] = make_float2(0.f, 0.f);
+			}
+		}
+		__syncthreads();
+	}
+}
+
+static int launch_channelize_real4(const void *in, size_t stream_stride, const void *wf, float *dm,
+                                   int K, int taps, int nch, int nstreams, int nblk, size_t nsamp, cudaStream_t stream)
+{
+	if (nblk == 0) return 0;
+	const int ngrp = (nch + CH_GROUP - 1) / CH_GROUP;
+	const size_t smem = 2 * (size_t)(C2_ROWS * 5 * 16 + 20 * CH_GROUP * 8);
+	cudaError_t e = cudaFuncSetAttribute(k_channelize_real4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) return (int)e;
+	e = cudaFuncSetAttribute(k_channelize_real4, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+	if (e != cudaSuccess) return (int)e;
+	dim3 grid(nblk, nstreams, ngrp);
+	k_channelize_real4<<<grid, R4_THREADS, smem, stream>>>(reinterpret_cast<const uint8_t *>(in), stream_stride,
+	                                                      reinterpret_cast<const uint8_t *>(wf), dm, K, taps, nch, ngrp, nsamp);
+	return (int)cudaGetLastError();
+}
+
 size_t channelize_smem_bytes(int mode)
 {
 	return mode == IN_F32REAL ? (size_t)C2<IN_F32REAL>::STAGES * C2<IN_F32REAL>::STAGE_BYTES
@@ -302,7 +417,11 @@ int launch_channelize(int mode, const void *in, size_t stream_stride_bytes, cons
                       int K, int taps, int nch, int nstreams, int nblk, size_t nsamp, cudaStream_t stream)
 {
 	switch (mode) {
-	case IN_F32REAL: return launch_channelize_t<IN_F32REAL>(in, stream_stride_bytes, wf, dm, K, taps, nch, nstreams, nblk, nsamp, stream);
+	case IN_F32REAL: {
+		static const bool two_rows = getenv("ACB_REAL_ROWS") && atoi(getenv("ACB_REAL_ROWS")) == 2;     /* A/B switch: the 2-rows-per-thread form */
+		return two_rows ? launch_channelize_t<IN_F32REAL>(in, stream_stride_bytes, wf, dm, K, taps, nch, nstreams, nblk, nsamp, stream)
+		                : launch_channelize_real4(in, stream_stride_bytes, wf, dm, K, taps, nch, nstreams, nblk, nsamp, stream);
+	}
 	case IN_CS16IQ: return launch_channelize_t<IN_CS16IQ>(in, stream_stride_bytes, wf, dm, K, taps, nch, nstreams, nblk, nsamp, stream);
 	default: return launch_channelize_t<IN_U8IQ>(in, stream_stride_bytes, wf, dm, K, taps, nch, nstreams, nblk, nsamp, stream);
 	}
