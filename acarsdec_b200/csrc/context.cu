@@ -13,6 +13,9 @@
  *
  * Up to two submits are in flight: input staging and the frame rings are double-buffered, so
  * the H2D copy of submit i+1 overlaps the kernels of i and the read-back of i overlaps i+1.
+ * The frames of a finished submit are sorted into emission order and queued by a CONSUMER THREAD (the role of the
+ * reference's blk_thread, acars.c:93-215, minus the FEC, which runs on the device): at a Tsample/s a step carries tens
+ * of thousands of messages, and that per-message host work must not sit between two launches.
  */
 #include <cuda_runtime.h>
 #include <math.h>
@@ -22,8 +25,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <deque>
 #include <memory>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/acars_b200.h"
@@ -91,7 +97,7 @@ struct acb_ctx {
 	                                back while the next submit's demod appends to the other */
 	RingCtl *d_ctl[2];
 	unsigned ring_cap;
-	RawFrame *h_ring;            /* pinned */
+	RawFrame *h_ring[2];         /* pinned, one per frame ring: the consumer may still read one while the next lands in the other */
 	RingCtl *h_ctl[2];           /* pinned */
 	int last_nsamp;
 	unsigned long long nsubmit;
@@ -103,6 +109,15 @@ struct acb_ctx {
 	struct Batch { std::unique_ptr<acb_msg_t[]> v; size_t n, rd; };
 	std::deque<Batch> outq;
 	size_t outq_count;
+	/* consumer thread: everything from `outq` to `jobs_done`, plus stats.raw_frames / fec_dropped, is guarded by mtx */
+	struct Job { std::vector<unsigned long long> group_starts; int ring; unsigned count; };
+	std::thread consumer;
+	std::mutex mtx;
+	std::condition_variable cv_job, cv_done;
+	std::deque<Job> jobs;
+	bool stop;
+	unsigned long long jobs_queued, jobs_done, ring_job[2];   /* ring_job[b]: sequence number of the last job reading h_ring[b] */
+	char consumer_err[256];
 	std::vector<EvTriple> ev_free;
 	cudaEvent_t mark[2];
 	bool overflowed;
@@ -123,6 +138,9 @@ struct acb_ctx {
 	int group_unit;              /* ACB_GROUP_*: how the streaming front-ends' frames are grouped for emission */
 	unsigned long long group_period;
 };
+
+static void consumer_main(acb_ctx *c);
+static void wait_consumer(acb_ctx *c, unsigned long long seq);
 
 static int ctx_use(acb_ctx *c)
 {
@@ -193,8 +211,11 @@ static int reset_states(acb_ctx *c)
 	CU(cudaStreamSynchronize(c->s_copy));
 	c->pos = 0;
 	c->carry = 0;
-	c->outq.clear();
-	c->outq_count = 0;
+	{
+		std::lock_guard<std::mutex> lk(c->mtx);
+		c->outq.clear();
+		c->outq_count = 0;
+	}
 	c->overflowed = false;
 	return ACB_OK;
 }
@@ -242,6 +263,11 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 	c->last_nsamp = 0;
 	c->nsubmit = 0;
 	c->outq_count = 0;
+	c->stop = false;
+	c->jobs_queued = c->jobs_done = 0;
+	c->ring_job[0] = c->ring_job[1] = 0;
+	c->consumer_err[0] = 0;
+	c->h_ring[0] = c->h_ring[1] = nullptr;
 	c->overflowed = false;
 	memset(&c->stats, 0, sizeof(c->stats));
 	*out = c;
@@ -316,7 +342,8 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 		CU(cudaMalloc(&c->d_ctl[i], sizeof(RingCtl)));
 		CU(cudaHostAlloc(&c->h_ctl[i], sizeof(RingCtl), cudaHostAllocDefault));
 	}
-	CU(cudaHostAlloc(&c->h_ring, cap * sizeof(RawFrame), cudaHostAllocDefault));
+	for (int i = 0; i < 2; i++) CU(cudaHostAlloc(&c->h_ring[i], cap * sizeof(RawFrame), cudaHostAllocDefault));
+	c->consumer = std::thread(consumer_main, c);
 
 	float h[FLENO];
 	acb_build_h(h);
@@ -333,6 +360,14 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 extern "C" void acb_destroy(acb_ctx_t *c)
 {
 	if (!c) return;
+	if (c->consumer.joinable()) {
+		{
+			std::lock_guard<std::mutex> lk(c->mtx);
+			c->stop = true;
+		}
+		c->cv_job.notify_all();
+		c->consumer.join();
+	}
 	if (ctx_use(c) == ACB_OK) {
 		cudaDeviceSynchronize();
 		for (int i = 0; i < 2; i++) {
@@ -350,7 +385,7 @@ extern "C" void acb_destroy(acb_ctx_t *c)
 		cudaFree(c->d_tw); cudaFree(c->d_twmeta);
 		for (int i = 0; i < 2; i++) { cudaFree(c->d_dm[i]); cudaEventDestroy(c->ev_k1_done[i]); cudaEventDestroy(c->ev_dm_free[i]); cudaEventDestroy(c->ev_ring_read[i]); }
 		for (int i = 0; i < 2; i++) { cudaFree(c->d_ring[i]); cudaFree(c->d_ctl[i]); cudaFreeHost(c->h_ctl[i]); }
-		cudaFreeHost(c->h_ring);
+		cudaFreeHost(c->h_ring[0]); cudaFreeHost(c->h_ring[1]);
 		cudaEventDestroy(c->mark[0]); cudaEventDestroy(c->mark[1]);
 		cudaStreamDestroy(c->s_copy); cudaStreamDestroy(c->s_comp); cudaStreamDestroy(c->s_dem); cudaStreamDestroy(c->s_d2h);
 	}
@@ -362,6 +397,7 @@ extern "C" int acb_reset(acb_ctx_t *c)
 	if (!c) return fail(ACB_ERR_ARG, "null context");
 	if (int r = ctx_use(c)) return r;
 	CU(cudaDeviceSynchronize());
+	wait_consumer(c, c->jobs_queued);
 	/* submits still in flight are abandoned with their frames: recycle their events, forget pending reads */
 	for (auto &t : c->inflight) c->ev_free.push_back(t.ev);
 	c->inflight.clear();
@@ -447,57 +483,19 @@ static EvTriple get_events(acb_ctx *c)
 }
 
 /* Collecting a submit has a device half and a host half:
- *   harvest_begin  waits until its demod kernel is done, reads the frame count and queues the D2H
- *                  copy of its frames (copy stream s_d2h, event ev_ring_read[ring]);
- *   harvest_finish waits for that copy and queues the frames the device block FEC (k_block_fec, the
+ *   harvest_begin  (submitting thread) waits until its demod kernel is done, reads the frame count, queues the D2H
+ *                  copy of its frames (copy stream s_d2h, event ev_ring_read[ring]) and hands the rest to the consumer;
+ *   consumer_main  (consumer thread) waits for that copy and queues the frames the device block FEC (k_block_fec, the
  *                  blk_thread role, acars.c:93-215) kept, in the reference's emission order: per input block, channel by
  *                  channel, then time (rtl.c:357-360; soundfile.c:71-77); streams are interleaved as
  *                  if the reference served them in turn.
- * A new submit is launched BETWEEN the two halves, so the host-side sort/copy of submit i-1 never
- * delays the channelizer of submit i+1. */
-struct Harvest {
-	Ticket t;
-	unsigned count;
-	bool active;
-};
-
-static int harvest_begin(acb_ctx *c, Harvest &h)
+ * So the host-side sort/copy of submit i-1 never delays the launches of submit i+1; acb_collect / acb_sync wait for the
+ * consumer to have caught up with what they collected. */
+static void consume(acb_ctx *c, const acb_ctx::Job &job)
 {
-	h.active = false;
-	if (c->inflight.empty()) return ACB_OK;
-	h.t = std::move(c->inflight.front());
-	c->inflight.pop_front();
-	h.active = true;
-	CU(cudaEventSynchronize(h.t.ev.c));           /* the RingCtl read-back was queued before ev.c */
-	float ms = 0;
-	if (h.t.ev.chan && cudaEventElapsedTime(&ms, h.t.ev.a, h.t.ev.b) == cudaSuccess) c->stats.chan_ms += ms;
-	if (cudaEventElapsedTime(&ms, h.t.ev.b2, h.t.ev.c) == cudaSuccess) c->stats.demod_ms += ms;
-	c->ev_free.push_back(h.t.ev);
-	h.count = c->h_ctl[h.t.ring]->count;
-	{
-		const unsigned shortf = c->h_ctl[h.t.ring]->short_frames;     /* dropped on the device like acars.c:124-129 */
-		c->stats.raw_frames += shortf;
-		c->stats.fec_dropped += shortf;
-	}
-	if (h.count > c->ring_cap) {                   /* reported once by the collecting call; decoding goes on */
-		c->overflowed = true;
-		c->stats.frames_lost += h.count - c->ring_cap;
-		h.count = c->ring_cap;
-	}
-	if (h.count)
-		CU(cudaMemcpyAsync(c->h_ring, c->d_ring[h.t.ring], (size_t)h.count * sizeof(RawFrame), cudaMemcpyDeviceToHost, c->s_d2h));
-	CU(cudaEventRecord(c->ev_ring_read[h.t.ring], c->s_d2h));
-	c->ring_read_pending[h.t.ring] = true;
-	return ACB_OK;
-}
-
-static int harvest_finish(acb_ctx *c, Harvest &h)
-{
-	if (!h.active) return ACB_OK;
-	h.active = false;
-	CU(cudaStreamSynchronize(c->s_d2h));
-	const unsigned count = h.count;
-	const auto &gs = h.t.group_starts;
+	const unsigned count = job.count;
+	const auto &gs = job.group_starts;
+	const RawFrame *ring = c->h_ring[job.ring];
 	/* emission order = (group, stream, channel, time).  The four fit one 64-bit key (12 + 20 + 12 + 20 bits: groups of a
 	 * submit, streams, channels, sample offset inside the submit), so the sort is on integers; contexts beyond those
 	 * widths take the comparator */
@@ -506,7 +504,7 @@ static int harvest_finish(acb_ctx *c, Harvest &h)
 	                    (unsigned long long)c->cfg.max_blocks * OUTBLK < (1u << 20);
 	std::vector<std::pair<unsigned long long, unsigned>> keys(count);
 	for (unsigned i = 0; i < count; i++) {
-		const RawFrame &f = c->h_ring[i];
+		const RawFrame &f = ring[i];
 		const unsigned long long g = (unsigned long long)(std::upper_bound(gs.begin(), gs.end(), f.pos) - gs.begin());
 		keys[i].second = i;
 		keys[i].first = packed ? (g << 52) | ((unsigned long long)f.stream << 32) | ((unsigned long long)f.chn << 20) | ((f.pos - base) & 0xFFFFFull) : g;
@@ -514,7 +512,6 @@ static int harvest_finish(acb_ctx *c, Harvest &h)
 	if (packed) {
 		std::sort(keys.begin(), keys.end());
 	} else {
-		const RawFrame *ring = c->h_ring;
 		std::sort(keys.begin(), keys.end(), [ring](const std::pair<unsigned long long, unsigned> &a, const std::pair<unsigned long long, unsigned> &b) {
 			if (a.first != b.first) return a.first < b.first;
 			const RawFrame &x = ring[a.second], &y = ring[b.second];
@@ -527,10 +524,10 @@ static int harvest_finish(acb_ctx *c, Harvest &h)
 	b.v.reset(new acb_msg_t[count ? count : 1]());      /* zeroed in one go */
 	b.n = 0;
 	b.rd = 0;
+	unsigned dropped = 0;
 	for (const auto &k : keys) {
-		const RawFrame &f = c->h_ring[k.second];
-		c->stats.raw_frames++;
-		if (f.pad0 != 1) { c->stats.fec_dropped++; continue; }        /* 1 = repaired and parity-stripped on the device (k_block_fec) */
+		const RawFrame &f = ring[k.second];
+		if (f.pad0 != 1) { dropped++; continue; }        /* 1 = repaired and parity-stripped on the device (k_block_fec) */
 		acb_msg_t &m = b.v[b.n++];
 		m.stream = f.stream; m.chn = f.chn; m.len = f.len; m.err = f.err;
 		m.lvl = (float)(10 * log10(f.lvlsum / f.bitcount));          /* acars.c:351 */
@@ -538,18 +535,89 @@ static int harvest_finish(acb_ctx *c, Harvest &h)
 		memcpy(m.txt, f.txt, ACB_TXTMAX);
 		m.crc[0] = f.crc[0]; m.crc[1] = f.crc[1];
 	}
+	std::lock_guard<std::mutex> lk(c->mtx);
+	c->stats.raw_frames += count;
+	c->stats.fec_dropped += dropped;
 	if (b.n) {
 		c->outq_count += b.n;
 		c->outq.push_back(std::move(b));
 	}
+}
+
+static void consumer_main(acb_ctx *c)
+{
+	cudaSetDevice(c->cfg.device);
+	for (;;) {
+		acb_ctx::Job job;
+		{
+			std::unique_lock<std::mutex> lk(c->mtx);
+			c->cv_job.wait(lk, [c] { return c->stop || !c->jobs.empty(); });
+			if (c->jobs.empty()) return;             /* stop requested and nothing left */
+			job = std::move(c->jobs.front());
+			c->jobs.pop_front();
+		}
+		const cudaError_t e = job.count ? cudaEventSynchronize(c->ev_ring_read[job.ring]) : cudaSuccess;
+		if (e == cudaSuccess) consume(c, job);
+		{
+			std::lock_guard<std::mutex> lk(c->mtx);
+			if (e != cudaSuccess && !c->consumer_err[0]) snprintf(c->consumer_err, sizeof(c->consumer_err), "frame read-back: %s", cudaGetErrorString(e));
+			c->jobs_done++;
+		}
+		c->cv_done.notify_all();
+	}
+}
+
+/* block until the consumer has finished job number `seq` (1-based count of jobs queued so far) */
+static void wait_consumer(acb_ctx *c, unsigned long long seq)
+{
+	std::unique_lock<std::mutex> lk(c->mtx);
+	c->cv_done.wait(lk, [c, seq] { return c->jobs_done >= seq; });
+}
+
+static int harvest_begin(acb_ctx *c)
+{
+	if (c->inflight.empty()) return ACB_OK;
+	Ticket t = std::move(c->inflight.front());
+	c->inflight.pop_front();
+	CU(cudaEventSynchronize(t.ev.c));           /* the RingCtl read-back was queued before ev.c */
+	float ms = 0;
+	if (t.ev.chan && cudaEventElapsedTime(&ms, t.ev.a, t.ev.b) == cudaSuccess) c->stats.chan_ms += ms;
+	if (cudaEventElapsedTime(&ms, t.ev.b2, t.ev.c) == cudaSuccess) c->stats.demod_ms += ms;
+	c->ev_free.push_back(t.ev);
+	unsigned count = c->h_ctl[t.ring]->count;
+	const unsigned shortf = c->h_ctl[t.ring]->short_frames;     /* dropped on the device like acars.c:124-129 */
+	/* h_ring[ring] was last filled two submits ago: the consumer must be done with it */
+	wait_consumer(c, c->ring_job[t.ring]);
+	{
+		std::lock_guard<std::mutex> lk(c->mtx);
+		c->stats.raw_frames += shortf;
+		c->stats.fec_dropped += shortf;
+		if (count > c->ring_cap) {                   /* reported once by the collecting call; decoding goes on */
+			c->overflowed = true;
+			c->stats.frames_lost += count - c->ring_cap;
+			count = c->ring_cap;
+		}
+	}
+	if (count)
+		CU(cudaMemcpyAsync(c->h_ring[t.ring], c->d_ring[t.ring], (size_t)count * sizeof(RawFrame), cudaMemcpyDeviceToHost, c->s_d2h));
+	CU(cudaEventRecord(c->ev_ring_read[t.ring], c->s_d2h));
+	c->ring_read_pending[t.ring] = true;
+	{
+		std::lock_guard<std::mutex> lk(c->mtx);
+		c->jobs.push_back(acb_ctx::Job{ std::move(t.group_starts), t.ring, count });
+		c->ring_job[t.ring] = ++c->jobs_queued;
+	}
+	c->cv_job.notify_one();
 	return ACB_OK;
 }
 
+/* oldest submit in flight -> output queue, complete on return */
 static int collect_oldest(acb_ctx *c)
 {
-	Harvest h;
-	if (int r = harvest_begin(c, h)) return r;
-	return harvest_finish(c, h);
+	if (int r = harvest_begin(c)) return r;
+	wait_consumer(c, c->jobs_queued);
+	if (c->consumer_err[0]) return fail(ACB_ERR_CUDA, "%s", c->consumer_err);
+	return ACB_OK;
 }
 
 /* queue K1+K2 (or K2 only) on the compute stream for `nblk` blocks / `nsamp` envelope samples */
@@ -561,16 +629,8 @@ static int run_kernels(acb_ctx *c, const uint8_t *d_iq, size_t stride, int nblk,
 	 * until the new kernels have been launched */
 	while (c->inflight.size() > 2)
 		if (int r = collect_oldest(c)) return r;
-	Harvest old;
-	old.active = false;
 	if (c->inflight.size() == 2)
-		if (int r = harvest_begin(c, old)) return r;
-	/* whatever happens below (a failed launch returns early), the frames of the submit just harvested are
-	 * queued: harvest_finish runs from this guard unless the normal path at the end already did it */
-	struct FinishGuard {
-		acb_ctx *c; Harvest *h;
-		~FinishGuard() { if (h->active) harvest_finish(c, *h); }
-	} finish_guard{ c, &old };
+		if (int r = harvest_begin(c)) return r;      /* its frames are the consumer's from here on, whatever happens below */
 	Ticket t;
 	t.ring = (int)(c->nsubmit & 1);
 	t.group_starts = std::move(groups);
@@ -634,7 +694,7 @@ static int run_kernels(acb_ctx *c, const uint8_t *d_iq, size_t stride, int nblk,
 	c->nsubmit++;
 	c->stats.submits++;
 	c->last_nsamp = nsamp;
-	return harvest_finish(c, old);
+	return ACB_OK;
 }
 
 static int check_blocks(acb_ctx *c, const void *p, size_t stride, int nblk)
@@ -855,10 +915,12 @@ extern "C" int acb_collect(acb_ctx_t *c)
 	if (!c) return fail(ACB_ERR_ARG, "null context");
 	if (int r = ctx_use(c)) return r;
 	if (int r = collect_oldest(c)) return r;
+	wait_consumer(c, c->jobs_queued);
 	if (c->overflowed) {
 		c->overflowed = false;
 		return fail(ACB_ERR_OVERFLOW, "device frame ring overflowed (%u slots): %llu frames lost so far", c->ring_cap, (unsigned long long)c->stats.frames_lost);
 	}
+	std::lock_guard<std::mutex> lk(c->mtx);
 	return (int)c->outq_count;
 }
 
@@ -870,10 +932,13 @@ extern "C" int acb_sync(acb_ctx_t *c)
 		if (int r = collect_oldest(c)) return r;
 	CU(cudaStreamSynchronize(c->s_comp));
 	CU(cudaStreamSynchronize(c->s_dem));
+	wait_consumer(c, c->jobs_queued);
+	if (c->consumer_err[0]) return fail(ACB_ERR_CUDA, "%s", c->consumer_err);
 	if (c->overflowed) {
 		c->overflowed = false;
 		return fail(ACB_ERR_OVERFLOW, "device frame ring overflowed (%u slots): %llu frames lost so far", c->ring_cap, (unsigned long long)c->stats.frames_lost);
 	}
+	std::lock_guard<std::mutex> lk(c->mtx);
 	return (int)c->outq_count;
 }
 
@@ -899,6 +964,7 @@ extern "C" int acb_drain(acb_ctx_t *c, acb_msg_t *out, int max)
 {
 	if (!c || (!out && max > 0)) return fail(ACB_ERR_ARG, "null argument");
 	int n = 0;
+	std::lock_guard<std::mutex> lk(c->mtx);
 	while (n < max && !c->outq.empty()) {
 		acb_ctx::Batch &b = c->outq.front();
 		const size_t take = std::min((size_t)(max - n), b.n - b.rd);
@@ -952,6 +1018,7 @@ extern "C" int acb_block_fec_batch(acb_ctx_t *c, acb_msg_t *msgs, int n, int *ke
 extern "C" int acb_pending(acb_ctx_t *c)
 {
 	if (!c) return fail(ACB_ERR_ARG, "null context");
+	std::lock_guard<std::mutex> lk(c->mtx);
 	return (int)c->outq_count;
 }
 
@@ -1023,6 +1090,7 @@ extern "C" int acb_set_state(acb_ctx_t *c, int stream, int chn, const acb_chan_s
 extern "C" int acb_get_stats(acb_ctx_t *c, acb_stats_t *out, int reset)
 {
 	if (!c || !out) return fail(ACB_ERR_ARG, "null argument");
+	std::lock_guard<std::mutex> lk(c->mtx);
 	*out = c->stats;
 	if (reset) memset(&c->stats, 0, sizeof(c->stats));
 	return ACB_OK;
