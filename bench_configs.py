@@ -35,12 +35,15 @@ class _LocalWide:
         self.ctx = api.Context(K, 1, nch, max_blocks, device=local, flags=flags, taps=taps)
         self.ctx.set_wf(0, wf_all)
         self.bufs = [api.PinnedBuffer(max_blocks * 2048 * K) for _ in range(2)]
+        self.holds = [None, None]
         self.n = 0
 
     def submit(self, iq, nblk):
-        b = self.bufs[self.n & 1]                  # two submits in flight at most: the buffer of two back is free
-        v = b.array[:iq.size]
-        v[:] = iq.reshape(-1)
+        i = self.n & 1                             # two submits in flight at most: the buffer of two back is free
+        v = self.bufs[i].array[:iq.size]
+        if self.holds[i] is not iq:                # the capture already sits in this pinned buffer (a receiver's DMA target)
+            v[:] = iq.reshape(-1)
+            self.holds[i] = iq
         self.ctx.submit_host(v.reshape(1, -1), nblk)
         self.n += 1
 
@@ -96,15 +99,19 @@ def _wide(dist, rank, world, local, dev, K, fm_mhz, taps, B, plan_kw, steps, do_
     if world == 1:
         ws = _LocalWide(local, K, len(fd), B, taps, wf, 0)
     else:
+        import torch
         from acarsdec_b200 import wide
         ws = wide.WideStream(dist, rank, world, local, K, fd, fc, B, taps=taps, wf_all=wf)
+        if rank == 0:
+            iq_host = iq
+            iq = torch.from_numpy(iq).pin_memory()       # the ingest rank's source is pinned host memory, like a receiver's DMA target
     ws.submit(iq, B)
     ws.sync()
     first = ws.gather()
     check = None
     if do_check and rank == 0:
         chans = sorted({m[2] for m in first} | ({b.chan for b in plan.bursts} if rank == 0 else set()) | {0, len(fd) - 1})
-        want = _oracle_fir_frames(K, taps, wf, iq, np.array(chans))
+        want = _oracle_fir_frames(K, taps, wf, iq if world == 1 else iq_host, np.array(chans))
         got = [_msgs_key(m) for m in first]
         check = {"frames": len(want), "bit_exact": sorted(got) == sorted(want), "channels_checked": len(chans)}
     for _ in range(2):
