@@ -755,6 +755,162 @@ static int launch_dft_t(const uint8_t *in, size_t stream_stride, const float2 *t
 	return (int)cudaGetLastError();
 }
 
+/* The folded fast form with ONE row per lane and the pair packing moved from "two rows" to "(re, im)": a lane's
+ * accumulators for channel c are A = (a, p) and B = (q, b), fed by two FFMA2 per complex MAC —
+ *     A += (yr, yr) * (Tr, Ti)        B += (yi, yi) * (Tr, Ti)          re = A.x - B.y, im = A.y + B.x
+ * — the very same four sums, term for term and in the same order, that the two-rows-per-lane kernel above keeps in
+ * a, b, p, q: the envelope is BIT-IDENTICAL to that kernel's (and to the CPU restatement orc_channelize_dft8).  The
+ * shared 4-point DFTs run on (I, Q) pairs, exact in float like before.  What changes is the footprint: a warp's tile
+ * is 32 rows (10.5 KB instead of 21 KB) and a thread holds one row's worth of state (~100 registers instead of 162),
+ * so 16-20 warps fit an SM instead of 10 — the two-row kernel is latency bound at 2.5 warps per scheduler (ncu: issue
+ * active 58 %, stall `wait` 35 %) — and the demod warps that share the SMs displace smaller pieces. */
+constexpr int DFT1_ROWS = 32;
+
+template <int UNITS, int WARPS> struct Dft1Plan {
+	static constexpr int ROWBYTES = UNITS * 16;
+	static constexpr int RPC = (UNITS % 8 == 4) ? 2 : 1;                      /* rows per bulk copy, see DftPlan */
+	static constexpr int GROUP = RPC * ROWBYTES + 16;
+	static constexpr int TILE_BYTES = DFT1_ROWS / RPC * GROUP;
+	static __device__ __forceinline__ int row_off(int r) { return (r / RPC) * GROUP + (r % RPC) * ROWBYTES; }
+	static constexpr int N2 = UNITS * 2;                                      /* K/4: twiddles are stored for the 4-way split */
+	static constexpr int TW_BYTES = N2 * CH_GROUP * 8;
+	static constexpr int BAR_OFF = WARPS * TILE_BYTES + TW_BYTES;
+	static constexpr int SMEM = BAR_OFF + WARPS * 8;
+};
+
+/* bytes `KB`, `KB+1` (I, Q of one sample) of word w as (32768 + I, 32768 + Q) */
+template <int KB> __device__ __forceinline__ float2 dft1_cvt(unsigned w)
+{
+	constexpr unsigned si = 0x7404u | (KB << 4), sq = 0x7404u | ((KB + 1) << 4);
+	return make_float2(__uint_as_float(__byte_perm(w, 0x47000000u, si)), __uint_as_float(__byte_perm(w, 0x47000000u, sq)));
+}
+
+template <int UNITS, int WARPS, int MINB>
+__global__ void __launch_bounds__(32 * WARPS, MINB)
+k_channelize_dft1(const uint8_t *__restrict__ in, size_t stream_stride, const float2 *__restrict__ tw,
+                  const unsigned *__restrict__ meta, float *__restrict__ dm, int nch, int ngrp, size_t nsamp)
+{
+	using P = Dft1Plan<UNITS, WARPS>;
+	constexpr int CU = UNITS / 4;                 /* groups of 4 samples per eighth of a row */
+	constexpr int N2 = P::N2;
+	constexpr int NTILE = OUTBLK / DFT1_ROWS;
+	extern __shared__ __align__(16) unsigned char smem[];
+	const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int blk = blockIdx.x, s = blockIdx.y, g = blockIdx.z;
+	unsigned char *mytile = smem + (size_t)w * P::TILE_BYTES;
+	const float4 *stw = reinterpret_cast<const float4 *>(smem + (size_t)WARPS * P::TILE_BYTES);   /* [ch][n2] (Tr, Ti) */
+	unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + P::BAR_OFF) + w;
+	const uint8_t *src_blk = in + (size_t)s * stream_stride + (size_t)blk * OUTBLK * P::ROWBYTES;
+	const unsigned m = meta[(size_t)s * ngrp + g];    /* (k_c / 2) mod 4 of channel slot c in bits 16 + 2c, 17 + 2c */
+
+	if (l == 0) mbar_init(bar, 1);
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	{
+		const uint4 *tsrc = reinterpret_cast<const uint4 *>(tw + ((size_t)s * ngrp + g) * N2 * CH_GROUP);
+		uint4 *tdst = reinterpret_cast<uint4 *>(smem + (size_t)WARPS * P::TILE_BYTES);
+		for (int q = threadIdx.x; q < P::TW_BYTES / 16; q += 32 * WARPS) cp_async16(tdst + q, tsrc + q);
+		cp_async_commit();
+		cp_async_wait_all();
+	}
+	__syncthreads();
+
+	const int ntile = (NTILE - w + WARPS - 1) / WARPS;    /* this warp's tiles: w, w + WARPS, ... */
+	auto issue = [&](int n) {
+		if (l == 0) {
+			mbar_expect_tx(bar, DFT1_ROWS * P::ROWBYTES);
+			const uint8_t *src = src_blk + (size_t)(w + n * WARPS) * DFT1_ROWS * P::ROWBYTES;
+#pragma unroll 4
+			for (int i = 0; i < DFT1_ROWS / P::RPC; i++)
+				bulk_g2s(mytile + (size_t)i * P::GROUP, src + (size_t)i * P::RPC * P::ROWBYTES, P::RPC * P::ROWBYTES, bar);
+		}
+	};
+	if (ntile > 0) issue(0);
+	const int nc = min(CH_GROUP, nch - g * CH_GROUP);
+
+	for (int n = 0; n < ntile; n++) {
+		const int tile = w + n * WARPS;
+		mbar_wait(bar, (unsigned)(n & 1));
+		const unsigned char *ra = mytile + P::row_off(l);
+		float2 A[CH_GROUP], B[CH_GROUP];
+#pragma unroll
+		for (int c = 0; c < CH_GROUP; c++) A[c] = B[c] = make_float2(0.f, 0.f);
+
+#pragma unroll 1
+		for (int g4 = 0; g4 < CU; g4++) {
+			uint2 e8[8];
+#pragma unroll
+			for (int e = 0; e < 8; e++) e8[e] = *reinterpret_cast<const uint2 *>(ra + e * (UNITS * 2) + g4 * 8);
+			float2 Y[4][4];                       /* [residue][sample of the group] = (re, im) */
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				float2 z[4];
+#pragma unroll
+				for (int n1 = 0; n1 < 4; n1++) {
+					const unsigned w0 = k < 2 ? e8[n1].x : e8[n1].y, w1 = k < 2 ? e8[n1 + 4].x : e8[n1 + 4].y;
+					z[n1] = (k & 1) ? __fadd2_rn(dft1_cvt<2>(w0), dft1_cvt<2>(w1)) : __fadd2_rn(dft1_cvt<0>(w0), dft1_cvt<0>(w1));
+				}
+				/* every z carries 2 x 32768 from the converter: sums of four carry 262144 (exact, < 2^24) and Y'_0 also
+				 * sheds the converter's mid-scale 8 x 127.5; differences carry nothing */
+				const float2 s02 = __fadd2_rn(z[0], z[2]), s13 = __fadd2_rn(z[1], z[3]);
+				const float2 d02 = fsub2(z[0], z[2]);
+				const float2 wj = make_float2(__fadd_rn(z[1].y, -z[3].y), __fadd_rn(z[3].x, -z[1].x));   /* -j (z1 - z3) */
+				Y[0][k] = __fadd2_rn(__fadd2_rn(s02, s13), make_float2(-263164.0f, -263164.0f));
+				Y[2][k] = fsub2(s02, s13);
+				Y[1][k] = __fadd2_rn(d02, wj);    /* (z0 - z2) - j (z1 - z3) */
+				Y[3][k] = fsub2(d02, wj);         /* (z0 - z2) + j (z1 - z3) */
+			}
+			const float4 *tj = stw + g4 * 2;
+#pragma unroll
+			for (int c = 0; c < CH_GROUP; c++) {
+				const float4 u0 = tj[c * (N2 / 2)], u1 = tj[c * (N2 / 2) + 1];
+				const float2 tt[4] = { make_float2(u0.x, u0.y), make_float2(u0.z, u0.w), make_float2(u1.x, u1.y), make_float2(u1.z, u1.w) };
+				const unsigned r8 = (m >> (16 + 2 * c)) & 3u;     /* warp-uniform: (k_c / 2) mod 4 */
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					const float2 y = r8 == 0 ? Y[0][k] : r8 == 1 ? Y[1][k] : r8 == 2 ? Y[2][k] : Y[3][k];
+					A[c] = ffma2(make_float2(y.x, y.x), tt[k], A[c]);
+					B[c] = ffma2(make_float2(y.y, y.y), tt[k], B[c]);
+				}
+			}
+		}
+		/* every lane has its row in registers: the buffer can take the warp's next tile */
+		__syncwarp();
+		if (n + 1 < ntile) issue(n + 1);
+		float e[CH_GROUP];
+#pragma unroll
+		for (int c = 0; c < CH_GROUP; c++) {
+			const float re = __fadd_rn(A[c].x, -B[c].y), im = __fadd_rn(A[c].y, B[c].x);
+			e[c] = __fsqrt_rn(__fmaf_rn(re, re, __fmul_rn(im, im)));
+		}
+		const size_t mrow = (size_t)blk * OUTBLK + (size_t)tile * DFT1_ROWS + l;
+		float *o = dm + ((size_t)s * nsamp + mrow) * nch + g * CH_GROUP;
+		if (nc == CH_GROUP && (nch & 3) == 0) {
+			reinterpret_cast<float4 *>(o)[0] = make_float4(e[0], e[1], e[2], e[3]);
+			reinterpret_cast<float4 *>(o)[1] = make_float4(e[4], e[5], e[6], e[7]);
+		} else {
+#pragma unroll
+			for (int c = 0; c < CH_GROUP; c++)
+				if (c < nc) o[c] = e[c];
+		}
+	}
+}
+
+template <int UNITS, int WARPS, int MINB>
+static int launch_dft1_t(const uint8_t *in, size_t stream_stride, const float2 *tw, const unsigned *meta, float *dm,
+                         int nch, int nstreams, int nblk, size_t nsamp, cudaStream_t stream)
+{
+	const int ngrp = (nch + CH_GROUP - 1) / CH_GROUP;
+	constexpr int smem = Dft1Plan<UNITS, WARPS>::SMEM;
+	auto kern = k_channelize_dft1<UNITS, WARPS, MINB>;
+	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	if (e != cudaSuccess) return (int)e;
+	e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+	if (e != cudaSuccess) return (int)e;
+	dim3 grid(nblk, nstreams, ngrp);
+	kern<<<grid, 32 * WARPS, smem, stream>>>(in, stream_stride, tw, meta, dm, nch, ngrp, nsamp);
+	return (int)cudaGetLastError();
+}
+
 bool channelize_dft_supports(int K) { return K == 160 || K == 192; }
 
 /* u8 IQ, K in {160, 192} (the reference's two rates), taps == K, every channel on the 12.5 kHz raster
@@ -768,7 +924,15 @@ int launch_channelize_dft(const void *in, size_t stream_stride, const float *tw,
 	/* 2 warps per CTA, one tile buffer per warp; K=160: 44.5 KB of shared memory and <= 200 registers
 	 * -> 5 CTAs = 10 warps per SM (measured: 0.97 ms; 3 or 4 warps per CTA 1.09-1.43 ms; two buffers per
 	 * warp with half the warps 1.73 ms) */
-	static const int minb = getenv("ACB_DFT_MINB") ? atoi(getenv("ACB_DFT_MINB")) : 0;     /* experiment switch: register cap */
+	const int minb = getenv("ACB_DFT_MINB") ? atoi(getenv("ACB_DFT_MINB")) : 0;     /* experiment switch: register cap */
+	const int rows1 = getenv("ACB_FAST_ROWS") ? atoi(getenv("ACB_FAST_ROWS")) : 2;  /* 1: one row per lane (k_channelize_dft1), 4 or 2 warps per CTA */
+	if (fold8 && rows1 == 1) {
+		const int w2 = getenv("ACB_FAST_WARPS") ? atoi(getenv("ACB_FAST_WARPS")) : 4;
+		if (K == 160) return w2 == 2 ? launch_dft1_t<20, 2, 8>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream)
+		                             : launch_dft1_t<20, 4, 4>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
+		if (K == 192) return w2 == 2 ? launch_dft1_t<24, 2, 8>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream)
+		                             : launch_dft1_t<24, 4, 4>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
+	}
 	if (K == 160 && fold8 && minb == 8) return launch_dft_t<20, 2, 1, 8, true>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
 	if (K == 160 && fold8 && minb == 6) return launch_dft_t<20, 2, 1, 6, true>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
 	if (K == 160) return fold8 ? launch_dft_t<20, 2, 1, 5, true>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream)

@@ -38,14 +38,20 @@ def _envelope_check(dm_fast, dm_ref, iq, K):
     return worst
 
 
-@pytest.mark.parametrize("fold8", [False, True])      # the 4-way split and the folded 8-way one (ACB_FAST_FOLD8)
-@pytest.mark.parametrize("K,freqs", [
+@pytest.mark.parametrize("fold8", [False, True, "1row4", "1row2"])      # the 4-way split, the folded 8-way one (ACB_FAST_FOLD8),
+@pytest.mark.parametrize("K,freqs", [                                   # and the folded form with one row per lane (4 / 2 warps per CTA)
     (160, synth.DEFAULT_FREQS_MHZ),
     (192, synth.DEFAULT_FREQS_MHZ),
     (160, (131.525, 131.725, 131.825)),             # partial channel group
     (192, (129.125, 130.025, 130.425, 130.45)),
 ])
 def test_fast_envelope_within_tolerance(native, oracle, monkeypatch, K, freqs, fold8):
+    if isinstance(fold8, str):                       # k_channelize_dft1: bit-identical to the two-row folded kernel
+        monkeypatch.setenv("ACB_FAST_ROWS", "1")
+        monkeypatch.setenv("ACB_FAST_WARPS", fold8[-1])
+        fold8 = True
+    else:
+        monkeypatch.setenv("ACB_FAST_ROWS", "2")
     monkeypatch.setenv("ACB_FAST_FOLD8", "1" if fold8 else "0")
     fd, _, fc = api.plan(K, freqs)
     nblk = 3
