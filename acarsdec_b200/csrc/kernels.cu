@@ -864,13 +864,14 @@ k_channelize_dft1(const uint8_t *__restrict__ in, size_t stream_stride, const fl
 			for (int c = 0; c < CH_GROUP; c++) {
 				const float4 u0 = tj[c * (N2 / 2)], u1 = tj[c * (N2 / 2) + 1];
 				const float2 tt[4] = { make_float2(u0.x, u0.y), make_float2(u0.z, u0.w), make_float2(u1.x, u1.y), make_float2(u1.z, u1.w) };
-				const unsigned r8 = (m >> (16 + 2 * c)) & 3u;     /* warp-uniform: (k_c / 2) mod 4 */
-#pragma unroll
-				for (int k = 0; k < 4; k++) {
-					const float2 y = r8 == 0 ? Y[0][k] : r8 == 1 ? Y[1][k] : r8 == 2 ? Y[2][k] : Y[3][k];
-					A[c] = ffma2(make_float2(y.x, y.x), tt[k], A[c]);
-					B[c] = ffma2(make_float2(y.y, y.y), tt[k], B[c]);
+				const unsigned r8 = (m >> (16 + 2 * c)) & 3u;     /* warp-uniform: (k_c / 2) mod 4 — a uniform branch, not selects */
+#define ACB_DFT1_MAC(R)                                                                    \
+				_Pragma("unroll") for (int k = 0; k < 4; k++) {                                        \
+					A[c] = ffma2(make_float2(Y[R][k].x, Y[R][k].x), tt[k], A[c]);                          \
+					B[c] = ffma2(make_float2(Y[R][k].y, Y[R][k].y), tt[k], B[c]);                          \
 				}
+				if (r8 == 0) { ACB_DFT1_MAC(0) } else if (r8 == 1) { ACB_DFT1_MAC(1) } else if (r8 == 2) { ACB_DFT1_MAC(2) } else { ACB_DFT1_MAC(3) }
+#undef ACB_DFT1_MAC
 			}
 		}
 		/* every lane has its row in registers: the buffer can take the warp's next tile */
