@@ -439,12 +439,16 @@ def main():
     # how much input one step may carry: the e2e leg pins a step's worth of host memory; if this host cannot pin
     # 12.4 GB the whole run uses half of that (all ranks agree through the min over ranks)
     cap = STEP_CAP
+    pinned_pool = None                                    # allocated once, kept for the e2e leg
     if not args.no_e2e:
-        try:
-            probe = api.PinnedBuffer(STEP_CAP * blk_bytes)
-            probe.close()
-        except Exception:
-            cap = STEP_CAP // 2
+        for cap in (STEP_CAP, STEP_CAP // 2, STEP_CAP // 4):
+            try:
+                pinned_pool = api.PinnedBuffer(cap * blk_bytes)
+                break
+            except Exception:
+                pinned_pool = None
+        if pinned_pool is None:
+            raise SystemExit("bench: cannot pin %d bytes of host memory for the e2e leg" % (STEP_CAP // 4 * blk_bytes))
     cap = int(-max_over_ranks(-float(cap)))
 
     # ---- stream-count sweep (device-resident, short): where does this GPU saturate?
@@ -502,8 +506,8 @@ def main():
         din = DeviceInput(ctx, pool_b, S, stride)
         pinned = host = None
         if with_e2e:
-            pinned = api.PinnedBuffer(S * stride)
-            host = pinned.array.reshape(S, stride)
+            pinned = pinned_pool
+            host = pinned.array[:S * stride].reshape(S, stride)
             for s in range(S):
                 host[s] = pool_b[s % len(pool_b)]
         # first pass from reset state (through the host path when this context has one)
@@ -574,7 +578,6 @@ def main():
                           "d2h_bytes_per_step": int((st2.raw_frames * FRAME_BYTES + 16 * st2.submits) / max(1, steps)) * world,
                           "ms_per_step": e_ms / steps, "frames_per_step": frames_e2e / steps,
                           "timing": "host wall clock between full device syncs, max over ranks"}
-            pinned.close()
         din.free()
         ctx.close()
         return out
