@@ -922,13 +922,17 @@ int launch_channelize_dft(const void *in, size_t stream_stride, const float *tw,
 	if (nblk == 0) return 0;
 	const uint8_t *i8 = reinterpret_cast<const uint8_t *>(in);
 	const float2 *t4 = reinterpret_cast<const float2 *>(tw);
-	/* 2 warps per CTA, one tile buffer per warp; K=160: 44.5 KB of shared memory and <= 200 registers
-	 * -> 5 CTAs = 10 warps per SM (measured: 0.97 ms; 3 or 4 warps per CTA 1.09-1.43 ms; two buffers per
-	 * warp with half the warps 1.73 ms) */
+	/* the two-rows-per-lane kernel: 2 warps per CTA, one tile buffer per warp; K=160: 44.5 KB of shared memory and <= 200
+	 * registers -> 5 CTAs = 10 warps per SM (measured: 0.97 ms for the 4-way split; 3 or 4 warps per CTA 1.09-1.43 ms; two
+	 * buffers per warp with half the warps 1.73 ms) */
 	const int minb = getenv("ACB_DFT_MINB") ? atoi(getenv("ACB_DFT_MINB")) : 0;     /* experiment switch: register cap */
-	const int rows1 = getenv("ACB_FAST_ROWS") ? atoi(getenv("ACB_FAST_ROWS")) : 2;  /* 1: one row per lane (k_channelize_dft1), 4 or 2 warps per CTA */
+	/* default: the folded form with one row per lane, 2 warps per CTA (profiles/r2_dft1.jsonl: 0.807 ms / 64.4 % of HBM peak at
+	 * 592 streams x 16 blocks, 68.0 % at 4736 x 8, against 0.899 ms / 57.8 % and 60.3 % for two rows per lane; in the pipeline at
+	 * 4736 streams 1273 vs 1165 Gsamples/s).  ACB_FAST_ROWS=2 selects the two-row kernel, ACB_FAST_WARPS=4 four warps per CTA:
+	 * comparison switches, all three bit-identical and tested. */
+	const int rows1 = getenv("ACB_FAST_ROWS") ? atoi(getenv("ACB_FAST_ROWS")) : 1;
 	if (fold8 && rows1 == 1) {
-		const int w2 = getenv("ACB_FAST_WARPS") ? atoi(getenv("ACB_FAST_WARPS")) : 4;
+		const int w2 = getenv("ACB_FAST_WARPS") ? atoi(getenv("ACB_FAST_WARPS")) : 2;
 		if (K == 160) return w2 == 2 ? launch_dft1_t<20, 2, 8>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream)
 		                             : launch_dft1_t<20, 4, 4>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
 		if (K == 192) return w2 == 2 ? launch_dft1_t<24, 2, 8>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream)

@@ -38,8 +38,8 @@ def _envelope_check(dm_fast, dm_ref, iq, K):
     return worst
 
 
-@pytest.mark.parametrize("fold8", [False, True, "1row4", "1row2"])      # the 4-way split, the folded 8-way one (ACB_FAST_FOLD8),
-@pytest.mark.parametrize("K,freqs", [                                   # and the folded form with one row per lane (4 / 2 warps per CTA)
+@pytest.mark.parametrize("fold8", [False, True, "1row4", "1row2"])      # two rows per lane: the 4-way split, the folded 8-way one (ACB_FAST_FOLD8);
+@pytest.mark.parametrize("K,freqs", [                                   # the folded form with one row per lane (4 / 2 warps per CTA; 2 = the default)
     (160, synth.DEFAULT_FREQS_MHZ),
     (192, synth.DEFAULT_FREQS_MHZ),
     (160, (131.525, 131.725, 131.825)),             # partial channel group
