@@ -38,7 +38,7 @@ try:
     peak = json.load(open(ROOT / "MEASURED_PEAKS.json"))["hbm_gbs"]
 except Exception:
     pass
-print(json.dumps({"channelizer": mode, "fast_rows_per_lane": __import__("os").environ.get("ACB_FAST_ROWS", "2"), "fast_warps": __import__("os").environ.get("ACB_FAST_WARPS", ""), "fast_launches": int(st.fast_chan_launches), "streams": S, "blocks": B, "K": K,
+print(json.dumps({"channelizer": mode, "fast_rows_per_lane": __import__("os").environ.get("ACB_FAST_ROWS", "1 (default)"), "fast_warps": __import__("os").environ.get("ACB_FAST_WARPS", "2 (default)"), "fast_launches": int(st.fast_chan_launches), "streams": S, "blocks": B, "K": K,
                   "k_channelize_ms": k1, "k_demod_ms": st.demod_ms / st.demod_launches, "algorithmic_bytes": alg,
                   "achieved_GBs": alg / k1 / 1e6, "peak_GBs": peak, "frac": alg / k1 / 1e6 / peak,
                   "frames_per_step": len(ctx.drain_records()) / steps}))
