@@ -516,6 +516,15 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 	             ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+/* one lane of a converged warp, chosen by the hardware: the compiler then knows the guarded block runs once per
+ * warp and keeps warp-uniform operands (addresses built from a shuffled warp index) in uniform registers */
+__device__ __forceinline__ bool elect_one()
+{
+	unsigned p;
+	asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(p));
+	return p != 0;
+}
+
 /* Shared-memory plan of one CTA: WARPS warps, each with STAGES private tile buffers of 64 rows. */
 template <int UNITS, int WARPS, int STAGES> struct DftPlan {
 	static constexpr int ROWBYTES = UNITS * 16;
@@ -785,7 +794,7 @@ template <int KB> __device__ __forceinline__ float2 dft1_cvt(unsigned w)
 	return make_float2(__uint_as_float(__byte_perm(w, 0x47000000u, si)), __uint_as_float(__byte_perm(w, 0x47000000u, sq)));
 }
 
-template <int UNITS, int WARPS, int MINB>
+template <int UNITS, int WARPS, int MINB, bool PF>
 __global__ void __launch_bounds__(32 * WARPS, MINB)
 k_channelize_dft1(const uint8_t *__restrict__ in, size_t stream_stride, const float2 *__restrict__ tw,
                   const unsigned *__restrict__ meta, float *__restrict__ dm, int nch, int ngrp, size_t nsamp)
@@ -795,20 +804,52 @@ k_channelize_dft1(const uint8_t *__restrict__ in, size_t stream_stride, const fl
 	constexpr int N2 = P::N2;
 	constexpr int NTILE = OUTBLK / DFT1_ROWS;
 	extern __shared__ __align__(16) unsigned char smem[];
-	const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int l = threadIdx.x & 31;
+	const int w = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);     /* warp-uniform for the compiler too: the bulk-copy operands stay in uniform registers */
 	const int blk = blockIdx.x, s = blockIdx.y, g = blockIdx.z;
 	unsigned char *mytile = smem + (size_t)w * P::TILE_BYTES;
 	const float4 *stw = reinterpret_cast<const float4 *>(smem + (size_t)WARPS * P::TILE_BYTES);   /* [ch][n2] (Tr, Ti) */
 	unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + P::BAR_OFF) + w;
 	const uint8_t *src_blk = in + (size_t)s * stream_stride + (size_t)blk * OUTBLK * P::ROWBYTES;
-	const unsigned m = meta[(size_t)s * ngrp + g];    /* (k_c / 2) mod 4 of channel slot c in bits 16 + 2c, 17 + 2c */
+	const unsigned m = __shfl_sync(0xffffffffu, meta[(size_t)s * ngrp + g], 0);    /* (k_c / 2) mod 4 of channel slot c in bits 16 + 2c, 17 + 2c */
 
 	if (l == 0) mbar_init(bar, 1);
 	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	/* Which Y a channel multiplies is its bin's residue (k_c / 2) mod 4 — warp-uniform, so a branch, not selects.  To
+	 * make that branch cheap the CTA works on its channel slots SORTED by residue (a stable counting sort of the eight
+	 * 2-bit fields, once per CTA): slot j holds channel perm[j], the twiddles are staged in slot order, the envelope is
+	 * stored through perm[], and the MAC section below is four straight-line columns (one per residue) that a warp walks
+	 * left to right, moving one column over where the next slot's residue is larger: one compare + branch per slot
+	 * instead of a compare-and-branch chain per channel (ncu, chain form: 137 BRA + 97 ISETP per 320 FFMA2). */
+	unsigned pw = 0;                             /* perm[j] in bits 3j .. 3j+2 */
+	int bnd0, bnd1, bnd2;                        /* first slot whose residue is > 0, > 1, > 2 */
+	{
+		int cnt[4] = { 0, 0, 0, 0 };
+#pragma unroll
+		for (int c = 0; c < CH_GROUP; c++) {
+			const unsigned r = (m >> (16 + 2 * c)) & 3u;
+#pragma unroll
+			for (int q = 0; q < 4; q++) cnt[q] += (r == (unsigned)q);
+		}
+		bnd0 = cnt[0]; bnd1 = bnd0 + cnt[1]; bnd2 = bnd1 + cnt[2];
+		int pos[4] = { 0, bnd0, bnd1, bnd2 };
+#pragma unroll
+		for (int c = 0; c < CH_GROUP; c++) {
+			const unsigned r = (m >> (16 + 2 * c)) & 3u;
+			int at = 0;
+#pragma unroll
+			for (int q = 0; q < 4; q++) { at = (r == (unsigned)q) ? pos[q] : at; pos[q] += (r == (unsigned)q); }
+			pw |= (unsigned)c << (3 * at);
+		}
+	}
 	{
 		const uint4 *tsrc = reinterpret_cast<const uint4 *>(tw + ((size_t)s * ngrp + g) * N2 * CH_GROUP);
 		uint4 *tdst = reinterpret_cast<uint4 *>(smem + (size_t)WARPS * P::TILE_BYTES);
-		for (int q = threadIdx.x; q < P::TW_BYTES / 16; q += 32 * WARPS) cp_async16(tdst + q, tsrc + q);
+		constexpr int PER = N2 * 8 / 16;         /* 16-byte pieces per channel */
+		for (int q = threadIdx.x; q < P::TW_BYTES / 16; q += 32 * WARPS) {
+			const int j = q / PER, off = q - j * PER;
+			cp_async16(tdst + q, tsrc + ((pw >> (3 * j)) & 7u) * PER + off);
+		}
 		cp_async_commit();
 		cp_async_wait_all();
 	}
@@ -816,10 +857,10 @@ k_channelize_dft1(const uint8_t *__restrict__ in, size_t stream_stride, const fl
 
 	const int ntile = (NTILE - w + WARPS - 1) / WARPS;    /* this warp's tiles: w, w + WARPS, ... */
 	auto issue = [&](int n) {
-		if (l == 0) {
+		if (elect_one()) {
 			mbar_expect_tx(bar, DFT1_ROWS * P::ROWBYTES);
 			const uint8_t *src = src_blk + (size_t)(w + n * WARPS) * DFT1_ROWS * P::ROWBYTES;
-#pragma unroll 4
+#pragma unroll
 			for (int i = 0; i < DFT1_ROWS / P::RPC; i++)
 				bulk_g2s(mytile + (size_t)i * P::GROUP, src + (size_t)i * P::RPC * P::ROWBYTES, P::RPC * P::ROWBYTES, bar);
 		}
@@ -860,19 +901,36 @@ k_channelize_dft1(const uint8_t *__restrict__ in, size_t stream_stride, const fl
 				Y[3][k] = fsub2(d02, wj);         /* (z0 - z2) + j (z1 - z3) */
 			}
 			const float4 *tj = stw + g4 * 2;
-#pragma unroll
-			for (int c = 0; c < CH_GROUP; c++) {
-				const float4 u0 = tj[c * (N2 / 2)], u1 = tj[c * (N2 / 2) + 1];
-				const float2 tt[4] = { make_float2(u0.x, u0.y), make_float2(u0.z, u0.w), make_float2(u1.x, u1.y), make_float2(u1.z, u1.w) };
-				const unsigned r8 = (m >> (16 + 2 * c)) & 3u;     /* warp-uniform: (k_c / 2) mod 4 — a uniform branch, not selects */
-#define ACB_DFT1_MAC(R)                                                                    \
+			float4 nu0 = make_float4(0.f, 0.f, 0.f, 0.f), nu1 = nu0;
+			if (PF) { nu0 = tj[0]; nu1 = tj[1]; }
+#define ACB_DFT1_MAC(J, R)                                                                 \
+			{                                                                                      \
+				const float4 u0 = PF ? nu0 : tj[(J) * (N2 / 2)], u1 = PF ? nu1 : tj[(J) * (N2 / 2) + 1];   \
+				/* PF: loaded one slot ahead, whichever column that was */                             \
+				if (PF && (J) + 1 < CH_GROUP) { nu0 = tj[((J) + 1) * (N2 / 2)]; nu1 = tj[((J) + 1) * (N2 / 2) + 1]; } \
+				const float2 tt[4] = { make_float2(u0.x, u0.y), make_float2(u0.z, u0.w),               \
+				                       make_float2(u1.x, u1.y), make_float2(u1.z, u1.w) };             \
 				_Pragma("unroll") for (int k = 0; k < 4; k++) {                                        \
-					A[c] = ffma2(make_float2(Y[R][k].x, Y[R][k].x), tt[k], A[c]);                          \
-					B[c] = ffma2(make_float2(Y[R][k].y, Y[R][k].y), tt[k], B[c]);                          \
-				}
-				if (r8 == 0) { ACB_DFT1_MAC(0) } else if (r8 == 1) { ACB_DFT1_MAC(1) } else if (r8 == 2) { ACB_DFT1_MAC(2) } else { ACB_DFT1_MAC(3) }
-#undef ACB_DFT1_MAC
+					A[J] = ffma2(make_float2(Y[R][k].x, Y[R][k].x), tt[k], A[J]);                          \
+					B[J] = ffma2(make_float2(Y[R][k].y, Y[R][k].y), tt[k], B[J]);                          \
+				}                                                                                      \
 			}
+#define ACB_DFT1_C0(J) if ((J) >= bnd0) goto c1_##J; ACB_DFT1_MAC(J, 0)
+#define ACB_DFT1_C1(J) c1_##J: if ((J) >= bnd1) goto c2_##J; ACB_DFT1_MAC(J, 1)
+#define ACB_DFT1_C2(J) c2_##J: if ((J) >= bnd2) goto c3_##J; ACB_DFT1_MAC(J, 2)
+#define ACB_DFT1_C3(J) c3_##J: ACB_DFT1_MAC(J, 3)
+#define ACB_DFT1_COL(C) C(0) C(1) C(2) C(3) C(4) C(5) C(6) C(7)
+			ACB_DFT1_COL(ACB_DFT1_C0) goto macs_done;
+			ACB_DFT1_COL(ACB_DFT1_C1) goto macs_done;
+			ACB_DFT1_COL(ACB_DFT1_C2) goto macs_done;
+			ACB_DFT1_COL(ACB_DFT1_C3)
+			macs_done:;
+#undef ACB_DFT1_COL
+#undef ACB_DFT1_C3
+#undef ACB_DFT1_C2
+#undef ACB_DFT1_C1
+#undef ACB_DFT1_C0
+#undef ACB_DFT1_MAC
 		}
 		/* every lane has its row in registers: the buffer can take the warp's next tile */
 		__syncwarp();
@@ -885,24 +943,22 @@ k_channelize_dft1(const uint8_t *__restrict__ in, size_t stream_stride, const fl
 		}
 		const size_t mrow = (size_t)blk * OUTBLK + (size_t)tile * DFT1_ROWS + l;
 		float *o = dm + ((size_t)s * nsamp + mrow) * nch + g * CH_GROUP;
-		if (nc == CH_GROUP && (nch & 3) == 0) {
-			reinterpret_cast<float4 *>(o)[0] = make_float4(e[0], e[1], e[2], e[3]);
-			reinterpret_cast<float4 *>(o)[1] = make_float4(e[4], e[5], e[6], e[7]);
-		} else {
+		/* slot j is channel perm[j]: eight 4-byte stores into the lane's own 32-byte sector */
 #pragma unroll
-			for (int c = 0; c < CH_GROUP; c++)
-				if (c < nc) o[c] = e[c];
+		for (int j = 0; j < CH_GROUP; j++) {
+			const int c = (int)((pw >> (3 * j)) & 7u);
+			if (c < nc) o[c] = e[j];
 		}
 	}
 }
 
-template <int UNITS, int WARPS, int MINB>
+template <int UNITS, int WARPS, int MINB, bool PF>
 static int launch_dft1_t(const uint8_t *in, size_t stream_stride, const float2 *tw, const unsigned *meta, float *dm,
                          int nch, int nstreams, int nblk, size_t nsamp, cudaStream_t stream)
 {
 	const int ngrp = (nch + CH_GROUP - 1) / CH_GROUP;
 	constexpr int smem = Dft1Plan<UNITS, WARPS>::SMEM;
-	auto kern = k_channelize_dft1<UNITS, WARPS, MINB>;
+	auto kern = k_channelize_dft1<UNITS, WARPS, MINB, PF>;
 	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	if (e != cudaSuccess) return (int)e;
 	e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -926,17 +982,19 @@ int launch_channelize_dft(const void *in, size_t stream_stride, const float *tw,
 	 * registers -> 5 CTAs = 10 warps per SM (measured: 0.97 ms for the 4-way split; 3 or 4 warps per CTA 1.09-1.43 ms; two
 	 * buffers per warp with half the warps 1.73 ms) */
 	const int minb = getenv("ACB_DFT_MINB") ? atoi(getenv("ACB_DFT_MINB")) : 0;     /* experiment switch: register cap */
-	/* default: the folded form with one row per lane, 2 warps per CTA (profiles/r2_dft1.jsonl: 0.807 ms / 64.4 % of HBM peak at
-	 * 592 streams x 16 blocks, 68.0 % at 4736 x 8, against 0.899 ms / 57.8 % and 60.3 % for two rows per lane; in the pipeline at
-	 * 4736 streams 1273 vs 1165 Gsamples/s).  ACB_FAST_ROWS=2 selects the two-row kernel, ACB_FAST_WARPS=4 four warps per CTA:
-	 * comparison switches, all three bit-identical and tested. */
+	/* default: the folded form with one row per lane, 2 warps per CTA (profiles/r2_dft1b.jsonl: 0.660 ms / 78.7 % of HBM peak at
+	 * 592 streams x 16 blocks, 82.9 % at 4736 x 8, against 0.896 ms / 58.0 % for two rows per lane; in the pipeline at 4736
+	 * streams 1442-1465 vs 1165 Gsamples/s).  ACB_FAST_ROWS=2 selects the two-row kernel, ACB_FAST_WARPS=4 four warps per CTA,
+	 * ACB_FAST_PF=0 twiddle loads in place instead of one slot ahead (no measurable difference): comparison switches, all
+	 * bit-identical and tested. */
 	const int rows1 = getenv("ACB_FAST_ROWS") ? atoi(getenv("ACB_FAST_ROWS")) : 1;
 	if (fold8 && rows1 == 1) {
 		const int w2 = getenv("ACB_FAST_WARPS") ? atoi(getenv("ACB_FAST_WARPS")) : 2;
-		if (K == 160) return w2 == 2 ? launch_dft1_t<20, 2, 8>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream)
-		                             : launch_dft1_t<20, 4, 4>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
-		if (K == 192) return w2 == 2 ? launch_dft1_t<24, 2, 8>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream)
-		                             : launch_dft1_t<24, 4, 4>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
+		const bool pf = getenv("ACB_FAST_PF") ? atoi(getenv("ACB_FAST_PF")) != 0 : true;   /* experiment switch: twiddles one slot ahead */
+#define ACB_DFT1_GO(U, W, M, F) launch_dft1_t<U, W, M, F>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream)
+		if (K == 160) return w2 != 2 ? ACB_DFT1_GO(20, 4, 4, true) : pf ? ACB_DFT1_GO(20, 2, 8, true) : ACB_DFT1_GO(20, 2, 8, false);
+		if (K == 192) return w2 != 2 ? ACB_DFT1_GO(24, 4, 4, true) : pf ? ACB_DFT1_GO(24, 2, 8, true) : ACB_DFT1_GO(24, 2, 8, false);
+#undef ACB_DFT1_GO
 	}
 	if (K == 160 && fold8 && minb == 8) return launch_dft_t<20, 2, 1, 8, true>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
 	if (K == 160 && fold8 && minb == 6) return launch_dft_t<20, 2, 1, 6, true>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);

@@ -38,17 +38,20 @@ def _envelope_check(dm_fast, dm_ref, iq, K):
     return worst
 
 
-@pytest.mark.parametrize("fold8", [False, True, "1row4", "1row2"])      # two rows per lane: the 4-way split, the folded 8-way one (ACB_FAST_FOLD8);
+@pytest.mark.parametrize("fold8", [False, True, "1row4", "1row2", "1row2n"])      # two rows per lane: the 4-way split, the folded 8-way one (ACB_FAST_FOLD8);
 @pytest.mark.parametrize("K,freqs", [                                   # the folded form with one row per lane (4 / 2 warps per CTA; 2 = the default)
     (160, synth.DEFAULT_FREQS_MHZ),
     (192, synth.DEFAULT_FREQS_MHZ),
     (160, (131.525, 131.725, 131.825)),             # partial channel group
     (192, (129.125, 130.025, 130.425, 130.45)),
+    # two channel groups, the second one partial, every residue of (k/2) mod 4 present and out of order
+    (160, (131.125, 131.45, 131.475, 131.525, 131.55, 131.725, 131.825, 131.85, 131.15, 131.25, 131.3, 131.6)),
 ])
 def test_fast_envelope_within_tolerance(native, oracle, monkeypatch, K, freqs, fold8):
     if isinstance(fold8, str):                       # k_channelize_dft1: bit-identical to the two-row folded kernel
         monkeypatch.setenv("ACB_FAST_ROWS", "1")
-        monkeypatch.setenv("ACB_FAST_WARPS", fold8[-1])
+        monkeypatch.setenv("ACB_FAST_WARPS", fold8[4])
+        monkeypatch.setenv("ACB_FAST_PF", "0" if fold8.endswith("n") else "1")      # twiddle loads one slot ahead or in place
         fold8 = True
     else:
         monkeypatch.setenv("ACB_FAST_ROWS", "2")
