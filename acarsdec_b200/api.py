@@ -64,7 +64,7 @@ class Stats(C.Structure):
     _fields_ = [("submits", C.c_uint64), ("kernel_launches", C.c_uint64), ("blocks", C.c_uint64),
                 ("raw_frames", C.c_uint64), ("fec_dropped", C.c_uint64), ("chan_ms", C.c_double),
                 ("demod_ms", C.c_double), ("chan_launches", C.c_uint64), ("demod_launches", C.c_uint64),
-                ("fast_chan_launches", C.c_uint64), ("frames_lost", C.c_uint64)]
+                ("fast_chan_launches", C.c_uint64), ("frames_lost", C.c_uint64), ("host_ms", C.c_double)]
 
 
 # every symbol include/acars_b200.h declares: (name, restype, argtypes)
@@ -78,6 +78,8 @@ ABI = [
     ("acb_air_build_wf", None, [C.c_int, C.c_int, C.c_uint, C.c_void_p]),
     ("acb_cs16_build_wf", None, [C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_void_p]),
     ("acb_fast_plan", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p, C.c_void_p]),
+    ("acb_fast_plan_cs16", C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p, C.c_void_p]),
+    ("acb_fast_plan_air", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p, C.c_void_p]),
     ("acb_build_h", None, [C.c_void_p]),
     ("acb_create", C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
     ("acb_destroy", None, [C.c_void_p]),

@@ -7,12 +7,13 @@
  *
  *   host u8 IQ --copy stream--> d_iq[buf] --channelizer stream--> K1 k_channelize -> d_dm[b] (HBM)
  *                                           --demod stream-------> K2 k_demod    -> frame ring[b]
+ *                                           --FEC stream---------> K3 k_block_fec on ring[b], frame count -> host
  *   K2 of submit i (latency bound: one serial recurrence per channel) runs concurrently with K1
- *   of submit i+1 (FP32-issue bound); envelope buffers are double-buffered between them.
- *   acb_collect / acb_sync: D2H of that submit's frames -> block FEC on the host -> output queue
+ *   of submits i+1, i+2; envelope buffers and frame rings come in threes (NPIPE) between them.
+ *   acb_collect / acb_sync: D2H of that submit's frames -> consumer thread -> output queue
  *
- * Up to two submits are in flight: input staging and the frame rings are double-buffered, so
- * the H2D copy of submit i+1 overlaps the kernels of i and the read-back of i overlaps i+1.
+ * Up to three submits are in flight: input staging is double-buffered, so the H2D copy of submit i+1
+ * overlaps the kernels of i, and the read-back of i overlaps the kernels of i+1 and i+2.
  * The frames of a finished submit are sorted into emission order and queued by a CONSUMER THREAD (the role of the
  * reference's blk_thread, acars.c:93-215, minus the FEC, which runs on the device): at a Tsample/s a step carries tens
  * of thousands of messages, and that per-message host work must not sit between two launches.
@@ -25,6 +26,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <memory>
@@ -60,7 +62,13 @@ static int fail(int code, const char *fmt, ...)
 extern "C" const char *acb_last_error(void) { return g_err; }
 extern "C" const char *acb_version(void) { return "acars_b200 0.1 (sm_100a)"; }
 
-struct EvTriple { cudaEvent_t a, b, b2, c; bool chan; };   /* a..b = K1 on s_comp, b2..c = K2 on s_dem */
+struct EvTriple { cudaEvent_t a, b, b2, c; bool chan; };   /* a..b = K1 on s_comp, b2 = K2 starts on s_dem, c = block FEC done on s_fec */
+
+/* Submits in flight = envelope buffers = frame rings.  Three, not two: with two, the host may queue the channelizer of
+ * submit N+2 only once the demod of submit N has finished (it reuses that submit's buffers), so every step ended with the
+ * demod running alone and began with both kernels starting together; with three the channelizer of N+2 is already queued
+ * behind that of N+1 and both kernels run back to back on their streams (profiles/r2_notes.md: pipeline depth). */
+constexpr int NPIPE = 3;
 
 /* one submit in flight: which frame ring it appends to and how its frames are grouped */
 struct Ticket {
@@ -73,7 +81,7 @@ struct acb_ctx {
 	acb_config_t cfg;
 	int ngrp;
 	size_t blk_bytes;            /* 1024*K*2 */
-	cudaStream_t s_copy, s_comp, s_dem;   /* H2D copies | channelizer (K1) | demod (K2) */
+	cudaStream_t s_copy, s_comp, s_dem, s_fec;   /* H2D copies | channelizer (K1) | demod (K2) | block FEC (K3) + its count read-back */
 	uint8_t *d_iq[2];
 	cudaEvent_t ev_copied[2], ev_consumed[2];
 	bool buf_used[2];
@@ -85,24 +93,25 @@ struct acb_ctx {
 	float *d_tw;                 /* fast form: [stream][grp][8 ch][K/4] (Tr, Ti) twiddles */
 	unsigned *d_twmeta;          /* fast form: [stream][grp] residues k_c mod 4, 2 bits per channel slot */
 	std::vector<unsigned char> fast_ok;   /* per stream: planned on the 12.5 kHz raster (0 after acb_set_wf: caller's own table) */
-	float *d_dm[2];              /* [stream][nsamp][nch], alternating per submit */
-	cudaEvent_t ev_k1_done[2], ev_dm_free[2], ev_ring_read[2];
-	bool ring_read_pending[2];
-	bool dm_used[2];
+	float *d_dm[NPIPE];          /* [stream][nsamp][nch], one per submit in flight */
+	cudaEvent_t ev_k1_done[NPIPE], ev_dm_free[NPIPE], ev_k2_done[NPIPE], ev_ring_read[NPIPE];
+	bool ring_read_pending[NPIPE];
+	bool dm_used[NPIPE];
+	bool k1_pending[NPIPE];      /* ev_k1_done[b] recorded and not yet waited for by the host */
 	int last_dm;
 	size_t dm_floats;
 	ChainState *d_state;
 	cudaStream_t s_d2h;
-	RawFrame *d_ring[2];         /* frame rings, alternating per submit so that one can be read
-	                                back while the next submit's demod appends to the other */
-	RingCtl *d_ctl[2];
+	RawFrame *d_ring[NPIPE];     /* frame rings, one per submit in flight so that one can be read
+	                                back while the next submits' demods append to the others */
+	RingCtl *d_ctl[NPIPE];
 	unsigned ring_cap;
-	RawFrame *h_ring[2];         /* pinned, one per frame ring: the consumer may still read one while the next lands in the other */
-	RingCtl *h_ctl[2];           /* pinned */
+	RawFrame *h_ring[NPIPE];     /* pinned, one per frame ring: the consumer may still read one while the next lands in another */
+	RingCtl *h_ctl[NPIPE];       /* pinned */
 	int last_nsamp;
 	unsigned long long nsubmit;
 	unsigned long long pos;      /* envelope samples submitted so far (all chains move together) */
-	std::deque<Ticket> inflight; /* oldest first; at most 2 */
+	std::deque<Ticket> inflight; /* oldest first; at most NPIPE */
 	/* output queue: one batch per harvested submit, already in emission order; drained by bulk copies (at a
 	 * Tsample/s a step carries tens of thousands of messages: per-message queue operations were the host's
 	 * largest cost) */
@@ -116,10 +125,10 @@ struct acb_ctx {
 	std::condition_variable cv_job, cv_done;
 	std::deque<Job> jobs;
 	bool stop;
-	unsigned long long jobs_queued, jobs_done, ring_job[2];   /* ring_job[b]: sequence number of the last job reading h_ring[b] */
+	unsigned long long jobs_queued, jobs_done, ring_job[NPIPE];   /* ring_job[b]: sequence number of the last job reading h_ring[b] */
 	char consumer_err[256];
 	std::vector<EvTriple> ev_free;
-	cudaEvent_t mark[2];
+	cudaEvent_t mark[2], ev_join;
 	bool overflowed;
 	acb_stats_t stats;
 	bool use_generic;
@@ -192,6 +201,7 @@ static int sync_streams(acb_ctx *c)
 {
 	CU(cudaStreamSynchronize(c->s_comp));
 	CU(cudaStreamSynchronize(c->s_dem));
+	CU(cudaStreamSynchronize(c->s_fec));
 	return ACB_OK;
 }
 
@@ -207,7 +217,7 @@ static int reset_states(acb_ctx *c)
 	/* everything stream-ordered on s_copy and complete on return: the context's streams are non-blocking,
 	 * so nothing on the legacy stream (plain cudaMemset/cudaMemcpy) is ordered against them */
 	if (int r = upload(c, c->d_state, init.data(), n * sizeof(ChainState))) return r;
-	for (int i = 0; i < 2; i++) CU(cudaMemsetAsync(c->d_ctl[i], 0, sizeof(RingCtl), c->s_copy));
+	for (int i = 0; i < NPIPE; i++) CU(cudaMemsetAsync(c->d_ctl[i], 0, sizeof(RingCtl), c->s_copy));
 	CU(cudaStreamSynchronize(c->s_copy));
 	c->pos = 0;
 	c->carry = 0;
@@ -275,6 +285,8 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 	CU(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
 	CU(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
 	CU(cudaStreamCreateWithFlags(&c->s_dem, cudaStreamNonBlocking));
+	CU(cudaStreamCreateWithFlags(&c->s_fec, cudaStreamNonBlocking));
+	CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
 	CU(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
 	CU(cudaEventCreate(&c->mark[0]));
 	CU(cudaEventCreate(&c->mark[1]));
@@ -286,7 +298,8 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 		if (c->real_input) {
 			/* room for the carried remainder (< K) plus one submit, rounded so streams stay 32-B aligned */
 			c->real_cap = (((size_t)cfg->max_blocks * OUTBLK + 1) * cfg->K + 7) & ~(size_t)7;     /* streams 32-B aligned: whole sectors per chunk */
-			CU(cudaMalloc(&c->d_real[i], (size_t)cfg->nstreams * c->real_cap * sizeof(float)));
+			/* + 32 rows: the fast CS16 kernel fetches whole 32-row tiles, the last one may reach past the last row */
+			CU(cudaMalloc(&c->d_real[i], ((size_t)cfg->nstreams * c->real_cap + 32 * (size_t)cfg->K) * sizeof(float)));
 			CU(cudaEventCreateWithFlags(&c->ev_real_free[i], cudaEventDisableTiming));
 			c->real_used[i] = false;
 		}
@@ -298,7 +311,8 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 	CU(cudaMalloc(&c->d_wf4, wf_floats * sizeof(float)));
 	CU(cudaMemsetAsync(c->d_wf4, 0, wf_floats * sizeof(float), c->s_copy));
 	CU(cudaStreamSynchronize(c->s_copy));
-	c->fast = (cfg->flags & ACB_FLAG_FAST_CHANNELIZER) && c->in_kind == IN_KIND_U8IQ && c->taps == cfg->K && channelize_dft_supports(cfg->K);
+	c->fast = (cfg->flags & ACB_FLAG_FAST_CHANNELIZER) && c->taps == cfg->K &&
+	          (c->in_kind == IN_KIND_F32REAL ? channelize_rdft_supports(cfg->K) : channelize_dft_supports(cfg->K));
 	c->fast_ok.assign(cfg->nstreams, 0);
 	c->fold8 = true;             /* 0.89 ms vs 0.95 ms for the plain 4-way split at 592 streams x 16 blocks */
 	if (const char *e = getenv("ACB_FAST_FOLD8")) c->fold8 = atoi(e) != 0;          /* comparison switch; both are tested */
@@ -319,13 +333,15 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 		CU(cudaMalloc(&c->d_twmeta, (size_t)cfg->nstreams * c->ngrp * sizeof(unsigned)));
 	}
 	c->dm_floats = (size_t)cfg->nstreams * cfg->max_blocks * OUTBLK * cfg->nch;
-	for (int i = 0; i < 2; i++) {
+	for (int i = 0; i < NPIPE; i++) {
 		CU(cudaMalloc(&c->d_dm[i], c->dm_floats * sizeof(float)));
 		CU(cudaEventCreateWithFlags(&c->ev_k1_done[i], cudaEventDisableTiming));
 		CU(cudaEventCreateWithFlags(&c->ev_dm_free[i], cudaEventDisableTiming));
+		CU(cudaEventCreateWithFlags(&c->ev_k2_done[i], cudaEventDisableTiming));
 		CU(cudaEventCreateWithFlags(&c->ev_ring_read[i], cudaEventDisableTiming));
 		c->ring_read_pending[i] = false;
 		c->dm_used[i] = false;
+		c->k1_pending[i] = false;
 	}
 	c->last_dm = 0;
 	const size_t nchain = (size_t)cfg->nstreams * cfg->nch;
@@ -337,12 +353,12 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 	size_t cap = nchain * (2 * (size_t)cfg->max_blocks + 4);
 	if (cap > (1u << 22)) cap = 1u << 22;
 	c->ring_cap = (unsigned)cap;
-	for (int i = 0; i < 2; i++) {
+	for (int i = 0; i < NPIPE; i++) {
 		CU(cudaMalloc(&c->d_ring[i], cap * sizeof(RawFrame)));
 		CU(cudaMalloc(&c->d_ctl[i], sizeof(RingCtl)));
 		CU(cudaHostAlloc(&c->h_ctl[i], sizeof(RingCtl), cudaHostAllocDefault));
 	}
-	for (int i = 0; i < 2; i++) CU(cudaHostAlloc(&c->h_ring[i], cap * sizeof(RawFrame), cudaHostAllocDefault));
+	for (int i = 0; i < NPIPE; i++) CU(cudaHostAlloc(&c->h_ring[i], cap * sizeof(RawFrame), cudaHostAllocDefault));
 	c->consumer = std::thread(consumer_main, c);
 
 	float h[FLENO];
@@ -383,11 +399,13 @@ extern "C" void acb_destroy(acb_ctx_t *c)
 		cudaFree(c->d_planar);
 		cudaFree(c->d_wf4); cudaFree(c->d_state);
 		cudaFree(c->d_tw); cudaFree(c->d_twmeta);
-		for (int i = 0; i < 2; i++) { cudaFree(c->d_dm[i]); cudaEventDestroy(c->ev_k1_done[i]); cudaEventDestroy(c->ev_dm_free[i]); cudaEventDestroy(c->ev_ring_read[i]); }
-		for (int i = 0; i < 2; i++) { cudaFree(c->d_ring[i]); cudaFree(c->d_ctl[i]); cudaFreeHost(c->h_ctl[i]); }
-		cudaFreeHost(c->h_ring[0]); cudaFreeHost(c->h_ring[1]);
-		cudaEventDestroy(c->mark[0]); cudaEventDestroy(c->mark[1]);
-		cudaStreamDestroy(c->s_copy); cudaStreamDestroy(c->s_comp); cudaStreamDestroy(c->s_dem); cudaStreamDestroy(c->s_d2h);
+		for (int i = 0; i < NPIPE; i++) {
+			cudaFree(c->d_dm[i]); cudaEventDestroy(c->ev_k1_done[i]); cudaEventDestroy(c->ev_dm_free[i]);
+			cudaEventDestroy(c->ev_k2_done[i]); cudaEventDestroy(c->ev_ring_read[i]);
+			cudaFree(c->d_ring[i]); cudaFree(c->d_ctl[i]); cudaFreeHost(c->h_ctl[i]); cudaFreeHost(c->h_ring[i]);
+		}
+		cudaEventDestroy(c->mark[0]); cudaEventDestroy(c->mark[1]); cudaEventDestroy(c->ev_join);
+		cudaStreamDestroy(c->s_copy); cudaStreamDestroy(c->s_comp); cudaStreamDestroy(c->s_dem); cudaStreamDestroy(c->s_fec); cudaStreamDestroy(c->s_d2h);
 	}
 	delete c;
 }
@@ -401,7 +419,8 @@ extern "C" int acb_reset(acb_ctx_t *c)
 	/* submits still in flight are abandoned with their frames: recycle their events, forget pending reads */
 	for (auto &t : c->inflight) c->ev_free.push_back(t.ev);
 	c->inflight.clear();
-	for (int i = 0; i < 2; i++) c->ring_read_pending[i] = false;
+	for (int i = 0; i < NPIPE; i++) c->ring_read_pending[i] = false;
+	for (int i = 0; i < NPIPE; i++) c->k1_pending[i] = false;
 	return reset_states(c);
 }
 
@@ -425,6 +444,26 @@ extern "C" int acb_set_wf(acb_ctx_t *c, int stream, const float *wf, int nch)
 	if (int r = sync_streams(c)) return r;
 	if (int r = upload(c, c->d_wf4 + (size_t)stream * t.size(), t.data(), t.size() * sizeof(float))) return r;
 	c->fast_ok[stream] = 0;                     /* a caller's table has no known structure: exact kernel */
+	return ACB_OK;
+}
+
+/* fast form: group the per-channel twiddles and bin residues the way k_channelize_dft* reads them and upload them;
+ * `ok` false (a channel off the raster) leaves the stream on the exact kernel */
+static int upload_fast_plan(acb_ctx *c, int stream, bool ok, const std::vector<int> &kbin, const std::vector<float> &tw1)
+{
+	if (!ok) return ACB_OK;
+	const int nch = c->cfg.nch, N2 = c->cfg.K / 4;
+	std::vector<float> tw((size_t)c->ngrp * CH_GROUP * N2 * 2, 0.0f);
+	std::vector<unsigned> meta(c->ngrp, 0u);
+	for (int ch = 0; ch < nch; ch++) {
+		const int g = ch / CH_GROUP, cc = ch % CH_GROUP;
+		meta[g] |= (unsigned)(((kbin[ch] % 4) + 4) % 4) << (2 * cc);      /* 0 or 2 */
+		meta[g] |= (unsigned)((((kbin[ch] / 2) % 4) + 4) % 4) << (16 + 2 * cc);   /* k even: residue of k/2, for the folded form */
+		memcpy(&tw[((size_t)g * CH_GROUP + cc) * N2 * 2], &tw1[(size_t)ch * N2 * 2], (size_t)N2 * 2 * sizeof(float));
+	}
+	if (int r = upload(c, c->d_tw + (size_t)stream * tw.size(), tw.data(), tw.size() * sizeof(float))) return r;
+	if (int r = upload(c, c->d_twmeta + (size_t)stream * meta.size(), meta.data(), meta.size() * sizeof(unsigned))) return r;
+	c->fast_ok[stream] = 1;
 	return ACB_OK;
 }
 
@@ -454,20 +493,7 @@ extern "C" int acb_set_plan_at(acb_ctx_t *c, int stream, const unsigned *freqs_h
 	std::vector<int> kbin(nch);
 	std::vector<float> tw1((size_t)nch * N2 * 2);
 	const bool ok = acb_fast_plan(freqs_hz, nch, K, fc, kbin.data(), tw1.data()) == 1;
-	std::vector<float> tw((size_t)c->ngrp * CH_GROUP * N2 * 2, 0.0f);
-	std::vector<unsigned> meta(c->ngrp, 0u);
-	for (int ch = 0; ch < nch && ok; ch++) {
-		const int g = ch / CH_GROUP, cc = ch % CH_GROUP;
-		meta[g] |= (unsigned)(((kbin[ch] % 4) + 4) % 4) << (2 * cc);      /* 0 or 2 */
-		meta[g] |= (unsigned)((((kbin[ch] / 2) % 4) + 4) % 4) << (16 + 2 * cc);   /* k even: residue of k/2, for the folded form */
-		memcpy(&tw[((size_t)g * CH_GROUP + cc) * N2 * 2], &tw1[(size_t)ch * N2 * 2], (size_t)N2 * 2 * sizeof(float));
-	}
-	if (ok) {
-		if (int r = upload(c, c->d_tw + (size_t)stream * tw.size(), tw.data(), tw.size() * sizeof(float))) return r;
-		if (int r = upload(c, c->d_twmeta + (size_t)stream * meta.size(), meta.data(), meta.size() * sizeof(unsigned))) return r;
-		c->fast_ok[stream] = 1;
-	}
-	return ACB_OK;
+	return upload_fast_plan(c, stream, ok, kbin, tw1);
 }
 
 static EvTriple get_events(acb_ctx *c)
@@ -496,48 +522,83 @@ static void consume(acb_ctx *c, const acb_ctx::Job &job)
 	const unsigned count = job.count;
 	const auto &gs = job.group_starts;
 	const RawFrame *ring = c->h_ring[job.ring];
-	/* emission order = (group, stream, channel, time).  The four fit one 64-bit key (12 + 20 + 12 + 20 bits: groups of a
-	 * submit, streams, channels, sample offset inside the submit), so the sort is on integers; contexts beyond those
-	 * widths take the comparator */
-	const unsigned long long base = gs.empty() ? 0 : gs.front();
-	const bool packed = gs.size() < 4096 && c->cfg.nstreams < (1 << 20) && c->cfg.nch < 4096 &&
-	                    (unsigned long long)c->cfg.max_blocks * OUTBLK < (1u << 20);
-	std::vector<std::pair<unsigned long long, unsigned>> keys(count);
-	for (unsigned i = 0; i < count; i++) {
-		const RawFrame &f = ring[i];
-		const unsigned long long g = (unsigned long long)(std::upper_bound(gs.begin(), gs.end(), f.pos) - gs.begin());
-		keys[i].second = i;
-		keys[i].first = packed ? (g << 52) | ((unsigned long long)f.stream << 32) | ((unsigned long long)f.chn << 20) | ((f.pos - base) & 0xFFFFFull) : g;
-	}
-	if (packed) {
-		std::sort(keys.begin(), keys.end());
+	/* emission order = (group, stream, channel, time).  A chain's frames reach the ring in time order (one thread
+	 * appends them as it decodes), so a STABLE bucket pass over (group, chain) is the whole sort: O(frames + buckets)
+	 * instead of a comparison sort (at a Tsample/s a step carries ~40 000 frames; std::sort on them was half of the
+	 * consumer's time, and the consumer, not the GPU, set the step time of the fast pipeline).  Contexts whose
+	 * (groups x chains) table would be unreasonable take the comparison sort. */
+	const auto t_begin = std::chrono::steady_clock::now();
+	const size_t nchain = (size_t)c->cfg.nstreams * c->cfg.nch, nbucket = (gs.size() + 1) * nchain;
+	std::vector<unsigned> order(count);
+	std::vector<unsigned char> keep(count);             /* 1 = repaired and parity-stripped on the device (k_block_fec) */
+	if (nbucket <= ((size_t)1 << 24)) {
+		std::vector<unsigned> start(nbucket + 1, 0u), bucket(count);
+		for (unsigned i = 0; i < count; i++) {          /* the one pass in ring order: sequential reads */
+			const RawFrame &f = ring[i];
+			keep[i] = f.pad0 == 1;
+			const size_t g = gs.size() == 1 ? (f.pos >= gs[0]) : (size_t)(std::upper_bound(gs.begin(), gs.end(), f.pos) - gs.begin());
+			const size_t bk = g * nchain + (size_t)f.stream * c->cfg.nch + f.chn;
+			bucket[i] = (unsigned)bk;
+			start[bk + 1]++;
+		}
+		for (size_t k = 0; k < nbucket; k++) start[k + 1] += start[k];
+		for (unsigned i = 0; i < count; i++) order[start[bucket[i]]++] = i;
 	} else {
-		std::sort(keys.begin(), keys.end(), [ring](const std::pair<unsigned long long, unsigned> &a, const std::pair<unsigned long long, unsigned> &b) {
-			if (a.first != b.first) return a.first < b.first;
-			const RawFrame &x = ring[a.second], &y = ring[b.second];
+		for (unsigned i = 0; i < count; i++) { order[i] = i; keep[i] = ring[i].pad0 == 1; }
+		std::stable_sort(order.begin(), order.end(), [ring, &gs](unsigned ia, unsigned ib) {
+			const RawFrame &x = ring[ia], &y = ring[ib];
+			const size_t gx = (size_t)(std::upper_bound(gs.begin(), gs.end(), x.pos) - gs.begin());
+			const size_t gy = (size_t)(std::upper_bound(gs.begin(), gs.end(), y.pos) - gs.begin());
+			if (gx != gy) return gx < gy;
 			if (x.stream != y.stream) return x.stream < y.stream;
 			if (x.chn != y.chn) return x.chn < y.chn;
 			return x.pos < y.pos;
 		});
 	}
-	acb_ctx::Batch b;
-	b.v.reset(new acb_msg_t[count ? count : 1]());      /* zeroed in one go */
-	b.n = 0;
-	b.rd = 0;
-	unsigned dropped = 0;
-	for (const auto &k : keys) {
-		const RawFrame &f = ring[k.second];
-		if (f.pad0 != 1) { dropped++; continue; }        /* 1 = repaired and parity-stripped on the device (k_block_fec) */
-		acb_msg_t &m = b.v[b.n++];
-		m.stream = f.stream; m.chn = f.chn; m.len = f.len; m.err = f.err;
-		m.lvl = (float)(10 * log10(f.lvlsum / f.bitcount));          /* acars.c:351 */
-		m.block = f.pos / OUTBLK; m.pos = f.pos; m.soh_pos = f.soh_pos;
-		memcpy(m.txt, f.txt, ACB_TXTMAX);
-		m.crc[0] = f.crc[0]; m.crc[1] = f.crc[1];
+	/* The records.  Frames are read in emission order, i.e. at random from an 11 MB ring when a step carries 40 000 of
+	 * them: a cache-miss-bound copy (5 ms on one core, more than the GPU needs for the step).  Output slots are fixed
+	 * first (a frame the block FEC rejected takes none), then the copy is cut into contiguous ranges of the output,
+	 * one helper thread each for large jobs. */
+	std::vector<unsigned> slot(count);
+	unsigned kept = 0;
+	for (unsigned j = 0; j < count; j++) {
+		slot[j] = kept;
+		kept += keep[order[j]];
 	}
+	acb_ctx::Batch b;
+	b.v.reset(new acb_msg_t[kept ? kept : 1]);
+	b.n = kept;
+	b.rd = 0;
+	const unsigned dropped = count - kept;
+	acb_msg_t *out = b.v.get();
+	auto fill = [ring, out, &order, &slot, &keep](unsigned j0, unsigned j1) {
+		for (unsigned j = j0; j < j1; j++) {
+			if (!keep[order[j]]) continue;
+			const RawFrame &f = ring[order[j]];
+			acb_msg_t &m = out[slot[j]];
+			memset(&m, 0, sizeof(m));
+			m.stream = f.stream; m.chn = f.chn; m.len = f.len; m.err = f.err;
+			m.lvl = (float)(10 * log10(f.lvlsum / f.bitcount));          /* acars.c:351 */
+			m.block = f.pos / OUTBLK; m.pos = f.pos; m.soh_pos = f.soh_pos;
+			memcpy(m.txt, f.txt, ACB_TXTMAX);
+			m.crc[0] = f.crc[0]; m.crc[1] = f.crc[1];
+		}
+	};
+	const unsigned helpers = count >= 8192 ? std::min(3u, std::max(1u, std::thread::hardware_concurrency()) - 1u) : 0u;
+	if (helpers == 0) {
+		fill(0, count);
+	} else {
+		std::vector<std::thread> pool;
+		const unsigned parts = helpers + 1, per = (count + parts - 1) / parts;
+		for (unsigned t = 1; t < parts; t++) pool.emplace_back(fill, std::min(count, t * per), std::min(count, (t + 1) * per));
+		fill(0, std::min(count, per));
+		for (auto &th : pool) th.join();
+	}
+	const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
 	std::lock_guard<std::mutex> lk(c->mtx);
 	c->stats.raw_frames += count;
 	c->stats.fec_dropped += dropped;
+	c->stats.host_ms += ms;
 	if (b.n) {
 		c->outq_count += b.n;
 		c->outq.push_back(std::move(b));
@@ -624,22 +685,31 @@ static int collect_oldest(acb_ctx *c)
 static int run_kernels(acb_ctx *c, const uint8_t *d_iq, size_t stride, int nblk, int nsamp, const float *dm_host,
                        std::vector<unsigned long long> &&groups)
 {
-	/* the ring this submit appends to was last used two submits ago: its frames must be on their
-	 * way back before the new demod may clear it — but the host-side FEC of those frames waits
+	/* the ring this submit appends to was last used NPIPE submits ago: its frames must be on their
+	 * way back before the new demod may clear it — but the host-side work on those frames waits
 	 * until the new kernels have been launched */
-	while (c->inflight.size() > 2)
+	while (c->inflight.size() > (size_t)NPIPE)
 		if (int r = collect_oldest(c)) return r;
-	if (c->inflight.size() == 2)
+	if (c->inflight.size() == (size_t)NPIPE)
 		if (int r = harvest_begin(c)) return r;      /* its frames are the consumer's from here on, whatever happens below */
+	/* Input lifetime: when submit N+2 returns, the channelizer of submit N has read its input (host buffer copied,
+	 * device buffer consumed) — callers rotating three input buffers, or two with a collect in between, rely on it */
+	if (c->nsubmit >= 2) {
+		const int b2 = (int)((c->nsubmit - 2) % NPIPE);
+		if (c->k1_pending[b2]) {
+			CU(cudaEventSynchronize(c->ev_k1_done[b2]));
+			c->k1_pending[b2] = false;
+		}
+	}
 	Ticket t;
-	t.ring = (int)(c->nsubmit & 1);
+	t.ring = (int)(c->nsubmit % NPIPE);
 	t.group_starts = std::move(groups);
 	t.ev = get_events(c);
 	t.ev.chan = d_iq != nullptr;
 	const int b = t.ring;                          /* envelope buffer and frame ring of this submit */
 	float *dmbuf = c->d_dm[b];
 	if (d_iq) {
-		/* K1 may overwrite d_dm[b] only after the demod of two submits ago has read it */
+		/* K1 may overwrite d_dm[b] only after the demod of NPIPE submits ago has read it */
 		if (c->dm_used[b]) CU(cudaStreamWaitEvent(c->s_comp, c->ev_dm_free[b], 0));
 		CU(cudaEventRecord(t.ev.a, c->s_comp));
 		int r = 0;
@@ -648,7 +718,18 @@ static int run_kernels(acb_ctx *c, const uint8_t *d_iq, size_t stride, int nblk,
 		const int fast = c->use_generic ? 0 : nsamp / OUTBLK;
 		bool dft = c->fast;                         /* every stream planned on the raster? */
 		for (int s = 0; dft && s < c->cfg.nstreams; s++) dft = c->fast_ok[s] != 0;
-		if (fast && dft) {
+		bool all_rows = false;                       /* the fast CS16 kernel takes partial blocks too */
+		if (dft && c->in_kind == IN_KIND_F32REAL && !c->use_generic) {
+			r = launch_channelize_rdft(d_iq, stride, c->d_tw, c->d_twmeta, dmbuf, c->cfg.K, c->cfg.nch, c->cfg.nstreams, (size_t)nsamp, c->s_comp);
+			c->stats.kernel_launches++;
+			c->stats.fast_chan_launches++;
+			all_rows = true;
+		} else if (dft && c->in_kind == IN_KIND_CS16IQ && !c->use_generic) {
+			r = launch_channelize_dft_cs16(d_iq, stride, c->d_tw, c->d_twmeta, dmbuf, c->cfg.K, c->cfg.nch, c->cfg.nstreams, (size_t)nsamp, c->s_comp);
+			c->stats.kernel_launches++;
+			c->stats.fast_chan_launches++;
+			all_rows = true;
+		} else if (fast && dft) {
 			r = launch_channelize_dft(d_iq, stride, c->d_tw, c->d_twmeta, dmbuf, c->cfg.K, c->cfg.nch, c->cfg.nstreams, fast, (size_t)nsamp, c->fold8, c->s_comp);
 			c->stats.kernel_launches++;
 			c->stats.fast_chan_launches++;
@@ -656,7 +737,7 @@ static int run_kernels(acb_ctx *c, const uint8_t *d_iq, size_t stride, int nblk,
 			r = launch_channelize(c->in_kind, d_iq, stride, c->d_wf4, dmbuf, c->cfg.K, c->taps_pad, c->cfg.nch, c->cfg.nstreams, fast, (size_t)nsamp, c->s_comp);
 			c->stats.kernel_launches++;
 		}
-		if (!r && nsamp > fast * OUTBLK) {
+		if (!r && !all_rows && nsamp > fast * OUTBLK) {
 			r = launch_channelize_generic(c->in_kind, d_iq, stride, c->d_wf4, dmbuf, c->cfg.K, c->taps_pad, c->cfg.nch, c->cfg.nstreams,
 			                              (size_t)fast * OUTBLK, (size_t)nsamp - (size_t)fast * OUTBLK, (size_t)nsamp, c->s_comp);
 			c->stats.kernel_launches++;
@@ -665,6 +746,7 @@ static int run_kernels(acb_ctx *c, const uint8_t *d_iq, size_t stride, int nblk,
 		c->stats.chan_launches++;
 		CU(cudaEventRecord(t.ev.b, c->s_comp));
 		CU(cudaEventRecord(c->ev_k1_done[b], c->s_comp));
+		c->k1_pending[b] = true;
 		CU(cudaStreamWaitEvent(c->s_dem, c->ev_k1_done[b], 0));
 	} else if (dm_host) {
 		/* envelope input: the copy is ordered behind the previous demod on the same stream, and
@@ -681,13 +763,16 @@ static int run_kernels(acb_ctx *c, const uint8_t *d_iq, size_t stride, int nblk,
 	if (r) return fail(ACB_ERR_CUDA, "demod launch: %s", cudaGetErrorString((cudaError_t)r));
 	c->stats.kernel_launches++;
 	c->stats.demod_launches++;
-	/* block FEC on the frames this submit appended (blk_thread's job, acars.c:93-215), in place */
-	r = launch_block_fec(c->d_ring[b], c->d_ctl[b], c->ring_cap, c->s_dem);
+	CU(cudaEventRecord(c->ev_dm_free[b], c->s_dem));       /* the envelope buffer is the next-but-two channelizer's from here */
+	CU(cudaEventRecord(c->ev_k2_done[b], c->s_dem));
+	/* block FEC on the frames this submit appended (blk_thread's job, acars.c:93-215), in place — on its own stream:
+	 * it touches this submit's ring only, and the next demod need not wait behind it */
+	CU(cudaStreamWaitEvent(c->s_fec, c->ev_k2_done[b], 0));
+	r = launch_block_fec(c->d_ring[b], c->d_ctl[b], c->ring_cap, c->s_fec);
 	if (r) return fail(ACB_ERR_CUDA, "block FEC launch: %s", cudaGetErrorString((cudaError_t)r));
 	c->stats.kernel_launches++;
-	CU(cudaMemcpyAsync(c->h_ctl[b], c->d_ctl[b], sizeof(RingCtl), cudaMemcpyDeviceToHost, c->s_dem));
-	CU(cudaEventRecord(t.ev.c, c->s_dem));
-	CU(cudaEventRecord(c->ev_dm_free[b], c->s_dem));
+	CU(cudaMemcpyAsync(c->h_ctl[b], c->d_ctl[b], sizeof(RingCtl), cudaMemcpyDeviceToHost, c->s_fec));
+	CU(cudaEventRecord(t.ev.c, c->s_fec));
 	c->dm_used[b] = true;
 	c->last_dm = b;
 	c->inflight.push_back(std::move(t));
@@ -871,7 +956,12 @@ extern "C" int acb_set_plan_cs16(acb_ctx_t *c, int stream, const unsigned *freqs
 	std::vector<float> wf((size_t)nch * c->cfg.K * 2);
 	for (int ch = 0; ch < nch; ch++) acb_cs16_build_wf(variant, freqs_hz[ch], fc, c->cfg.K, &wf[(size_t)ch * c->cfg.K * 2]);
 	if (fc_out) *fc_out = fc;
-	return acb_set_wf(c, stream, wf.data(), nch);
+	if (int r = acb_set_wf(c, stream, wf.data(), nch)) return r;
+	if (!c->fast) return ACB_OK;
+	std::vector<int> kbin(nch);
+	std::vector<float> tw1((size_t)nch * (c->cfg.K / 4) * 2);
+	const bool ok = acb_fast_plan_cs16(variant, freqs_hz, nch, c->cfg.K, fc, kbin.data(), tw1.data()) == 1;
+	return upload_fast_plan(c, stream, ok, kbin, tw1);
 }
 
 extern "C" int acb_set_plan_air(acb_ctx_t *c, int stream, const unsigned *freqs_hz, int nch, unsigned *fc_out)
@@ -886,7 +976,12 @@ extern "C" int acb_set_plan_air(acb_ctx_t *c, int stream, const unsigned *freqs_
 	std::vector<float> wf((size_t)nch * c->cfg.K * 2);
 	for (int ch = 0; ch < nch; ch++) acb_air_build_wf((int)freqs_hz[ch], (int)fc, rate, &wf[(size_t)ch * c->cfg.K * 2]);
 	if (fc_out) *fc_out = fc;
-	return acb_set_wf(c, stream, wf.data(), nch);
+	if (int r = acb_set_wf(c, stream, wf.data(), nch)) return r;
+	if (!c->fast) return ACB_OK;
+	std::vector<int> kbin(nch);
+	std::vector<float> tw1((size_t)nch * (c->cfg.K / 4) * 2);
+	const bool ok = acb_fast_plan_air(freqs_hz, nch, c->cfg.K, fc, kbin.data(), tw1.data()) == 1;
+	return upload_fast_plan(c, stream, ok, kbin, tw1);
 }
 
 extern "C" int acb_submit_dm_host(acb_ctx_t *c, const float *dm, int nsamp)
@@ -932,6 +1027,7 @@ extern "C" int acb_sync(acb_ctx_t *c)
 		if (int r = collect_oldest(c)) return r;
 	CU(cudaStreamSynchronize(c->s_comp));
 	CU(cudaStreamSynchronize(c->s_dem));
+	CU(cudaStreamSynchronize(c->s_fec));
 	wait_consumer(c, c->jobs_queued);
 	if (c->consumer_err[0]) return fail(ACB_ERR_CUDA, "%s", c->consumer_err);
 	if (c->overflowed) {
@@ -946,8 +1042,14 @@ extern "C" int acb_mark(acb_ctx_t *c, int which)
 {
 	if (!c || which < 0 || which > 1) return fail(ACB_ERR_ARG, "bad argument");
 	if (int r = ctx_use(c)) return r;
-	/* a timed region starts on the channelizer stream and ends behind the last demod */
-	CU(cudaEventRecord(c->mark[which], which == 0 ? c->s_comp : c->s_dem));
+	/* a timed region starts on the channelizer stream and ends behind the last demod and the last block FEC */
+	if (which == 0) {
+		CU(cudaEventRecord(c->mark[0], c->s_comp));
+	} else {
+		CU(cudaEventRecord(c->ev_join, c->s_dem));
+		CU(cudaStreamWaitEvent(c->s_fec, c->ev_join, 0));
+		CU(cudaEventRecord(c->mark[1], c->s_fec));
+	}
 	return ACB_OK;
 }
 

@@ -214,6 +214,54 @@ extern "C" int acb_fast_plan(const unsigned *freqs_hz, int nch, int K, unsigned 
 	return 1;
 }
 
+extern "C" int acb_fast_plan_cs16(int variant, const unsigned *freqs_hz, int nch, int K, unsigned fc_hz, int *k_out, float *tw)
+{
+	/* soapy.c:159-165 / sdrplay.c:133-137: the oscillator is a sampled exponential of (float)Fr - (float)Fc over the input
+	 * rate; when that offset is a whole EVEN number k of 12.5 kHz steps, D is bin k of the row's K-point DFT and the
+	 * folded kernel applies.  The variant's power-of-two scale (acb_cs16_build_wf) goes into the twiddles. */
+	if (!freqs_hz || nch <= 0 || K <= 0 || (K & 7)) return 0;
+	if (variant != ACB_CS16_SOAPY && variant != ACB_CS16_SDRPLAY) return 0;
+	const int N2 = K / 4;
+	const double scale = variant == ACB_CS16_SOAPY ? 1.0 / 32768.0 : 0.25;
+	for (int ch = 0; ch < nch; ch++) {
+		const float d = (float)freqs_hz[ch] - (float)fc_hz;
+		const float kf = d / (float)ACB_INTRATE;
+		const int k = (int)kf;
+		if ((float)k != kf || (k & 1) || k == 0 || k <= -K / 2 || k >= K / 2) return 0;
+		if (k_out) k_out[ch] = k;
+		if (!tw) continue;
+		for (int n2 = 0; n2 < N2; n2++) {
+			const double ph = -2.0 * M_PI * (double)(((long long)k * n2) % K) / (double)K;
+			tw[((size_t)ch * N2 + n2) * 2] = (float)(cos(ph) / K * scale);
+			tw[((size_t)ch * N2 + n2) * 2 + 1] = (float)(sin(ph) / K * scale);
+		}
+	}
+	return 1;
+}
+
+extern "C" int acb_fast_plan_air(const unsigned *freqs_hz, int nch, int K, unsigned fc_hz, int *k_out, float *tw)
+{
+	/* air.c:278-285: AMFreq = 2*pi*(Fc - Fr + rate/4)/rate, wf[i] = cexpf(-j*i*AMFreq)/K: bin k = (Fc - Fr + rate/4)/12500
+	 * of the K-point DFT of the real row when that is a whole number (air.c:66 puts Fc on the 12.5 kHz raster). */
+	if (!freqs_hz || nch <= 0 || K <= 0 || (K & 7)) return 0;
+	const unsigned rate = (unsigned)K * ACB_INTRATE;
+	const int N2 = K / 4;
+	for (int ch = 0; ch < nch; ch++) {
+		const unsigned off = (unsigned)((int)fc_hz - (int)freqs_hz[ch] + (int)(rate / 4));
+		if (off % ACB_INTRATE) return 0;
+		const int k = (int)(off / ACB_INTRATE);
+		if (k <= 0 || k >= K) return 0;
+		if (k_out) k_out[ch] = k;
+		if (!tw) continue;
+		for (int n2 = 0; n2 < N2; n2++) {
+			const double ph = -2.0 * M_PI * (double)(((long long)k * n2) % K) / (double)K;
+			tw[((size_t)ch * N2 + n2) * 2] = (float)(cos(ph) / K);
+			tw[((size_t)ch * N2 + n2) * 2 + 1] = (float)(sin(ph) / K);
+		}
+	}
+	return 1;
+}
+
 extern "C" void acb_build_h(float *h)
 {
 	/* msk.c:44-48: cos(2*pi*600/INTRATE/12 * (i - 66)) evaluated by cosf on the float-rounded

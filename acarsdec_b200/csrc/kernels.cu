@@ -775,9 +775,13 @@ static int launch_dft_t(const uint8_t *in, size_t stream_stride, const float2 *t
  * active 58 %, stall `wait` 35 %) — and the demod warps that share the SMs displace smaller pieces. */
 constexpr int DFT1_ROWS = 32;
 
-template <int UNITS, int WARPS> struct Dft1Plan {
-	static constexpr int ROWBYTES = UNITS * 16;
-	static constexpr int RPC = (UNITS % 8 == 4) ? 2 : 1;                      /* rows per bulk copy, see DftPlan */
+/* KIND: IN_U8IQ (2 bytes per complex sample, UNITS = K/8 sixteen-byte units per row) or IN_CS16IQ (4 bytes per complex
+ * sample: the same kernel with rows twice as long, another converter, and rows padded one by one — 16·UNITS·2 bytes is a
+ * multiple of 128, so every row needs its own 16-byte shift to spread the lanes over the bank groups) */
+template <int KIND, int UNITS, int WARPS> struct Dft1Plan {
+	static constexpr int BPS = KIND == IN_CS16IQ ? 4 : 2;                     /* bytes per complex sample */
+	static constexpr int ROWBYTES = UNITS * 8 * BPS;
+	static constexpr int RPC = (KIND != IN_CS16IQ && UNITS % 8 == 4) ? 2 : 1; /* rows per bulk copy, see DftPlan */
 	static constexpr int GROUP = RPC * ROWBYTES + 16;
 	static constexpr int TILE_BYTES = DFT1_ROWS / RPC * GROUP;
 	static __device__ __forceinline__ int row_off(int r) { return (r / RPC) * GROUP + (r % RPC) * ROWBYTES; }
@@ -793,13 +797,18 @@ template <int KB> __device__ __forceinline__ float2 dft1_cvt(unsigned w)
 	constexpr unsigned si = 0x7404u | (KB << 4), sq = 0x7404u | ((KB + 1) << 4);
 	return make_float2(__uint_as_float(__byte_perm(w, 0x47000000u, si)), __uint_as_float(__byte_perm(w, 0x47000000u, sq)));
 }
+/* CS16: the two 16-bit halves of w (already XORed, see the kernel) planted in the mantissa of 2^23: (2^23 + lo, 2^23 + hi) */
+__device__ __forceinline__ float2 dft1_cvt16(unsigned w)
+{
+	return make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7410)), __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7432)));
+}
 
-template <int UNITS, int WARPS, int MINB, bool PF>
+template <int KIND, int UNITS, int WARPS, int MINB, bool PF>
 __global__ void __launch_bounds__(32 * WARPS, MINB)
 k_channelize_dft1(const uint8_t *__restrict__ in, size_t stream_stride, const float2 *__restrict__ tw,
                   const unsigned *__restrict__ meta, float *__restrict__ dm, int nch, int ngrp, size_t nsamp)
 {
-	using P = Dft1Plan<UNITS, WARPS>;
+	using P = Dft1Plan<KIND, UNITS, WARPS>;
 	constexpr int CU = UNITS / 4;                 /* groups of 4 samples per eighth of a row */
 	constexpr int N2 = P::N2;
 	constexpr int NTILE = OUTBLK / DFT1_ROWS;
@@ -855,7 +864,11 @@ k_channelize_dft1(const uint8_t *__restrict__ in, size_t stream_stride, const fl
 	}
 	__syncthreads();
 
-	const int ntile = (NTILE - w + WARPS - 1) / WARPS;    /* this warp's tiles: w, w + WARPS, ... */
+	/* this warp's tiles: w, w + WARPS, ...; the streaming inputs (CS16) may end inside a block: tiles that start past
+	 * the last row are not touched, the last one reads up to 31 rows of slack behind the input (context.cu allocates it) */
+	const size_t rows_left = nsamp - (size_t)blk * OUTBLK;
+	const int tiles_here = rows_left >= (size_t)OUTBLK ? NTILE : (int)((rows_left + DFT1_ROWS - 1) / DFT1_ROWS);
+	const int ntile = (tiles_here - w + WARPS - 1) / WARPS;
 	auto issue = [&](int n) {
 		if (elect_one()) {
 			mbar_expect_tx(bar, DFT1_ROWS * P::ROWBYTES);
@@ -879,23 +892,38 @@ k_channelize_dft1(const uint8_t *__restrict__ in, size_t stream_stride, const fl
 #pragma unroll 1
 		for (int g4 = 0; g4 < CU; g4++) {
 			uint2 e8[8];
+			uint4 e16[8];
 #pragma unroll
-			for (int e = 0; e < 8; e++) e8[e] = *reinterpret_cast<const uint2 *>(ra + e * (UNITS * 2) + g4 * 8);
+			for (int e = 0; e < 8; e++) {
+				if (KIND == IN_CS16IQ) e16[e] = *reinterpret_cast<const uint4 *>(ra + e * (UNITS * 4) + g4 * 16);
+				else e8[e] = *reinterpret_cast<const uint2 *>(ra + e * (UNITS * 2) + g4 * 8);
+			}
 			float2 Y[4][4];                       /* [residue][sample of the group] = (re, im) */
 #pragma unroll
 			for (int k = 0; k < 4; k++) {
 				float2 z[4];
 #pragma unroll
 				for (int n1 = 0; n1 < 4; n1++) {
-					const unsigned w0 = k < 2 ? e8[n1].x : e8[n1].y, w1 = k < 2 ? e8[n1 + 4].x : e8[n1 + 4].y;
-					z[n1] = (k & 1) ? __fadd2_rn(dft1_cvt<2>(w0), dft1_cvt<2>(w1)) : __fadd2_rn(dft1_cvt<0>(w0), dft1_cvt<0>(w1));
+					if (KIND == IN_CS16IQ) {
+						/* int16 v as the unsigned v + 32768 (XOR 0x8000) in the first half of the row, as 32767 - v (XOR 0x7fff) in
+						 * the second: both planted in the mantissa of 2^23, their DIFFERENCE is v0 + v1 + 1, exact (operands in
+						 * [2^23, 2^24)) — one XOR per word, two PRMT, one packed subtraction per folded sample */
+						const uint4 a = e16[n1], b = e16[n1 + 4];
+						const unsigned w0 = (k == 0 ? a.x : k == 1 ? a.y : k == 2 ? a.z : a.w) ^ 0x80008000u;
+						const unsigned w1 = (k == 0 ? b.x : k == 1 ? b.y : k == 2 ? b.z : b.w) ^ 0x7fff7fffu;
+						z[n1] = fsub2(dft1_cvt16(w0), dft1_cvt16(w1));
+					} else {
+						const unsigned w0 = k < 2 ? e8[n1].x : e8[n1].y, w1 = k < 2 ? e8[n1 + 4].x : e8[n1 + 4].y;
+						z[n1] = (k & 1) ? __fadd2_rn(dft1_cvt<2>(w0), dft1_cvt<2>(w1)) : __fadd2_rn(dft1_cvt<0>(w0), dft1_cvt<0>(w1));
+					}
 				}
-				/* every z carries 2 x 32768 from the converter: sums of four carry 262144 (exact, < 2^24) and Y'_0 also
-				 * sheds the converter's mid-scale 8 x 127.5; differences carry nothing */
+				/* u8: every z carries 2 x 32768 from the converter: sums of four carry 262144 (exact, < 2^24) and Y'_0 also
+				 * sheds the converter's mid-scale 8 x 127.5; CS16: every z carries + 1, |z| < 2^17; differences carry nothing */
 				const float2 s02 = __fadd2_rn(z[0], z[2]), s13 = __fadd2_rn(z[1], z[3]);
 				const float2 d02 = fsub2(z[0], z[2]);
 				const float2 wj = make_float2(__fadd_rn(z[1].y, -z[3].y), __fadd_rn(z[3].x, -z[1].x));   /* -j (z1 - z3) */
-				Y[0][k] = __fadd2_rn(__fadd2_rn(s02, s13), make_float2(-263164.0f, -263164.0f));
+				const float y0bias = KIND == IN_CS16IQ ? -4.0f : -263164.0f;
+				Y[0][k] = __fadd2_rn(__fadd2_rn(s02, s13), make_float2(y0bias, y0bias));
 				Y[2][k] = fsub2(s02, s13);
 				Y[1][k] = __fadd2_rn(d02, wj);    /* (z0 - z2) - j (z1 - z3) */
 				Y[3][k] = fsub2(d02, wj);         /* (z0 - z2) + j (z1 - z3) */
@@ -947,18 +975,18 @@ k_channelize_dft1(const uint8_t *__restrict__ in, size_t stream_stride, const fl
 #pragma unroll
 		for (int j = 0; j < CH_GROUP; j++) {
 			const int c = (int)((pw >> (3 * j)) & 7u);
-			if (c < nc) o[c] = e[j];
+			if (c < nc && mrow < nsamp) o[c] = e[j];
 		}
 	}
 }
 
-template <int UNITS, int WARPS, int MINB, bool PF>
+template <int KIND, int UNITS, int WARPS, int MINB, bool PF>
 static int launch_dft1_t(const uint8_t *in, size_t stream_stride, const float2 *tw, const unsigned *meta, float *dm,
                          int nch, int nstreams, int nblk, size_t nsamp, cudaStream_t stream)
 {
 	const int ngrp = (nch + CH_GROUP - 1) / CH_GROUP;
-	constexpr int smem = Dft1Plan<UNITS, WARPS>::SMEM;
-	auto kern = k_channelize_dft1<UNITS, WARPS, MINB, PF>;
+	constexpr int smem = Dft1Plan<KIND, UNITS, WARPS>::SMEM;
+	auto kern = k_channelize_dft1<KIND, UNITS, WARPS, MINB, PF>;
 	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	if (e != cudaSuccess) return (int)e;
 	e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -966,6 +994,205 @@ static int launch_dft1_t(const uint8_t *in, size_t stream_stride, const float2 *
 	dim3 grid(nblk, nstreams, ngrp);
 	kern<<<grid, 32 * WARPS, smem, stream>>>(in, stream_stride, tw, meta, dm, nch, ngrp, nsamp);
 	return (int)cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Fast form of the REAL-input channelizer (air.c:291-341 with the table of air.c:278-285): wf[i] = exp(-j*2*pi*k*i/K)/K is
+ * a sampled exponential with k = (Fc - Fr + rate/4) / 12.5 kHz a whole number whenever the channels and the tuner
+ * centre sit on the 12.5 kHz raster (air.c:66 puts Fc there), so D is bin k of the K-point DFT of a REAL row:
+ *   D = sum_{n2 < K/4} T[n2] * Y_r[n2],  r = k mod 4,  T[n2] = exp(-j*2*pi*k*n2/K)/K,
+ *   Y_0 = (x0 + x2) + (x1 + x3)   Y_2 = (x0 + x2) - (x1 + x3)          real
+ *   Y_1 = (x0 - x2) - j (x1 - x3) Y_3 = (x0 - x2) + j (x1 - x3)        x_q = x[(K/4) q + n2]
+ * 6 additions per n2 shared by all channels, then K/4 real x complex (r even: one FFMA2 per n2) or complex x complex
+ * (r odd: two) MACs per channel instead of K: 8 channels cost ~10 FP32 lane-ops per input sample where the reference's
+ * order costs 32 — the kernel becomes a memory streamer.  Same shape as k_channelize_dft1: one row per lane, whole rows
+ * by cp.async.bulk into a private 32-row tile per warp, channel slots sorted so that the MAC section is straight-line
+ * columns (r = 0 | r = 2 | r odd; residues 1 and 3 accumulate the same two sums and differ in one sign at the end).
+ * NOT the reference's operation order (tolerance: include/acars_b200.h); bit-identical to oracle's orc_channelize_rdft.
+ * ---------------------------------------------------------------------------------------- */
+template <int K8, int WARPS> struct RdftPlan {
+	static constexpr int K = K8 * 8;
+	static constexpr int ROWBYTES = K * 4;
+	static constexpr int GROUP = ROWBYTES + 16;                       /* every row shifted by one more 16-byte unit */
+	static constexpr int TILE_BYTES = DFT1_ROWS * GROUP;
+	static constexpr int N2 = K / 4;
+	static constexpr int TW_BYTES = N2 * CH_GROUP * 8;
+	static constexpr int BAR_OFF = WARPS * TILE_BYTES + TW_BYTES;
+	static constexpr int SMEM = BAR_OFF + WARPS * 8;
+};
+
+template <int K8, int WARPS, int MINB>
+__global__ void __launch_bounds__(32 * WARPS, MINB)
+k_channelize_rdft(const uint8_t *__restrict__ in, size_t stream_stride, const float2 *__restrict__ tw,
+                  const unsigned *__restrict__ meta, float *__restrict__ dm, int nch, int ngrp, size_t nsamp)
+{
+	using P = RdftPlan<K8, WARPS>;
+	constexpr int N2 = P::N2;
+	constexpr int NTILE = OUTBLK / DFT1_ROWS;
+	extern __shared__ __align__(16) unsigned char smem[];
+	const int l = threadIdx.x & 31;
+	const int w = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+	const int blk = blockIdx.x, s = blockIdx.y, g = blockIdx.z;
+	unsigned char *mytile = smem + (size_t)w * P::TILE_BYTES;
+	const float4 *stw = reinterpret_cast<const float4 *>(smem + (size_t)WARPS * P::TILE_BYTES);   /* [slot][n2] (Tr, Ti) */
+	unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + P::BAR_OFF) + w;
+	const uint8_t *src_blk = in + (size_t)s * stream_stride + (size_t)blk * OUTBLK * P::ROWBYTES;
+	const unsigned m = __shfl_sync(0xffffffffu, meta[(size_t)s * ngrp + g], 0);    /* k_c mod 4 of channel c in bits 2c, 2c + 1 */
+
+	if (l == 0) mbar_init(bar, 1);
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	/* slots sorted by column: residue 0, residue 2, odd residues (stable); perm[j] in bits 3j.., sign of slot j in bit j */
+	unsigned pw = 0, neg = 0;
+	int bnd0, bnd1;
+	{
+		int cnt[3] = { 0, 0, 0 };
+#pragma unroll
+		for (int c = 0; c < CH_GROUP; c++) {
+			const unsigned r = (m >> (2 * c)) & 3u;
+			const int cls = r == 0 ? 0 : r == 2 ? 1 : 2;
+#pragma unroll
+			for (int q = 0; q < 3; q++) cnt[q] += (cls == q);
+		}
+		bnd0 = cnt[0]; bnd1 = bnd0 + cnt[1];
+		int pos[3] = { 0, bnd0, bnd1 };
+#pragma unroll
+		for (int c = 0; c < CH_GROUP; c++) {
+			const unsigned r = (m >> (2 * c)) & 3u;
+			const int cls = r == 0 ? 0 : r == 2 ? 1 : 2;
+			int at = 0;
+#pragma unroll
+			for (int q = 0; q < 3; q++) { at = (cls == q) ? pos[q] : at; pos[q] += (cls == q); }
+			pw |= (unsigned)c << (3 * at);
+			neg |= (unsigned)(r == 3) << at;
+		}
+	}
+	{
+		const uint4 *tsrc = reinterpret_cast<const uint4 *>(tw + ((size_t)s * ngrp + g) * N2 * CH_GROUP);
+		uint4 *tdst = reinterpret_cast<uint4 *>(smem + (size_t)WARPS * P::TILE_BYTES);
+		constexpr int PER = N2 * 8 / 16;
+		for (int q = threadIdx.x; q < P::TW_BYTES / 16; q += 32 * WARPS) {
+			const int j = q / PER, off = q - j * PER;
+			cp_async16(tdst + q, tsrc + ((pw >> (3 * j)) & 7u) * PER + off);
+		}
+		cp_async_commit();
+		cp_async_wait_all();
+	}
+	__syncthreads();
+
+	const size_t rows_left = nsamp - (size_t)blk * OUTBLK;
+	const int tiles_here = rows_left >= (size_t)OUTBLK ? NTILE : (int)((rows_left + DFT1_ROWS - 1) / DFT1_ROWS);
+	const int ntile = (tiles_here - w + WARPS - 1) / WARPS;
+	auto issue = [&](int n) {
+		if (elect_one()) {
+			mbar_expect_tx(bar, DFT1_ROWS * P::ROWBYTES);
+			const uint8_t *src = src_blk + (size_t)(w + n * WARPS) * DFT1_ROWS * P::ROWBYTES;
+#pragma unroll
+			for (int i = 0; i < DFT1_ROWS; i++)
+				bulk_g2s(mytile + (size_t)i * P::GROUP, src + (size_t)i * P::ROWBYTES, P::ROWBYTES, bar);
+		}
+	};
+	if (ntile > 0) issue(0);
+	const int nc = min(CH_GROUP, nch - g * CH_GROUP);
+
+	for (int n = 0; n < ntile; n++) {
+		const int tile = w + n * WARPS;
+		mbar_wait(bar, (unsigned)(n & 1));
+		const unsigned char *ra = mytile + (size_t)l * P::GROUP;
+		float2 A[CH_GROUP], B[CH_GROUP];
+#pragma unroll
+		for (int c = 0; c < CH_GROUP; c++) A[c] = B[c] = make_float2(0.f, 0.f);
+
+#pragma unroll 1
+		for (int gp = 0; gp < K8; gp++) {                 /* n2 = 2 gp, 2 gp + 1 */
+			const float2 x0 = *reinterpret_cast<const float2 *>(ra + 0 * P::K + gp * 8);
+			const float2 x1 = *reinterpret_cast<const float2 *>(ra + 1 * P::K + gp * 8);
+			const float2 x2 = *reinterpret_cast<const float2 *>(ra + 2 * P::K + gp * 8);
+			const float2 x3 = *reinterpret_cast<const float2 *>(ra + 3 * P::K + gp * 8);
+			const float2 s02 = __fadd2_rn(x0, x2), s13 = __fadd2_rn(x1, x3);
+			const float2 y0 = __fadd2_rn(s02, s13), y2 = fsub2(s02, s13);
+			const float2 d02 = fsub2(x0, x2), d13 = fsub2(x1, x3);
+			const float4 *tj = stw + gp;
+#define ACB_RDFT_E(J, Y)                                                                   \
+			{                                                                                      \
+				const float4 u = tj[(J) * (N2 / 2)];                                                   \
+				A[J] = ffma2(make_float2(Y.x, Y.x), make_float2(u.x, u.y), A[J]);                      \
+				A[J] = ffma2(make_float2(Y.y, Y.y), make_float2(u.z, u.w), A[J]);                      \
+			}
+#define ACB_RDFT_O(J)                                                                      \
+			{                                                                                      \
+				const float4 u = tj[(J) * (N2 / 2)];                                                   \
+				A[J] = ffma2(make_float2(d02.x, d02.x), make_float2(u.x, u.y), A[J]);                  \
+				B[J] = ffma2(make_float2(d13.x, d13.x), make_float2(u.x, u.y), B[J]);                  \
+				A[J] = ffma2(make_float2(d02.y, d02.y), make_float2(u.z, u.w), A[J]);                  \
+				B[J] = ffma2(make_float2(d13.y, d13.y), make_float2(u.z, u.w), B[J]);                  \
+			}
+#define ACB_RDFT_C0(J) if ((J) >= bnd0) goto r1_##J; ACB_RDFT_E(J, y0)
+#define ACB_RDFT_C1(J) r1_##J: if ((J) >= bnd1) goto r2_##J; ACB_RDFT_E(J, y2)
+#define ACB_RDFT_C2(J) r2_##J: ACB_RDFT_O(J)
+#define ACB_RDFT_COL(C) C(0) C(1) C(2) C(3) C(4) C(5) C(6) C(7)
+			ACB_RDFT_COL(ACB_RDFT_C0) goto rmacs_done;
+			ACB_RDFT_COL(ACB_RDFT_C1) goto rmacs_done;
+			ACB_RDFT_COL(ACB_RDFT_C2)
+			rmacs_done:;
+#undef ACB_RDFT_COL
+#undef ACB_RDFT_C2
+#undef ACB_RDFT_C1
+#undef ACB_RDFT_C0
+#undef ACB_RDFT_O
+#undef ACB_RDFT_E
+		}
+		__syncwarp();
+		if (n + 1 < ntile) issue(n + 1);
+		const size_t mrow = (size_t)blk * OUTBLK + (size_t)tile * DFT1_ROWS + l;
+		float *o = dm + ((size_t)s * nsamp + mrow) * nch + g * CH_GROUP;
+#pragma unroll
+		for (int j = 0; j < CH_GROUP; j++) {
+			/* r = 1: D = (A.x + B.y) + j (A.y - B.x); r = 3: the other signs; r even: B is zero */
+			const float sg = ((neg >> j) & 1u) ? -1.0f : 1.0f;
+			const float re = __fadd_rn(A[j].x, __fmul_rn(sg, B[j].y)), im = __fadd_rn(A[j].y, -__fmul_rn(sg, B[j].x));
+			const float e = __fsqrt_rn(__fmaf_rn(re, re, __fmul_rn(im, im)));
+			const int c = (int)((pw >> (3 * j)) & 7u);
+			if (c < nc && mrow < nsamp) o[c] = e;
+		}
+	}
+}
+
+template <int K8, int WARPS, int MINB>
+static int launch_rdft_t(const uint8_t *in, size_t stream_stride, const float2 *tw, const unsigned *meta, float *dm,
+                         int nch, int nstreams, int nblk, size_t nsamp, cudaStream_t stream)
+{
+	const int ngrp = (nch + CH_GROUP - 1) / CH_GROUP;
+	constexpr int smem = RdftPlan<K8, WARPS>::SMEM;
+	auto kern = k_channelize_rdft<K8, WARPS, MINB>;
+	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	if (e != cudaSuccess) return (int)e;
+	e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+	if (e != cudaSuccess) return (int)e;
+	dim3 grid(nblk, nstreams, ngrp);
+	kern<<<grid, 32 * WARPS, smem, stream>>>(in, stream_stride, tw, meta, dm, nch, ngrp, nsamp);
+	return (int)cudaGetLastError();
+}
+
+/* the Airspy rates whose 32-row tile fits a CTA: 2.5 MS/s (K = 200), 5 (400), 6 (480), 10 (800) */
+bool channelize_rdft_supports(int K) { return K == 200 || K == 400 || K == 480 || K == 800; }
+
+/* float32 real input (air.c), taps == K, every channel on the 12.5 kHz raster around Fc; `nsamp` output rows per stream,
+ * any count (the input buffer carries 32 rows of slack).  stream_stride in bytes. */
+int launch_channelize_rdft(const void *in, size_t stream_stride, const float *tw, const unsigned *meta, float *dm,
+                           int K, int nch, int nstreams, size_t nsamp, cudaStream_t stream)
+{
+	if (nsamp == 0) return 0;
+	const uint8_t *i8 = reinterpret_cast<const uint8_t *>(in);
+	const float2 *t4 = reinterpret_cast<const float2 *>(tw);
+	const int nblk = (int)((nsamp + OUTBLK - 1) / OUTBLK);
+	const int w2 = getenv("ACB_FAST_WARPS") ? atoi(getenv("ACB_FAST_WARPS")) : 2;
+#define ACB_RDFT_GO(K8, W, M) launch_rdft_t<K8, W, M>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream)
+	if (K == 200) return w2 == 1 ? ACB_RDFT_GO(25, 1, 8) : ACB_RDFT_GO(25, 2, 4);       /* 26 KB of tile per warp */
+	if (K == 400) return ACB_RDFT_GO(50, 1, 4);                                         /* 52 KB */
+	if (K == 480) return ACB_RDFT_GO(60, 1, 3);                                         /* 62 KB */
+	if (K == 800) return ACB_RDFT_GO(100, 1, 2);                                        /* 103 KB */
+#undef ACB_RDFT_GO
+	return (int)cudaErrorInvalidValue;
 }
 
 bool channelize_dft_supports(int K) { return K == 160 || K == 192; }
@@ -991,7 +1218,7 @@ int launch_channelize_dft(const void *in, size_t stream_stride, const float *tw,
 	if (fold8 && rows1 == 1) {
 		const int w2 = getenv("ACB_FAST_WARPS") ? atoi(getenv("ACB_FAST_WARPS")) : 2;
 		const bool pf = getenv("ACB_FAST_PF") ? atoi(getenv("ACB_FAST_PF")) != 0 : true;   /* experiment switch: twiddles one slot ahead */
-#define ACB_DFT1_GO(U, W, M, F) launch_dft1_t<U, W, M, F>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream)
+#define ACB_DFT1_GO(U, W, M, F) launch_dft1_t<IN_U8IQ, U, W, M, F>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream)
 		if (K == 160) return w2 != 2 ? ACB_DFT1_GO(20, 4, 4, true) : pf ? ACB_DFT1_GO(20, 2, 8, true) : ACB_DFT1_GO(20, 2, 8, false);
 		if (K == 192) return w2 != 2 ? ACB_DFT1_GO(24, 4, 4, true) : pf ? ACB_DFT1_GO(24, 2, 8, true) : ACB_DFT1_GO(24, 2, 8, false);
 #undef ACB_DFT1_GO
@@ -1002,6 +1229,24 @@ int launch_channelize_dft(const void *in, size_t stream_stride, const float *tw,
 	                           : launch_dft_t<20, 2, 1, 5, false>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
 	if (K == 192) return fold8 ? launch_dft_t<24, 2, 1, 4, true>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream)
 	                           : launch_dft_t<24, 2, 1, 4, false>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream);
+	return (int)cudaErrorInvalidValue;
+}
+
+/* CS16 IQ (soapy.c / sdrplay.c), same conditions as above; `nsamp` output rows per stream, any count: the last block may be
+ * partial (the input buffer carries 32 rows of slack).  stream_stride in bytes. */
+int launch_channelize_dft_cs16(const void *in, size_t stream_stride, const float *tw, const unsigned *meta, float *dm,
+                               int K, int nch, int nstreams, size_t nsamp, cudaStream_t stream)
+{
+	if (nsamp == 0) return 0;
+	const uint8_t *i8 = reinterpret_cast<const uint8_t *>(in);
+	const float2 *t4 = reinterpret_cast<const float2 *>(tw);
+	const int nblk = (int)((nsamp + OUTBLK - 1) / OUTBLK);
+	/* a warp's tile is 32 rows x (4K + 16) bytes = 20.5 KB at K = 160: 2 warps per CTA -> 5 CTAs = 10 warps per SM */
+	const int w2 = getenv("ACB_FAST_WARPS") ? atoi(getenv("ACB_FAST_WARPS")) : 2;
+#define ACB_DFT1_GO(U, W, M) launch_dft1_t<IN_CS16IQ, U, W, M, true>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream)
+	if (K == 160) return w2 == 1 ? ACB_DFT1_GO(20, 1, 8) : ACB_DFT1_GO(20, 2, 5);
+	if (K == 192) return w2 == 1 ? ACB_DFT1_GO(24, 1, 8) : ACB_DFT1_GO(24, 2, 4);
+#undef ACB_DFT1_GO
 	return (int)cudaErrorInvalidValue;
 }
 

@@ -490,14 +490,18 @@ def main():
         out = {}
         kept, per_stream, nframes = [], np.zeros(S, dtype=np.int64), []
 
+        take_s = [0.0]
+
         def take():
             # what the checker needs: every record of the distinct pool streams, and a per-stream count of the rest
             # (a step carries tens of thousands of messages at this rate: nothing else is kept)
+            t_in = time.perf_counter()
             r = ctx.drain_records()
             if len(r):
                 per_stream[:] += np.bincount(r["stream"], minlength=S)
                 kept.append(r[r["stream"] < len(pool_b)].copy())
             nframes.append(len(r))
+            take_s[0] += time.perf_counter() - t_in
 
         flags = fastflag[channelizer] | (0 if with_e2e else 1)
         ctx = api.Context(K, S, nch, B, device=local, flags=flags)
@@ -528,6 +532,7 @@ def main():
         barrier()
         t0 = time.perf_counter()
         ctx.mark(0)
+        take_s[0] = 0.0
         for _ in range(steps):
             ctx.submit_device(din.ptr, B, stride)
             take()
@@ -535,6 +540,7 @@ def main():
         ctx.sync()
         take()
         t1 = time.perf_counter()
+        out["drain_ms_per_step"] = take_s[0] * 1e3 / steps      # this process draining the output queue (bench's own host work)
         ev_ms = ctx.elapsed_ms()
         barrier()
         st = ctx.stats(reset=True)
@@ -613,6 +619,7 @@ def main():
         other = {"channelizer": alt, "value": sum_over_ranks(float(samples_per_step_rank * nst)) / (am["ev_ms"] * 1e-3) / 1e6, "unit": UNIT,
                  "steps": nst, "ms_per_step": am["ev_ms"] / nst, "k_channelize_ms": k1b,
                  "k_demod_and_fec_ms": am["st"].demod_ms / max(1, am["st"].demod_launches),
+                 "host_consumer_ms_per_step": am["st"].host_ms / max(1, am["st"].submits),
                  "fast_launches": int(am["st"].fast_chan_launches), "checked": chk2,
                  "roofline": roofline_obj(alt, am["st"].fast_chan_launches > 0, k1b, am["k1_iso_ms"], S, B, K, nch, sm_mhz)}
 
@@ -648,7 +655,9 @@ def main():
         "gpu_launches": int(st.kernel_launches),
         "wall_ms_per_step": main_m["wall_ms"] / args.steps,
         "kernels": {"k_channelize_ms": k1_ms, "k_demod_and_fec_ms": k2_ms, "k_channelize_isolated_ms": main_m["k1_iso_ms"],
-                    "k_demod_and_fec_isolated_ms": main_m["k2_iso_ms"], "launches_per_step": st.kernel_launches / args.steps},
+                    "k_demod_and_fec_isolated_ms": main_m["k2_iso_ms"], "launches_per_step": st.kernel_launches / args.steps,
+                    # the library's consumer thread (frames of a finished submit -> emission order -> output queue), wall time
+                    "host_consumer_ms_per_step": st.host_ms / args.steps, "host_drain_ms_per_step": main_m["drain_ms_per_step"]},
         "alt_channelizer": other,
         "configs": configs,
         "real_time_receivers": {"device_resident": value / (K * 12500 / 1e6),

@@ -57,7 +57,10 @@ typedef struct {
 #define ACB_FLAG_NO_INPUT_STAGING 1   /* caller only uses acb_submit_device / acb_submit_dm_* */
 #define ACB_FLAG_CS16_INPUT 4         /* SoapySDR / SDRplay front-ends (soapy.c, sdrplay.c): int16 I,Q samples;
                                          use acb_set_plan_cs16 / acb_submit_cs16_host (or _planar_host) */
-#define ACB_FLAG_FAST_CHANNELIZER 8    /* u8 IQ contexts planned with acb_set_plan, K = 160 or 192: run the channelizer
+#define ACB_FLAG_FAST_CHANNELIZER 8    /* u8 IQ contexts planned with acb_set_plan and CS16 contexts planned with
+                                         acb_set_plan_cs16, K = 160 or 192 (real-input contexts planned with
+                                         acb_set_plan_air, K = 200, 400, 480 or 800: the same idea on a real row,
+                                         k_channelize_rdft): run the channelizer
                                          as a shared 4-point DFT across the row quarters + K/4 MACs per channel
                                          (5x less FP32 work) when every stream's channels sit on the 12.5 kHz raster
                                          around Fc; otherwise the exact kernel runs.  NOT the reference's operation
@@ -125,6 +128,12 @@ void acb_cs16_build_wf(int variant, unsigned freq_hz, unsigned fc_hz, int K, flo
  * 12.5 kHz steps with 0 < |k| < K/2; then k_out[ch] = k and tw[(ch*(K/4) + n2)*2 + {0,1}] =
  * exp(-j*2*pi*k*n2/K)/K/127.5.  k_out and tw may be NULL.  Returns 0 otherwise (the exact kernel runs). */
 int acb_fast_plan(const unsigned *freqs_hz, int nch, int K, unsigned fc_hz, int *k_out, float *tw);
+/* The same for CS16 contexts (soapy.c:159-165 / sdrplay.c:133-137: the offset is (float)Fr - (float)Fc); the twiddles
+ * carry the variant's power-of-two scale, exp(-j*2*pi*k*n2/K)/K/32768 (soapy.c:242) or /K/4 (sdrplay.c:225). */
+int acb_fast_plan_cs16(int variant, const unsigned *freqs_hz, int nch, int K, unsigned fc_hz, int *k_out, float *tw);
+/* The same for real-input contexts (air.c:278-285): k = (Fc - Fr + rate/4)/12500 must be whole, 0 < k < K (any parity: the
+ * real form splits the row in quarters only), tw = exp(-j*2*pi*k*n2/K)/K; K a multiple of 8. */
+int acb_fast_plan_air(const unsigned *freqs_hz, int nch, int K, unsigned fc_hz, int *k_out, float *tw);
 /* msk.c:44-48 — 133-tap oversampled half-cosine matched filter */
 void acb_build_h(float *h);
 
@@ -158,7 +167,10 @@ int acb_reset(acb_ctx_t *ctx);
  * Asynchronous: host->device copy, channelizer and demod are queued; call acb_sync to
  * collect.  `iq` should come from acb_host_alloc (pinned) for full PCIe overlap. */
 int acb_submit_host(acb_ctx_t *ctx, const uint8_t *iq, size_t stream_stride, int nblk);
-/* Same with the input already resident in device memory (no copy). */
+/* Same with the input already resident in device memory (no copy).
+ * Input lifetime, both calls: up to three submits are in flight; when submit N+2 returns, the input of submit N
+ * (the host buffer, or the device buffer) has been read and may be overwritten — as it may after an acb_collect /
+ * acb_sync that covered submit N. */
 int acb_submit_device(acb_ctx_t *ctx, const uint8_t *iq_dev, size_t stream_stride, int nblk);
 /* Replaces rx_callback (air.c:291-341): `nsamples` float32 real samples per stream (stream s at
  * x + s*stream_stride_samples), ANY count per call — what does not fill a K-sample output row is
@@ -186,7 +198,7 @@ int acb_submit_dm_host(acb_ctx_t *ctx, const float *dm, int nsamp);
 /* Order the next acb_submit_device behind work of ANOTHER CUDA stream: `cuda_event` is a cudaEvent_t recorded there
  * (e.g. behind the NCCL broadcast that fills the input buffer; torch.cuda.Event.cuda_event).  No host sync. */
 int acb_wait_event(acb_ctx_t *ctx, void *cuda_event);
-/* Wait for the OLDEST submit still in flight only (at most two are), run the block FEC on its
+/* Wait for the OLDEST submit still in flight only (at most three are), run the block FEC on its
  * frames and queue the survivors; later submits keep running.  This is what lets the H2D copy
  * of step i+1 overlap the kernels of step i.  Returns the number of messages waiting. */
 int acb_collect(acb_ctx_t *ctx);
@@ -236,6 +248,7 @@ typedef struct {
 	uint64_t chan_launches, demod_launches;
 	uint64_t fast_chan_launches; /* channelizer launches that took the ACB_FLAG_FAST_CHANNELIZER form */
 	uint64_t frames_lost;       /* frames that found the device ring full (ACB_ERR_OVERFLOW was returned once per submit) */
+	double   host_ms;           /* accumulated wall time the consumer thread spent ordering and queuing frames */
 } acb_stats_t;
 int acb_get_stats(acb_ctx_t *ctx, acb_stats_t *out, int reset);
 

@@ -239,6 +239,63 @@ void orc_channelize_dft8(const uint8_t *iq, int nout, int K, int nch, const int 
 	}
 }
 
+/* The same folded form for CS16 IQ input (soapy.c:232-254, sdrplay.c:215-236): oscillator[ind] = cexpf(-j*AMFreq*ind)/K is a
+ * sampled exponential too; with (float)Fr - (float)Fc a whole even number k of 12.5 kHz steps, D is bin k of the row's
+ * K-point DFT.  Twiddles carry the variant's power-of-two scale (soapy.c:242 divides by 32768, sdrplay.c:225 by 4).
+ * No mid-scale term: the samples are signed. */
+int orc_fast_plan_cs16(int variant, const unsigned *freqs_hz, int nch, int K, unsigned fc, int *kbin, float *tw)
+{
+	const int N2 = K / 4;
+	const double scale = variant == 0 ? 1.0 / 32768.0 : 0.25;
+	for (int ch = 0; ch < nch; ch++) {
+		const float d = (float)freqs_hz[ch] - (float)fc;
+		const float kf = d / (float)ORC_INTRATE;
+		const int k = (int)kf;
+		if ((float)k != kf || (k & 1) || k == 0 || k <= -K / 2 || k >= K / 2) return 0;
+		kbin[ch] = k;
+		for (int n2 = 0; n2 < N2; n2++) {
+			const double ph = -2.0 * M_PI * (double)(((long long)k * n2) % K) / (double)K;
+			tw[((size_t)ch * N2 + n2) * 2] = (float)(cos(ph) / K * scale);
+			tw[((size_t)ch * N2 + n2) * 2 + 1] = (float)(sin(ph) / K * scale);
+		}
+	}
+	return 1;
+}
+
+void orc_channelize_dft8_cs16(const int16_t *iq, int nout, int K, int nch, const int *kbin, const float *tw, float *dm)
+{
+	const int N2 = K / 4, N8 = K / 8;
+	for (int m = 0; m < nout; m++) {
+		const int16_t *p = iq + (size_t)m * K * 2;
+		for (int ch = 0; ch < nch; ch++) {
+			const int r = (((kbin[ch] / 2) % 4) + 4) % 4;
+			const float *t = tw + (size_t)ch * N2 * 2;
+			float a = 0, b = 0, pp = 0, q = 0;
+			for (int n2 = 0; n2 < N8; n2++) {
+				int zi[4], zq[4];
+				for (int n1 = 0; n1 < 4; n1++) {
+					zi[n1] = p[2 * (N8 * n1 + n2)] + p[2 * (N8 * (n1 + 4) + n2)];
+					zq[n1] = p[2 * (N8 * n1 + n2) + 1] + p[2 * (N8 * (n1 + 4) + n2) + 1];
+				}
+				int yr, yi;
+				switch (r) {
+				case 0: yr = zi[0] + zi[1] + zi[2] + zi[3]; yi = zq[0] + zq[1] + zq[2] + zq[3]; break;
+				case 2: yr = zi[0] - zi[1] + zi[2] - zi[3]; yi = zq[0] - zq[1] + zq[2] - zq[3]; break;
+				case 1: yr = (zi[0] - zi[2]) + (zq[1] - zq[3]); yi = (zq[0] - zq[2]) - (zi[1] - zi[3]); break;
+				default: yr = (zi[0] - zi[2]) - (zq[1] - zq[3]); yi = (zq[0] - zq[2]) + (zi[1] - zi[3]); break;
+				}
+				const float fr = (float)yr, fi = (float)yi, tr = t[2 * n2], ti = t[2 * n2 + 1];
+				a = fmaf(fr, tr, a);
+				b = fmaf(fi, ti, b);
+				pp = fmaf(fr, ti, pp);
+				q = fmaf(fi, tr, q);
+			}
+			const float re = a - b, im = pp + q;
+			dm[(size_t)ch * nout + m] = sqrtf(fmaf(re, re, im * im));
+		}
+	}
+}
+
 /* ------------------------------------------------------------------ Airspy front-end (air.c) */
 
 /* air.c:42-64 with filter == 0 (every rate but 5 MS/s): centre of the span on the 12.5 kHz raster */
@@ -262,6 +319,63 @@ void orc_air_build_wf(int fr, int fc, unsigned rate, float *wf)
 		ph += step;
 		if (ph > 2.0 * M_PI) ph -= 2.0 * M_PI;
 		if (ph < -2.0 * M_PI) ph += 2.0 * M_PI;
+	}
+}
+
+/* Fast form of the same (k_channelize_rdft restated operation for operation): with Fc and the channels on the 12.5 kHz
+ * raster the table of orc_air_build_wf is exp(-j*2*pi*k*i/K)/K, k = (Fc - Fr + rate/4)/12500, and D is bin k of the REAL
+ * row's K-point DFT; split over the row's quarters,
+ *   D = sum_{n2<K/4} T[n2] * Y_r[n2],  r = k mod 4,  T[n2] = exp(-j*2*pi*k*n2/K)/K,
+ *   Y_0 = (x0+x2)+(x1+x3), Y_2 = (x0+x2)-(x1+x3), Y_1 = (x0-x2) - j(x1-x3), Y_3 = (x0-x2) + j(x1-x3), x_q = x[(K/4)q + n2]. */
+int orc_fast_plan_air(const int *freqs_hz, int nch, int K, int fc, int *kbin, float *tw)
+{
+	const int N2 = K / 4;
+	const unsigned rate = (unsigned)K * ORC_INTRATE;
+	if (K & 7) return 0;
+	for (int ch = 0; ch < nch; ch++) {
+		const unsigned off = (unsigned)(fc - freqs_hz[ch] + (int)(rate / 4));      /* air.c:278 */
+		if (off % ORC_INTRATE) return 0;
+		const int k = (int)(off / ORC_INTRATE);
+		if (k <= 0 || k >= K) return 0;
+		kbin[ch] = k;
+		for (int n2 = 0; n2 < N2; n2++) {
+			const double ph = -2.0 * M_PI * (double)(((long long)k * n2) % K) / (double)K;
+			tw[((size_t)ch * N2 + n2) * 2] = (float)(cos(ph) / K);
+			tw[((size_t)ch * N2 + n2) * 2 + 1] = (float)(sin(ph) / K);
+		}
+	}
+	return 1;
+}
+
+void orc_channelize_rdft(const float *x, int nout, int K, int nch, const int *kbin, const float *tw, float *dm)
+{
+	const int N2 = K / 4;
+	for (int m = 0; m < nout; m++) {
+		const float *p = x + (size_t)m * K;
+		for (int ch = 0; ch < nch; ch++) {
+			const int r = kbin[ch] & 3;
+			const float *t = tw + (size_t)ch * N2 * 2;
+			float ax = 0, ay = 0, bx = 0, by = 0;       /* A = sum Ye*T (or (x0-x2)*T), B = sum (x1-x3)*T, as (re, im) */
+			for (int n2 = 0; n2 < N2; n2++) {
+				const float x0 = p[n2], x1 = p[N2 + n2], x2 = p[2 * N2 + n2], x3 = p[3 * N2 + n2];
+				const float tr = t[2 * n2], ti = t[2 * n2 + 1];
+				if (r == 0 || r == 2) {
+					const float s02 = x0 + x2, s13 = x1 + x3;
+					const float y = r == 0 ? s02 + s13 : s02 - s13;
+					ax = fmaf(y, tr, ax);
+					ay = fmaf(y, ti, ay);
+				} else {
+					const float d02 = x0 - x2, d13 = x1 - x3;
+					ax = fmaf(d02, tr, ax);
+					ay = fmaf(d02, ti, ay);
+					bx = fmaf(d13, tr, bx);
+					by = fmaf(d13, ti, by);
+				}
+			}
+			const float sg = r == 3 ? -1.0f : 1.0f;
+			const float re = ax + sg * by, im = ay - sg * bx;
+			dm[(size_t)ch * nout + m] = sqrtf(fmaf(re, re, im * im));
+		}
 	}
 }
 

@@ -72,6 +72,12 @@ void orc_channelize_fir(const uint8_t *iq, int nout, int K, int taps, int nch,
 int  orc_fast_plan(const unsigned *freqs_hz, int nch, int K, unsigned fc, int *kbin /*nch*/, float *tw /*nch x K/4 x 2*/);
 void orc_channelize_dft(const uint8_t *iq, int nout, int K, int nch, const int *kbin, const float *tw, float *dm /*nch x nout*/);
 void orc_channelize_dft8(const uint8_t *iq, int nout, int K, int nch, const int *kbin, const float *tw, float *dm);   /* folded variant */
+/* the folded form on CS16 IQ (variant 0 = soapy.c, 1 = sdrplay.c: the power-of-two scale in the twiddles) */
+int  orc_fast_plan_cs16(int variant, const unsigned *freqs_hz, int nch, int K, unsigned fc, int *kbin, float *tw);
+/* the real-input (air.c) fast form: bin k = (Fc - Fr + rate/4)/12500 of the real row's DFT, 4-way split */
+int  orc_fast_plan_air(const int *freqs_hz, int nch, int K, int fc, int *kbin, float *tw);
+void orc_channelize_rdft(const float *x, int nout, int K, int nch, const int *kbin, const float *tw, float *dm);
+void orc_channelize_dft8_cs16(const int16_t *iq, int nout, int K, int nch, const int *kbin, const float *tw, float *dm);
 
 /* Airspy front-end (air.c): float32 real samples at IF = rate/4 */
 unsigned orc_air_choose_fc(unsigned minf, unsigned maxf);                 /* air.c:42-64, no-filter branch */

@@ -354,6 +354,10 @@ class OracleLib:
         L.orc_fast_plan.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p, C.c_void_p]
         L.orc_channelize_dft.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_channelize_dft8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_fast_plan_air.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_channelize_rdft.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_fast_plan_cs16.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p, C.c_void_p]
+        L.orc_channelize_dft8_cs16.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_cs16_build_osc.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_void_p]
         L.orc_channelize_cs16.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_chan_init.argtypes = [C.POINTER(OrcChan), C.c_int]
@@ -446,6 +450,42 @@ class OracleLib:
         tw = np.ascontiguousarray(tw, dtype=np.float32)
         fn = self.lib.orc_channelize_dft8 if fold8 else self.lib.orc_channelize_dft
         fn(iq.ctypes.data, nout, K, len(k), k.ctypes.data, tw.ctypes.data, dm.ctypes.data)
+        return dm
+
+    def fast_plan_air(self, K: int, freqs_hz, fc: int):
+        """(k per channel, twiddles (nch, K/4, 2) float32) of the fast real-input channelizer's restatement, or None."""
+        f = np.asarray(freqs_hz, dtype=np.int32)
+        k = np.zeros(len(f), dtype=np.int32)
+        tw = np.zeros((len(f), K // 4, 2), dtype=np.float32)
+        if self.lib.orc_fast_plan_air(f.ctypes.data, len(f), K, int(fc), k.ctypes.data, tw.ctypes.data) != 1:
+            return None
+        return k, tw
+
+    def channelize_rdft(self, x: np.ndarray, K: int, k: np.ndarray, tw: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
+        nout = x.size // K
+        dm = np.empty((len(k), nout), dtype=np.float32)
+        k = np.ascontiguousarray(k, dtype=np.int32)
+        tw = np.ascontiguousarray(tw, dtype=np.float32)
+        self.lib.orc_channelize_rdft(x.ctypes.data, nout, K, len(k), k.ctypes.data, tw.ctypes.data, dm.ctypes.data)
+        return dm
+
+    def fast_plan_cs16(self, variant: int, K: int, freqs_hz, fc: int):
+        """(k per channel, twiddles (nch, K/4, 2) float32) of the fast CS16 channelizer's restatement, or None."""
+        f = np.asarray(freqs_hz, dtype=np.uint32)
+        k = np.zeros(len(f), dtype=np.int32)
+        tw = np.zeros((len(f), K // 4, 2), dtype=np.float32)
+        if self.lib.orc_fast_plan_cs16(variant, f.ctypes.data, len(f), K, int(fc), k.ctypes.data, tw.ctypes.data) != 1:
+            return None
+        return k, tw
+
+    def channelize_dft8_cs16(self, iq: np.ndarray, K: int, k: np.ndarray, tw: np.ndarray) -> np.ndarray:
+        iq = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1)
+        nout = iq.size // (2 * K)
+        dm = np.empty((len(k), nout), dtype=np.float32)
+        k = np.ascontiguousarray(k, dtype=np.int32)
+        tw = np.ascontiguousarray(tw, dtype=np.float32)
+        self.lib.orc_channelize_dft8_cs16(iq.ctypes.data, nout, K, len(k), k.ctypes.data, tw.ctypes.data, dm.ctypes.data)
         return dm
 
     def cs16_osc(self, variant: int, K: int, freqs_hz, fc: int) -> np.ndarray:

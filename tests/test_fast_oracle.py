@@ -113,3 +113,80 @@ def test_fast_intermediates_stated_bounds(oracle):
     assert r["envelope_diff_over_total_inband_signal"]["max"] <= 1e-5                   # the bound that does hold (measured 1.6e-6)
     assert r["MskDf_abs_diff"]["max"] <= 1e-3 and r["MskDf_abs_diff"]["p50"] <= 1e-7    # PLL range is +-3.8e-3
     assert r["lvl_dB_abs_diff_max"] <= 0.05 and r["raw_frames_identical"] >= 8
+
+
+@pytest.mark.parametrize("variant,K", [(0, 160), (1, 192)])
+def test_cs16_fast_restatement(native, oracle, variant, K):
+    """The folded form on CS16 input (soapy.c / sdrplay.c tables are sampled exponentials too): the library's plan equals
+    the restatement's, the envelope stays within the literal arithmetic's table rounding and closer to the exact DFT
+    bin than the literal tables are, and the messages are the same."""
+    import ctypes as C
+    freqs = (131.525, 131.725, 131.825, 131.450, 131.550)
+    fd, _, fc = oracle.plan(K, freqs)
+    k, tw = oracle.fast_plan_cs16(variant, K, fd, fc)
+    f = np.asarray(fd, dtype=np.uint32)
+    k2, tw2 = np.zeros(len(f), dtype=np.int32), np.zeros((len(f), K // 4, 2), dtype=np.float32)
+    assert native.acb_fast_plan_cs16(variant, f.ctypes.data, len(f), K, int(fc), k2.ctypes.data, tw2.ctypes.data) == 1
+    assert (k == k2).all() and np.array_equal(tw, tw2)
+    assert oracle.fast_plan_cs16(variant, K, fd, fc - 12500) is None            # odd bins: no folded form
+    plan = synth.StreamPlan(K=K, freqs_hz=tuple(fd), fc_hz=fc, seed=21, noise_sigma=1.5)
+    rng = np.random.default_rng(21)
+    for ch in range(len(freqs)):
+        t = 0.01 + 0.02 * ch
+        for _ in range(3):
+            fr = synth.frame_bytes(synth.random_text(rng, int(rng.integers(8, 40))))
+            plan.bursts.append(synth.Burst(chan=ch, t0=t, frame=fr, amp=float(rng.uniform(10, 25)), phase=float(rng.uniform(0, 6))))
+            t += len(fr) * 8 / 2400 + 0.03
+    n = int(0.5 * plan.rate) // K * K
+    iq = synth.render_cs16(plan, 0, n)
+    lit = oracle.channelize_cs16(variant, iq, K, oracle.cs16_osc(variant, K, fd, fc))
+    fast = oracle.channelize_dft8_cs16(iq, K, k, tw)
+    scale = 1.0 / 32768 if variant == 0 else 0.25
+    x = iq.astype(np.float64).reshape(-1, K, 2)
+    total = np.hypot(x[..., 0], x[..., 1]).sum(axis=1) / K * scale
+    xc = x[..., 0] + 1j * x[..., 1]
+    ideal = np.stack([np.abs(xc @ (np.exp(-2j * np.pi * int(kk) * np.arange(K) / K) / K * scale)) for kk in k])
+    err_fast = (np.abs(fast - ideal) / total[None, :]).max()
+    err_lit = (np.abs(lit - ideal) / total[None, :]).max()
+    assert (np.abs(fast.astype(np.float64) - lit) / total[None, :]).max() <= TABLE_EPS
+    assert err_fast <= IDEAL_EPS and err_fast < err_lit, (err_fast, err_lit)
+    a, b = _decode(oracle, lit), _decode(oracle, fast)
+    assert len(a) >= len(freqs) and [m[:-1] for m in a] == [m[:-1] for m in b]
+    assert max(abs(x[-1] - y[-1]) for x, y in zip(a, b)) < 0.05                 # lvl, dB
+
+
+@pytest.mark.parametrize("rate,fm", [(2500000, (131.525, 131.725, 131.825, 131.450)),
+                                     (10000000, (131.125, 131.1375, 131.15, 131.1625, 131.55))])
+def test_real_input_fast_restatement(native, oracle, rate, fm):
+    """The real-input fast form (air.c's table is a sampled exponential of a whole bin number when Fc and the channels sit on
+    the 12.5 kHz raster): library plan == restatement plan, envelope within the literal arithmetic's table rounding and
+    closer to the exact DFT bin, same messages."""
+    fd, fc, K = oracle.air_plan(rate, fm)
+    k, tw = oracle.fast_plan_air(K, fd, fc)
+    f = np.asarray(fd, dtype=np.uint32)
+    k2, tw2 = np.zeros(len(f), dtype=np.int32), np.zeros((len(f), K // 4, 2), dtype=np.float32)
+    assert native.acb_fast_plan_air(f.ctypes.data, len(f), K, int(fc), k2.ctypes.data, tw2.ctypes.data) == 1
+    assert (k == k2).all() and np.array_equal(tw, tw2) and len(set(int(x) % 4 for x in k)) >= 2
+    assert oracle.fast_plan_air(K, [fd[0] + 1000] + list(fd[1:]), fc) is None     # off the raster: no DFT bin
+    plan = synth.StreamPlan(K=K, freqs_hz=tuple(fd), fc_hz=fc, seed=31, noise_sigma=1.0)
+    rng = np.random.default_rng(31)
+    for ch in range(len(fm)):
+        t = 0.01 + 0.02 * ch
+        for _ in range(2):
+            fr = synth.frame_bytes(synth.random_text(rng, int(rng.integers(8, 40))))
+            plan.bursts.append(synth.Burst(chan=ch, t0=t, frame=fr, amp=float(rng.uniform(10, 25)), phase=float(rng.uniform(0, 6))))
+            t += len(fr) * 8 / 2400 + 0.03
+    n = int(0.35 * rate) // K * K
+    x = synth.render_real(plan, 0, n)
+    lit = oracle.channelize_real(x, K, oracle.air_wf(rate, fm))
+    fast = oracle.channelize_rdft(x, K, k, tw)
+    xr = x.astype(np.float64).reshape(-1, K)
+    total = np.abs(xr).sum(axis=1) / K
+    ideal = np.stack([np.abs(xr @ (np.exp(-2j * np.pi * int(kk) * np.arange(K) / K) / K)) for kk in k])
+    err_fast = (np.abs(fast - ideal) / total[None, :]).max()
+    err_lit = (np.abs(lit - ideal) / total[None, :]).max()
+    assert (np.abs(fast.astype(np.float64) - lit) / total[None, :]).max() <= TABLE_EPS
+    assert err_fast <= IDEAL_EPS and err_fast < err_lit, (err_fast, err_lit)
+    a, b = _decode(oracle, lit), _decode(oracle, fast)
+    assert len(a) >= len(fm) and [m[:-1] for m in a] == [m[:-1] for m in b]
+    assert max(abs(p[-1] - q[-1]) for p, q in zip(a, b)) < 0.05                 # lvl, dB

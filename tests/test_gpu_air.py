@@ -89,6 +89,58 @@ def test_real_input_envelope_and_frames(native, oracle, rate, fm):
         assert [f for f in frames if f[0] == c] == [f for f in want if f[0] == c]
 
 
+@pytest.mark.parametrize("rate,fm,warps", [
+    (2500000, (131.525, 131.725, 131.825, 131.450), 2),              # K=200, odd residues
+    (2500000, synth.DEFAULT_FREQS_MHZ, 1),                           # K=200, 8 channels, one warp per CTA
+    (6000000, (129.125, 130.025, 131.550), 2),                       # K=480
+    (10000000, (131.125, 131.1375, 131.15, 131.1625, 131.55, 131.825, 131.85, 131.475, 131.525, 131.725), 2),   # K=800, two groups, every residue
+    (5000000, (131.45, 131.4625, 131.55), 2),                        # K=400 (the kernel only: air.c's 5 MS/s tuner-filter offset is not modelled)
+])
+def test_real_input_fast_form(native, oracle, monkeypatch, rate, fm, warps):
+    """ACB_FLAG_FAST_CHANNELIZER on a real-input context (k_channelize_rdft): held to its CPU restatement bit for bit
+    (orc_channelize_rdft; ragged submits, partial blocks), to the literal arithmetic within 1e-5 of the row's total
+    signal, and to the same decoded messages."""
+    monkeypatch.setenv("ACB_FAST_WARPS", str(warps))
+    secs = 0.4
+    plan, fd, fc, K = _plan(oracle, rate, fm, secs, seed=rate // 100000 + 1)
+    total = int(secs * rate)
+    x = synth.render_real(plan, 0, total)
+    nout_all = total // K
+    lit = oracle.channelize_real(x[: nout_all * K], K, oracle.air_wf(rate, fm))
+    kbin, tw = oracle.fast_plan_air(K, fd, fc)
+    want_dm = oracle.channelize_rdft(x[: nout_all * K], K, kbin, tw)
+    tot = np.abs(x[: nout_all * K].astype(np.float64)).reshape(nout_all, K).sum(axis=1) / K
+    assert (np.abs(want_dm.astype(np.float64) - lit) / tot[None, :]).max() <= 1e-5
+    max_blocks = nout_all // 1024 + 2
+    rng = np.random.default_rng(4)
+    with api.Context(K, 1, len(fm), max_blocks, flags=FLAG_REAL | 8) as ctx:
+        assert ctx.set_plan_air(0, fd) == fc
+        sizes, pos, done, i, frames = [K // 3, 5 * K + 7, 1024 * K + 13, 3, 2 * 1024 * K + 999, 33 * K, 31 * K + 1], 0, 0, 0, []
+        while pos < total:
+            n = sizes[i] if i < len(sizes) else int(rng.integers(1, 1500 * K))
+            n = min(n, total - pos, (max_blocks * 1024 - 1) * K)
+            i += 1
+            m = ctx.submit_real(x[None, pos:pos + n])
+            pos += n
+            ctx.sync()
+            frames += [msg_tuple(f) for f in ctx.drain()]
+            if m:
+                assert bits_equal(ctx.read_dm(m)[0], want_dm[:, done:done + m].T.copy()), (pos, m)
+                done += m
+        assert done == nout_all
+        st = ctx.stats()
+        assert st.fast_chan_launches == st.chan_launches > 0
+    sink, want = refs.Sink(), []
+    for c in range(len(fm)):
+        oracle.demod(oracle.new_chan(c), lit[c], sink)         # the LITERAL envelope: same messages expected
+    for msg in sink.msgs():
+        f = oracle.fec(msg)
+        if f is not None:
+            want.append(msg_tuple(f))
+    strip = lambda t: t[:5]                                    # (chn, len, err, txt, crc): lvl moves by < 0.05 dB
+    assert sorted(map(strip, frames)) == sorted(map(strip, want)) and len(want) >= len(fm)
+
+
 def test_real_input_multistream_chunking_independence(native, oracle):
     rate, fm = 2500000, (131.525, 131.725, 131.825)
     fd, fc, K = oracle.air_plan(rate, fm)

@@ -1,7 +1,7 @@
 """Pipeline stress: a few hundred randomised submits against one context — block counts 1..max, pageable / pinned /
 device-resident sources, collect vs sync vs nothing between submits, drains at random, mid-run acb_reset and
 get/set_state round trips — with every stream held to the CPU oracle frame for frame and state for state.
-The context keeps two submits in flight on four non-blocking streams (copy, channelizer, demod, read-back);
+The context keeps up to three submits in flight on five non-blocking streams (copy, channelizer, demod, block FEC, read-back);
 any ordering hole (a kernel reading a staging buffer before its copy landed, a frame ring cleared while it is
 being read back, a reset racing a launch) shows up here as a difference from the oracle."""
 import numpy as np
@@ -50,7 +50,7 @@ def test_randomised_submits_match_oracle(native, oracle, seed, flags):
             n = int(min(rng.integers(1, maxblk + 1), total_blk - pos))
             chunk = np.ascontiguousarray(iq[:, pos * bb:(pos + n) * bb])
             kind = int(rng.integers(0, 3))
-            slot = nsub % 3                          # three buffers, two submits in flight: the third is free
+            slot = nsub % 3                          # three buffers: when submit N+2 has returned, the input of submit N has been read (acars_b200.h)
             if kind == 0:
                 ctx.submit_host(chunk, n)            # pageable
             elif kind == 1:

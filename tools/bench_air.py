@@ -13,6 +13,7 @@ import refs
 rate = int(sys.argv[1]) if len(sys.argv) > 1 else 2500000
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 296
 C = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+fast = len(sys.argv) > 4 and sys.argv[4] == "fast"              # ACB_FLAG_FAST_CHANNELIZER: k_channelize_rdft
 B = 16
 fm = synth.DEFAULT_FREQS_MHZ[:C]
 fd, fc, K = api.air_plan(rate, fm)
@@ -23,7 +24,7 @@ for ch in range(C):
 n = B * 1024 * K
 base = synth.render_real(plan, 0, n)
 x = np.ascontiguousarray(np.broadcast_to(base, (S, n)))
-ctx = api.Context(K, S, C, B, flags=2)
+ctx = api.Context(K, S, C, B, flags=2 | (8 if fast else 0))
 for s in range(S):
     ctx.set_plan_air(s, fd)
 for _ in range(2):
@@ -42,7 +43,8 @@ except Exception:
     pass
 # oracle check of stream 0's frames
 orc = refs.OracleLib()
-print(json.dumps({"front_end": "air.c real float32", "rate": rate, "K": K, "streams": S, "channels": C, "blocks": B,
+print(json.dumps({"front_end": "air.c real float32", "channelizer": "fast" if fast else "exact",
+                  "fast_launches": int(st.fast_chan_launches), "rate": rate, "K": K, "streams": S, "channels": C, "blocks": B,
                   "k_channelize_real_ms": k1, "k_demod_ms": st.demod_ms / st.demod_launches,
                   "Msamples_per_s_kernel": S * n / k1 / 1e3, "algorithmic_bytes": alg,
                   "achieved_GBs": alg / k1 / 1e6, "peak_GBs": peak, "frac": alg / k1 / 1e6 / peak,

@@ -11,6 +11,7 @@ from acarsdec_b200 import api, synth
 variant = int(sys.argv[1]) if len(sys.argv) > 1 else 0          # 0 soapy.c, 1 sdrplay.c
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 296
 C = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+fast = len(sys.argv) > 4 and sys.argv[4] == "fast"              # ACB_FLAG_FAST_CHANNELIZER: the folded DFT form
 K, B = 160, 16
 fm = synth.DEFAULT_FREQS_MHZ[:C]
 fd, _, fc = api.plan(K, fm)
@@ -21,7 +22,7 @@ for ch in range(C):
 n = B * 1024 * K
 base = synth.render_cs16(plan, 0, n)
 x = np.ascontiguousarray(np.broadcast_to(base, (S, n, 2)))
-ctx = api.Context(K, S, C, B, flags=4)
+ctx = api.Context(K, S, C, B, flags=4 | (8 if fast else 0))
 for s in range(S):
     ctx.set_plan_cs16(s, fd, variant)
 for _ in range(2):
@@ -38,7 +39,8 @@ try:
     peak = json.load(open(ROOT / "MEASURED_PEAKS.json"))["hbm_gbs"]
 except Exception:
     pass
-print(json.dumps({"front_end": ["soapy.c", "sdrplay.c"][variant] + " CS16", "K": K, "streams": S, "channels": C, "blocks": B,
+print(json.dumps({"front_end": ["soapy.c", "sdrplay.c"][variant] + " CS16", "channelizer": "fast" if fast else "exact",
+                  "fast_launches": int(st.fast_chan_launches), "K": K, "streams": S, "channels": C, "blocks": B,
                   "k_channelize_cs16_ms": k1, "k_demod_ms": st.demod_ms / st.demod_launches,
                   "Msamples_per_s_kernel": S * n / k1 / 1e3, "algorithmic_bytes": alg,
                   "achieved_GBs": alg / k1 / 1e6, "peak_GBs": peak, "frac": alg / k1 / 1e6 / peak,
