@@ -1010,25 +1010,31 @@ static int launch_dft1_t(const uint8_t *in, size_t stream_stride, const float2 *
  * columns (r = 0 | r = 2 | r odd; residues 1 and 3 accumulate the same two sums and differ in one sign at the end).
  * NOT the reference's operation order (tolerance: include/acars_b200.h); bit-identical to oracle's orc_channelize_rdft.
  * ---------------------------------------------------------------------------------------- */
-template <int K8, int WARPS> struct RdftPlan {
+/* LPR lanes share a row: lane l works on row l % ROWS of the warp's tile and takes the h-th contiguous range of n2 pairs,
+ * h = l / ROWS; the LPR partial sums are added pairwise (h ^ 1, then h ^ 2, ...) at the end.  A row of K floats is 800 bytes
+ * and more: with one lane per row a warp's tile is 26-103 KB, 8 warps or fewer fit an SM and the kernel sits at 29 % issue
+ * utilisation waiting for its own dependent FFMA2 chains (ncu, K = 200: 0.93 ms); LPR = K/100 keeps the tile at 13 KB. */
+template <int K8, int LPR, int WARPS> struct RdftPlan {
 	static constexpr int K = K8 * 8;
+	static constexpr int ROWS = 32 / LPR;                             /* rows per warp tile */
 	static constexpr int ROWBYTES = K * 4;
 	static constexpr int GROUP = ROWBYTES + 16;                       /* every row shifted by one more 16-byte unit */
-	static constexpr int TILE_BYTES = DFT1_ROWS * GROUP;
+	static constexpr int TILE_BYTES = ROWS * GROUP;
 	static constexpr int N2 = K / 4;
 	static constexpr int TW_BYTES = N2 * CH_GROUP * 8;
 	static constexpr int BAR_OFF = WARPS * TILE_BYTES + TW_BYTES;
 	static constexpr int SMEM = BAR_OFF + WARPS * 8;
+	static constexpr int PER = (K8 + LPR - 1) / LPR;                  /* n2 pairs per lane */
 };
 
-template <int K8, int WARPS, int MINB>
+template <int K8, int LPR, int WARPS, int MINB>
 __global__ void __launch_bounds__(32 * WARPS, MINB)
 k_channelize_rdft(const uint8_t *__restrict__ in, size_t stream_stride, const float2 *__restrict__ tw,
                   const unsigned *__restrict__ meta, float *__restrict__ dm, int nch, int ngrp, size_t nsamp)
 {
-	using P = RdftPlan<K8, WARPS>;
-	constexpr int N2 = P::N2;
-	constexpr int NTILE = OUTBLK / DFT1_ROWS;
+	using P = RdftPlan<K8, LPR, WARPS>;
+	constexpr int N2 = P::N2, ROWS = P::ROWS;
+	constexpr int NTILE = OUTBLK / ROWS;
 	extern __shared__ __align__(16) unsigned char smem[];
 	const int l = threadIdx.x & 31;
 	const int w = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -1069,10 +1075,10 @@ k_channelize_rdft(const uint8_t *__restrict__ in, size_t stream_stride, const fl
 	{
 		const uint4 *tsrc = reinterpret_cast<const uint4 *>(tw + ((size_t)s * ngrp + g) * N2 * CH_GROUP);
 		uint4 *tdst = reinterpret_cast<uint4 *>(smem + (size_t)WARPS * P::TILE_BYTES);
-		constexpr int PER = N2 * 8 / 16;
+		constexpr int PER16 = N2 * 8 / 16;
 		for (int q = threadIdx.x; q < P::TW_BYTES / 16; q += 32 * WARPS) {
-			const int j = q / PER, off = q - j * PER;
-			cp_async16(tdst + q, tsrc + ((pw >> (3 * j)) & 7u) * PER + off);
+			const int j = q / PER16, off = q - j * PER16;
+			cp_async16(tdst + q, tsrc + ((pw >> (3 * j)) & 7u) * PER16 + off);
 		}
 		cp_async_commit();
 		cp_async_wait_all();
@@ -1080,30 +1086,32 @@ k_channelize_rdft(const uint8_t *__restrict__ in, size_t stream_stride, const fl
 	__syncthreads();
 
 	const size_t rows_left = nsamp - (size_t)blk * OUTBLK;
-	const int tiles_here = rows_left >= (size_t)OUTBLK ? NTILE : (int)((rows_left + DFT1_ROWS - 1) / DFT1_ROWS);
+	const int tiles_here = rows_left >= (size_t)OUTBLK ? NTILE : (int)((rows_left + ROWS - 1) / ROWS);
 	const int ntile = (tiles_here - w + WARPS - 1) / WARPS;
 	auto issue = [&](int n) {
 		if (elect_one()) {
-			mbar_expect_tx(bar, DFT1_ROWS * P::ROWBYTES);
-			const uint8_t *src = src_blk + (size_t)(w + n * WARPS) * DFT1_ROWS * P::ROWBYTES;
+			mbar_expect_tx(bar, ROWS * P::ROWBYTES);
+			const uint8_t *src = src_blk + (size_t)(w + n * WARPS) * ROWS * P::ROWBYTES;
 #pragma unroll
-			for (int i = 0; i < DFT1_ROWS; i++)
+			for (int i = 0; i < ROWS; i++)
 				bulk_g2s(mytile + (size_t)i * P::GROUP, src + (size_t)i * P::ROWBYTES, P::ROWBYTES, bar);
 		}
 	};
 	if (ntile > 0) issue(0);
 	const int nc = min(CH_GROUP, nch - g * CH_GROUP);
+	const int row = l % ROWS, h = l / ROWS;
+	const int gp0 = h * P::PER, gp1 = min(K8, gp0 + P::PER);
 
 	for (int n = 0; n < ntile; n++) {
 		const int tile = w + n * WARPS;
 		mbar_wait(bar, (unsigned)(n & 1));
-		const unsigned char *ra = mytile + (size_t)l * P::GROUP;
+		const unsigned char *ra = mytile + (size_t)row * P::GROUP;
 		float2 A[CH_GROUP], B[CH_GROUP];
 #pragma unroll
 		for (int c = 0; c < CH_GROUP; c++) A[c] = B[c] = make_float2(0.f, 0.f);
 
 #pragma unroll 1
-		for (int gp = 0; gp < K8; gp++) {                 /* n2 = 2 gp, 2 gp + 1 */
+		for (int gp = gp0; gp < gp1; gp++) {              /* n2 = 2 gp, 2 gp + 1 */
 			const float2 x0 = *reinterpret_cast<const float2 *>(ra + 0 * P::K + gp * 8);
 			const float2 x1 = *reinterpret_cast<const float2 *>(ra + 1 * P::K + gp * 8);
 			const float2 x2 = *reinterpret_cast<const float2 *>(ra + 2 * P::K + gp * 8);
@@ -1143,27 +1151,40 @@ k_channelize_rdft(const uint8_t *__restrict__ in, size_t stream_stride, const fl
 		}
 		__syncwarp();
 		if (n + 1 < ntile) issue(n + 1);
-		const size_t mrow = (size_t)blk * OUTBLK + (size_t)tile * DFT1_ROWS + l;
-		float *o = dm + ((size_t)s * nsamp + mrow) * nch + g * CH_GROUP;
+		/* the row's LPR partial sums, pairwise: (p0 + p1) + (p2 + p3) ... — both partners compute the same sum */
 #pragma unroll
-		for (int j = 0; j < CH_GROUP; j++) {
-			/* r = 1: D = (A.x + B.y) + j (A.y - B.x); r = 3: the other signs; r even: B is zero */
-			const float sg = ((neg >> j) & 1u) ? -1.0f : 1.0f;
-			const float re = __fadd_rn(A[j].x, __fmul_rn(sg, B[j].y)), im = __fadd_rn(A[j].y, -__fmul_rn(sg, B[j].x));
-			const float e = __fsqrt_rn(__fmaf_rn(re, re, __fmul_rn(im, im)));
-			const int c = (int)((pw >> (3 * j)) & 7u);
-			if (c < nc && mrow < nsamp) o[c] = e;
+		for (int step = ROWS; step < 32; step *= 2) {
+#pragma unroll
+			for (int j = 0; j < CH_GROUP; j++) {
+				A[j].x = __fadd_rn(A[j].x, __shfl_xor_sync(0xffffffffu, A[j].x, step));
+				A[j].y = __fadd_rn(A[j].y, __shfl_xor_sync(0xffffffffu, A[j].y, step));
+				B[j].x = __fadd_rn(B[j].x, __shfl_xor_sync(0xffffffffu, B[j].x, step));
+				B[j].y = __fadd_rn(B[j].y, __shfl_xor_sync(0xffffffffu, B[j].y, step));
+			}
+		}
+		const size_t mrow = (size_t)blk * OUTBLK + (size_t)tile * ROWS + row;
+		if (h == 0 && mrow < nsamp) {
+			float *o = dm + ((size_t)s * nsamp + mrow) * nch + g * CH_GROUP;
+#pragma unroll
+			for (int j = 0; j < CH_GROUP; j++) {
+				/* r = 1: D = (A.x + B.y) + j (A.y - B.x); r = 3: the other signs; r even: B is zero */
+				const float sg = ((neg >> j) & 1u) ? -1.0f : 1.0f;
+				const float re = __fadd_rn(A[j].x, __fmul_rn(sg, B[j].y)), im = __fadd_rn(A[j].y, -__fmul_rn(sg, B[j].x));
+				const float e = __fsqrt_rn(__fmaf_rn(re, re, __fmul_rn(im, im)));
+				const int c = (int)((pw >> (3 * j)) & 7u);
+				if (c < nc) o[c] = e;
+			}
 		}
 	}
 }
 
-template <int K8, int WARPS, int MINB>
+template <int K8, int LPR, int WARPS, int MINB>
 static int launch_rdft_t(const uint8_t *in, size_t stream_stride, const float2 *tw, const unsigned *meta, float *dm,
                          int nch, int nstreams, int nblk, size_t nsamp, cudaStream_t stream)
 {
 	const int ngrp = (nch + CH_GROUP - 1) / CH_GROUP;
-	constexpr int smem = RdftPlan<K8, WARPS>::SMEM;
-	auto kern = k_channelize_rdft<K8, WARPS, MINB>;
+	constexpr int smem = RdftPlan<K8, LPR, WARPS>::SMEM;
+	auto kern = k_channelize_rdft<K8, LPR, WARPS, MINB>;
 	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	if (e != cudaSuccess) return (int)e;
 	e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1173,8 +1194,10 @@ static int launch_rdft_t(const uint8_t *in, size_t stream_stride, const float2 *
 	return (int)cudaGetLastError();
 }
 
-/* the Airspy rates whose 32-row tile fits a CTA: 2.5 MS/s (K = 200), 5 (400), 6 (480), 10 (800) */
+/* the Airspy rates: 2.5 MS/s (K = 200), 5 (400), 6 (480), 10 (800) */
 bool channelize_rdft_supports(int K) { return K == 200 || K == 400 || K == 480 || K == 800; }
+/* lanes per row of k_channelize_rdft (the CPU restatement needs it: it fixes the order of the partial sums) */
+int channelize_rdft_lanes_per_row(int K) { return K >= 800 ? 8 : K >= 400 ? 4 : 2; }
 
 /* float32 real input (air.c), taps == K, every channel on the 12.5 kHz raster around Fc; `nsamp` output rows per stream,
  * any count (the input buffer carries 32 rows of slack).  stream_stride in bytes. */
@@ -1185,12 +1208,13 @@ int launch_channelize_rdft(const void *in, size_t stream_stride, const float *tw
 	const uint8_t *i8 = reinterpret_cast<const uint8_t *>(in);
 	const float2 *t4 = reinterpret_cast<const float2 *>(tw);
 	const int nblk = (int)((nsamp + OUTBLK - 1) / OUTBLK);
-	const int w2 = getenv("ACB_FAST_WARPS") ? atoi(getenv("ACB_FAST_WARPS")) : 2;
-#define ACB_RDFT_GO(K8, W, M) launch_rdft_t<K8, W, M>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream)
-	if (K == 200) return w2 == 1 ? ACB_RDFT_GO(25, 1, 8) : ACB_RDFT_GO(25, 2, 4);       /* 26 KB of tile per warp */
-	if (K == 400) return ACB_RDFT_GO(50, 1, 4);                                         /* 52 KB */
-	if (K == 480) return ACB_RDFT_GO(60, 1, 3);                                         /* 62 KB */
-	if (K == 800) return ACB_RDFT_GO(100, 1, 2);                                        /* 103 KB */
+	const int w2 = getenv("ACB_FAST_WARPS") ? atoi(getenv("ACB_FAST_WARPS")) : 4;
+#define ACB_RDFT_GO(K8, LPR, W, M) launch_rdft_t<K8, LPR, W, M>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream)
+	/* 13-16 KB of tile per warp everywhere; 4 warps per CTA: 16 warps per SM at K = 200, 12 at the other rates */
+	if (K == 200) return w2 == 2 ? ACB_RDFT_GO(25, 2, 2, 7) : ACB_RDFT_GO(25, 2, 4, 4);
+	if (K == 400) return ACB_RDFT_GO(50, 4, 4, 3);
+	if (K == 480) return ACB_RDFT_GO(60, 4, 4, 3);
+	if (K == 800) return ACB_RDFT_GO(100, 8, 4, 3);
 #undef ACB_RDFT_GO
 	return (int)cudaErrorInvalidValue;
 }
@@ -1689,8 +1713,8 @@ int upload_matched_filter(const float *h, cudaStream_t stream)
 	return (int)cudaStreamSynchronize(stream);
 }
 
-template <int L, bool F2F, bool PIN>
-__global__ void __launch_bounds__(32)
+template <int L, bool F2F, bool PIN, int MINB = 1>
+__global__ void __launch_bounds__(32, MINB)
 k_demod2(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp, int nch, int nstreams,
          int wps, RawFrame *__restrict__ ring, RingCtl *__restrict__ ctl, unsigned cap)
 {
@@ -1738,7 +1762,7 @@ k_demod2(ChainState *__restrict__ states, const float *__restrict__ dm, int nsam
 	for (int k = 0; k < FLEN; k++) { st->inb_re[k] = sm.ring[k][grp].x; st->inb_im[k] = sm.ring[k][grp].y; }
 }
 
-template <int LANES, bool F2F, bool PIN>
+template <int LANES, bool F2F, bool PIN, int MINB = 1>
 static int launch_demod_t(ChainState *st, const float *dm, int nsamp, int nch, int nstreams,
                           RawFrame *ring, RingCtl *ctl, unsigned cap, cudaStream_t stream)
 {
@@ -1746,9 +1770,9 @@ static int launch_demod_t(ChainState *st, const float *dm, int nsamp, int nch, i
 	const int wps = (nch + CPW - 1) / CPW;
 	const long long nchain = (long long)nstreams * nch;
 	const int grid = (int)((nchain + CPW - 1) / CPW);    /* one warp per CTA so that chains spread over all SMs */
-	cudaError_t e = cudaFuncSetAttribute(k_demod2<LANES, F2F, PIN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+	cudaError_t e = cudaFuncSetAttribute(k_demod2<LANES, F2F, PIN, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 	if (e != cudaSuccess) return (int)e;
-	k_demod2<LANES, F2F, PIN><<<grid, 32, 0, stream>>>(st, dm, nsamp, nch, nstreams, wps, ring, ctl, cap);
+	k_demod2<LANES, F2F, PIN, MINB><<<grid, 32, 0, stream>>>(st, dm, nsamp, nch, nstreams, wps, ring, ctl, cap);
 	return (int)cudaGetLastError();
 }
 
@@ -1795,6 +1819,7 @@ int launch_demod(ChainState *st, const float *dm, int nsamp, int nch, int nstrea
 	case 8: return launch_demod_t<8, false, true>(ACB_DEMOD_ARGS);
 	case 2: return launch_demod_t<2, false, true>(ACB_DEMOD_ARGS);
 	case 1: return launch_demod_t<1, false, false>(ACB_DEMOD_ARGS);
+	case 17: return launch_demod_t<1, true, false>(ACB_DEMOD_ARGS);          /* F2F bit clock at one lane: no different (profiles/r2_notes.md) */
 	case 24: return launch_demod_t<8, true, true>(ACB_DEMOD_ARGS);
 	case 20: return launch_demod_t<4, true, true>(ACB_DEMOD_ARGS);
 	case 40: return launch_demod_t<8, false, false>(ACB_DEMOD_ARGS);

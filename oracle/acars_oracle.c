@@ -347,33 +347,43 @@ int orc_fast_plan_air(const int *freqs_hz, int nch, int K, int fc, int *kbin, fl
 	return 1;
 }
 
+/* `lpr` lanes of the kernel share a row (K/100 rounded down to a power of two: 2, 4, 4, 8 for K = 200, 400, 480, 800): lane h
+ * sums the h-th range of ceil(K/8 / lpr) n2 PAIRS in n2 order, the partial sums are added pairwise (h^1, then h^2, ...). */
 void orc_channelize_rdft(const float *x, int nout, int K, int nch, const int *kbin, const float *tw, float *dm)
 {
-	const int N2 = K / 4;
+	const int N2 = K / 4, K8 = K / 8;
+	const int lpr = K >= 800 ? 8 : K >= 400 ? 4 : 2, per = (K8 + lpr - 1) / lpr;
 	for (int m = 0; m < nout; m++) {
 		const float *p = x + (size_t)m * K;
 		for (int ch = 0; ch < nch; ch++) {
 			const int r = kbin[ch] & 3;
 			const float *t = tw + (size_t)ch * N2 * 2;
-			float ax = 0, ay = 0, bx = 0, by = 0;       /* A = sum Ye*T (or (x0-x2)*T), B = sum (x1-x3)*T, as (re, im) */
-			for (int n2 = 0; n2 < N2; n2++) {
-				const float x0 = p[n2], x1 = p[N2 + n2], x2 = p[2 * N2 + n2], x3 = p[3 * N2 + n2];
-				const float tr = t[2 * n2], ti = t[2 * n2 + 1];
-				if (r == 0 || r == 2) {
-					const float s02 = x0 + x2, s13 = x1 + x3;
-					const float y = r == 0 ? s02 + s13 : s02 - s13;
-					ax = fmaf(y, tr, ax);
-					ay = fmaf(y, ti, ay);
-				} else {
-					const float d02 = x0 - x2, d13 = x1 - x3;
-					ax = fmaf(d02, tr, ax);
-					ay = fmaf(d02, ti, ay);
-					bx = fmaf(d13, tr, bx);
-					by = fmaf(d13, ti, by);
+			float ax[8] = { 0 }, ay[8] = { 0 }, bx[8] = { 0 }, by[8] = { 0 };   /* A = sum Ye*T (or (x0-x2)*T), B = sum (x1-x3)*T */
+			for (int h = 0; h < lpr; h++) {
+				const int g0 = h * per, g1 = g0 + per < K8 ? g0 + per : K8;
+				for (int n2 = 2 * g0; n2 < 2 * g1; n2++) {
+					const float x0 = p[n2], x1 = p[N2 + n2], x2 = p[2 * N2 + n2], x3 = p[3 * N2 + n2];
+					const float tr = t[2 * n2], ti = t[2 * n2 + 1];
+					if (r == 0 || r == 2) {
+						const float s02 = x0 + x2, s13 = x1 + x3;
+						const float y = r == 0 ? s02 + s13 : s02 - s13;
+						ax[h] = fmaf(y, tr, ax[h]);
+						ay[h] = fmaf(y, ti, ay[h]);
+					} else {
+						const float d02 = x0 - x2, d13 = x1 - x3;
+						ax[h] = fmaf(d02, tr, ax[h]);
+						ay[h] = fmaf(d02, ti, ay[h]);
+						bx[h] = fmaf(d13, tr, bx[h]);
+						by[h] = fmaf(d13, ti, by[h]);
+					}
 				}
 			}
+			for (int step = 1; step < lpr; step *= 2)
+				for (int h = 0; h < lpr; h += 2 * step) {
+					ax[h] += ax[h + step]; ay[h] += ay[h + step]; bx[h] += bx[h + step]; by[h] += by[h + step];
+				}
 			const float sg = r == 3 ? -1.0f : 1.0f;
-			const float re = ax + sg * by, im = ay - sg * bx;
+			const float re = ax[0] + sg * by[0], im = ay[0] - sg * bx[0];
 			dm[(size_t)ch * nout + m] = sqrtf(fmaf(re, re, im * im));
 		}
 	}

@@ -254,7 +254,7 @@ def test_full_path_synthetic_vs_oracle(native, oracle, K, seed, nstreams):
     assert keys == sorted(keys)
 
 
-@pytest.mark.parametrize("lanes", [1, 2, 4, 8, 20, 24, 33, 34, 36, 40, -4, -8])
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8, 17, 20, 24, 33, 34, 36, 40, -4, -8])
 def test_demod_every_lane_width(native, oracle, lanes, monkeypatch):
     """k_demod2 with 1, 2, 4 and 8 lanes per channel (the context picks by chain count; ACB_DEMOD_LANES forces),
     both bit-clock rounding forms (+16), with and without pinned constants (+32), and the round-1 kernel (negative): same frames, same bit-identical
