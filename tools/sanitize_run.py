@@ -46,4 +46,20 @@ with api.Context(K, 1, 8, 2, flags=4) as ctx:
     m.txt[3] ^= 0x04
     out = ctx.block_fec_batch([m] * 70)
     assert all(o is not None and o.err == 1 for o in out)
-print("sanitize run ok", n1, n3, n4)
+# the fast forms of the streaming front-ends (partial blocks, tiles past the end, the 32 rows of slack), four submits so that
+# every one of the three pipeline slots is reused
+with api.Context(K, 1, 8, 2, flags=4 | 8) as ctx:
+    ctx.set_plan_cs16(0, fd, 1)
+    for part in (iqc, iqc[:, :4000], iqc[:, :33 * K + 5], iqc):
+        ctx.submit_cs16(part)
+    ctx.sync()
+    assert ctx.stats().fast_chan_launches >= 3
+    n5 = len(ctx.drain())
+xr = synth.render_real(synth.StreamPlan(K=Ka, freqs_hz=tuple(fda), fc_hz=fca, seed=2, noise_sigma=1.0), 0, 1024 * Ka + 777)[None]
+with api.Context(Ka, 1, 3, 3, flags=2 | 8) as ctx:
+    ctx.set_plan_air(0, fda)
+    for part in (xr, xr[:, :5000], xr[:, :17 * Ka + 3], xr):
+        ctx.submit_real(part)
+    ctx.sync()
+    assert ctx.stats().fast_chan_launches >= 3
+print("sanitize run ok", n1, n3, n4, n5)
