@@ -1713,7 +1713,7 @@ int upload_matched_filter(const float *h, cudaStream_t stream)
 	return (int)cudaStreamSynchronize(stream);
 }
 
-template <int L, bool F2F, bool PIN, int MINB = 1>
+template <int L, bool F2F, bool PIN, int MINB = 1>     /* MINB = 0: no occupancy request */
 __global__ void __launch_bounds__(32, MINB)
 k_demod2(ChainState *__restrict__ states, const float *__restrict__ dm, int nsamp, int nch, int nstreams,
          int wps, RawFrame *__restrict__ ring, RingCtl *__restrict__ ctl, unsigned cap)
@@ -1776,6 +1776,25 @@ static int launch_demod_t(ChainState *st, const float *dm, int nsamp, int nch, i
 	return (int)cudaGetLastError();
 }
 
+/* The pinned forms (2, 4, 8 lanes) in two register budgets.  Told that one CTA per SM is all it asks for
+ * (__launch_bounds__(32, 1)), ptxas spends 144 instead of 124 registers on a wider schedule: 1.4 % fewer instructions and 9 %
+ * less time where the kernel is latency bound (592 streams, 4 lanes: 2.75 -> 2.51 ms under ncu) — and two warps per SM fewer
+ * where it is not (2368 streams forced to 4 lanes: 16 -> 14 warps per SM, 4.31 -> 5.76 ms).  So: the wide schedule while
+ * there are at most 8 warps per SM, the lean one beyond. */
+template <int LANES, bool F2F>
+static int launch_demod_pinned(ChainState *st, const float *dm, int nsamp, int nch, int nstreams,
+                               RawFrame *ring, RingCtl *ctl, unsigned cap, cudaStream_t stream)
+{
+	static int sm_count = 0;
+	if (sm_count == 0) {
+		int dev = 0;
+		if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sm_count = 148;
+	}
+	const long long warps = ((long long)nstreams * nch * LANES + 31) / 32;
+	return warps <= 8LL * sm_count ? launch_demod_t<LANES, F2F, true, 1>(st, dm, nsamp, nch, nstreams, ring, ctl, cap, stream)
+	                               : launch_demod_t<LANES, F2F, true, 0>(st, dm, nsamp, nch, nstreams, ring, ctl, cap, stream);
+}
+
 template <int LANES>
 static int launch_demod_v1(ChainState *st, const float *dm, int nsamp, int nch, int nstreams,
                            RawFrame *ring, RingCtl *ctl, unsigned cap, cudaStream_t stream)
@@ -1816,17 +1835,17 @@ int launch_demod(ChainState *st, const float *dm, int nsamp, int nch, int nstrea
 	switch (lanes) {
 	case -8: return launch_demod_v1<8>(ACB_DEMOD_ARGS);
 	case -4: return launch_demod_v1<4>(ACB_DEMOD_ARGS);
-	case 8: return launch_demod_t<8, false, true>(ACB_DEMOD_ARGS);
-	case 2: return launch_demod_t<2, false, true>(ACB_DEMOD_ARGS);
+	case 8: return launch_demod_pinned<8, false>(ACB_DEMOD_ARGS);
+	case 2: return launch_demod_pinned<2, false>(ACB_DEMOD_ARGS);
 	case 1: return launch_demod_t<1, false, false>(ACB_DEMOD_ARGS);
 	case 17: return launch_demod_t<1, true, false>(ACB_DEMOD_ARGS);          /* F2F bit clock at one lane: no different (profiles/r2_notes.md) */
-	case 24: return launch_demod_t<8, true, true>(ACB_DEMOD_ARGS);
-	case 20: return launch_demod_t<4, true, true>(ACB_DEMOD_ARGS);
+	case 24: return launch_demod_pinned<8, true>(ACB_DEMOD_ARGS);
+	case 20: return launch_demod_pinned<4, true>(ACB_DEMOD_ARGS);
 	case 40: return launch_demod_t<8, false, false>(ACB_DEMOD_ARGS);
 	case 36: return launch_demod_t<4, false, false>(ACB_DEMOD_ARGS);
 	case 34: return launch_demod_t<2, false, false>(ACB_DEMOD_ARGS);
 	case 33: return launch_demod_t<1, false, true>(ACB_DEMOD_ARGS);
-	default: return launch_demod_t<4, false, true>(ACB_DEMOD_ARGS);
+	default: return launch_demod_pinned<4, false>(ACB_DEMOD_ARGS);
 	}
 #undef ACB_DEMOD_ARGS
 }
