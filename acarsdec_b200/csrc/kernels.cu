@@ -1194,8 +1194,8 @@ static int launch_rdft_t(const uint8_t *in, size_t stream_stride, const float2 *
 	return (int)cudaGetLastError();
 }
 
-/* the Airspy rates: 2.5 MS/s (K = 200), 5 (400), 6 (480), 10 (800) */
-bool channelize_rdft_supports(int K) { return K == 200 || K == 400 || K == 480 || K == 800; }
+/* the Airspy rates: 2.5 MS/s (K = 200), 3 (240), 5 (400), 6 (480), 10 (800) */
+bool channelize_rdft_supports(int K) { return K == 200 || K == 240 || K == 400 || K == 480 || K == 800; }
 /* lanes per row of k_channelize_rdft (the CPU restatement needs it: it fixes the order of the partial sums) */
 int channelize_rdft_lanes_per_row(int K) { return K >= 800 ? 8 : K >= 400 ? 4 : 2; }
 
@@ -1212,6 +1212,7 @@ int launch_channelize_rdft(const void *in, size_t stream_stride, const float *tw
 #define ACB_RDFT_GO(K8, LPR, W, M) launch_rdft_t<K8, LPR, W, M>(i8, stream_stride, t4, meta, dm, nch, nstreams, nblk, nsamp, stream)
 	/* 13-16 KB of tile per warp everywhere; 4 warps per CTA: 16 warps per SM at K = 200, 12 at the other rates */
 	if (K == 200) return w2 == 2 ? ACB_RDFT_GO(25, 2, 2, 7) : ACB_RDFT_GO(25, 2, 4, 4);
+	if (K == 240) return ACB_RDFT_GO(30, 2, 4, 3);
 	if (K == 400) return ACB_RDFT_GO(50, 4, 4, 3);
 	if (K == 480) return ACB_RDFT_GO(60, 4, 4, 3);
 	if (K == 800) return ACB_RDFT_GO(100, 8, 4, 3);

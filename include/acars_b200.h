@@ -59,7 +59,7 @@ typedef struct {
                                          use acb_set_plan_cs16 / acb_submit_cs16_host (or _planar_host) */
 #define ACB_FLAG_FAST_CHANNELIZER 8    /* u8 IQ contexts planned with acb_set_plan and CS16 contexts planned with
                                          acb_set_plan_cs16, K = 160 or 192 (real-input contexts planned with
-                                         acb_set_plan_air, K = 200, 400, 480 or 800: the same idea on a real row,
+                                         acb_set_plan_air, K = 200, 240, 400, 480 or 800: the same idea on a real row,
                                          k_channelize_rdft): run the channelizer
                                          as a shared 4-point DFT across the row quarters + K/4 MACs per channel
                                          (5x less FP32 work) when every stream's channels sit on the 12.5 kHz raster

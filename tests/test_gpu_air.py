@@ -93,6 +93,7 @@ def test_real_input_envelope_and_frames(native, oracle, rate, fm):
     (2500000, (131.525, 131.725, 131.825, 131.450), 2),              # K=200, odd residues
     (2500000, synth.DEFAULT_FREQS_MHZ, 4),                           # K=200, 8 channels, four warps per CTA (the default)
     (6000000, (129.125, 130.025, 131.550), 2),                       # K=480
+    (3000000, synth.DEFAULT_FREQS_MHZ, 4),                           # K=240 (Airspy Mini)
     (10000000, (131.125, 131.1375, 131.15, 131.1625, 131.55, 131.825, 131.85, 131.475, 131.525, 131.725), 2),   # K=800, two groups, every residue
     (5000000, (131.45, 131.4625, 131.55), 2),                        # K=400 (the kernel only: air.c's 5 MS/s tuner-filter offset is not modelled)
 ])
