@@ -531,7 +531,10 @@ static void consume(acb_ctx *c, const acb_ctx::Job &job)
 	const size_t nchain = (size_t)c->cfg.nstreams * c->cfg.nch, nbucket = (gs.size() + 1) * nchain;
 	std::vector<unsigned> order(count);
 	std::vector<unsigned char> keep(count);             /* 1 = repaired and parity-stripped on the device (k_block_fec) */
-	if (nbucket <= ((size_t)1 << 24)) {
+	/* test hooks (tests/test_gpu_parity.py): ACB_CONSUMER_SORT=1 forces the comparison sort, ACB_CONSUMER_HELPERS_MIN=n the
+	 * helper threads from n frames on */
+	const bool force_sort = getenv("ACB_CONSUMER_SORT") && atoi(getenv("ACB_CONSUMER_SORT")) != 0;
+	if (!force_sort && nbucket <= ((size_t)1 << 24)) {
 		std::vector<unsigned> start(nbucket + 1, 0u), bucket(count);
 		for (unsigned i = 0; i < count; i++) {          /* the one pass in ring order: sequential reads */
 			const RawFrame &f = ring[i];
@@ -584,7 +587,8 @@ static void consume(acb_ctx *c, const acb_ctx::Job &job)
 			m.crc[0] = f.crc[0]; m.crc[1] = f.crc[1];
 		}
 	};
-	const unsigned helpers = count >= 8192 ? std::min(3u, std::max(1u, std::thread::hardware_concurrency()) - 1u) : 0u;
+	const unsigned helpers_min = getenv("ACB_CONSUMER_HELPERS_MIN") ? (unsigned)atoi(getenv("ACB_CONSUMER_HELPERS_MIN")) : 8192u;
+	const unsigned helpers = count >= helpers_min ? std::min(3u, std::max(1u, std::thread::hardware_concurrency()) - 1u) : 0u;
 	if (helpers == 0) {
 		fill(0, count);
 	} else {

@@ -254,6 +254,38 @@ def test_full_path_synthetic_vs_oracle(native, oracle, K, seed, nstreams):
     assert keys == sorted(keys)
 
 
+@pytest.mark.parametrize("hook", ["sort", "helpers"])
+def test_consumer_thread_paths_agree(native, monkeypatch, hook):
+    """The consumer thread orders a submit's frames with a stable bucket pass and, for large submits, fills the records
+    on helper threads; the comparison-sort fallback (contexts with an unreasonable bucket table) and the helper path are
+    forced here through the library's test hooks and must queue exactly the same records in the same order."""
+    K, fm, nstreams = 160, synth.DEFAULT_FREQS_MHZ, 6
+    fd, _, fc = api.plan(K, fm)
+    secs = 0.5
+    nblk = synth.blocks_for_seconds(K, secs)
+    iq = np.stack([synth.render_blocks(synth.make_plan(K, fm, fc, seconds=secs, seed=70 + s, msgs_per_chan_per_sec=3.0, text_len=(5, 40)), 0, nblk).reshape(-1)
+                   for s in range(nstreams)])
+
+    def run():
+        with api.Context(K, nstreams, len(fm), nblk) as ctx:
+            for s in range(nstreams):
+                ctx.set_plan(s, fd)
+            half = nblk // 2
+            ctx.submit_host(np.ascontiguousarray(iq[:, :half * 2048 * K]), half)
+            ctx.submit_host(np.ascontiguousarray(iq[:, half * 2048 * K:]), nblk - half)
+            ctx.sync()
+            return ctx.drain_records()
+
+    base = run()
+    monkeypatch.setenv("ACB_CONSUMER_SORT" if hook == "sort" else "ACB_CONSUMER_HELPERS_MIN", "1")
+    other = run()
+    rec = lambda r: [(int(m["stream"]), int(m["chn"]), int(m["len"]), int(m["err"]), float(m["lvl"]), int(m["block"]), int(m["pos"]),
+                      int(m["soh_pos"]), bytes(m["txt"][:int(m["len"])]), bytes(m["crc"])) for m in r]
+    assert len(base) >= 4 * nstreams and rec(base) == rec(other)
+    keys = [(int(m["block"]), int(m["stream"]), int(m["chn"]), int(m["pos"])) for m in base]
+    assert keys == sorted(keys)
+
+
 @pytest.mark.parametrize("lanes", [1, 2, 4, 8, 17, 20, 24, 33, 34, 36, 40, -4, -8])
 def test_demod_every_lane_width(native, oracle, lanes, monkeypatch):
     """k_demod2 with 1, 2, 4 and 8 lanes per channel (the context picks by chain count; ACB_DEMOD_LANES forces),
