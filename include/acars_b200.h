@@ -244,7 +244,7 @@ typedef struct {
 	uint64_t raw_frames;        /* frames handed from the device to the FEC */
 	uint64_t fec_dropped;       /* frames the FEC rejected */
 	double   chan_ms;           /* accumulated device time of the channelizer kernel (CUDA events) */
-	double   demod_ms;          /* accumulated device time of the demod kernel */
+	double   demod_ms;          /* accumulated device time from a demod kernel's start to the end of its block FEC */
 	uint64_t chan_launches, demod_launches;
 	uint64_t fast_chan_launches; /* channelizer launches that took the ACB_FLAG_FAST_CHANNELIZER form */
 	uint64_t frames_lost;       /* frames that found the device ring full (ACB_ERR_OVERFLOW was returned once per submit) */
