@@ -171,6 +171,59 @@ def test_unmodified_acarsdec_main_links_against_shim(tmp_path, K, outtype):
     assert a == b
 
 
+def _run_with_udp_sink(cmd, env, port):
+    """Run `cmd` while listening on 127.0.0.1:port; returns (returncode, stderr, [datagram, ...])."""
+    import socket, threading
+    sock = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+    sock.bind(("127.0.0.1", port))
+    sock.settimeout(0.2)
+    got, stop = [], threading.Event()
+
+    def rx():
+        while True:
+            try:
+                got.append(sock.recv(65536))
+            except socket.timeout:
+                if stop.is_set():
+                    return
+
+    th = threading.Thread(target=rx)
+    th.start()
+    try:
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=120)
+    finally:
+        stop.set()
+        th.join()
+        sock.close()
+    return r.returncode, r.stderr, got
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not (REFBIN / "acarsdec_b200").exists() or not (REFBIN / "acarsdec_ref").exists(),
+                    reason="oracle/_ref program builds absent")
+@pytest.mark.parametrize("opt", ["-n", "-N", "-j"])          # netout.c: native "sv" datagrams, planeplotter, JSON
+def test_unmodified_acarsdec_main_udp_sinks(tmp_path, opt):
+    """The UDP wire formats (netout.c:100-153, fed by outputmsg output.c:486-706) of the unmodified program linked against
+    the shim: the same datagrams, in the same order, as the program linked against its own DSP."""
+    K = 160
+    orc = refs.OracleLib()
+    fm = (131.525, 131.725, 131.825, 131.450, 131.550)
+    _, _, fc = orc.plan(K, fm)
+    plan = synth.make_plan(K, fm, fc, seconds=1.2, seed=91, text_len=(10, 120), msgs_per_chan_per_sec=3.0)
+    cap = tmp_path / "cap.iq"
+    synth.render_blocks(plan, 0, synth.blocks_for_seconds(K, 1.2)).tofile(cap)
+    freqs = [str(f) for f in fm]
+    port = 20000 + (os.getpid() * 7 + {"-n": 0, "-N": 1, "-j": 2}[opt]) % 20000
+    args = ["-o", "0", opt, f"127.0.0.1:{port}", "-m", str(K), "-r"]
+    rc, err, ref = _run_with_udp_sink([str(REFBIN / "acarsdec_ref"), *args, "0", *freqs], dict(os.environ, ACARSDEC_STUB_IQ=str(cap)), port)
+    assert rc == 0, err
+    rc, err, mine = _run_with_udp_sink([str(REFBIN / "acarsdec_b200"), *args, str(cap), *freqs], dict(os.environ, ACARSDEC_B200_BLOCKS="4"), port)
+    assert rc == 0, err
+    strip = lambda d: re.sub(r"\d\d/\d\d/\d{4} \d\d:\d\d:\d\d", "<time>", _strip_time(d.decode("latin-1")))
+    a, b = [strip(d) for d in ref], [strip(d) for d in mine]
+    assert len(a) >= 6 and a == b
+
+
 @pytest.mark.gpu
 def test_rtl_trio_through_test_host(tmp_path, oracle):
     exe = _host(tmp_path)
