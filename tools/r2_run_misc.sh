@@ -1,5 +1,4 @@
-# one gpurun job (1 GPU): K=240 real fast form, the consumer thread's fallback/helper paths
+# one gpurun job (1 GPU): drop-in tests incl. the UDP sinks
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_air.py tests/test_gpu_parity.py -m gpu -q -x -k "fast_form or consumer or full_path" > gpurun_out/r2_pytest_misc.log 2>&1; tail -4 gpurun_out/r2_pytest_misc.log
-python tools/bench_air.py 3000000 246 8 fast | tail -1
+timeout 900 python -m pytest tests/test_compat.py -m gpu -q > gpurun_out/r2_pytest_misc.log 2>&1; tail -6 gpurun_out/r2_pytest_misc.log
