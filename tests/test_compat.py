@@ -171,11 +171,12 @@ def test_unmodified_acarsdec_main_links_against_shim(tmp_path, K, outtype):
     assert a == b
 
 
-def _run_with_udp_sink(cmd, env, port):
-    """Run `cmd` while listening on 127.0.0.1:port; returns (returncode, stderr, [datagram, ...])."""
+def _run_with_udp_sink(make_cmd, env):
+    """Run make_cmd(port) while listening on a free UDP port of 127.0.0.1; returns (returncode, stderr, [datagram, ...])."""
     import socket, threading
     sock = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
-    sock.bind(("127.0.0.1", port))
+    sock.bind(("127.0.0.1", 0))
+    cmd = make_cmd(sock.getsockname()[1])
     sock.settimeout(0.2)
     got, stop = [], threading.Event()
 
@@ -213,11 +214,10 @@ def test_unmodified_acarsdec_main_udp_sinks(tmp_path, opt):
     cap = tmp_path / "cap.iq"
     synth.render_blocks(plan, 0, synth.blocks_for_seconds(K, 1.2)).tofile(cap)
     freqs = [str(f) for f in fm]
-    port = 20000 + (os.getpid() * 7 + {"-n": 0, "-N": 1, "-j": 2}[opt]) % 20000
-    args = ["-o", "0", opt, f"127.0.0.1:{port}", "-m", str(K), "-r"]
-    rc, err, ref = _run_with_udp_sink([str(REFBIN / "acarsdec_ref"), *args, "0", *freqs], dict(os.environ, ACARSDEC_STUB_IQ=str(cap)), port)
+    args = lambda port: ["-o", "0", opt, f"127.0.0.1:{port}", "-m", str(K), "-r"]
+    rc, err, ref = _run_with_udp_sink(lambda port: [str(REFBIN / "acarsdec_ref"), *args(port), "0", *freqs], dict(os.environ, ACARSDEC_STUB_IQ=str(cap)))
     assert rc == 0, err
-    rc, err, mine = _run_with_udp_sink([str(REFBIN / "acarsdec_b200"), *args, str(cap), *freqs], dict(os.environ, ACARSDEC_B200_BLOCKS="4"), port)
+    rc, err, mine = _run_with_udp_sink(lambda port: [str(REFBIN / "acarsdec_b200"), *args(port), str(cap), *freqs], dict(os.environ, ACARSDEC_B200_BLOCKS="4"))
     assert rc == 0, err
     strip = lambda d: re.sub(r"\d\d/\d\d/\d{4} \d\d:\d\d:\d\d", "<time>", _strip_time(d.decode("latin-1")))
     a, b = [strip(d) for d in ref], [strip(d) for d in mine]
