@@ -31,6 +31,7 @@
 #include <deque>
 #include <memory>
 #include <mutex>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -298,7 +299,7 @@ extern "C" int acb_create(const acb_config_t *cfg, acb_ctx_t **out)
 		if (c->real_input) {
 			/* room for the carried remainder (< K) plus one submit, rounded so streams stay 32-B aligned */
 			c->real_cap = (((size_t)cfg->max_blocks * OUTBLK + 1) * cfg->K + 7) & ~(size_t)7;     /* streams 32-B aligned: whole sectors per chunk */
-			/* + 32 rows: the fast CS16 kernel fetches whole 32-row tiles, the last one may reach past the last row */
+			/* + 32 rows: the fast CS16 / real-input kernels fetch whole tiles of up to 32 rows, the last one may reach past the last row */
 			CU(cudaMalloc(&c->d_real[i], ((size_t)cfg->nstreams * c->real_cap + 32 * (size_t)cfg->K) * sizeof(float)));
 			CU(cudaEventCreateWithFlags(&c->ev_real_free[i], cudaEventDisableTiming));
 			c->real_used[i] = false;
@@ -457,7 +458,7 @@ static int upload_fast_plan(acb_ctx *c, int stream, bool ok, const std::vector<i
 	std::vector<unsigned> meta(c->ngrp, 0u);
 	for (int ch = 0; ch < nch; ch++) {
 		const int g = ch / CH_GROUP, cc = ch % CH_GROUP;
-		meta[g] |= (unsigned)(((kbin[ch] % 4) + 4) % 4) << (2 * cc);      /* 0 or 2 */
+		meta[g] |= (unsigned)(((kbin[ch] % 4) + 4) % 4) << (2 * cc);      /* k mod 4: the 4-way split (u8: 0 or 2; real input: any) */
 		meta[g] |= (unsigned)((((kbin[ch] / 2) % 4) + 4) % 4) << (16 + 2 * cc);   /* k even: residue of k/2, for the folded form */
 		memcpy(&tw[((size_t)g * CH_GROUP + cc) * N2 * 2], &tw1[(size_t)ch * N2 * 2], (size_t)N2 * 2 * sizeof(float));
 	}
@@ -594,7 +595,14 @@ static void consume(acb_ctx *c, const acb_ctx::Job &job)
 	} else {
 		std::vector<std::thread> pool;
 		const unsigned parts = helpers + 1, per = (count + parts - 1) / parts;
-		for (unsigned t = 1; t < parts; t++) pool.emplace_back(fill, std::min(count, t * per), std::min(count, (t + 1) * per));
+		for (unsigned t = 1; t < parts; t++) {
+			const unsigned j0 = std::min(count, t * per), j1 = std::min(count, (t + 1) * per);
+			try {
+				pool.emplace_back(fill, j0, j1);
+			} catch (const std::system_error &) {        /* no thread to be had: this one does the range itself */
+				fill(j0, j1);
+			}
+		}
 		fill(0, std::min(count, per));
 		for (auto &th : pool) th.join();
 	}

@@ -1786,11 +1786,9 @@ template <int LANES, bool F2F>
 static int launch_demod_pinned(ChainState *st, const float *dm, int nsamp, int nch, int nstreams,
                                RawFrame *ring, RingCtl *ctl, unsigned cap, cudaStream_t stream)
 {
-	static int sm_count = 0;
-	if (sm_count == 0) {
-		int dev = 0;
-		if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sm_count = 148;
-	}
+	int dev = 0, sm_count = 0;               /* asked per launch: contexts of one process may sit on different devices */
+	if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0)
+		sm_count = 148;
 	const long long warps = ((long long)nstreams * nch * LANES + 31) / 32;
 	return warps <= 8LL * sm_count ? launch_demod_t<LANES, F2F, true, 1>(st, dm, nsamp, nch, nstreams, ring, ctl, cap, stream)
 	                               : launch_demod_t<LANES, F2F, true, 0>(st, dm, nsamp, nch, nstreams, ring, ctl, cap, stream);
