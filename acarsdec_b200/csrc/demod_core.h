@@ -43,6 +43,14 @@
 
 namespace acb {
 
+/* loop unrolling is a request to nvcc's device pass; the host compilers that build the same loop (nvcc's host pass,
+ * hostmath.cpp, the tests' emulation) are not asked */
+#if defined(__CUDA_ARCH__)
+#define DC_UNROLL _Pragma("unroll")
+#else
+#define DC_UNROLL
+#endif
+
 #if defined(__CUDA_ARCH__)
 #define DC_DADD(a, b) __dadd_rn((a), (b))
 #define DC_DMUL(a, b) __dmul_rn((a), (b))
@@ -228,7 +236,7 @@ ACB_HD void demod_run(DemodRegs &r, DemodShared<CPW> &sm, const float *in, int n
 	else {
 		const volatile double *src = reinterpret_cast<const volatile double *>(&g_dcc);
 		double *dst = reinterpret_cast<double *>(&DCK_);
-#pragma unroll
+DC_UNROLL
 		for (int i = 0; i < (int)(sizeof(DcConsts) / sizeof(double)); i++) dst[i] = src[i];
 	}
 #else
@@ -244,7 +252,7 @@ ACB_HD void demod_run(DemodRegs &r, DemodShared<CPW> &sm, const float *in, int n
 	 * past the launch are clamped: such values are never stored (the general path loads its own). */
 	float xn[ROUNDS];
 	const int last = nsamp - 1;
-#pragma unroll
+DC_UNROLL
 	for (int i = 0; i < ROUNDS; i++) {
 		const int k = sub + i * L;
 		xn[i] = nsamp > 0 ? in[(size_t)(k < last ? k : last) * nch] : 0.f;
@@ -272,7 +280,7 @@ ACB_HD void demod_run(DemodRegs &r, DemodShared<CPW> &sm, const float *in, int n
 		double pk[DEMOD_LOOK], ck[DEMOD_LOOK];
 		{
 			double p = r.phi, c = clkd;
-#pragma unroll
+DC_UNROLL
 			for (int k = 0; k < DEMOD_LOOK; k++) {
 				p = phase_step(DCK_, p, sv);
 				c = round_to_f32<F2F>(DC_DADD(c, sv));
@@ -285,11 +293,11 @@ ACB_HD void demod_run(DemodRegs &r, DemodShared<CPW> &sm, const float *in, int n
 		 * path is taken, compute a value nobody stores) */
 		DcF2 mv[ROUNDS];
 		const bool inside = m >= DEMOD_LOOK;                   /* all six candidate samples exist */
-#pragma unroll
+DC_UNROLL
 		for (int i = 0; i < ROUNDS; i++) {
 			const int k0 = i * L;
 			double ps = pk[k0];
-#pragma unroll
+DC_UNROLL
 			for (int j = 1; j < L; j++)
 				if (k0 + j < DEMOD_LOOK && sub == j) ps = pk[k0 + j];
 			mv[i] = mix_sample(DCK_, xn[i], ps, sm.tcos, sm.tsin);
@@ -309,14 +317,14 @@ ACB_HD void demod_run(DemodRegs &r, DemodShared<CPW> &sm, const float *in, int n
 			fired = true;
 			r.phi = five ? pk[4] : pk[5];
 			clkd = five ? ck[4] : ck[5];
-#pragma unroll
+DC_UNROLL
 			for (int i = 0; i < ROUNDS; i++) {                     /* next iteration's samples: in flight during the bit part */
 				const int k = n + cnt + sub + i * L;
 				xn[i] = in[(size_t)(k < last ? k : last) * nch];
 			}
 			o = bit_clock_fire<F2F>(DCK_, clkd, sv, r.df);
 			if (L > 1) Env::sync();  /* the previous bit's matched filter has read the rows being replaced */
-#pragma unroll
+DC_UNROLL
 			for (int i = 0; i < ROUNDS; i++) {
 				const int k = i * L + sub;
 				if (k < cnt) {
@@ -350,7 +358,7 @@ ACB_HD void demod_run(DemodRegs &r, DemodShared<CPW> &sm, const float *in, int n
 			r.phi = p;
 			clkd = c;
 			if (fired) o = bit_clock_fire<F2F>(DCK_, clkd, sv, r.df);
-#pragma unroll
+DC_UNROLL
 			for (int i = 0; i < ROUNDS; i++) {
 				const int k = n + cnt + sub + i * L;
 				xn[i] = last >= 0 ? in[(size_t)(k < last ? k : last) * nch] : 0.f;
@@ -365,7 +373,7 @@ ACB_HD void demod_run(DemodRegs &r, DemodShared<CPW> &sm, const float *in, int n
 			const DcF4 h0 = sm.h2[o][0], h1 = sm.h2[o][1], h2 = sm.h2[o][2];
 			const float hh11[12] = { h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w, h2.x, h2.y, h2.z, h2.w };
 			const DcF2 *rp = &sm.ring[r.idx][grp];
-#pragma unroll
+DC_UNROLL
 			for (int j = 0; j < FLEN; j++) {
 				const float hh = hh11[j];
 				const DcF2 e = rp[(size_t)j * CPW];
