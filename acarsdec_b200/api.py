@@ -44,6 +44,24 @@ MSG_DTYPE = np.dtype([("stream", "<i4"), ("chn", "<i4"), ("len", "<i4"), ("err",
 assert MSG_DTYPE.itemsize == C.sizeof(Msg)
 
 
+class Fields(C.Structure):
+    """acb_fields_t: outputmsg's field split + label.c's OOOI fields (include/acars_b200.h)."""
+    _fields_ = [("mode", C.c_char), ("ack", C.c_char), ("bid", C.c_char), ("bs", C.c_char), ("be", C.c_char),
+                ("addr", C.c_char * 8), ("label", C.c_char * 3), ("no", C.c_char * 5), ("fid", C.c_char * 7),
+                ("downlink", C.c_int), ("txt_off", C.c_int), ("txt_len", C.c_int), ("has_oooi", C.c_int),
+                ("da", C.c_char * 5), ("sa", C.c_char * 5), ("eta", C.c_char * 5), ("gout", C.c_char * 5),
+                ("gin", C.c_char * 5), ("woff", C.c_char * 5), ("won", C.c_char * 5)]
+
+
+class FmtOpts(C.Structure):
+    """acb_fmt_opts_t"""
+    _fields_ = [("tv_sec", C.c_int64), ("tv_usec", C.c_int64), ("freq_hz", C.c_uint), ("inmode", C.c_int),
+                ("airflt", C.c_int), ("emptymsg", C.c_int), ("labels", C.c_char_p), ("station_id", C.c_char_p)]
+
+
+FMT_ONELINE, FMT_FULL, FMT_JSON, FMT_NET_PP, FMT_NET_NATIVE, FMT_NET_JSON = 1, 2, 4, 11, 12, 13
+
+
 class ChanState(C.Structure):
     _fields_ = [("MskPhi", C.c_double), ("MskDf", C.c_double), ("MskLvlSum", C.c_double), ("MskClk", C.c_float),
                 ("MskBitCount", C.c_int), ("MskS", C.c_uint), ("idx", C.c_uint), ("nbits", C.c_int),
@@ -116,6 +134,8 @@ ABI = [
     ("acb_multi_set_state", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(ChanState)]),
     ("acb_mark", C.c_int, [C.c_void_p, C.c_int]),
     ("acb_elapsed_ms", C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    ("acb_msg_fields", C.c_int, [C.POINTER(Msg), C.POINTER(Fields)]),
+    ("acb_format_msg", C.c_int, [C.POINTER(Msg), C.c_int, C.POINTER(FmtOpts), C.c_char_p, C.c_size_t]),
     ("acb_drain", C.c_int, [C.c_void_p, C.POINTER(Msg), C.c_int]),
     ("acb_pending", C.c_int, [C.c_void_p]),
     ("acb_host_alloc", C.c_void_p, [C.c_size_t]),
@@ -204,6 +224,23 @@ def fast_plan(K: int, freqs_hz, fc: int):
     if lib.acb_fast_plan(f.ctypes.data, len(f), K, fc, k.ctypes.data, tw.ctypes.data) != 1:
         return None
     return k, tw[..., 0] + 1j * tw[..., 1]
+
+
+def msg_fields(m: Msg) -> Fields | None:
+    f = Fields()
+    return f if load().acb_msg_fields(C.byref(m), C.byref(f)) == 1 else None
+
+
+def format_msg(m: Msg, fmt: int, *, tv_sec: int = 0, tv_usec: int = 0, freq_hz: int = 0, inmode: int = 0, airflt: bool = False,
+               emptymsg: bool = False, labels: str | None = None, station_id: str | None = None) -> bytes | None:
+    """One decoded block in one of the reference's wire formats (FMT_*), byte for byte; None when a filter drops it."""
+    o = FmtOpts(tv_sec, tv_usec, freq_hz, inmode, int(airflt), int(emptymsg),
+                labels.encode() if labels else None, station_id.encode() if station_id else None)
+    buf = C.create_string_buffer(8192)
+    n = load().acb_format_msg(C.byref(m), fmt, C.byref(o), buf, len(buf))
+    if n < 0:
+        raise AcbError(f"acb_format_msg: error {n} (bad block, unknown format or buffer too small)")
+    return buf.raw[:n] if n else None
 
 
 def air_plan(rate: int, freqs_mhz):

@@ -28,7 +28,7 @@ COMPAT_AIR = PKG / "libacarsdec_compat_air.so"      # same shim built for -DWITH
 COMPAT_VARIANTS = [("WITH_RTL", COMPAT), ("WITH_AIR", COMPAT_AIR),
                    ("WITH_SOAPY", PKG / "libacarsdec_compat_soapy.so"),
                    ("WITH_SDRPLAY", PKG / "libacarsdec_compat_sdrplay.so")]
-LIB_SRC = [CSRC / "kernels.cu", CSRC / "context.cu", CSRC / "hostmath.cpp", CSRC / "multi.cpp"]
+LIB_SRC = [CSRC / "kernels.cu", CSRC / "context.cu", CSRC / "hostmath.cpp", CSRC / "multi.cpp", CSRC / "outfmt.c"]
 COMPAT_SRC = [CSRC / "compat.c"]
 HEADERS = [CSRC / "acb_internal.h", CSRC / "frame_sm.h", CSRC / "demod_core.h", ROOT / "include" / "acars_b200.h",
            ROOT / "include" / "acarsdec_compat.h"]

@@ -100,6 +100,34 @@ typedef struct {
 	unsigned char blk_txt[ACB_TXTMAX];
 } acb_chan_state_t;
 
+/* ---- message formatting: for hosts that take acb_msg_t blocks and do not link the reference's output.c ----
+ * outputmsg()'s field split (output.c:486-640), label.c's OOOI fields, and the reference's wire formats, byte for byte
+ * (tests/test_outfmt.py diffs them against output.c / label.c / netout.c / cJSON.c compiled in place).  Host only. */
+#define ACB_REFERENCE_VERSION "3.7"      /* ACARSDEC_VERSION (acarsdec.h:28): the "app" object of the JSON format carries it */
+typedef struct {
+	char mode, ack, bid, bs, be;          /* ack: '!' for NAK; bs / be: the text's start and end bytes (STX/ETX/ETB) */
+	char addr[8], label[3], no[5], fid[7];
+	int downlink;                         /* block id '0'..'9' (output.c:31): message number and flight id are present */
+	int txt_off, txt_len;                 /* the message text inside acb_msg_t.txt */
+	int has_oooi;                         /* label.c's DecodeLabel matched; fields below are 4 characters or empty */
+	char da[5], sa[5], eta[5], gout[5], gin[5], woff[5], won[5];
+} acb_fields_t;
+/* 1 = split done, 0 = not a block blk_thread would deliver (len < 13) */
+int acb_msg_fields(const acb_msg_t *m, acb_fields_t *out);
+typedef struct {
+	int64_t tv_sec, tv_usec;              /* msgblk_t.tv */
+	unsigned freq_hz;                     /* channel[chn].Fr: printed by the full format when inmode >= 3, and by JSON */
+	int inmode;                           /* acarsdec.c's input mode: >= 3 shows the frequency, 2 (sound file) shows no date */
+	int airflt, emptymsg;                 /* -A: downlinks only; -e: messages with text only */
+	const char *labels;                   /* -i "H1:Q0:...": labels to keep; NULL keeps all */
+	const char *station_id;               /* idstation; NULL or "" for none */
+} acb_fmt_opts_t;
+enum { ACB_FMT_ONELINE = 1, ACB_FMT_FULL = 2, ACB_FMT_JSON = 4,          /* -o 1 / 2 / 4 (without the JSON line's "\n") */
+       ACB_FMT_NET_PP = 11, ACB_FMT_NET_NATIVE = 12, ACB_FMT_NET_JSON = 13 };   /* -N / -n / -j datagrams */
+/* Writes the message in `format` to out (NUL-terminated; the formats may contain NUL bytes themselves where the reference
+ * prints one).  Returns the length, 0 when a filter of `opt` drops the message, or a negative ACB_ERR_*. */
+int acb_format_msg(const acb_msg_t *m, int format, const acb_fmt_opts_t *opt, char *out, size_t cap);
+
 /* ---- front-end planning: host-side, bit-identical to the reference's initRtl ---- */
 
 /* rtl.c:245-247 — "131.525" -> Hz on the 12.5 kHz raster */
