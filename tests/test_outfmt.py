@@ -144,3 +144,36 @@ def test_field_split_api():
     assert api.msg_fields(m) is None
     with pytest.raises(api.AcbError):
         api.format_msg(m, api.FMT_JSON)
+
+
+@pytest.mark.skipif(not (refs.ORACLE_DIR / "_ref" / "acarsdec_ref").exists(), reason="oracle/_ref/acarsdec_ref absent")
+@pytest.mark.parametrize("outtype,fmt", [("2", api.FMT_FULL), ("1", api.FMT_ONELINE), ("4", api.FMT_JSON)])
+def test_formatter_reproduces_the_reference_programs_stdout(tmp_path, oracle, outtype, fmt):
+    """End to end on the CPU: the unmodified reference program (its own DSP and its own output.c) on a synthetic capture,
+    against the same capture decoded by the restatement and printed by the product's formatter — same stdout, time stamps
+    masked (the program stamps wall-clock time)."""
+    import os
+    import re
+    from acarsdec_b200 import synth
+    K, fm = 160, (131.525, 131.725, 131.825, 131.450, 131.550)
+    fd, _, fc = oracle.plan(K, fm)
+    plan = synth.make_plan(K, fm, fc, seconds=1.5, seed=123, text_len=(10, 120), msgs_per_chan_per_sec=3.0)
+    nblk = synth.blocks_for_seconds(K, 1.5)
+    iq = synth.render_blocks(plan, 0, nblk)
+    cap = tmp_path / "cap.iq"
+    iq.tofile(cap)
+    ref = subprocess.run([str(refs.ORACLE_DIR / "_ref" / "acarsdec_ref"), "-o", outtype, "-m", str(K), "-i", "STA1", "-r", "0", *[str(f) for f in fm]],
+                         env=dict(os.environ, ACARSDEC_STUB_IQ=str(cap)), capture_output=True, timeout=120)
+    assert ref.returncode == 0, ref.stderr
+    o = refs.OracleStream(oracle, K, oracle.wf(K, fm))
+    o.blocks(iq.reshape(-1))
+    mine = b""
+    for om in o.msgs():
+        m = api.Msg()
+        m.chn, m.len, m.err, m.lvl = om.chn, om.len, om.err, om.lvl
+        m.txt[:om.len] = om.txt[:om.len]
+        # rtl.c:255 keeps the frequency as int <- float <- unsigned: what channel[].Fr holds and the formats print
+        s = api.format_msg(m, fmt, tv_sec=T0, tv_usec=123000, freq_hz=api.load().acb_stored_fr(fd[m.chn]), inmode=3, station_id="STA1")
+        mine += s + (b"\n" if fmt == api.FMT_JSON else b"")
+    mask = lambda b: re.sub(rb"\d\d/\d\d/\d{4} \d\d:\d\d:\d\d\.\d{3}", b"<time>", re.sub(rb'"timestamp":[0-9.e+]+', b'"timestamp":<time>', b))
+    assert mask(ref.stdout).count(b"<time>") >= 8 and mask(ref.stdout) == mask(mine)
