@@ -136,6 +136,10 @@ ABI = [
     ("acb_elapsed_ms", C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     ("acb_msg_fields", C.c_int, [C.POINTER(Msg), C.POINTER(Fields)]),
     ("acb_format_msg", C.c_int, [C.POINTER(Msg), C.c_int, C.POINTER(FmtOpts), C.c_char_p, C.c_size_t]),
+    ("acb_flights_new", C.c_void_p, [C.c_int]),
+    ("acb_flights_free", None, [C.c_void_p]),
+    ("acb_flights_route_json", C.c_int, [C.c_void_p, C.POINTER(Msg), C.POINTER(FmtOpts), C.c_char_p, C.c_size_t]),
+    ("acb_flights_monitor", C.c_int, [C.c_void_p, C.POINTER(Msg), C.c_int, C.POINTER(FmtOpts), C.c_char_p, C.c_size_t]),
     ("acb_drain", C.c_int, [C.c_void_p, C.POINTER(Msg), C.c_int]),
     ("acb_pending", C.c_int, [C.c_void_p]),
     ("acb_host_alloc", C.c_void_p, [C.c_size_t]),
@@ -241,6 +245,45 @@ def format_msg(m: Msg, fmt: int, *, tv_sec: int = 0, tv_usec: int = 0, freq_hz: 
     if n < 0:
         raise AcbError(f"acb_format_msg: error {n} (bad block, unknown format or buffer too small)")
     return buf.raw[:n] if n else None
+
+
+class Flights:
+    """The flight table behind acarsdec's route JSON (-o 5) and monitor screen (-o 3): feed every block in emission order."""
+
+    def __init__(self, mdly_seconds: int = 600):
+        self.lib = load()
+        self.h = C.c_void_p(self.lib.acb_flights_new(mdly_seconds))
+        if not self.h:
+            raise AcbError("acb_flights_new failed")
+
+    @staticmethod
+    def _opts(kw):
+        lab, sta = kw.get("labels"), kw.get("station_id")
+        return FmtOpts(kw.get("tv_sec", 0), kw.get("tv_usec", 0), kw.get("freq_hz", 0), kw.get("inmode", 0), int(kw.get("airflt", False)),
+                       int(kw.get("emptymsg", False)), lab.encode() if lab else None, sta.encode() if sta else None)
+
+    def _call(self, fn, *args):
+        buf = C.create_string_buffer(16384)
+        n = fn(*args, buf, len(buf))
+        if n < 0:
+            raise AcbError(f"flight table: error {n}")
+        return buf.raw[:n] if n else None
+
+    def route_json(self, m: Msg, **kw) -> bytes | None:
+        o = self._opts(kw)
+        return self._call(self.lib.acb_flights_route_json, self.h, C.byref(m), C.byref(o))
+
+    def monitor(self, m: Msg, nbch: int, **kw) -> bytes | None:
+        o = self._opts(kw)
+        return self._call(self.lib.acb_flights_monitor, self.h, C.byref(m), nbch, C.byref(o))
+
+    def close(self):
+        if self.h:
+            self.lib.acb_flights_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
 
 
 def air_plan(rate: int, freqs_mhz):

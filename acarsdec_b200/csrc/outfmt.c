@@ -10,12 +10,14 @@
  * label.c / netout.c / cJSON.c compiled in place), with two stated exceptions where the reference's behaviour is undefined:
  *   - label.c reads fixed offsets of the text without looking at its length; here bytes past the end of the text read as 0;
  *   - a block shorter than 13 bytes cannot come out of blk_thread (acars.c:124-129) and is refused.
- * Not covered: the monitor screen and the route JSON (stateful flight table, output.c:361-484), MQTT, libacars decoding.
+ * The flight table behind the route JSON (-o 5) and the monitor screen (-o 3) is the acb_flights_* object at the end
+ * (output.c:349-484).  Not covered: MQTT, libacars decoding, log-file rotation.
  */
 #define _GNU_SOURCE
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <time.h>
 
@@ -463,6 +465,152 @@ int acb_format_msg(const acb_msg_t *m, int format, const acb_fmt_opts_t *opt, ch
 	case ACB_FMT_NET_NATIVE: fmt_net_native(&s, m, &f, o); break;
 	case ACB_FMT_NET_JSON: fmt_json(&s, m, &f, o); putc1(&s, '\n'); break;
 	default: return ACB_ERR_ARG;
+	}
+	if (s.overflow) return ACB_ERR_ARG;
+	out[s.n] = 0;
+	return (int)s.n;
+}
+
+/* ---------------------------------------------------------------------------------------- flight table
+ * output.c:349-426: one entry per aircraft address seen on a downlink, most recent first; an entry keeps the flight id of
+ * its last message, first / last time, the channels it was heard on, a message count and whatever OOOI fields its messages
+ * have yielded so far; entries silent for more than `mdly` seconds are dropped whenever a message is added. */
+typedef struct flight {
+	struct flight *next;
+	char addr[8], fid[7];
+	int64_t first_sec, first_usec, last_sec;
+	int chmask, count, route_sent;
+	char da[5], sa[5], eta[5], gout[5], gin[5], woff[5], won[5];
+} flight_t;
+
+struct acb_flights { flight_t *head; int mdly; };
+
+acb_flights_t *acb_flights_new(int mdly_seconds)
+{
+	acb_flights_t *t = (acb_flights_t *)calloc(1, sizeof *t);
+	if (t) t->mdly = mdly_seconds > 0 ? mdly_seconds : 600;           /* acarsdec.c:44 */
+	return t;
+}
+
+void acb_flights_free(acb_flights_t *t)
+{
+	if (!t) return;
+	for (flight_t *f = t->head; f;) {
+		flight_t *n = f->next;
+		free(f);
+		f = n;
+	}
+	free(t);
+}
+
+static void keep4(char *dst, const char *src) { if (src[0]) memcpy(dst, src, 5); }
+
+/* addFlight: only downlinks with a text part reach it (outflg, output.c:553-575) */
+static flight_t *flights_add(acb_flights_t *t, const acb_msg_t *m, const acb_fields_t *f, const acb_fmt_opts_t *o)
+{
+	flight_t *fl = t->head, *prev = NULL;
+	while (fl && strcmp(f->addr, fl->addr) != 0) { prev = fl; fl = fl->next; }
+	if (!fl) {
+		fl = (flight_t *)calloc(1, sizeof *fl);
+		if (!fl) return NULL;
+		strncpy(fl->addr, f->addr, sizeof fl->addr);
+		fl->first_sec = o->tv_sec;
+		fl->first_usec = o->tv_usec;
+		fl->next = t->head;                                           /* new entries go to the front */
+		t->head = fl;
+	} else if (prev) {                                                /* a known one moves to the front */
+		prev->next = fl->next;
+		fl->next = t->head;
+		t->head = fl;
+	}
+	strncpy(fl->fid, f->fid, sizeof fl->fid);
+	fl->last_sec = o->tv_sec;
+	fl->chmask |= 1 << m->chn;
+	fl->count++;
+	if (f->has_oooi) {
+		keep4(fl->da, f->da); keep4(fl->sa, f->sa); keep4(fl->eta, f->eta); keep4(fl->gout, f->gout);
+		keep4(fl->gin, f->gin); keep4(fl->woff, f->woff); keep4(fl->won, f->won);
+	}
+	for (flight_t **pp = &t->head; *pp;) {                            /* expiry */
+		if ((*pp)->last_sec < o->tv_sec - t->mdly) {
+			flight_t *dead = *pp;
+			*pp = dead->next;
+			free(dead);
+		} else {
+			pp = &(*pp)->next;
+		}
+	}
+	return fl;
+}
+
+static int flights_gate(const acb_msg_t *m, const acb_fmt_opts_t *o, acb_fields_t *f)
+{
+	if (!acb_msg_fields(m, f)) return ACB_ERR_ARG;
+	if (o->airflt && !f->downlink) return 0;
+	if (!label_passes(o->labels, f->label)) return 0;
+	return 1;
+}
+
+int acb_flights_route_json(acb_flights_t *t, const acb_msg_t *m, const acb_fmt_opts_t *opt, char *out, size_t cap)
+{
+	static const acb_fmt_opts_t none = { 0, 0, 0, 0, 0, 0, NULL, NULL };
+	if (!t || !m || !out || cap == 0) return ACB_ERR_ARG;
+	const acb_fmt_opts_t *o = opt ? opt : &none;
+	acb_fields_t f;
+	const int g = flights_gate(m, o, &f);
+	if (g <= 0) return g;
+	out[0] = 0;
+	if (!(f.downlink && f.bs != 0x03)) return 0;                      /* uplinks and squitters never enter the table */
+	flight_t *fl = flights_add(t, m, &f, o);
+	if (!fl) return ACB_ERR_NOMEM;
+	if (o->emptymsg && text_strlen(&f, m->txt) == 0) return 0;
+	if (fl->route_sent || !fl->fid[0] || !fl->sa[0] || !fl->da[0]) return 0;       /* routejson, output.c:428-456: once per flight */
+	sink_t s = { out, cap, 0, 0 };
+	int first = 1;
+	putc1(&s, '{');
+	json_kv_num(&s, &first, "timestamp", (double)o->tv_sec + ((double)o->tv_usec) / 1e6);
+	if (o->station_id && o->station_id[0]) json_kv_str(&s, &first, "station_id", o->station_id, strlen(o->station_id));
+	json_kv_str(&s, &first, "flight", fl->fid, 6);
+	json_kv_str(&s, &first, "depa", fl->sa, 4);
+	json_kv_str(&s, &first, "dsta", fl->da, 4);
+	putc1(&s, '}');
+	if (s.overflow) return ACB_ERR_ARG;
+	fl->route_sent = 1;
+	out[s.n] = 0;
+	return (int)s.n;
+}
+
+/* the monitor screen (printmonitor, output.c:458-484) after this message; `nbch` = channels of the receiver */
+int acb_flights_monitor(acb_flights_t *t, const acb_msg_t *m, int nbch, const acb_fmt_opts_t *opt, char *out, size_t cap)
+{
+	static const acb_fmt_opts_t none = { 0, 0, 0, 0, 0, 0, NULL, NULL };
+	if (!t || !m || !out || cap == 0 || nbch < 0 || nbch > 16) return ACB_ERR_ARG;
+	const acb_fmt_opts_t *o = opt ? opt : &none;
+	acb_fields_t f;
+	const int g = flights_gate(m, o, &f);
+	if (g <= 0) return g;
+	out[0] = 0;
+	if (f.downlink && f.bs != 0x03 && !flights_add(t, m, &f, o)) return ACB_ERR_NOMEM;
+	if (o->emptymsg && text_strlen(&f, m->txt) == 0) return 0;
+	sink_t s = { out, cap, 0, 0 };
+	struct tm tmv;
+	time_t sec = (time_t)o->tv_sec;
+	gmtime_r(&sec, &tmv);
+	puts0(&s, "\x1b[H\x1b[2J");
+	putf(&s, "             Acarsdec monitor %02d:%02d:%02d.%03ld", tmv.tm_hour, tmv.tm_min, tmv.tm_sec, (long)(o->tv_usec / 1000));
+	puts0(&s, "\n Aircraft Flight   Nb Channels     First    DEP   ARR   ETA\n");
+	for (const flight_t *fl = t->head; fl; fl = fl->next) {
+		putf(&s, " %-8s %-7s %3d ", fl->addr, fl->fid, fl->count);
+		int i = 0;
+		for (; i < nbch; i++) putc1(&s, (fl->chmask & (1 << i)) ? 'x' : '.');
+		for (; i < 16; i++) putc1(&s, ' ');                            /* MAXNBCHANNELS columns */
+		sec = (time_t)fl->first_sec;
+		gmtime_r(&sec, &tmv);
+		putf(&s, " %02d:%02d:%02d.%03ld", tmv.tm_hour, tmv.tm_min, tmv.tm_sec, (long)(fl->first_usec / 1000));
+		if (fl->sa[0]) putf(&s, " %4s ", fl->sa); else puts0(&s, "      ");
+		if (fl->da[0]) putf(&s, " %4s ", fl->da); else puts0(&s, "      ");
+		if (fl->eta[0]) putf(&s, " %4s ", fl->eta); else puts0(&s, "      ");
+		putc1(&s, '\n');
 	}
 	if (s.overflow) return ACB_ERR_ARG;
 	out[s.n] = 0;

@@ -102,7 +102,8 @@ typedef struct {
 
 /* ---- message formatting: for hosts that take acb_msg_t blocks and do not link the reference's output.c ----
  * outputmsg()'s field split (output.c:486-640), label.c's OOOI fields, and the reference's wire formats, byte for byte
- * (tests/test_outfmt.py diffs them against output.c / label.c / netout.c / cJSON.c compiled in place).  Host only. */
+ * (tests/test_outfmt.py diffs them against output.c / label.c / netout.c / cJSON.c compiled in place).  Host only.
+ * Not rebuilt: MQTT, libacars decoding, log-file rotation. */
 #define ACB_REFERENCE_VERSION "3.7"      /* ACARSDEC_VERSION (acarsdec.h:28): the "app" object of the JSON format carries it */
 typedef struct {
 	char mode, ack, bid, bs, be;          /* ack: '!' for NAK; bs / be: the text's start and end bytes (STX/ETX/ETB) */
@@ -127,6 +128,18 @@ enum { ACB_FMT_ONELINE = 1, ACB_FMT_FULL = 2, ACB_FMT_JSON = 4,          /* -o 1
 /* Writes the message in `format` to out (NUL-terminated; the formats may contain NUL bytes themselves where the reference
  * prints one).  Returns the length, 0 when a filter of `opt` drops the message, or a negative ACB_ERR_*. */
 int acb_format_msg(const acb_msg_t *m, int format, const acb_fmt_opts_t *opt, char *out, size_t cap);
+/* The flight table of output.c:349-426 (one entry per aircraft heard on a downlink; entries silent for `mdly_seconds`,
+ * acarsdec's -t, default 600, are dropped) and the two outputs that need it.  Feed every block, in emission order, to ONE
+ * of the two calls:
+ *   acb_flights_route_json  -o 5: one JSON object per flight, the first time flight id, departure and destination are all
+ *                           known (output.c:428-456); returns its length, 0 when this block produces none;
+ *   acb_flights_monitor     -o 3: the monitor screen as redrawn after this block (output.c:458-484), `nbch` = channels
+ *                           of the receiver (<= 16). */
+typedef struct acb_flights acb_flights_t;
+acb_flights_t *acb_flights_new(int mdly_seconds);
+void acb_flights_free(acb_flights_t *t);
+int acb_flights_route_json(acb_flights_t *t, const acb_msg_t *m, const acb_fmt_opts_t *opt, char *out, size_t cap);
+int acb_flights_monitor(acb_flights_t *t, const acb_msg_t *m, int nbch, const acb_fmt_opts_t *opt, char *out, size_t cap);
 
 /* ---- front-end planning: host-side, bit-identical to the reference's initRtl ---- */
 

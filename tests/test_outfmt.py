@@ -177,3 +177,45 @@ def test_formatter_reproduces_the_reference_programs_stdout(tmp_path, oracle, ou
         mine += s + (b"\n" if fmt == api.FMT_JSON else b"")
     mask = lambda b: re.sub(rb"\d\d/\d\d/\d{4} \d\d:\d\d:\d\d\.\d{3}", b"<time>", re.sub(rb'"timestamp":[0-9.e+]+', b'"timestamp":<time>', b))
     assert mask(ref.stdout).count(b"<time>") >= 8 and mask(ref.stdout) == mask(mine)
+
+
+def _flight_sequence():
+    """Downlinks of a handful of aircraft over 25 minutes: route information arriving in pieces, flight ids changing, one
+    aircraft falling silent for longer than the table keeps it (600 s) and coming back."""
+    rng = np.random.default_rng(5)
+    tails = [b".N123AB", b"..G-ABC", b".D-AIXY", b"JA8089.", b".F-GZZZ"]
+    fids = [b"XX1234", b"BA0042", b"LH0400", b"JL0005", b"AF0011"]
+    texts = [(b"QA", b"EDDF1234"), (b"Q2", b"KJFK0915"), (b"12", b"EDDF,KJFK rest"), (b"H1", b"no route information in here"), (b"2Z", b"RJTT"),
+             (b"QE", b"LFPG0830EGLL"), (b"10", b"ARR01ABCDEFGEGLL1015"), (b"5Z", b"")]
+    blocks, t = [], T0
+    for i in range(90):
+        a = int(rng.integers(len(tails))) if i not in range(30, 60) else int(rng.integers(1, len(tails)))      # tail 0 silent for a while
+        lab, txt = texts[int(rng.integers(len(texts)))]
+        t += int(rng.integers(1, 40)) if i != 45 else 700
+        fid = fids[a] if rng.random() < 0.8 else fids[(a + 1) % len(fids)]
+        blocks.append((int(rng.integers(0, 8)), 131525000, _block(addr=tails[a], label=lab, bid=bytes([48 + i % 10]), text=txt + b" " * 24, fid=fid,
+                                                                   no=b"M%02dA" % (i % 100)), -10.0, 0, t, int(rng.integers(0, 10**6))))
+    return blocks
+
+
+def test_route_json_and_monitor_follow_the_reference_flight_table():
+    blocks = _flight_sequence()
+    raw, msgs = _records(blocks)
+    want = _reference(raw, 5, "-", 3, False, False, None, "STA1")              # -o 5: route JSON
+    fl = api.Flights()
+    got = [fl.route_json(m, tv_sec=b[5], tv_usec=b[6], station_id="STA1") for b, m in zip(blocks, msgs)]
+    got = [g + b"\n" if g else None for g in got]
+    assert got == want and sum(g is not None for g in got) >= 4
+    # an uplink or a squitter never enters the table (and the reference reads an unset pointer for them in this mode)
+    up = api.Msg()
+    txt = _block(bid=b"A", label=b"12", text=b"EDDF,KJFK")
+    up.len = len(txt)
+    up.txt[:len(txt)] = txt
+    assert fl.route_json(up, tv_sec=T0) is None
+    fl.close()
+    mixed = blocks[:40] + [(2, 131525000, _block(bid=b"B", label=b"H1", text=b"uplink text"), -5.0, 0, blocks[39][5] + 5, 0)] + blocks[40:]
+    raw, msgs = _records(mixed)
+    want = _reference(raw, 3, "-", 3, False, False, None, "STA1")              # -o 3: the monitor screen after every block
+    fl = api.Flights()
+    got = [fl.monitor(m, 16, tv_sec=b[5], tv_usec=b[6], station_id="STA1") for b, m in zip(mixed, msgs)]
+    assert got == want and all(g is not None for g in got)
