@@ -525,7 +525,7 @@ static flight_t *flights_add(acb_flights_t *t, const acb_msg_t *m, const acb_fie
 	}
 	strncpy(fl->fid, f->fid, sizeof fl->fid);
 	fl->last_sec = o->tv_sec;
-	fl->chmask |= 1 << m->chn;
+	if (m->chn >= 0 && m->chn < 31) fl->chmask |= 1 << m->chn;
 	fl->count++;
 	if (f->has_oooi) {
 		keep4(fl->da, f->da); keep4(fl->sa, f->sa); keep4(fl->eta, f->eta); keep4(fl->gout, f->gout);

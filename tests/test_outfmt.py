@@ -219,3 +219,19 @@ def test_route_json_and_monitor_follow_the_reference_flight_table():
     fl = api.Flights()
     got = [fl.monitor(m, 16, tv_sec=b[5], tv_usec=b[6], station_id="STA1") for b, m in zip(mixed, msgs)]
     assert got == want and all(g is not None for g in got)
+
+
+def test_formatter_fuzz_under_sanitizers(tmp_path):
+    """Random and malformed blocks (any bytes, lengths outside 13..248, tiny output buffers, unknown formats) through every
+    entry point of outfmt.c, compiled with AddressSanitizer and UBSan."""
+    import shutil
+    cc = shutil.which("gcc")
+    exe = tmp_path / "fuzz_outfmt"
+    root = refs.ORACLE_DIR.parent
+    r = subprocess.run([cc, "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-I", str(root / "include"), "-o", str(exe),
+                        str(root / "tests" / "host" / "fuzz_outfmt.c"), str(root / "acarsdec_b200" / "csrc" / "outfmt.c")], capture_output=True, text=True)
+    if r.returncode != 0 and "sanitize" in r.stderr:
+        pytest.skip("this gcc has no sanitizer runtime")
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.startswith("fuzz ok"), r.stderr[-2000:]
